@@ -1,0 +1,436 @@
+"""Image corruption generators -- CPU oracle (numpy / cv2 / scipy).  TEST INFRASTRUCTURE ONLY.
+
+The reference has no server-side corruption generator (only display-only JS effects,
+platform/frontend/js/app.js:789-799, :834-851); its "corruption config" is two sliders and
+four modes (platform/backend/vision_simulator.py:25-36).  These generators restate the
+Hendrycks & Dietterich (ICLR'19) definitions as recorded in SURVEY.md Appendix A.2, with all
+randomness re-expressed on the counter-based Philox stream of oracle/philox.py so that a GPU
+kernel can reproduce every draw (PARITY UNPINNED by the reference; this file is the definition).
+
+Input : uint8 [N,H,W,3] (RGB order), severity 1..5.
+Output: float32 [N,H,W,3] in [0,1].
+"""
+import math
+import numpy as np
+
+from . import philox as px
+
+CORRUPTIONS = (
+    "gaussian_noise", "shot_noise", "impulse_noise", "defocus_blur", "glass_blur",
+    "motion_blur", "zoom_blur", "snow", "frost", "fog", "brightness", "contrast",
+    "elastic_transform", "pixelate", "jpeg_compression",
+)
+CORRUPTION_ID = {name: i + 1 for i, name in enumerate(CORRUPTIONS)}   # 0 = clean
+
+# per-severity constants: [profile][name][severity-1]
+CONSTANTS = {
+    "imagenet": {
+        "gaussian_noise": [.08, .12, .18, .26, .38],
+        "shot_noise": [60, 25, 12, 5, 3],
+        "impulse_noise": [.03, .06, .09, .17, .27],
+        "defocus_blur": [(3, .1), (4, .5), (6, .5), (8, .5), (10, .5)],
+        "motion_blur": [(10, 3), (15, 5), (15, 8), (15, 12), (20, 15)],
+        "zoom_blur": [(1.11, .01), (1.16, .01), (1.21, .02), (1.26, .02), (1.33, .03)],
+        "fog": [(1.5, 2), (2., 2), (2.5, 1.7), (2.5, 1.5), (3., 1.4)],
+        "brightness": [.1, .2, .3, .4, .5],
+        "contrast": [.4, .3, .2, .1, .05],
+        "pixelate": [.6, .5, .4, .3, .25],
+        "jpeg_compression": [25, 18, 15, 10, 7],
+        "glass_blur": [(.7, 1, 2), (.9, 2, 1), (1, 2, 3), (1.1, 3, 2), (1.5, 4, 2)],
+        "snow": [(.1, .3, 3, .5, 10, 4, .8), (.2, .3, 2, .5, 12, 4, .7), (.55, .3, 4, .9, 12, 8, .7),
+                 (.55, .3, 4.5, .85, 12, 8, .65), (.55, .3, 2.5, .85, 12, 12, .55)],
+        "frost": [(1, .4), (.8, .6), (.7, .7), (.65, .7), (.6, .75)],
+        "elastic_transform": [(2., .7, .1), (2., .08, .2), (.05, .01, .02), (.07, .01, .02), (.12, .01, .02)],
+    },
+    "cifar": {
+        "gaussian_noise": [.04, .06, .08, .09, .10],
+        "shot_noise": [500, 250, 100, 75, 50],
+        "impulse_noise": [.01, .02, .03, .05, .07],
+        "defocus_blur": [(.3, .4), (.4, .5), (.5, .6), (1, .2), (1.5, .1)],
+        "motion_blur": [(10, 1), (10, 1.5), (10, 2), (10, 2.5), (12, 3)],
+        "zoom_blur": [(1.06, .01), (1.11, .01), (1.16, .01), (1.21, .01), (1.26, .01)],
+        "fog": [(.2, 3), (.5, 3), (.75, 2.5), (1, 2), (1.5, 1.75)],
+        "brightness": [.05, .1, .15, .2, .3],
+        "contrast": [.75, .5, .4, .3, .15],
+        "pixelate": [.95, .9, .85, .75, .65],
+        "jpeg_compression": [80, 65, 58, 50, 40],
+        "glass_blur": [(.05, 1, 1), (.25, 1, 1), (.4, 1, 1), (.25, 1, 2), (.4, 1, 2)],
+        "snow": [(.1, .2, 1, .6, 8, 3, .95), (.1, .2, 1, .5, 10, 4, .9), (.15, .3, 1.75, .55, 10, 4, .9),
+                 (.25, .3, 2.25, .6, 12, 6, .85), (.3, .3, 1.25, .65, 14, 12, .8)],
+        "frost": [(1, .2), (1, .3), (.9, .4), (.85, .4), (.75, .45)],
+        "elastic_transform": [(0, 0, .08), (.05, .2, .07), (.08, .06, .06), (.1, .04, .05), (.1, .03, .03)],
+    },
+}
+
+
+def profile_for(h, w):
+    """CIFAR-10-C constants for small frames, ImageNet-C constants otherwise."""
+    return "cifar" if max(h, w) <= 64 else "imagenet"
+
+
+def _to_float(x_u8):
+    return (x_u8.astype(np.float32) / np.float32(255.0)).astype(np.float32)
+
+
+def _stream(name, severity, kind=px.KIND_CORRUPT):
+    return px.stream_id(kind, CORRUPTION_ID[name], severity)
+
+
+def _elem_draws(n, per, name, severity, seed, first_image, sub=0):
+    """One u32 per element: [n, per] uint32. Element e uses word e%4 of Philox call e//4."""
+    nch = (per + 3) // 4
+    img = np.arange(first_image, first_image + n, dtype=np.uint64)[:, None]
+    ch = np.arange(nch, dtype=np.uint64)[None, :]
+    xs = px.philox4x32_10(ch, img, sub, _stream(name, severity), seed)
+    return np.stack(xs, axis=-1).reshape(n, nch * 4)[:, :per]
+
+
+# ----------------------------------------------------------------------------- noise family
+def gaussian_noise(x_u8, severity, seed=0, first_image=0, profile=None):
+    n, h, w, _ = x_u8.shape
+    c = np.float32(CONSTANTS[profile or profile_for(h, w)]["gaussian_noise"][severity - 1])
+    per = h * w * 3
+    nch = (per + 3) // 4
+    img = np.arange(first_image, first_image + n, dtype=np.uint64)[:, None]
+    ch = np.arange(nch, dtype=np.uint64)[None, :]
+    x0, x1, x2, x3 = px.philox4x32_10(ch, img, 0, _stream("gaussian_noise", severity), seed)
+    z0, z1 = px.box_muller(x0, x1)
+    z2, z3 = px.box_muller(x2, x3)
+    z = np.stack([z0, z1, z2, z3], axis=-1).reshape(n, nch * 4)[:, :per].reshape(x_u8.shape)
+    return np.clip(_to_float(x_u8) + c * z, 0, 1).astype(np.float32)
+
+
+def poisson_table(c):
+    """Inverse-CDF tables for Poisson(lambda = v/255*c), v = 0..255.
+
+    Returns (kmin[256] int32, width int, thr[256, width] uint32) with
+    thr[v, j] = floor(CDF(kmin[v] + j) * 2^32) clipped to 2^32-1; a draw u (uint32) maps to
+    k = kmin[v] + #{j : thr[v, j] <= u}.  Integer compares only -> bit-exact on any device.
+    """
+    from scipy.stats import poisson
+    lam = np.arange(256, dtype=np.float64) / 255.0 * float(c)
+    sd = np.sqrt(lam)
+    kmin = np.maximum(0, np.floor(lam - 7.5 * sd - 4)).astype(np.int64)
+    width = int(np.max(np.ceil(lam + 7.5 * sd + 12) - kmin)) + 1
+    width = (width + 3) // 4 * 4
+    ks = kmin[:, None] + np.arange(width)[None, :]
+    cdf = poisson.cdf(ks, lam[:, None])
+    thr = np.minimum(np.floor(cdf * 2.0 ** 32), 2.0 ** 32 - 1).astype(np.uint64).astype(np.uint32)
+    return kmin.astype(np.int32), width, thr
+
+
+def shot_noise(x_u8, severity, seed=0, first_image=0, profile=None):
+    n, h, w, _ = x_u8.shape
+    c = CONSTANTS[profile or profile_for(h, w)]["shot_noise"][severity - 1]
+    kmin, width, thr = poisson_table(c)
+    per = h * w * 3
+    u = _elem_draws(n, per, "shot_noise", severity, seed, first_image).reshape(x_u8.shape)
+    rows = thr[x_u8]                                              # [n,h,w,3,width]
+    k = kmin[x_u8] + (rows <= u[..., None]).sum(-1).astype(np.int32)
+    return np.clip(k.astype(np.float32) / np.float32(c), 0, 1).astype(np.float32)
+
+
+def impulse_thresholds(c):
+    return int(math.floor(c / 2 * 2.0 ** 32)), int(math.floor(c * 2.0 ** 32))
+
+
+def impulse_noise(x_u8, severity, seed=0, first_image=0, profile=None):
+    n, h, w, _ = x_u8.shape
+    c = CONSTANTS[profile or profile_for(h, w)]["impulse_noise"][severity - 1]
+    tp, ts = impulse_thresholds(c)
+    u = _elem_draws(n, h * w * 3, "impulse_noise", severity, seed, first_image).reshape(x_u8.shape)
+    x = _to_float(x_u8)
+    x = np.where(u < np.uint32(ts), np.float32(1.0), x)
+    x = np.where(u < np.uint32(tp), np.float32(0.0), x)
+    return x.astype(np.float32)
+
+
+# ----------------------------------------------------------------------------- tap stencils
+def disk_kernel(radius, alias_blur):
+    """Aliased disk blurred by a small Gaussian (cv2), as in make_imagenet_c.disk()."""
+    import cv2
+    if radius <= 8:
+        L = np.arange(-8, 8 + 1)
+        ksize = (3, 3)
+    else:
+        L = np.arange(-int(radius), int(radius) + 1)
+        ksize = (5, 5)
+    X, Y = np.meshgrid(L, L)
+    disk = np.array((X ** 2 + Y ** 2) <= radius ** 2, dtype=np.float32)
+    disk /= disk.sum()
+    return cv2.GaussianBlur(disk, ksize=ksize, sigmaX=alias_blur)
+
+
+def _reflect101(i, n):
+    i = np.abs(i)
+    i = np.where(i >= n, 2 * (n - 1) - i, i)
+    # very wide kernels on tiny images can overshoot twice
+    i = np.abs(i)
+    return np.where(i >= n, 2 * (n - 1) - i, i)
+
+
+def _apply_taps(x, dys, dxs, ws, border):
+    """x float32 [N,H,W,3]; out = sum_i w_i * x[border(y+dy_i), border(x+dx_i)], fp32 in tap order."""
+    n, h, w, _ = x.shape
+    ys = np.arange(h)
+    xs = np.arange(w)
+    out = np.zeros_like(x)
+    for dy, dx, wt in zip(dys, dxs, ws):
+        if border == "reflect101":
+            yy, xx = _reflect101(ys + dy, h), _reflect101(xs + dx, w)
+        else:
+            yy, xx = np.clip(ys + dy, 0, h - 1), np.clip(xs + dx, 0, w - 1)
+        out += np.float32(wt) * x[:, yy][:, :, xx]
+    return out
+
+
+def defocus_taps(radius, alias_blur):
+    k = disk_kernel(radius, alias_blur)
+    r = k.shape[0] // 2
+    dys, dxs, ws = [], [], []
+    for iy in range(k.shape[0]):
+        for ix in range(k.shape[1]):
+            if k[iy, ix] != 0:
+                # cv2.filter2D is correlation: out(y,x) = sum k(iy,ix) * src(y+iy-r, x+ix-r)
+                dys.append(iy - r), dxs.append(ix - r), ws.append(np.float32(k[iy, ix]))
+    return dys, dxs, ws
+
+
+def defocus_blur(x_u8, severity, seed=0, first_image=0, profile=None):
+    n, h, w, _ = x_u8.shape
+    radius, alias = CONSTANTS[profile or profile_for(h, w)]["defocus_blur"][severity - 1]
+    dys, dxs, ws = defocus_taps(radius, alias)
+    return np.clip(_apply_taps(_to_float(x_u8), dys, dxs, ws, "reflect101"), 0, 1).astype(np.float32)
+
+
+MOTION_ANGLES = 91          # integer degrees -45..45
+
+
+def motion_taps(radius, sigma, angle_deg):
+    """Shift-and-add motion blur taps (imagecorruptions-package formulation, no Wand)."""
+    width = radius * 2 + 1
+    k = np.exp(-(np.arange(width, dtype=np.float64) ** 2) / (2.0 * sigma ** 2))
+    k = (k / k.sum()).astype(np.float32)
+    a = math.radians(angle_deg)
+    p0, p1 = width * math.sin(a), width * math.cos(a)
+    hyp = math.hypot(p0, p1)
+    dys, dxs = [], []
+    for i in range(width):
+        dy = -math.ceil((i * p0) / hyp - 0.5)
+        dx = -math.ceil((i * p1) / hyp - 0.5)
+        # shifted image S(y,x) = X(clamp(y-dy), clamp(x-dx))  ->  tap offset = (-dy, -dx)
+        dys.append(-dy), dxs.append(-dx)
+    return dys, dxs, list(k)
+
+
+def motion_angle_index(n, severity, seed, first_image):
+    img = np.arange(first_image, first_image + n, dtype=np.uint64)
+    x0, _, _, _ = px.philox4x32_10(0, img, 0, _stream("motion_blur", severity, px.KIND_AUX), seed)
+    return (x0 % np.uint32(MOTION_ANGLES)).astype(np.int32)
+
+
+def motion_blur(x_u8, severity, seed=0, first_image=0, profile=None):
+    n, h, w, _ = x_u8.shape
+    radius, sigma = CONSTANTS[profile or profile_for(h, w)]["motion_blur"][severity - 1]
+    aidx = motion_angle_index(n, severity, seed, first_image)
+    x = _to_float(x_u8)
+    out = np.empty_like(x)
+    for i in range(n):
+        dys, dxs, ws = motion_taps(radius, sigma, int(aidx[i]) - 45)
+        # taps whose shift leaves the frame are dropped from that point on (reference 'break')
+        keep = len(ws)
+        for j, (dy, dx) in enumerate(zip(dys, dxs)):
+            if abs(dy) >= h or abs(dx) >= w:
+                keep = j
+                break
+        out[i] = _apply_taps(x[i:i + 1], dys[:keep], dxs[:keep], ws[:keep], "clamp")[0]
+    return np.clip(out, 0, 1).astype(np.float32)
+
+
+def zoom_factors(spec):
+    zmax, step = spec
+    return [float(z) for z in np.arange(1.0, zmax, step)]
+
+
+def zoom_geometry(h, z):
+    """clipped_zoom geometry: crop hc rows at `top`, bilinear-zoom to ho rows, trim `trim` rows."""
+    hc = int(math.ceil(h / z))
+    top = (h - hc) // 2
+    ho = int(round(hc * z))
+    trim = (ho - h) // 2
+    return hc, top, ho, trim
+
+
+def _zoom_sample_axis(h, z):
+    """For each output index o in [0,h): (i0, i1, frac) into the uncropped axis."""
+    hc, top, ho, trim = zoom_geometry(h, z)
+    o = np.arange(h, dtype=np.float32) + np.float32(trim)
+    scale = np.float32((hc - 1) / (ho - 1)) if ho > 1 else np.float32(0)
+    src = (o * scale).astype(np.float32)
+    i0 = np.floor(src).astype(np.int32)
+    i0 = np.clip(i0, 0, hc - 1)
+    i1 = np.minimum(i0 + 1, hc - 1)
+    fr = (src - i0.astype(np.float32)).astype(np.float32)
+    return i0 + top, i1 + top, fr
+
+
+def zoom_blur(x_u8, severity, seed=0, first_image=0, profile=None):
+    n, h, w, _ = x_u8.shape
+    zs = zoom_factors(CONSTANTS[profile or profile_for(h, w)]["zoom_blur"][severity - 1])
+    x = _to_float(x_u8)
+    acc = x.copy()
+    for z in zs:
+        y0, y1, fy = _zoom_sample_axis(h, z)
+        x0, x1, fx = _zoom_sample_axis(w, z)
+        fy_ = fy[None, :, None, None]
+        fx_ = fx[None, None, :, None]
+        top = x[:, y0][:, :, x0] * (1 - fx_) + x[:, y0][:, :, x1] * fx_
+        bot = x[:, y1][:, :, x0] * (1 - fx_) + x[:, y1][:, :, x1] * fx_
+        acc += (top * (1 - fy_) + bot * fy_).astype(np.float32)
+    out = acc / np.float32(len(zs) + 1)
+    return np.clip(out, 0, 1).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------- colour / stats
+def brightness(x_u8, severity, seed=0, first_image=0, profile=None):
+    """HSV value shift: V <- clip(V+c)  ==  RGB * min(V+c,1)/V  (V = max RGB; V = 0 -> grey c)."""
+    n, h, w, _ = x_u8.shape
+    c = np.float32(CONSTANTS[profile or profile_for(h, w)]["brightness"][severity - 1])
+    x = _to_float(x_u8)
+    v = x.max(axis=-1, keepdims=True)
+    v2 = np.minimum(v + c, np.float32(1.0))
+    safe = np.where(v > 0, v, np.float32(1.0))
+    out = np.where(v > 0, x * (v2 / safe), v2)
+    return np.clip(out, 0, 1).astype(np.float32)
+
+
+def contrast(x_u8, severity, seed=0, first_image=0, profile=None):
+    n, h, w, _ = x_u8.shape
+    c = np.float32(CONSTANTS[profile or profile_for(h, w)]["contrast"][severity - 1])
+    s = x_u8.astype(np.int64).sum(axis=(1, 2), keepdims=True)               # exact integer sums
+    mu = (s.astype(np.float32) / np.float32(255.0 * h * w)).astype(np.float32)
+    x = _to_float(x_u8)
+    return np.clip((x - mu) * c + mu, 0, 1).astype(np.float32)
+
+
+def fog_mapsize(h, w):
+    m = 1
+    while m < max(h, w):
+        m *= 2
+    return m
+
+
+def plasma_fractal(n, mapsize, wibbledecay, severity, seed=0, first_image=0):
+    """Diamond-square plasma on a torus, fp32, noise from Philox keyed by the written cell."""
+    img = np.arange(first_image, first_image + n, dtype=np.uint64)[:, None]
+    cell = np.arange(mapsize * mapsize, dtype=np.uint64)[None, :]
+    x0, _, _, _ = px.philox4x32_10(cell, img, 0, _stream("fog", severity), seed)
+    u = px.u32_to_uniform(x0).reshape(n, mapsize, mapsize)
+    noise = (np.float32(2.0) * u - np.float32(1.0)).astype(np.float32)       # U(-1,1)
+    M = np.zeros((n, mapsize, mapsize), dtype=np.float32)
+    step = mapsize
+    wib = np.float32(100.0)
+    dec = np.float32(wibbledecay)
+    while step >= 2:
+        hf = step // 2
+        w2 = np.float32(wib * wib)
+        ul = M[:, 0:mapsize:step, 0:mapsize:step]
+        sq = (ul + np.roll(ul, -1, axis=1)) + (np.roll(ul, -1, axis=2) + np.roll(np.roll(ul, -1, axis=1), -1, axis=2))
+        M[:, hf:mapsize:step, hf:mapsize:step] = sq * np.float32(0.25) + w2 * noise[:, hf:mapsize:step, hf:mapsize:step]
+        dr = M[:, hf:mapsize:step, hf:mapsize:step]
+        ul = M[:, 0:mapsize:step, 0:mapsize:step]
+        lt = (dr + np.roll(dr, 1, axis=1)) + (ul + np.roll(ul, -1, axis=2))
+        M[:, 0:mapsize:step, hf:mapsize:step] = lt * np.float32(0.25) + w2 * noise[:, 0:mapsize:step, hf:mapsize:step]
+        tt = (dr + np.roll(dr, 1, axis=2)) + (ul + np.roll(ul, -1, axis=1))
+        M[:, hf:mapsize:step, 0:mapsize:step] = tt * np.float32(0.25) + w2 * noise[:, hf:mapsize:step, 0:mapsize:step]
+        step //= 2
+        wib = np.float32(wib / dec)
+    mn = M.min(axis=(1, 2), keepdims=True)
+    M = M - mn
+    mx = M.max(axis=(1, 2), keepdims=True)
+    return (M / mx).astype(np.float32)
+
+
+def fog(x_u8, severity, seed=0, first_image=0, profile=None):
+    n, h, w, _ = x_u8.shape
+    c0, c1 = CONSTANTS[profile or profile_for(h, w)]["fog"][severity - 1]
+    c0 = np.float32(c0)
+    pl = plasma_fractal(n, fog_mapsize(h, w), c1, severity, seed, first_image)[:, :h, :w, None]
+    x = _to_float(x_u8)
+    mx = x.max(axis=(1, 2, 3), keepdims=True)
+    out = (x + c0 * pl) * (mx / (mx + c0))
+    return np.clip(out, 0, 1).astype(np.float32)
+
+
+def pixelate_geometry(size, c):
+    """BOX down-sample to int(size*c) then nearest (BOX) up-sample: per output index the
+    [lo,hi) source range whose integer mean it takes."""
+    small = max(1, int(size * c))
+    scale = size / small
+    lo = np.empty(small, dtype=np.int32)
+    hi = np.empty(small, dtype=np.int32)
+    for j in range(small):
+        centre = (j + 0.5) * scale
+        a = int(centre - 0.5 * scale + 0.5)
+        b = int(centre + 0.5 * scale + 0.5)
+        a, b = max(a, 0), min(b, size)
+        if b <= a:
+            b = a + 1
+        lo[j], hi[j] = a, b
+    up = np.minimum(((np.arange(size) + 0.5) * small / size).astype(np.int32), small - 1)
+    return lo[up], hi[up]
+
+
+def pixelate(x_u8, severity, seed=0, first_image=0, profile=None):
+    n, h, w, _ = x_u8.shape
+    c = CONSTANTS[profile or profile_for(h, w)]["pixelate"][severity - 1]
+    ylo, yhi = pixelate_geometry(h, c)
+    xlo, xhi = pixelate_geometry(w, c)
+    # integral image -> exact integer box sums; u8 rounding (2*s+cnt)//(2*cnt) like a u8 resize
+    ii = np.zeros((n, h + 1, w + 1, 3), dtype=np.int64)
+    ii[:, 1:, 1:] = x_u8.astype(np.int64).cumsum(1).cumsum(2)
+    Y0, Y1 = ylo[:, None], yhi[:, None]
+    X0, X1 = xlo[None, :], xhi[None, :]
+    s = ii[:, Y1, X1] - ii[:, Y0, X1] - ii[:, Y1, X0] + ii[:, Y0, X0]
+    cnt = ((Y1 - Y0) * (X1 - X0))[None, :, :, None]
+    v = (2 * s + cnt) // (2 * cnt)
+    return (v.astype(np.float32) / np.float32(255.0)).astype(np.float32)
+
+
+GENERATORS = {
+    "gaussian_noise": gaussian_noise, "shot_noise": shot_noise, "impulse_noise": impulse_noise,
+    "defocus_blur": defocus_blur, "motion_blur": motion_blur, "zoom_blur": zoom_blur,
+    "brightness": brightness, "contrast": contrast, "fog": fog, "pixelate": pixelate,
+}
+
+
+def corrupt(x_u8, name, severity, seed=0, first_image=0, profile=None):
+    """float32 [N,H,W,3] in [0,1].  name None / 'clean' -> x/255."""
+    if name in (None, "clean", "none"):
+        return _to_float(x_u8)
+    if name not in GENERATORS:
+        raise NotImplementedError(f"corruption '{name}' has no oracle yet")
+    if not 1 <= int(severity) <= 5:
+        raise ValueError("severity must be 1..5")
+    return GENERATORS[name](x_u8, int(severity), seed=seed, first_image=first_image, profile=profile)
+
+
+MEAN_STD = {
+    "imagenet": ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225)),
+    "cifar": ((0.4914, 0.4822, 0.4465), (0.2470, 0.2435, 0.2616)),
+}
+
+
+def normalize(x, mean, std):
+    """(x - mean_c) * (1/std_c) in fp32 -- same two ops (sub, mul by fp32 reciprocal) as the kernel."""
+    m = np.asarray(mean, dtype=np.float32)
+    inv = (np.float32(1.0) / np.asarray(std, dtype=np.float32)).astype(np.float32)
+    return ((x - m) * inv).astype(np.float32)
+
+
+def to_bf16(x):
+    """Round-to-nearest-even fp32 -> bf16, returned as fp32 values."""
+    b = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    r = ((b >> np.uint32(16)) & np.uint32(1)) + np.uint32(0x7FFF)
+    out = ((b + r) & np.uint32(0xFFFF0000)).view(np.float32)
+    return np.where(np.isnan(x), x, out).astype(np.float32)
