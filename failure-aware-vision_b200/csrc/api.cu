@@ -1,0 +1,80 @@
+// api.cu -- handle lifetime, error plumbing.
+#include <cstdarg>
+#include <cstdio>
+#include "common.cuh"
+
+namespace fav {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void plan_destroy(Plan* p);   // forward.cu
+}  // namespace fav
+
+using namespace fav;
+
+extern "C" int fav_abi_version(void) { return FAV_ABI_VERSION; }
+extern "C" const char* fav_last_error(void) { return g_err; }
+
+extern "C" int fav_init(int device, fav_handle* out) {
+  FAV_REQUIRE(out, "fav_init: out is null");
+  *out = nullptr;
+  int count = 0;
+  FAV_CUDA_OK(cudaGetDeviceCount(&count));
+  FAV_REQUIRE(device >= 0 && device < count, "fav_init: device %d out of range (%d devices)", device, count);
+  cudaDeviceProp prop;
+  FAV_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("fav_init: device %d is sm_%d%d; this library is built for sm_100a (B200) only and has no fallback",
+              device, prop.major, prop.minor);
+    return FAV_E_DEVICE;
+  }
+  FAV_CUDA_OK(cudaSetDevice(device));
+  fav_ctx* c = new fav_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  *out = c;
+  return FAV_OK;
+}
+
+extern "C" int fav_reset(fav_handle h) {
+  FAV_REQUIRE(h, "fav_reset: null handle");
+  if (h->ws) { FAV_CUDA_OK(cudaFree(h->ws)); h->ws = nullptr; h->ws_bytes = 0; }
+  return FAV_OK;
+}
+
+extern "C" int fav_destroy(fav_handle h) {
+  if (!h) return FAV_OK;
+  if (h->ws) cudaFree(h->ws);
+  if (h->plan) plan_destroy(h->plan);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  delete h;
+  return FAV_OK;
+}
+
+extern "C" uint64_t fav_launch_count(fav_handle h) { return h ? h->launches : 0; }
+
+extern "C" int fav_conv_timing_enable(fav_handle h, int on) {
+  FAV_REQUIRE(h, "null handle");
+  h->timing = on != 0;
+  h->ev_used = 0;
+  return FAV_OK;
+}
+
+extern "C" int fav_conv_timing_read(fav_handle h, float* total_ms, int* n_launches) {
+  FAV_REQUIRE(h && total_ms && n_launches, "fav_conv_timing_read: null pointer");
+  float tot = 0.f;
+  for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+    FAV_CUDA_OK(cudaEventSynchronize(h->ev_pool[i + 1]));
+    float ms = 0.f;
+    FAV_CUDA_OK(cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]));
+    tot += ms;
+  }
+  *total_ms = tot;
+  *n_launches = int(h->ev_used / 2);
+  h->ev_used = 0;
+  return FAV_OK;
+}

@@ -1,0 +1,96 @@
+// common.cuh -- shared device helpers (Philox, bf16 packing) and the host-side context.
+// sm_100a only.  RNG contract: SURVEY.md Appendix A.1; oracle twin: oracle/philox.py.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/fav_b200.h"
+
+namespace fav {
+
+// ---------------------------------------------------------------- error plumbing (host)
+void set_error(const char* fmt, ...);
+#define FAV_CUDA_OK(expr)                                                                    \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      fav::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return FAV_E_CUDA;                                                                     \
+    }                                                                                        \
+  } while (0)
+#define FAV_REQUIRE(cond, ...)          \
+  do {                                  \
+    if (!(cond)) {                      \
+      fav::set_error(__VA_ARGS__);      \
+      return FAV_E_ARG;                 \
+    }                                   \
+  } while (0)
+
+// ---------------------------------------------------------------- Philox4x32-10
+constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
+constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
+
+constexpr int KIND_IMAGES = 1, KIND_LABELS = 2, KIND_CORRUPT = 3, KIND_DROPOUT = 4, KIND_AUX = 5;
+__host__ __device__ constexpr uint32_t stream_id(int kind, int a = 0, int b = 0) {
+  return (uint32_t(kind) << 16) | (uint32_t(a) << 8) | uint32_t(b);
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(PHILOX_M0, c0), lo0 = PHILOX_M0 * c0;
+    const uint32_t hi1 = __umulhi(PHILOX_M1, c2), lo1 = PHILOX_M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += PHILOX_W0; k1 += PHILOX_W1;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// (0,1] uniform: fl(fl(x>>8) * 2^-24 + 2^-25), two separately rounded fp32 ops (no FMA).
+__device__ __forceinline__ float u32_to_uniform(uint32_t x) {
+  return __fadd_rn(__fmul_rn(float(x >> 8), 5.9604644775390625e-08f), 2.98023223876953125e-08f);
+}
+
+// Box-Muller: two u32 -> (r cos th, r sin th)
+__device__ __forceinline__ float2 box_muller(uint32_t xa, uint32_t xb) {
+  const float u1 = u32_to_uniform(xa), u2 = u32_to_uniform(xb);
+  const float r = sqrtf(-2.0f * logf(u1));
+  float s, c;
+  sincosf(6.283185307179586f * u2, &s, &c);
+  return make_float2(r * c, r * s);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+// ---------------------------------------------------------------- host context
+struct ConvLayer;   // conv.cu
+struct Plan;        // forward.cu
+
+struct Ctx {
+  int device = 0;
+  int num_sms = 148;
+  uint64_t launches = 0;
+  // weights + plan
+  Plan* plan = nullptr;
+  // workspace
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  // optional per-launch timing of the conv kernel (bench roofline)
+  bool timing = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+};
+
+}  // namespace fav
+
+struct fav_ctx : fav::Ctx {};

@@ -1,0 +1,532 @@
+// conv.cu -- K2: implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM), bf16 x bf16 -> fp32.
+//
+// Replaces (reference): nothing executable -- the reference names "image classification" as its perception
+// task (README.md:15-20) and lists torchvision in requirements.txt:2 but ships no classifier; this is the
+// forward of stock torchvision ResNet-18/50 with BN folded (oracle twin: oracle/model.py).
+//
+// GEMM view:  D[M = pixels, N = Cout] = A[M, K = R*S*Cin] * W[N, K]^T
+//   A tile  128 x 64 bf16, K-major, SWIZZLE_128B in shared memory
+//        a_mode 0: TMA tiled load of the NHWC activation with a 4-D box (64 ch, bw, bh, bn images) per filter
+//                  tap; the box origin is shifted by (s - pad, r - pad) and TMA's out-of-bounds zero fill
+//                  supplies the padding halo (stride-1 convs, Cin % 64 == 0)
+//        a_mode 1: 128 producer threads gather 16-byte channel vectors (any stride / padding, Cin % 8 == 0)
+//        a_mode 2: scalar gather (the 7x7 stem, Cin = 3)
+//   W tile  BN x 64 bf16 by TMA (2-D box, SWIZZLE_128B), BN in {16..256}
+//   D       128 lanes x BN fp32 columns in TMEM, one tcgen05.mma (M=128, N=BN, K=16) per 32 bytes of K
+//   epilogue: tcgen05.ld -> +bias (+residual) -> ReLU -> MC-dropout mask from Philox (optionally T masked
+//             replicas of a pass-invariant tile) -> bf16 NHWC (or fp32 logits)
+// Warp roles (192 threads): warps 0-3 gather producers + epilogue, warp 4 TMA issuer, warp 5 MMA issuer + TMEM
+// allocator.  smem ring of `stages` {A,B} slots with full/empty mbarriers; tcgen05.commit frees slots.
+#include <cuda.h>
+#include <cstdio>
+#include <mutex>
+#include "conv.cuh"
+
+namespace fav {
+
+constexpr int BM = 128, BK = 64;
+constexpr int A_TILE_BYTES = BM * BK * 2;          // 16 KiB
+constexpr int CONV_THREADS = 192;
+
+struct ConvArgs {
+  const __nv_bfloat16* x;
+  void* y;
+  const float* bias;
+  const __nv_bfloat16* res;
+  int P, H, W, Cin, OH, OW, Cout;
+  int R, S, stride, pad;
+  int K, num_kb, M, BN, stages;
+  int relu, out_f32, a_mode;
+  int bw, bh, bn_img, tiles_w, tiles_h, cin_blocks;
+  int T, rep, drop;
+  uint32_t drop_thr16;
+  float drop_scale;
+  uint32_t k0, k1, first_image, drop_stream;
+  uint32_t tmem_cols, idesc;
+};
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug traps (sticky CUDA error) instead of hanging the GPU box
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("fav conv: mbarrier timeout block (%d,%d) thread %d bar %u parity %u\n", blockIdx.x, blockIdx.y,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const void* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 covers bf16 inputs with fp32 accumulation
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"): 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ------------------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(CONV_THREADS)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t pad_to_1k = ((raw + 1023u) & ~1023u) - raw;
+  uint8_t* smem = smem_raw + pad_to_1k;
+  const int stage_bytes = A_TILE_BYTES + a.BN * 128;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bars = smem_base + a.stages * stage_bytes;                 // full[s], empty[s], tmem_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + a.stages * stage_bytes + (2 * a.stages + 1) * 8);
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (a.stages + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (2 * a.stages);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x, nt = blockIdx.y;
+
+  // tile origin
+  int q0 = 0, oh0 = 0, ow0 = 0;
+  if (a.a_mode == 0) {
+    const int tw = mt % a.tiles_w, th = (mt / a.tiles_w) % a.tiles_h, tn = mt / (a.tiles_w * a.tiles_h);
+    q0 = tn * a.bn_img; oh0 = th * a.bh; ow0 = tw * a.bw;
+  }
+  // a k-block is skipped when its filter tap only sees padding for this whole tile (a_mode 0)
+  auto kb_active = [&](int kb) -> bool {
+    if (a.a_mode != 0) return true;
+    const int tap = kb / a.cin_blocks, r = tap / a.S, s = tap - r * a.S;
+    const int ih_lo = oh0 + r - a.pad, ih_hi = min(oh0 + a.bh, a.OH) - 1 + r - a.pad;
+    const int iw_lo = ow0 + s - a.pad, iw_hi = min(ow0 + a.bw, a.OW) - 1 + s - a.pad;
+    return !(ih_hi < 0 || ih_lo >= a.H || iw_hi < 0 || iw_lo >= a.W);
+  };
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmB);
+    if (a.a_mode == 0) tma_prefetch_desc(&tmA);
+    const uint32_t full_count = a.a_mode == 0 ? 1u : 1u + 128u;
+    for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), full_count); mbar_init(empty_bar(s), 1u); }
+    mbar_init(tmem_full_bar, 1u);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(smem_u32(tmem_slot), a.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ================================================================= TMA issuer
+    if (lane == 0) {
+      const uint32_t a_bytes = a.a_mode == 0 ? uint32_t(a.bn_img * a.bh * a.bw) * 128u : 0u;
+      const uint32_t tx = a_bytes + uint32_t(a.BN) * 128u;
+      int it = 0;
+      for (int kb = 0; kb < a.num_kb; ++kb) {
+        if (!kb_active(kb)) continue;
+        const int s = it % a.stages, ph = (it / a.stages) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        mbar_arrive_expect_tx(full_bar(s), tx);
+        const uint32_t sa = smem_base + s * stage_bytes;
+        if (a.a_mode == 0) {
+          const int tap = kb / a.cin_blocks, cb = kb - tap * a.cin_blocks, r = tap / a.S, ss = tap - r * a.S;
+          tma_load_4d(sa, &tmA, full_bar(s), cb * 64, ow0 + ss - a.pad, oh0 + r - a.pad, q0);
+        }
+        tma_load_2d(sa + A_TILE_BYTES, &tmB, full_bar(s), kb * BK, nt * a.BN);
+        ++it;
+      }
+    }
+  } else if (warp == 5) {
+    // ================================================================= MMA issuer
+    if (lane == 0) {
+      int it = 0;
+      for (int kb = 0; kb < a.num_kb; ++kb) {
+        if (!kb_active(kb)) continue;
+        const int s = it % a.stages, ph = (it / a.stages) & 1;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * stage_bytes;
+        const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sa + A_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)          // 32 bytes of K per MMA: +2 in the (addr >> 4) field
+          umma_f16(tmem_base, da + 2u * k, db + 2u * k, a.idesc, (it > 0 || k > 0) ? 1u : 0u);
+        umma_commit(empty_bar(s));
+        ++it;
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ================================================================= warps 0-3: gather producers, then epilogue
+    const int row = threadIdx.x;                    // 0..127 = A-tile row = TMEM lane
+    int q = 0, oh = 0, ow = 0;
+    bool valid;
+    if (a.a_mode == 0) {
+      const int per_img = a.bw * a.bh;
+      const int nl = row / per_img, rem = row - nl * per_img, hl = rem / a.bw, wl = rem - hl * a.bw;
+      q = q0 + nl; oh = oh0 + hl; ow = ow0 + wl;
+      valid = nl < a.bn_img && q < a.P && oh < a.OH && ow < a.OW;
+    } else {
+      const long long m = (long long)mt * BM + row;
+      valid = m < a.M;
+      if (valid) {
+        q = int(m / (a.OH * a.OW));
+        const int rem = int(m - (long long)q * (a.OH * a.OW));
+        oh = rem / a.OW; ow = rem - oh * a.OW;
+      }
+    }
+
+    if (a.a_mode != 0) {
+      const int ih0 = oh * a.stride - a.pad, iw0 = ow * a.stride - a.pad;
+      const __nv_bfloat16* ximg = a.x + (size_t)q * a.H * a.W * a.Cin;
+      int it = 0;
+      for (int kb = 0; kb < a.num_kb; ++kb, ++it) {
+        const int s = it % a.stages, ph = (it / a.stages) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        uint8_t* rowp = smem + s * stage_bytes + row * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 v = make_uint4(0, 0, 0, 0);
+          const int k = kb * BK + c * 8;
+          if (valid && k < a.K) {
+            if (a.a_mode == 1) {
+              const int tap = k / a.Cin, ci = k - tap * a.Cin, r = tap / a.S, ss = tap - r * a.S;
+              const int ih = ih0 + r, iw = iw0 + ss;
+              if (ih >= 0 && ih < a.H && iw >= 0 && iw < a.W)
+                v = __ldg(reinterpret_cast<const uint4*>(ximg + ((size_t)ih * a.W + iw) * a.Cin + ci));
+            } else {
+              uint32_t w4[4] = {0, 0, 0, 0};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int kk = k + e;
+                if (kk < a.K) {
+                  const int tap = kk / a.Cin, ci = kk - tap * a.Cin, r = tap / a.S, ss = tap - r * a.S;
+                  const int ih = ih0 + r, iw = iw0 + ss;
+                  if (ih >= 0 && ih < a.H && iw >= 0 && iw < a.W) {
+                    const uint32_t b = __ldg(reinterpret_cast<const unsigned short*>(ximg) + ((size_t)ih * a.W + iw) * a.Cin + ci);
+                    w4[e >> 1] |= b << (16 * (e & 1));
+                  }
+                }
+              }
+              v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            }
+          }
+          *reinterpret_cast<uint4*>(rowp + ((c ^ (row & 7)) << 4)) = v;      // 128B swizzle: chunk ^= row % 8
+        }
+        fence_proxy_async();                        // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(full_bar(s));
+      }
+    }
+
+    // ----------------------------------------------------------------- epilogue
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + (uint32_t(warp * 32) << 16);
+    const int hw = oh * a.OW + ow, ohw = a.OH * a.OW;
+    const size_t res_off = ((size_t)q * ohw + hw) * a.Cout;
+    const int n_rep = a.rep > 1 ? a.rep : 1;
+    for (int j = 0; j < a.BN / 16; ++j) {
+      uint32_t acc[16];
+      tmem_ld16(trow + uint32_t(j * 16), acc);       // warp-collective: executed by every lane, valid or not
+      tmem_ld_wait();
+      const int c0 = nt * a.BN + j * 16;
+      if (!valid || c0 >= a.Cout) continue;
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]) + __ldg(a.bias + c0 + i);
+      if (a.res) {
+        if ((a.Cout & 7) == 0) {
+          const uint4* rp = reinterpret_cast<const uint4*>(a.res + res_off + c0);
+#pragma unroll
+          for (int hseg = 0; hseg < 2; ++hseg) {
+            if (c0 + 8 * hseg >= a.Cout) break;
+            const uint4 rv = __ldg(rp + hseg);
+            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { v[8 * hseg + 2 * i] += bf16_lo(rw[i]); v[8 * hseg + 2 * i + 1] += bf16_hi(rw[i]); }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (c0 + i < a.Cout) v[i] += __bfloat162float(a.res[res_off + c0 + i]);
+        }
+      }
+      if (a.relu) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+      for (int rp = 0; rp < n_rep; ++rp) {
+        const int p_out = a.rep > 1 ? q * a.rep + rp : q;
+        const size_t off = ((size_t)p_out * ohw + hw) * a.Cout + c0;
+        float o[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = v[i];
+        if (a.drop) {
+          const int n_img = a.rep > 1 ? q : q / a.T;
+          const int t = a.rep > 1 ? rp : q - n_img * a.T;
+          const uint32_t e8 = uint32_t((size_t)hw * a.Cout + c0) >> 3;
+#pragma unroll
+          for (int hseg = 0; hseg < 2; ++hseg) {
+            const uint4 r = philox4x32_10(e8 + hseg, a.first_image + uint32_t(n_img), uint32_t(t), a.drop_stream, a.k0, a.k1);
+            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              o[8 * hseg + 2 * i] = (rw[i] & 0xFFFFu) >= a.drop_thr16 ? o[8 * hseg + 2 * i] * a.drop_scale : 0.f;
+              o[8 * hseg + 2 * i + 1] = (rw[i] >> 16) >= a.drop_thr16 ? o[8 * hseg + 2 * i + 1] * a.drop_scale : 0.f;
+            }
+          }
+        }
+        if (a.out_f32) {
+          float* yp = reinterpret_cast<float*>(a.y) + off;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (c0 + i < a.Cout) yp[i] = o[i];
+        } else if ((a.Cout & 7) == 0) {
+          uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + off);
+          yp[0] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+          if (c0 + 8 < a.Cout)
+            yp[1] = make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
+        } else {
+          __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + off;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (c0 + i < a.Cout) yp[i] = __float2bfloat16_rn(o[i]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                      const cuuint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return FAV_E_CUDA; }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", int(r), rank); return FAV_E_CUDA; }
+  return FAV_OK;
+}
+
+int conv_out_dim(int in, int k, int stride, int pad) { return (in + 2 * pad - k) / stride + 1; }
+int conv_pick_bn(int cout) { return cout <= 16 ? 16 : cout <= 32 ? 32 : cout <= 64 ? 64 : 128; }
+
+int conv_layer_finalize(ConvLayer& L) {
+  L.k = L.r * L.s * L.cin;
+  L.kpad = (L.k + BK - 1) / BK * BK;
+  L.bn = conv_pick_bn(L.cout);
+  L.cout_pad = (L.cout + L.bn - 1) / L.bn * L.bn;
+  if (L.w) {
+    const cuuint64_t dims[2] = {(cuuint64_t)L.kpad, (cuuint64_t)L.cout_pad};
+    const cuuint64_t strides[1] = {(cuuint64_t)L.kpad * 2};
+    const cuuint32_t box[2] = {BK, (cuuint32_t)L.bn};
+    int rc = encode_map(reinterpret_cast<CUtensorMap*>(L.tmap_w), L.w, 2, dims, strides, box);
+    if (rc) return rc;
+    L.tmap_ok = true;
+  }
+  return FAV_OK;
+}
+
+int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
+  const ConvLayer& L = *c.L;
+  FAV_REQUIRE(L.tmap_ok, "conv: layer not finalized");
+  FAV_REQUIRE(c.p > 0 && c.h > 0 && c.w > 0, "conv: bad shape p=%d h=%d w=%d", c.p, c.h, c.w);
+  ConvArgs a{};
+  a.x = reinterpret_cast<const __nv_bfloat16*>(c.x); a.y = c.y; a.bias = L.bias;
+  a.res = reinterpret_cast<const __nv_bfloat16*>(c.res);
+  a.P = c.p; a.H = c.h; a.W = c.w; a.Cin = L.cin; a.Cout = L.cout;
+  a.R = L.r; a.S = L.s; a.stride = L.stride; a.pad = L.pad;
+  a.OH = conv_out_dim(c.h, L.r, L.stride, L.pad); a.OW = conv_out_dim(c.w, L.s, L.stride, L.pad);
+  FAV_REQUIRE(a.OH > 0 && a.OW > 0, "conv: empty output");
+  a.K = L.k; a.num_kb = L.kpad / BK; a.BN = L.bn;
+  const long long M = (long long)c.p * a.OH * a.OW;
+  FAV_REQUIRE(M < (1ll << 31), "conv: too many output pixels (%lld)", M);
+  a.M = int(M);
+  a.relu = c.relu; a.out_f32 = c.out_f32;
+  a.T = c.T > 0 ? c.T : 1; a.rep = c.rep > 1 ? c.rep : 1; a.drop = c.drop;
+  if (c.drop) {
+    FAV_REQUIRE((L.cout & 15) == 0 && !c.out_f32, "conv: dropout epilogue needs Cout %% 16 == 0 and bf16 output");
+    FAV_REQUIRE(c.p_drop >= 0.f && c.p_drop < 1.f, "conv: p_drop must be in [0,1)");
+    a.drop_thr16 = uint32_t(floor(double(c.p_drop) * 65536.0));
+    a.drop_scale = 1.0f / (1.0f - c.p_drop);
+    a.k0 = uint32_t(c.seed); a.k1 = uint32_t(c.seed >> 32); a.first_image = uint32_t(c.first_image);
+    a.drop_stream = stream_id(KIND_DROPOUT, c.layer_id, 0);
+  }
+  // operand-A mode
+  const bool tma_ok = L.stride == 1 && (L.cin % 64) == 0 && L.r == L.s && 2 * L.pad == L.r - 1 && a.OW <= 128;
+  int mode = c.a_mode;
+  if (mode < 0) mode = tma_ok ? 0 : ((L.cin % 8) == 0 ? 1 : 2);
+  FAV_REQUIRE(mode != 0 || tma_ok, "conv: a_mode 0 (TMA) needs stride 1, Cin %% 64 == 0, 'same' padding");
+  FAV_REQUIRE(mode != 1 || (L.cin % 8) == 0, "conv: a_mode 1 needs Cin %% 8 == 0");
+  a.a_mode = mode;
+  CUtensorMap tmA;
+  memset(&tmA, 0, sizeof(tmA));
+  int mtiles;
+  if (mode == 0) {
+    if (a.OH * a.OW <= BM) { a.bw = a.OW; a.bh = a.OH; a.bn_img = BM / (a.OH * a.OW); }
+    else { a.bw = a.OW; a.bh = BM / a.OW; a.bn_img = 1; }
+    if (a.bn_img > c.p) a.bn_img = c.p;
+    a.tiles_w = (a.OW + a.bw - 1) / a.bw; a.tiles_h = (a.OH + a.bh - 1) / a.bh;
+    const int tiles_n = (c.p + a.bn_img - 1) / a.bn_img;
+    a.cin_blocks = L.cin / 64;
+    mtiles = a.tiles_w * a.tiles_h * tiles_n;
+    const cuuint64_t dims[4] = {(cuuint64_t)L.cin, (cuuint64_t)c.w, (cuuint64_t)c.h, (cuuint64_t)c.p};
+    const cuuint64_t strides[3] = {(cuuint64_t)L.cin * 2, (cuuint64_t)c.w * L.cin * 2, (cuuint64_t)c.h * c.w * L.cin * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)a.bw, (cuuint32_t)a.bh, (cuuint32_t)a.bn_img};
+    int rc = encode_map(&tmA, c.x, 4, dims, strides, box);
+    if (rc) return rc;
+  } else {
+    mtiles = int((M + BM - 1) / BM);
+  }
+  const int stage_bytes = A_TILE_BYTES + a.BN * 128;
+  int stages = (100 * 1024) / stage_bytes;
+  stages = stages < 2 ? 2 : (stages > 6 ? 6 : stages);
+  a.stages = stages;
+  uint32_t cols = 32;
+  while (cols < uint32_t(a.BN)) cols *= 2;
+  a.tmem_cols = cols;
+  // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128
+  a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(a.BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  FAV_CUDA_OK(attr_err);
+  dim3 grid(mtiles, L.cout_pad / a.BN);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx->timing) {
+    while (ctx->ev_pool.size() < ctx->ev_used + 2) {
+      cudaEvent_t e;
+      FAV_CUDA_OK(cudaEventCreate(&e));
+      ctx->ev_pool.push_back(e);
+    }
+    e0 = ctx->ev_pool[ctx->ev_used]; e1 = ctx->ev_pool[ctx->ev_used + 1];
+    ctx->ev_used += 2;
+    FAV_CUDA_OK(cudaEventRecord(e0, st));
+  }
+  conv_igemm_kernel<<<grid, CONV_THREADS, smem, st>>>(tmA, *reinterpret_cast<const CUtensorMap*>(L.tmap_w), a);
+  if (e1) FAV_CUDA_OK(cudaEventRecord(e1, st));
+  ctx->launches++;
+  FAV_CUDA_OK(cudaGetLastError());
+  return FAV_OK;
+}
+
+}  // namespace fav
+
+using namespace fav;
+
+// Unit-test / tooling entry: one convolution with caller-provided (unpadded) device weights.
+extern "C" int fav_conv2d(fav_handle h, const void* d_x, const void* d_w, const float* d_bias, const void* d_res,
+                          void* d_y, int p, int height, int width, int cin, int cout, int r, int s, int stride,
+                          int pad, int relu, int out_f32, int a_mode, void* stream) {
+  FAV_REQUIRE(h && d_x && d_w && d_y, "fav_conv2d: null pointer");
+  FAV_REQUIRE(cin > 0 && cout > 0 && r > 0 && s > 0 && stride > 0 && pad >= 0, "fav_conv2d: bad conv geometry");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ConvLayer L;
+  L.cin = cin; L.cout = cout; L.r = r; L.s = s; L.stride = stride; L.pad = pad;
+  conv_layer_finalize(L);                          // sizes only (w == nullptr)
+  __nv_bfloat16* wpad = nullptr;
+  float* bpad = nullptr;
+  FAV_CUDA_OK(cudaMalloc(&wpad, (size_t)L.cout_pad * L.kpad * 2));
+  FAV_CUDA_OK(cudaMalloc(&bpad, (size_t)L.cout_pad * 4));
+  FAV_CUDA_OK(cudaMemsetAsync(wpad, 0, (size_t)L.cout_pad * L.kpad * 2, st));
+  FAV_CUDA_OK(cudaMemsetAsync(bpad, 0, (size_t)L.cout_pad * 4, st));
+  FAV_CUDA_OK(cudaMemcpy2DAsync(wpad, (size_t)L.kpad * 2, d_w, (size_t)L.k * 2, (size_t)L.k * 2, cout,
+                                cudaMemcpyDeviceToDevice, st));
+  if (d_bias) FAV_CUDA_OK(cudaMemcpyAsync(bpad, d_bias, (size_t)cout * 4, cudaMemcpyDeviceToDevice, st));
+  L.w = wpad; L.bias = bpad;
+  int rc = conv_layer_finalize(L);
+  if (rc == FAV_OK) {
+    ConvCall c;
+    c.L = &L; c.x = d_x; c.y = d_y; c.res = d_res; c.p = p; c.h = height; c.w = width;
+    c.relu = relu; c.out_f32 = out_f32; c.a_mode = a_mode;
+    rc = conv_launch(h, c, st);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(wpad);
+  cudaFree(bpad);
+  if (rc == FAV_OK && e != cudaSuccess) { set_error("fav_conv2d: %s", cudaGetErrorString(e)); return FAV_E_CUDA; }
+  return rc;
+}

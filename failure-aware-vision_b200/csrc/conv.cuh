@@ -1,0 +1,39 @@
+// conv.cuh -- launcher interface of the tcgen05 implicit-GEMM convolution (conv.cu).
+#pragma once
+#include "common.cuh"
+
+namespace fav {
+
+struct ConvLayer {          // device-resident, BN folded
+  const __nv_bfloat16* w = nullptr;   // [cout_pad][kpad]  (k = (r*S + s)*cin + c), zero padded
+  const float* bias = nullptr;        // [cout_pad]
+  int cin = 0, cout = 0, r = 0, s = 0, stride = 1, pad = 0;
+  int k = 0, kpad = 0, cout_pad = 0, bn = 0;
+  alignas(64) unsigned char tmap_w[128];   // CUtensorMap for the weights (box 64 x bn, SWIZZLE_128B)
+  bool tmap_ok = false;
+};
+
+struct ConvCall {
+  const ConvLayer* L = nullptr;
+  const void* x = nullptr;        // bf16 NHWC [p, h, w, cin]
+  void* y = nullptr;              // bf16 / fp32 NHWC [p*rep, oh, ow, cout]
+  const void* res = nullptr;      // bf16 NHWC [p, oh, ow, cout] or null
+  int p = 0, h = 0, w = 0;
+  int relu = 0, out_f32 = 0;
+  int a_mode = -1;                // -1 auto, 0 TMA-tiled, 1 vector gather, 2 scalar gather
+  // MC-dropout in the epilogue
+  int T = 1;                      // passes; rows of x are pass-images (image = row / T, t = row % T) unless rep > 1
+  int rep = 1;                    // rep == T: x holds plain images, each output row is written T times with mask t
+  int drop = 0;
+  float p_drop = 0.f;
+  uint64_t seed = 0, first_image = 0;
+  int layer_id = 0;
+};
+
+int conv_out_dim(int in, int k, int stride, int pad);
+int conv_pick_bn(int cout);
+// fills k/kpad/cout_pad/bn and encodes the weight tensor map (weights must already be on the device)
+int conv_layer_finalize(ConvLayer& L);
+int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st);
+
+}  // namespace fav

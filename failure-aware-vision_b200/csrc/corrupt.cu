@@ -1,0 +1,657 @@
+// corrupt.cu -- K1: image-corruption generators fused with normalize (uint8 NHWC -> bf16 NHWC).
+//
+// Replaces (reference): the two noise/brightness sliders of platform/backend/vision_simulator.py:25-36
+// and the display-only JS effects of platform/frontend/js/app.js:789-799,834-851 -- the reference has
+// no server-side generator.  Definitions follow oracle/corruptions.py.
+//
+// HBM-bound design: one thread owns a group of 16 whole pixels (48 source bytes = three 128-bit
+// loads, 96 output bytes = six 128-bit stores); noise comes from counter-based Philox keyed by
+// (seed, global image index, element chunk) so nothing but the source and the result touches HBM.
+// Blur stencils stage the source tile plus halo in shared memory as packed RGBX words.
+#include "common.cuh"
+
+namespace fav {
+
+enum { PW_CLEAN = 0, PW_GAUSS, PW_SHOT, PW_IMPULSE, PW_BRIGHT, PW_CONTRAST, PW_FOG };
+
+struct PointwiseArgs {
+  const uint8_t* src;
+  void* dst;
+  int n, per;                 // images, elements per image (h*w*3)
+  int groups_per_image;       // ceil(per/48)
+  uint32_t k0, k1;            // Philox key
+  uint32_t first_image;
+  uint32_t stream;            // Philox c3
+  float f0, f1;               // corruption constants
+  uint32_t u0, u1;            // integer constants (thresholds / table width)
+  const void* table;          // shot: int32 kmin[256] then uint32 thr[256][width]
+  const void* scratch;        // contrast: uint64 sums[n][3]; fog: float stats[n][4] + maps
+  int hw, width, mapsize;     // fog geometry
+  size_t map_offset;          // bytes from scratch to the plasma maps
+  float mean[3], inv_std[3];
+  unsigned flags;
+};
+
+__device__ __forceinline__ float u8f(uint32_t b) { return __fdiv_rn(float(b), 255.0f); }
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k1_pointwise(const PointwiseArgs a) {
+  const long long total = (long long)a.n * a.groups_per_image;
+  const bool vec = (a.per % 48) == 0 && ((reinterpret_cast<uintptr_t>(a.src) & 15) == 0);
+  const bool bgr = a.flags & FAV_SRC_BGR;
+  const bool out_f32 = a.flags & FAV_OUT_F32;
+  const bool no_norm = a.flags & FAV_NO_NORMALIZE;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int img = int(g / a.groups_per_image);
+    const int gi = int(g - (long long)img * a.groups_per_image);
+    const int e0 = gi * 48;
+    const int cnt = min(48, a.per - e0);
+    const size_t base = (size_t)img * a.per + e0;
+    uint32_t w[12];
+    if (vec) {
+      const uint4* p = reinterpret_cast<const uint4*>(a.src + base);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        uint4 v = __ldg(p + i);
+        w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (4 * i + b < cnt) v |= uint32_t(a.src[base + 4 * i + b]) << (8 * b);
+        w[i] = v;
+      }
+    }
+    float x[48];
+#pragma unroll
+    for (int i = 0; i < 48; ++i) {
+      const int sb = i - (i % 3) + 2 - (i % 3);                // logical RGB element i <- BGR source sb
+      const uint32_t va = (w[i >> 2] >> (8 * (i & 3))) & 0xFF, vb = (w[sb >> 2] >> (8 * (sb & 3))) & 0xFF;
+      x[i] = float(bgr ? vb : va);
+    }
+    const uint32_t gimg = a.first_image + uint32_t(img);
+
+    if (MODE == PW_GAUSS) {
+#pragma unroll
+      for (int j = 0; j < 12; ++j) {
+        const uint4 r = philox4x32_10(uint32_t(e0 / 4 + j), gimg, 0u, a.stream, a.k0, a.k1);
+        const float2 za = box_muller(r.x, r.y), zb = box_muller(r.z, r.w);
+        x[4 * j + 0] = __fdiv_rn(x[4 * j + 0], 255.0f) + a.f0 * za.x;
+        x[4 * j + 1] = __fdiv_rn(x[4 * j + 1], 255.0f) + a.f0 * za.y;
+        x[4 * j + 2] = __fdiv_rn(x[4 * j + 2], 255.0f) + a.f0 * zb.x;
+        x[4 * j + 3] = __fdiv_rn(x[4 * j + 3], 255.0f) + a.f0 * zb.y;
+      }
+    } else if (MODE == PW_SHOT) {
+      const int* kmin = reinterpret_cast<const int*>(a.table);
+      const uint32_t* thr = reinterpret_cast<const uint32_t*>(a.table) + 256;
+      const int width = int(a.u0);
+#pragma unroll
+      for (int j = 0; j < 12; ++j) {
+        const uint4 r = philox4x32_10(uint32_t(e0 / 4 + j), gimg, 0u, a.stream, a.k0, a.k1);
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int v = int(x[4 * j + q]);
+          const uint32_t* row = thr + (size_t)v * width;
+          int lo = 0, hi = width;                       // first index with row[idx] > u
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(row + mid) <= rr[q]) lo = mid + 1; else hi = mid;
+          }
+          x[4 * j + q] = __fdiv_rn(float(__ldg(kmin + v) + lo), a.f0);
+        }
+      }
+    } else if (MODE == PW_IMPULSE) {
+#pragma unroll
+      for (int j = 0; j < 12; ++j) {
+        const uint4 r = philox4x32_10(uint32_t(e0 / 4 + j), gimg, 0u, a.stream, a.k0, a.k1);
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float v = __fdiv_rn(x[4 * j + q], 255.0f);
+          if (rr[q] < a.u1) v = 1.0f;
+          if (rr[q] < a.u0) v = 0.0f;
+          x[4 * j + q] = v;
+        }
+      }
+    } else if (MODE == PW_BRIGHT) {
+#pragma unroll
+      for (int p = 0; p < 16; ++p) {
+        const float r = u8f(x[3 * p]), gg = u8f(x[3 * p + 1]), b = u8f(x[3 * p + 2]);
+        const float v = fmaxf(r, fmaxf(gg, b));
+        const float v2 = fminf(__fadd_rn(v, a.f0), 1.0f);
+        if (v > 0.0f) {
+          const float s = __fdiv_rn(v2, v);
+          x[3 * p] = r * s; x[3 * p + 1] = gg * s; x[3 * p + 2] = b * s;
+        } else {
+          x[3 * p] = v2; x[3 * p + 1] = v2; x[3 * p + 2] = v2;
+        }
+      }
+    } else if (MODE == PW_CONTRAST) {
+      const unsigned long long* sums = reinterpret_cast<const unsigned long long*>(a.scratch) + 3 * (size_t)img;
+      float mu[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) mu[c] = __fdiv_rn(__ull2float_rn(sums[bgr ? 2 - c : c]), 255.0f * float(a.hw));
+#pragma unroll
+      for (int i = 0; i < 48; ++i)
+        x[i] = __fadd_rn(__fmul_rn(__fsub_rn(u8f(x[i]), mu[i % 3]), a.f0), mu[i % 3]);
+    } else if (MODE == PW_FOG) {
+      const float* st = reinterpret_cast<const float*>(a.scratch) + 4 * (size_t)img;
+      const float* map = reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.scratch) + a.map_offset) +
+                         (size_t)img * a.mapsize * a.mapsize;
+      const float mn = st[0], pmx = st[1], xmx = st[2];
+      const float gain = __fdiv_rn(xmx, __fadd_rn(xmx, a.f0));
+#pragma unroll
+      for (int p = 0; p < 16; ++p) {
+        const int pix = e0 / 3 + p;
+        float pl = 0.f;
+        if (pix < a.hw) {
+          const int yy = pix / a.width, xx = pix - yy * a.width;
+          pl = __fdiv_rn(__fsub_rn(map[yy * a.mapsize + xx], mn), pmx);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          x[3 * p + c] = __fmul_rn(__fadd_rn(u8f(x[3 * p + c]), __fmul_rn(a.f0, pl)), gain);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 48; ++i) x[i] = u8f(x[i]);
+    }
+
+    // clip + normalize + store
+#pragma unroll
+    for (int i = 0; i < 48; ++i) {
+      float v = fminf(fmaxf(x[i], 0.0f), 1.0f);
+      if (!no_norm) v = __fmul_rn(__fsub_rn(v, a.mean[i % 3]), a.inv_std[i % 3]);
+      x[i] = v;
+    }
+    if (out_f32) {
+      float* o = reinterpret_cast<float*>(a.dst) + base;
+      if (cnt == 48 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i)
+          reinterpret_cast<float4*>(o)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 48; ++i) if (i < cnt) o[i] = x[i];
+      }
+    } else {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.dst) + base;
+      if (cnt == 48 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+          reinterpret_cast<uint4*>(o)[i] =
+              make_uint4(pack_bf16x2(x[8 * i], x[8 * i + 1]), pack_bf16x2(x[8 * i + 2], x[8 * i + 3]),
+                         pack_bf16x2(x[8 * i + 4], x[8 * i + 5]), pack_bf16x2(x[8 * i + 6], x[8 * i + 7]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 48; ++i) if (i < cnt) o[i] = __float2bfloat16_rn(x[i]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- per-image channel sums (contrast)
+__global__ void __launch_bounds__(256) k1_channel_sums(const uint8_t* __restrict__ src, int per,
+                                                       unsigned long long* __restrict__ sums) {
+  const int img = blockIdx.y;
+  const uint8_t* p = src + (size_t)img * per;
+  unsigned int s[3] = {0, 0, 0};
+  // each thread walks whole pixels so channel = position % 3 is static
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix * 3 < per; pix += gridDim.x * blockDim.x) {
+    s[0] += p[3 * pix]; s[1] += p[3 * pix + 1]; s[2] += p[3 * pix + 2];
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    unsigned int v = s[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sums[3 * (size_t)img + c], (unsigned long long)v);
+  }
+}
+
+// ---------------------------------------------------------------- fog: diamond-square plasma, one CTA per image
+__global__ void __launch_bounds__(1024) k1_plasma(const uint8_t* __restrict__ src, int per, int mapsize,
+                                                  float decay, uint32_t k0, uint32_t k1, uint32_t first_image,
+                                                  uint32_t stream, float* __restrict__ stats,
+                                                  float* __restrict__ maps) {
+  const int img = blockIdx.x;
+  float* M = maps + (size_t)img * mapsize * mapsize;
+  const uint32_t gimg = first_image + uint32_t(img);
+  const int mask = mapsize - 1;
+  auto noise = [&](int y, int x) {
+    const uint4 r = philox4x32_10(uint32_t(y * mapsize + x), gimg, 0u, stream, k0, k1);
+    return __fsub_rn(__fmul_rn(2.0f, u32_to_uniform(r.x)), 1.0f);
+  };
+  if (threadIdx.x == 0) M[0] = 0.0f;
+  __syncthreads();
+  float wib = 100.0f;
+  for (int step = mapsize; step >= 2; step >>= 1) {
+    const int hf = step >> 1, cells = mapsize / step;
+    const float w2 = __fmul_rn(wib, wib);
+    // squares
+    for (int i = threadIdx.x; i < cells * cells; i += blockDim.x) {
+      const int y = (i / cells) * step, x = (i % cells) * step;
+      const float a = M[y * mapsize + x], b = M[((y + step) & mask) * mapsize + x];
+      const float c = M[y * mapsize + ((x + step) & mask)], d = M[((y + step) & mask) * mapsize + ((x + step) & mask)];
+      const float sq = __fadd_rn(__fadd_rn(a, b), __fadd_rn(c, d));
+      M[(y + hf) * mapsize + x + hf] = __fadd_rn(__fmul_rn(sq, 0.25f), __fmul_rn(w2, noise(y + hf, x + hf)));
+    }
+    __syncthreads();
+    // diamonds
+    for (int i = threadIdx.x; i < cells * cells; i += blockDim.x) {
+      const int y = (i / cells) * step, x = (i % cells) * step;
+      const float ul = M[y * mapsize + x];
+      const float dr = M[(y + hf) * mapsize + x + hf];
+      {  // M[y, x+hf] = (dr + dr_up) + (ul + ul_right)
+        const float dru = M[((y - hf) & mask) * mapsize + x + hf];
+        const float ulr = M[y * mapsize + ((x + step) & mask)];
+        const float lt = __fadd_rn(__fadd_rn(dr, dru), __fadd_rn(ul, ulr));
+        M[y * mapsize + x + hf] = __fadd_rn(__fmul_rn(lt, 0.25f), __fmul_rn(w2, noise(y, x + hf)));
+      }
+      {  // M[y+hf, x] = (dr + dr_left) + (ul + ul_down)
+        const float drl = M[(y + hf) * mapsize + ((x - hf) & mask)];
+        const float uld = M[((y + step) & mask) * mapsize + x];
+        const float tt = __fadd_rn(__fadd_rn(dr, drl), __fadd_rn(ul, uld));
+        M[(y + hf) * mapsize + x] = __fadd_rn(__fmul_rn(tt, 0.25f), __fmul_rn(w2, noise(y + hf, x)));
+      }
+    }
+    __syncthreads();
+    wib = __fdiv_rn(wib, decay);
+  }
+  // min / max of the map, max of the image
+  __shared__ float s_mn[32], s_mx[32];
+  __shared__ unsigned s_xm[32];
+  float mn = 3.4e38f, mx = -3.4e38f;
+  for (int i = threadIdx.x; i < mapsize * mapsize; i += blockDim.x) {
+    const float v = M[i];
+    mn = fminf(mn, v); mx = fmaxf(mx, v);
+  }
+  unsigned xm = 0;
+  const uint8_t* p = src + (size_t)img * per;
+  for (int i = threadIdx.x; i < per; i += blockDim.x) xm = max(xm, (unsigned)p[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    xm = max(xm, __shfl_xor_sync(0xffffffffu, xm, o));
+  }
+  if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; s_xm[threadIdx.x >> 5] = xm; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < int(blockDim.x >> 5); ++i) { mn = fminf(mn, s_mn[i]); mx = fmaxf(mx, s_mx[i]); xm = max(xm, s_xm[i]); }
+    stats[4 * img + 0] = mn;
+    stats[4 * img + 1] = __fsub_rn(mx, mn);
+    stats[4 * img + 2] = __fdiv_rn(float(xm), 255.0f);
+    stats[4 * img + 3] = 0.f;
+  }
+}
+
+// ---------------------------------------------------------------- shared store helper for the gather kernels
+struct OutArgs {
+  void* dst;
+  float mean[3], inv_std[3];
+  unsigned flags;
+};
+__device__ __forceinline__ void store_pixel(const OutArgs& o, size_t pix, float r, float g, float b) {
+  float v[3] = {r, g, b};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float t = fminf(fmaxf(v[c], 0.0f), 1.0f);
+    if (!(o.flags & FAV_NO_NORMALIZE)) t = __fmul_rn(__fsub_rn(t, o.mean[c]), o.inv_std[c]);
+    v[c] = t;
+  }
+  if (o.flags & FAV_OUT_F32) {
+    float* d = reinterpret_cast<float*>(o.dst) + 3 * pix;
+    d[0] = v[0]; d[1] = v[1]; d[2] = v[2];
+  } else {
+    __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(o.dst) + 3 * pix;
+    d[0] = __float2bfloat16_rn(v[0]); d[1] = __float2bfloat16_rn(v[1]); d[2] = __float2bfloat16_rn(v[2]);
+  }
+}
+
+// ---------------------------------------------------------------- tap-list stencil (defocus, motion)
+// table: n_entries x [ int32 ntaps, pad[3], then max_taps x {int16 dy, int16 dx, float w} ]
+struct TapArgs {
+  const uint8_t* src;
+  OutArgs out;
+  int n, h, w;
+  int n_entries, max_taps, border;       // border 0 = reflect101, 1 = clamp
+  int dy_min, dy_max, dx_min, dx_max;
+  const uint8_t* table;
+  uint32_t k0, k1, first_image, stream;  // entry = Philox(AUX).x % n_entries when n_entries > 1
+  int tiles_x, tiles_y;
+  unsigned src_bgr;
+};
+constexpr int TAP_TILE = 32;
+
+__device__ __forceinline__ int border_idx(int i, int n, int mode) {
+  if (mode == 1) return min(max(i, 0), n - 1);
+  i = abs(i);
+  if (i >= n) i = 2 * (n - 1) - i;
+  i = abs(i);
+  if (i >= n) i = 2 * (n - 1) - i;
+  return min(max(i, 0), n - 1);
+}
+
+__global__ void __launch_bounds__(256) k1_taps(const TapArgs a) {
+  extern __shared__ uint32_t s_tile[];
+  const int SW = TAP_TILE + a.dx_max - a.dx_min, SH = TAP_TILE + a.dy_max - a.dy_min;
+  uint2* s_taps = reinterpret_cast<uint2*>(s_tile + SW * SH);
+  const int img = blockIdx.y;
+  const int ty = blockIdx.x / a.tiles_x, tx = blockIdx.x - ty * a.tiles_x;
+  const int y0 = ty * TAP_TILE, x0 = tx * TAP_TILE;
+  int entry = 0;
+  if (a.n_entries > 1) {
+    const uint4 r = philox4x32_10(0u, a.first_image + uint32_t(img), 0u, a.stream, a.k0, a.k1);
+    entry = int(r.x % uint32_t(a.n_entries));
+  }
+  const uint8_t* ent = a.table + (size_t)entry * (16 + 8 * (size_t)a.max_taps);
+  const int ntaps = *reinterpret_cast<const int*>(ent);
+  for (int i = threadIdx.x; i < ntaps; i += blockDim.x) {
+    const uint2 t = reinterpret_cast<const uint2*>(ent + 16)[i];
+    const int dy = int(short(t.x & 0xFFFF)), dx = int(short(t.x >> 16));
+    s_taps[i] = make_uint2(uint32_t((dy - a.dy_min) * SW + (dx - a.dx_min)), t.y);
+  }
+  const uint8_t* p = a.src + (size_t)img * a.h * a.w * 3;
+  for (int i = threadIdx.x; i < SW * SH; i += blockDim.x) {
+    const int sy = i / SW, sx = i - sy * SW;
+    const int yy = border_idx(y0 + sy + a.dy_min, a.h, a.border);
+    const int xx = border_idx(x0 + sx + a.dx_min, a.w, a.border);
+    const uint8_t* q = p + ((size_t)yy * a.w + xx) * 3;
+    uint32_t c0 = q[0], c1 = q[1], c2 = q[2];
+    if (a.src_bgr) { const uint32_t t = c0; c0 = c2; c2 = t; }
+    s_tile[i] = c0 | (c1 << 8) | (c2 << 16);
+  }
+  __syncthreads();
+  const int lx = threadIdx.x & 31, ly0 = threadIdx.x >> 5;     // 8 rows of threads, 4 pixels each
+  float acc[4][3];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = 0.f;
+  for (int t = 0; t < ntaps; ++t) {
+    const uint2 tp = s_taps[t];
+    const float wgt = __uint_as_float(tp.y);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t v = s_tile[(ly0 + 8 * j) * SW + lx + tp.x];
+      // byte -> float via the 2^23 mantissa trick (full-rate PRMT + FADD instead of I2F)
+      const float r = __uint_as_float(0x4B000000u | (v & 0xFF)) - 8388608.0f;
+      const float g = __uint_as_float(0x4B000000u | ((v >> 8) & 0xFF)) - 8388608.0f;
+      const float b = __uint_as_float(0x4B000000u | ((v >> 16) & 0xFF)) - 8388608.0f;
+      acc[j][0] = fmaf(wgt, r, acc[j][0]);
+      acc[j][1] = fmaf(wgt, g, acc[j][1]);
+      acc[j][2] = fmaf(wgt, b, acc[j][2]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int y = y0 + ly0 + 8 * j, x = x0 + lx;
+    if (y < a.h && x < a.w)
+      store_pixel(a.out, ((size_t)img * a.h + y) * a.w + x, __fdiv_rn(acc[j][0], 255.0f), __fdiv_rn(acc[j][1], 255.0f),
+                  __fdiv_rn(acc[j][2], 255.0f));
+  }
+}
+
+// ---------------------------------------------------------------- zoom blur (bilinear gathers)
+// table: nz x [ (h + w) x {int16 i0, int16 i1, float frac} ]  rows first then columns
+struct ZoomArgs {
+  const uint8_t* src;
+  OutArgs out;
+  int n, h, w, nz;
+  const uint2* table;
+  unsigned src_bgr;
+};
+__global__ void __launch_bounds__(256) k1_zoom(const ZoomArgs a) {
+  const long long total = (long long)a.n * a.h * a.w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int img = int(i / (a.h * a.w));
+    const int rem = int(i - (long long)img * a.h * a.w);
+    const int y = rem / a.w, x = rem - y * a.w;
+    const uint8_t* p = a.src + (size_t)img * a.h * a.w * 3;
+    float acc[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[c] = u8f(p[((size_t)y * a.w + x) * 3 + c]);
+    for (int z = 0; z < a.nz; ++z) {
+      const uint2 ry = __ldg(a.table + (size_t)z * (a.h + a.w) + y);
+      const uint2 rx = __ldg(a.table + (size_t)z * (a.h + a.w) + a.h + x);
+      const int y0 = int(ry.x & 0xFFFF), y1 = int(ry.x >> 16), x0 = int(rx.x & 0xFFFF), x1 = int(rx.x >> 16);
+      const float fy = __uint_as_float(ry.y), fx = __uint_as_float(rx.y);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v00 = u8f(p[((size_t)y0 * a.w + x0) * 3 + c]), v01 = u8f(p[((size_t)y0 * a.w + x1) * 3 + c]);
+        const float v10 = u8f(p[((size_t)y1 * a.w + x0) * 3 + c]), v11 = u8f(p[((size_t)y1 * a.w + x1) * 3 + c]);
+        const float top = __fadd_rn(__fmul_rn(v00, __fsub_rn(1.0f, fx)), __fmul_rn(v01, fx));
+        const float bot = __fadd_rn(__fmul_rn(v10, __fsub_rn(1.0f, fx)), __fmul_rn(v11, fx));
+        acc[c] = __fadd_rn(acc[c], __fadd_rn(__fmul_rn(top, __fsub_rn(1.0f, fy)), __fmul_rn(bot, fy)));
+      }
+    }
+    const float inv = float(a.nz + 1);
+    float r = __fdiv_rn(acc[0], inv), g = __fdiv_rn(acc[1], inv), b = __fdiv_rn(acc[2], inv);
+    if (a.src_bgr) { const float t = r; r = b; b = t; }
+    store_pixel(a.out, (size_t)i, r, g, b);
+  }
+}
+
+// ---------------------------------------------------------------- pixelate (integer box means)
+// table: (h + w) x {int16 lo, int16 hi}
+struct PixArgs {
+  const uint8_t* src;
+  OutArgs out;
+  int n, h, w;
+  const uint32_t* table;
+  unsigned src_bgr;
+};
+__global__ void __launch_bounds__(256) k1_pixelate(const PixArgs a) {
+  const long long total = (long long)a.n * a.h * a.w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int img = int(i / (a.h * a.w));
+    const int rem = int(i - (long long)img * a.h * a.w);
+    const int y = rem / a.w, x = rem - y * a.w;
+    const uint32_t ry = __ldg(a.table + y), rx = __ldg(a.table + a.h + x);
+    const int y0 = int(ry & 0xFFFF), y1 = int(ry >> 16), x0 = int(rx & 0xFFFF), x1 = int(rx >> 16);
+    const uint8_t* p = a.src + (size_t)img * a.h * a.w * 3;
+    unsigned s[3] = {0, 0, 0};
+    for (int yy = y0; yy < y1; ++yy)
+      for (int xx = x0; xx < x1; ++xx) {
+        const uint8_t* q = p + ((size_t)yy * a.w + xx) * 3;
+        s[0] += q[0]; s[1] += q[1]; s[2] += q[2];
+      }
+    const unsigned cnt = unsigned((y1 - y0) * (x1 - x0));
+    float v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = u8f((2 * s[c] + cnt) / (2 * cnt));
+    if (a.src_bgr) { const float t = v[0]; v[0] = v[2]; v[2] = t; }
+    store_pixel(a.out, (size_t)i, v[0], v[1], v[2]);
+  }
+}
+
+// ---------------------------------------------------------------- synthetic inputs
+__global__ void k_synth_images(uint8_t* dst, int n, int per, uint32_t k0, uint32_t k1, uint32_t first_image) {
+  const int nch = (per + 15) / 16;
+  const long long total = (long long)n * nch;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int img = int(i / nch), ch = int(i - (long long)img * nch);
+    const uint4 r = philox4x32_10(uint32_t(ch), first_image + uint32_t(img), 0u, stream_id(KIND_IMAGES), k0, k1);
+    uint8_t* o = dst + (size_t)img * per + (size_t)ch * 16;
+    const int cnt = min(16, per - ch * 16);
+    if (cnt == 16 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+      *reinterpret_cast<uint4*>(o) = r;
+    } else {
+      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+      for (int b = 0; b < cnt; ++b) o[b] = uint8_t(w[b >> 2] >> (8 * (b & 3)));
+    }
+  }
+}
+__global__ void k_synth_labels(int32_t* dst, int n, int C, uint32_t k0, uint32_t k1, uint32_t first_image) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const uint4 r = philox4x32_10(0u, first_image + uint32_t(i), 0u, stream_id(KIND_LABELS), k0, k1);
+    dst[i] = int32_t(r.x % uint32_t(C));
+  }
+}
+
+static inline int grid_for(long long work, int threads, int num_sms, int waves = 8) {
+  long long b = (work + threads - 1) / threads;
+  long long cap = (long long)num_sms * waves;
+  return int(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace fav
+
+using namespace fav;
+
+extern "C" size_t fav_corrupt_scratch_bytes(int corruption, int n, int height, int width) {
+  if (corruption == FAV_CONTRAST) return (size_t)n * 3 * sizeof(unsigned long long);
+  if (corruption == FAV_FOG) {
+    int m = 1;
+    while (m < (height > width ? height : width)) m *= 2;
+    const size_t stats = (((size_t)n * 16) + 255) / 256 * 256;
+    return stats + (size_t)n * m * m * sizeof(float);
+  }
+  return 0;
+}
+
+extern "C" int fav_corrupt_normalize(fav_handle h, const uint8_t* d_src, void* d_dst, int n, int height,
+                                     int width, int corruption, int severity, const float* fparams,
+                                     int n_fparams, const int32_t* iparams, int n_iparams,
+                                     const void* d_table, size_t table_bytes, void* d_scratch,
+                                     size_t scratch_bytes, uint64_t seed, uint64_t first_image,
+                                     const float mean[3], const float std[3], unsigned flags, void* stream) {
+  FAV_REQUIRE(h && d_src && d_dst, "fav_corrupt_normalize: null handle/pointer");
+  FAV_REQUIRE(n >= 0 && height > 0 && width > 0, "fav_corrupt_normalize: bad shape n=%d h=%d w=%d", n, height, width);
+  FAV_REQUIRE(corruption == FAV_CLEAN || (severity >= 1 && severity <= 5), "severity must be 1..5 (got %d)", severity);
+  FAV_REQUIRE(mean && std, "fav_corrupt_normalize: mean/std required");
+  if (n == 0) return FAV_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int per = height * width * 3;
+  const uint32_t k0 = uint32_t(seed), k1 = uint32_t(seed >> 32);
+  auto need_f = [&](int k) { return fparams && n_fparams >= k; };
+  auto need_i = [&](int k) { return iparams && n_iparams >= k; };
+
+  OutArgs out;
+  out.dst = d_dst;
+  out.flags = flags;
+  for (int c = 0; c < 3; ++c) { out.mean[c] = mean[c]; out.inv_std[c] = 1.0f / std[c]; }
+
+  PointwiseArgs a{};
+  a.src = d_src; a.dst = d_dst; a.n = n; a.per = per; a.groups_per_image = (per + 47) / 48;
+  a.k0 = k0; a.k1 = k1; a.first_image = uint32_t(first_image);
+  a.stream = stream_id(KIND_CORRUPT, corruption, severity);
+  a.table = d_table; a.scratch = d_scratch; a.hw = height * width; a.width = width; a.flags = flags;
+  for (int c = 0; c < 3; ++c) { a.mean[c] = mean[c]; a.inv_std[c] = 1.0f / std[c]; }
+  const long long groups = (long long)n * a.groups_per_image;
+  const int grid = grid_for(groups, 256, h->num_sms, 16);
+
+  switch (corruption) {
+    case FAV_CLEAN:
+      k1_pointwise<PW_CLEAN><<<grid, 256, 0, st>>>(a); h->launches++; break;
+    case FAV_GAUSSIAN_NOISE:
+      FAV_REQUIRE(need_f(1), "gaussian_noise needs fparams[0]=sigma");
+      a.f0 = fparams[0];
+      k1_pointwise<PW_GAUSS><<<grid, 256, 0, st>>>(a); h->launches++; break;
+    case FAV_SHOT_NOISE:
+      FAV_REQUIRE(need_f(1) && need_i(1) && d_table, "shot_noise needs fparams[0]=c, iparams[0]=width, table");
+      FAV_REQUIRE(table_bytes >= 1024 + (size_t)iparams[0] * 1024, "shot_noise table too small");
+      a.f0 = fparams[0]; a.u0 = uint32_t(iparams[0]);
+      k1_pointwise<PW_SHOT><<<grid, 256, 0, st>>>(a); h->launches++; break;
+    case FAV_IMPULSE_NOISE:
+      FAV_REQUIRE(need_i(2), "impulse_noise needs iparams[0..1]=pepper,salt thresholds");
+      a.u0 = uint32_t(iparams[0]); a.u1 = uint32_t(iparams[1]);
+      k1_pointwise<PW_IMPULSE><<<grid, 256, 0, st>>>(a); h->launches++; break;
+    case FAV_BRIGHTNESS:
+      FAV_REQUIRE(need_f(1), "brightness needs fparams[0]=c");
+      a.f0 = fparams[0];
+      k1_pointwise<PW_BRIGHT><<<grid, 256, 0, st>>>(a); h->launches++; break;
+    case FAV_CONTRAST: {
+      FAV_REQUIRE(need_f(1), "contrast needs fparams[0]=c");
+      FAV_REQUIRE(d_scratch && scratch_bytes >= fav_corrupt_scratch_bytes(corruption, n, height, width),
+                  "contrast needs %zu scratch bytes", fav_corrupt_scratch_bytes(corruption, n, height, width));
+      a.f0 = fparams[0];
+      FAV_CUDA_OK(cudaMemsetAsync(d_scratch, 0, (size_t)n * 24, st));
+      const int bx = max(1, min(64, (height * width + 1023) / 1024));
+      k1_channel_sums<<<dim3(bx, n), 256, 0, st>>>(d_src, per, reinterpret_cast<unsigned long long*>(d_scratch));
+      k1_pointwise<PW_CONTRAST><<<grid, 256, 0, st>>>(a); h->launches += 2; break;
+    }
+    case FAV_FOG: {
+      FAV_REQUIRE(need_f(2), "fog needs fparams[0]=c, fparams[1]=wibble decay");
+      FAV_REQUIRE(d_scratch && scratch_bytes >= fav_corrupt_scratch_bytes(corruption, n, height, width),
+                  "fog needs %zu scratch bytes", fav_corrupt_scratch_bytes(corruption, n, height, width));
+      int m = 1;
+      while (m < max(height, width)) m *= 2;
+      a.f0 = fparams[0]; a.mapsize = m;
+      a.map_offset = (((size_t)n * 16) + 255) / 256 * 256;
+      float* stats = reinterpret_cast<float*>(d_scratch);
+      float* maps = reinterpret_cast<float*>(reinterpret_cast<char*>(d_scratch) + a.map_offset);
+      k1_plasma<<<n, 1024, 0, st>>>(d_src, per, m, fparams[1], k0, k1, uint32_t(first_image), a.stream, stats, maps);
+      k1_pointwise<PW_FOG><<<grid, 256, 0, st>>>(a); h->launches += 2; break;
+    }
+    case FAV_DEFOCUS_BLUR:
+    case FAV_MOTION_BLUR: {
+      FAV_REQUIRE(need_i(7) && d_table, "tap stencil needs iparams[0..6] and a tap table");
+      TapArgs t{};
+      t.src = d_src; t.out = out; t.n = n; t.h = height; t.w = width;
+      t.n_entries = iparams[0]; t.max_taps = iparams[1]; t.border = iparams[2];
+      t.dy_min = iparams[3]; t.dy_max = iparams[4]; t.dx_min = iparams[5]; t.dx_max = iparams[6];
+      FAV_REQUIRE(t.n_entries >= 1 && t.max_taps >= 1 && t.dy_min <= 0 && t.dy_max >= 0 && t.dx_min <= 0 && t.dx_max >= 0,
+                  "tap stencil: bad table geometry");
+      FAV_REQUIRE(table_bytes >= (size_t)t.n_entries * (16 + 8 * (size_t)t.max_taps), "tap table too small");
+      t.table = reinterpret_cast<const uint8_t*>(d_table);
+      t.k0 = k0; t.k1 = k1; t.first_image = uint32_t(first_image);
+      t.stream = stream_id(KIND_AUX, corruption, severity);
+      t.tiles_x = (width + TAP_TILE - 1) / TAP_TILE; t.tiles_y = (height + TAP_TILE - 1) / TAP_TILE;
+      t.src_bgr = flags & FAV_SRC_BGR;
+      const size_t smem = (size_t)(TAP_TILE + t.dx_max - t.dx_min) * (TAP_TILE + t.dy_max - t.dy_min) * 4 + (size_t)t.max_taps * 8;
+      FAV_REQUIRE(smem <= 200 * 1024, "tap stencil halo too large (%zu B of shared memory)", smem);
+      if (smem > 48 * 1024) FAV_CUDA_OK(cudaFuncSetAttribute(k1_taps, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      k1_taps<<<dim3(t.tiles_x * t.tiles_y, n), 256, smem, st>>>(t); h->launches++; break;
+    }
+    case FAV_ZOOM_BLUR: {
+      FAV_REQUIRE(need_i(1) && d_table, "zoom_blur needs iparams[0]=nz and a table");
+      FAV_REQUIRE(table_bytes >= (size_t)iparams[0] * (height + width) * 8, "zoom table too small");
+      ZoomArgs z{};
+      z.src = d_src; z.out = out; z.n = n; z.h = height; z.w = width; z.nz = iparams[0];
+      z.table = reinterpret_cast<const uint2*>(d_table); z.src_bgr = flags & FAV_SRC_BGR;
+      k1_zoom<<<grid_for((long long)n * height * width, 256, h->num_sms, 16), 256, 0, st>>>(z); h->launches++; break;
+    }
+    case FAV_PIXELATE: {
+      FAV_REQUIRE(d_table && table_bytes >= (size_t)(height + width) * 4, "pixelate needs a range table");
+      PixArgs p{};
+      p.src = d_src; p.out = out; p.n = n; p.h = height; p.w = width;
+      p.table = reinterpret_cast<const uint32_t*>(d_table); p.src_bgr = flags & FAV_SRC_BGR;
+      k1_pixelate<<<grid_for((long long)n * height * width, 256, h->num_sms, 16), 256, 0, st>>>(p); h->launches++; break;
+    }
+    default:
+      set_error("corruption id %d is not implemented on the device yet", corruption);
+      return FAV_E_UNSUPPORTED;
+  }
+  FAV_CUDA_OK(cudaGetLastError());
+  return FAV_OK;
+}
+
+extern "C" int fav_synth_images(fav_handle h, uint8_t* d_dst, int n, int height, int width, uint64_t seed,
+                                uint64_t first_image, void* stream) {
+  FAV_REQUIRE(h && d_dst && n >= 0 && height > 0 && width > 0, "fav_synth_images: bad arguments");
+  if (n == 0) return FAV_OK;
+  const int per = height * width * 3;
+  const long long work = (long long)n * ((per + 15) / 16);
+  k_synth_images<<<grid_for(work, 256, h->num_sms, 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      d_dst, n, per, uint32_t(seed), uint32_t(seed >> 32), uint32_t(first_image));
+  h->launches++;
+  FAV_CUDA_OK(cudaGetLastError());
+  return FAV_OK;
+}
+
+extern "C" int fav_synth_labels(fav_handle h, int32_t* d_dst, int n, int C, uint64_t seed, uint64_t first_image,
+                                void* stream) {
+  FAV_REQUIRE(h && d_dst && n >= 0 && C > 0, "fav_synth_labels: bad arguments");
+  if (n == 0) return FAV_OK;
+  k_synth_labels<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      d_dst, n, C, uint32_t(seed), uint32_t(seed >> 32), uint32_t(first_image));
+  h->launches++;
+  FAV_CUDA_OK(cudaGetLastError());
+  return FAV_OK;
+}

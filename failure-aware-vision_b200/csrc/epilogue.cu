@@ -1,0 +1,264 @@
+// epilogue.cu -- K3 uncertainty epilogue and K4 calibration / detection aggregates.
+//
+// Replaces (reference): nothing executable -- README.md:2 ("uncertainty estimation"), README.md:22-24
+// (failure = incorrect prediction with high confidence; threshold left open -> tau is an argument).
+// Nearest reference code: histogram entropy of a gray frame, platform/backend/signal_analyzer.py:100-112,
+// and the summary counters of failure_attributor.py:93-108.  Definitions: oracle/uncertainty.py,
+// oracle/metrics.py.
+//
+// K3: one warp per sample; lanes stride over classes; warp-shuffle reductions for max / sum / entropy;
+// the pass-mean probabilities live in registers (C <= 1024) so logits are read from HBM exactly once.
+// K4: per-CTA shared-memory histograms (ECE bins + AUROC buckets, u32) flushed with one 64-bit global
+// atomic per non-empty slot; all accumulators are integers (counts, Q32 fixed-point sums).
+#include "common.cuh"
+
+namespace fav {
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct SampleOut {
+  float conf, H, mi;
+  int pred;
+};
+
+// NC = ceil(C / 32) register slots per lane
+template <int NC>
+__device__ __forceinline__ SampleOut sample_uncertainty(const float* __restrict__ z, int T, int C, int lane) {
+  float pbar[NC];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) pbar[i] = 0.f;
+  float hsum = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float* zt = z + (size_t)t * C;
+    float v[NC];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = c < C ? zt[c] : -INFINITY;
+      m = fmaxf(m, v[i]);
+    }
+    m = warp_max(m);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) { v[i] = expf(v[i] - m); s += v[i]; }   // exp(-inf) = 0 for padding lanes
+    s = warp_sum(s);
+    float h = 0.f;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const float p = __fdiv_rn(v[i], s);
+      pbar[i] += p;
+      if (p > 0.f) h -= p * logf(p);
+    }
+    hsum += warp_sum(h);
+  }
+  const float invT = 1.0f / float(T);
+  float best = -1.f;
+  int arg = 0x7fffffff;
+  float H = 0.f;
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int c = lane + 32 * i;
+    const float p = pbar[i] * invT;
+    if (c < C) {
+      if (p > best) { best = p; arg = c; }          // ascending c inside a lane: first max kept
+      if (p > 0.f) H -= p * logf(p);
+    }
+  }
+  H = warp_sum(H);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {                // argmax, lowest index on ties
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+  }
+  SampleOut r;
+  r.conf = best; r.pred = arg; r.H = H;
+  r.mi = fmaxf(H - hsum * invT, 0.f);
+  return r;
+}
+
+struct HistGeom {
+  int C, n_bins, n_buckets;
+  float tau, inv_lnC;
+};
+
+__device__ __forceinline__ unsigned long long q32(float x) {
+  return __float2ull_rn(x * 4294967296.0f);
+}
+__device__ __forceinline__ float clip01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
+
+// shared histogram: [3*n_bins (count, correct, pad)] + [6*n_buckets]; Q32 sums go straight to global.
+__device__ __forceinline__ void accumulate_sample(const HistGeom& g, unsigned* s_hist, unsigned long long* hist,
+                                                  float conf, float H, float mi, int pred, int label) {
+  const bool correct = pred == label;
+  int b = int(ceilf(conf * float(g.n_bins))) - 1;
+  b = min(max(b, 0), g.n_bins - 1);
+  atomicAdd(&s_hist[2 * b], 1u);
+  if (correct) atomicAdd(&s_hist[2 * b + 1], 1u);
+  atomicAdd(&hist[FAV_HIST_HDR + 3 * b + 1], q32(conf));
+  const float s0 = clip01(1.0f - conf), s1 = clip01(H * g.inv_lnC), s2 = clip01(mi * g.inv_lnC);
+  const float sc[3] = {s0, s1, s2};
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    int k = int(floorf(sc[s] * float(g.n_buckets)));
+    k = min(max(k, 0), g.n_buckets - 1);
+    atomicAdd(&s_hist[2 * g.n_bins + (s * g.n_buckets + k) * 2 + (correct ? 0 : 1)], 1u);
+  }
+  const size_t cb = FAV_HIST_HDR + 3 * (size_t)g.n_bins + 6 * (size_t)g.n_buckets;
+  if (g.C <= 100) {
+    atomicAdd(&hist[cb + (size_t)label * g.C + pred], 1ull);
+  } else {
+    atomicAdd(&hist[cb + 2 * (size_t)label], 1ull);
+    if (correct) atomicAdd(&hist[cb + 2 * (size_t)label + 1], 1ull);
+  }
+}
+
+// block-level header sums: n, correct, flag, sum conf / H / MI (Q32) reduced in shared then one atomic each
+struct BlockSums {
+  unsigned long long v[6];
+};
+
+template <int NC, bool FUSED>
+__global__ void __launch_bounds__(256) k34_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
+                                                  int n, int T, HistGeom g, unsigned long long* __restrict__ hist,
+                                                  float* __restrict__ o_conf, float* __restrict__ o_H,
+                                                  float* __restrict__ o_mi, int32_t* __restrict__ o_pred,
+                                                  uint8_t* __restrict__ o_flag,
+                                                  // K4-only inputs (FUSED == false and logits == nullptr)
+                                                  const float* __restrict__ i_conf, const float* __restrict__ i_H,
+                                                  const float* __restrict__ i_mi, const int32_t* __restrict__ i_pred) {
+  extern __shared__ unsigned s_hist[];
+  __shared__ unsigned long long s_sums[6];
+  const int n_slots = 2 * g.n_bins + 6 * g.n_buckets;
+  const bool do_hist = hist != nullptr;
+  if (do_hist) {
+    for (int i = threadIdx.x; i < n_slots; i += blockDim.x) s_hist[i] = 0;
+    if (threadIdx.x < 6) s_sums[threadIdx.x] = 0;
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  unsigned long long my[6] = {0, 0, 0, 0, 0, 0};
+  if (logits) {
+    for (int i = blockIdx.x * warps_per_block + (threadIdx.x >> 5); i < n; i += gridDim.x * warps_per_block) {
+      const SampleOut r = sample_uncertainty<NC>(logits + (size_t)i * T * g.C, T, g.C, lane);
+      if (lane == 0) {
+        const int label = labels ? labels[i] : -1;
+        const bool flag = labels && r.pred != label && r.conf >= g.tau;
+        if (o_conf) o_conf[i] = r.conf;
+        if (o_H) o_H[i] = r.H;
+        if (o_mi) o_mi[i] = r.mi;
+        if (o_pred) o_pred[i] = r.pred;
+        if (o_flag) o_flag[i] = flag ? 1 : 0;
+        if (do_hist) {
+          accumulate_sample(g, s_hist, hist, r.conf, r.H, r.mi, r.pred, label);
+          my[0] += 1; my[1] += (r.pred == label); my[2] += flag;
+          my[3] += q32(r.conf); my[4] += q32(clip01(r.H * g.inv_lnC)); my[5] += q32(clip01(r.mi * g.inv_lnC));
+        }
+      }
+    }
+  } else {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      const float conf = i_conf[i], H = i_H[i], mi = i_mi[i];
+      const int pred = i_pred[i], label = labels[i];
+      accumulate_sample(g, s_hist, hist, conf, H, mi, pred, label);
+      my[0] += 1; my[1] += (pred == label); my[2] += (pred != label && conf >= g.tau);
+      my[3] += q32(conf); my[4] += q32(clip01(H * g.inv_lnC)); my[5] += q32(clip01(mi * g.inv_lnC));
+    }
+  }
+  if (!do_hist) return;
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+    if (my[k]) atomicAdd(&s_sums[k], my[k]);
+  __syncthreads();
+  if (threadIdx.x < 6 && s_sums[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_sums[threadIdx.x]);
+  for (int i = threadIdx.x; i < n_slots; i += blockDim.x) {
+    const unsigned v = s_hist[i];
+    if (!v) continue;
+    size_t dst;
+    if (i < 2 * g.n_bins) dst = FAV_HIST_HDR + 3 * (size_t)(i >> 1) + ((i & 1) ? 2 : 0);
+    else dst = FAV_HIST_HDR + 3 * (size_t)g.n_bins + (size_t)(i - 2 * g.n_bins);
+    atomicAdd(&hist[dst], (unsigned long long)v);
+  }
+}
+
+}  // namespace fav
+
+using namespace fav;
+
+extern "C" size_t fav_hist_words(int C, int n_bins, int n_buckets) {
+  const size_t conf = C <= 100 ? (size_t)C * C : 2 * (size_t)C;
+  return FAV_HIST_HDR + 3 * (size_t)n_bins + 6 * (size_t)n_buckets + conf;
+}
+
+static int launch_k34(fav_handle h, const float* d_logits, const int32_t* d_labels, int n, int T, int C, float tau,
+                      int n_bins, int n_buckets, int64_t* d_hist, float* d_conf, float* d_entropy, float* d_mi,
+                      int32_t* d_pred, uint8_t* d_flag, const float* i_conf, const float* i_H, const float* i_mi,
+                      const int32_t* i_pred, void* stream) {
+  FAV_REQUIRE(h, "null handle");
+  FAV_REQUIRE(n >= 0 && C >= 2 && C <= 1024, "C must be in [2,1024] (got %d), n >= 0 (got %d)", C, n);
+  FAV_REQUIRE(!d_logits || T >= 1, "T must be >= 1 (got %d)", T);
+  if (n == 0) return FAV_OK;
+  HistGeom g;
+  g.C = C; g.n_bins = n_bins; g.n_buckets = n_buckets; g.tau = tau; g.inv_lnC = float(1.0 / log(double(C)));
+  size_t smem = 0;
+  if (d_hist) {
+    FAV_REQUIRE(d_labels, "histogram accumulation needs labels");
+    FAV_REQUIRE(n_bins >= 1 && n_bins <= 1024 && n_buckets >= 1 && n_buckets <= 8192, "bad n_bins/n_buckets");
+    smem = (2 * (size_t)n_bins + 6 * (size_t)n_buckets) * 4;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  unsigned long long* hist = reinterpret_cast<unsigned long long*>(d_hist);
+  const int nc = C <= 32 ? 1 : (C <= 128 ? 4 : 32);
+  const int warps = 8;
+  long long blocks = d_logits ? (n + warps - 1) / warps : (n + 255) / 256;
+  const long long cap = (long long)h->num_sms * (smem > 64 * 1024 ? 2 : 4);
+  if (blocks > cap) blocks = cap;
+#define FAV_K34(NC)                                                                                           \
+  do {                                                                                                        \
+    if (smem > 48 * 1024)                                                                                     \
+      FAV_CUDA_OK(cudaFuncSetAttribute(k34_kernel<NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); \
+    k34_kernel<NC, true><<<int(blocks), 256, smem, st>>>(d_logits, d_labels, n, T, g, hist, d_conf, d_entropy, d_mi,  \
+                                                         d_pred, d_flag, i_conf, i_H, i_mi, i_pred);          \
+  } while (0)
+  if (nc == 1) FAV_K34(1); else if (nc == 4) FAV_K34(4); else FAV_K34(32);
+#undef FAV_K34
+  h->launches++;
+  FAV_CUDA_OK(cudaGetLastError());
+  return FAV_OK;
+}
+
+extern "C" int fav_epilogue(fav_handle h, const float* d_logits, const int32_t* d_labels, int n, int T, int C, float tau,
+                            float* d_conf, float* d_entropy, float* d_mi, int32_t* d_pred, uint8_t* d_flag,
+                            void* stream) {
+  FAV_REQUIRE(d_logits, "fav_epilogue: logits required");
+  FAV_REQUIRE(!d_flag || d_labels, "fav_epilogue: failure flags need labels");
+  return launch_k34(h, d_logits, d_labels, n, T, C, tau, 0, 0, nullptr, d_conf, d_entropy, d_mi, d_pred, d_flag,
+                    nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int fav_accumulate(fav_handle h, const float* d_conf, const float* d_entropy, const float* d_mi,
+                              const int32_t* d_pred, const int32_t* d_labels, int n, int C, float tau, int n_bins,
+                              int n_buckets, int64_t* d_hist, void* stream) {
+  FAV_REQUIRE(d_conf && d_entropy && d_mi && d_pred && d_labels && d_hist, "fav_accumulate: null pointer");
+  return launch_k34(h, nullptr, d_labels, n, 1, C, tau, n_bins, n_buckets, d_hist, nullptr, nullptr, nullptr, nullptr,
+                    nullptr, d_conf, d_entropy, d_mi, d_pred, stream);
+}
+
+extern "C" int fav_epilogue_accumulate(fav_handle h, const float* d_logits, const int32_t* d_labels, int n, int T,
+                                       int C, float tau, int n_bins, int n_buckets, int64_t* d_hist, float* d_conf,
+                                       float* d_entropy, float* d_mi, int32_t* d_pred, uint8_t* d_flag, void* stream) {
+  FAV_REQUIRE(d_logits && d_labels && d_hist, "fav_epilogue_accumulate: null pointer");
+  return launch_k34(h, d_logits, d_labels, n, T, C, tau, n_bins, n_buckets, d_hist, d_conf, d_entropy, d_mi, d_pred,
+                    d_flag, nullptr, nullptr, nullptr, nullptr, stream);
+}

@@ -1,0 +1,317 @@
+// forward.cu -- weights arena, layer plan and the batched MC-dropout forward (stem -> blocks -> pool -> fc).
+//
+// Replaces (reference): the ML-score slot documented at platform/backend/anomaly_simulator.py:34-77 ("No PyTorch
+// dependency ... heuristic proxy") with a real classifier forward; topology = stock torchvision ResNet (oracle/model.py).
+// MC-dropout: a mask after every residual block and on the pooled feature; everything before the
+// first mask (stem, max-pool, block 0) is pass-invariant and runs once per image, block 0's epilogue then writes
+// the T masked replicas, and all later layers run on N*T pass-images as one batched launch sequence.
+#include <cstring>
+#include "conv.cuh"
+
+namespace fav {
+
+struct BlockDesc { int n_convs; int ds; int conv0; };   // conv0 = index of the block's first conv; ds = index or -1
+
+struct Plan {
+  int model_id = 0, num_classes = 0, in_h = 0, in_w = 0;
+  std::vector<ConvLayer> convs;      // [0] stem, blocks..., [last] fc (1x1)
+  std::vector<BlockDesc> blocks;
+  void* arena = nullptr;             // device weights
+  size_t arena_bytes = 0;
+  // workspace geometry (set by fav_reserve)
+  int max_images = 0, max_T = 0;
+  size_t buf_bytes = 0;              // each of the 5 activation buffers
+};
+
+void plan_destroy(Plan* p) {
+  if (!p) return;
+  if (p->arena) cudaFree(p->arena);
+  delete p;
+}
+
+// ------------------------------------------------------------------------------------------ small kernels
+// 3x3 / stride 2 / pad 1 max-pool over bf16 NHWC, 8 channels (16 B) per thread.
+__global__ void __launch_bounds__(256) k_maxpool3x3s2(const uint4* __restrict__ x, uint4* __restrict__ y, int P, int H,
+                                                      int W, int C8, int OH, int OW) {
+  const long long total = (long long)P * OH * OW * C8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % C8);
+    long long r = i / C8;
+    const int ow = int(r % OW); r /= OW;
+    const int oh = int(r % OH);
+    const int p = int(r / OH);
+    float m[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+    for (int dy = 0; dy < 3; ++dy) {
+      const int ih = oh * 2 - 1 + dy;
+      if (ih < 0 || ih >= H) continue;
+      for (int dx = 0; dx < 3; ++dx) {
+        const int iw = ow * 2 - 1 + dx;
+        if (iw < 0 || iw >= W) continue;
+        const uint4 v = __ldg(x + (((size_t)p * H + ih) * W + iw) * C8 + c);
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { m[2 * k] = fmaxf(m[2 * k], bf16_lo(w4[k])); m[2 * k + 1] = fmaxf(m[2 * k + 1], bf16_hi(w4[k])); }
+      }
+    }
+    y[i] = make_uint4(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]), pack_bf16x2(m[4], m[5]), pack_bf16x2(m[6], m[7]));
+  }
+}
+
+// global average pool + MC-dropout on the pooled feature: [P, HW, C] bf16 -> [P, C] bf16
+__global__ void __launch_bounds__(256) k_pool_dropout(const uint4* __restrict__ x, uint4* __restrict__ y, int P, int HW,
+                                                      int C8, int T, int drop, uint32_t thr16, float scale, uint32_t k0,
+                                                      uint32_t k1, uint32_t first_image, uint32_t stream) {
+  const long long total = (long long)P * C8;
+  const float inv = 1.0f / float(HW);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % C8), p = int(i / C8);
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int j = 0; j < HW; ++j) {
+      const uint4 v = __ldg(x + ((size_t)p * HW + j) * C8 + c);
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { s[2 * k] += bf16_lo(w4[k]); s[2 * k + 1] += bf16_hi(w4[k]); }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] = HW == 1 ? s[k] : s[k] * inv;
+    if (drop) {
+      const int n_img = p / T, t = p - n_img * T;
+      const uint4 r = philox4x32_10(uint32_t(c), first_image + uint32_t(n_img), uint32_t(t), stream, k0, k1);
+      const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        s[2 * k] = (rw[k] & 0xFFFFu) >= thr16 ? s[2 * k] * scale : 0.f;
+        s[2 * k + 1] = (rw[k] >> 16) >= thr16 ? s[2 * k + 1] * scale : 0.f;
+      }
+    }
+    y[i] = make_uint4(pack_bf16x2(s[0], s[1]), pack_bf16x2(s[2], s[3]), pack_bf16x2(s[4], s[5]), pack_bf16x2(s[6], s[7]));
+  }
+}
+
+static inline int grid_for(long long work, int threads, int num_sms) {
+  long long b = (work + threads - 1) / threads, cap = (long long)num_sms * 16;
+  return int(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// geometry walk shared by reserve() and forward(): calls f(bytes) for every activation tensor produced
+template <class F>
+static void walk_activations(const Plan& pl, int n, int T, F&& f) {
+  const ConvLayer& stem = pl.convs[0];
+  int h = conv_out_dim(pl.in_h, stem.r, stem.stride, stem.pad), w = conv_out_dim(pl.in_w, stem.s, stem.stride, stem.pad);
+  f((size_t)n * h * w * stem.cout * 2);
+  h = conv_out_dim(h, 3, 2, 1); w = conv_out_dim(w, 3, 2, 1);
+  f((size_t)n * h * w * stem.cout * 2);
+  long long P = n;
+  for (size_t b = 0; b < pl.blocks.size(); ++b) {
+    const BlockDesc& bd = pl.blocks[b];
+    int hh = h, ww = w;
+    for (int k = 0; k < bd.n_convs; ++k) {
+      const ConvLayer& L = pl.convs[bd.conv0 + k];
+      hh = conv_out_dim(hh, L.r, L.stride, L.pad); ww = conv_out_dim(ww, L.s, L.stride, L.pad);
+      const bool last = k == bd.n_convs - 1;
+      const long long Pout = (last && b == 0 && T > 1) ? P * T : P;
+      f((size_t)Pout * hh * ww * L.cout * 2);
+    }
+    if (bd.ds >= 0) f((size_t)P * hh * ww * pl.convs[bd.ds].cout * 2);
+    if (b == 0 && T > 1) P *= T;
+    h = hh; w = ww;
+  }
+}
+
+}  // namespace fav
+
+using namespace fav;
+
+extern "C" int fav_load_weights(fav_handle h, const void* blob, size_t nbytes, int model_id, int num_classes, int in_h,
+                                int in_w) {
+  FAV_REQUIRE(h && blob, "fav_load_weights: null pointer");
+  FAV_REQUIRE(in_h > 0 && in_w > 0 && num_classes >= 2, "fav_load_weights: bad input size / classes");
+  const uint8_t* p = reinterpret_cast<const uint8_t*>(blob);
+  const uint8_t* end = p + nbytes;
+  FAV_REQUIRE(nbytes >= 32 && memcmp(p, "FAVW1\0\0\0", 8) == 0, "fav_load_weights: bad magic (expected FAVW1)");
+  const int32_t* hdr = reinterpret_cast<const int32_t*>(p + 8);
+  const int n_convs = hdr[0], blob_classes = hdr[1], blob_model = hdr[2], n_blocks = hdr[3];
+  FAV_REQUIRE(blob_model == model_id && blob_classes == num_classes, "fav_load_weights: blob is model %d / %d classes, asked %d / %d",
+              blob_model, blob_classes, model_id, num_classes);
+  FAV_REQUIRE(n_convs >= 3 && n_convs < 256 && n_blocks >= 1 && n_blocks < 64, "fav_load_weights: implausible header");
+  p += 8 + 16;
+  FAV_REQUIRE(p + 8 * (size_t)n_blocks <= end, "fav_load_weights: truncated block table");
+  Plan* pl = new Plan();
+  pl->model_id = model_id; pl->num_classes = num_classes; pl->in_h = in_h; pl->in_w = in_w;
+  const int32_t* bt = reinterpret_cast<const int32_t*>(p);
+  int ci = 1;
+  for (int b = 0; b < n_blocks; ++b) {
+    BlockDesc bd;
+    bd.n_convs = bt[2 * b]; bd.conv0 = ci; ci += bd.n_convs;
+    bd.ds = bt[2 * b + 1] ? ci++ : -1;
+    pl->blocks.push_back(bd);
+  }
+  if (ci + 1 != n_convs) { delete pl; set_error("fav_load_weights: block table (%d convs) disagrees with header (%d)", ci + 1, n_convs); return FAV_E_ARG; }
+  p += 8 * (size_t)n_blocks;
+  p = reinterpret_cast<const uint8_t*>(blob) + (((p - reinterpret_cast<const uint8_t*>(blob)) + 15) / 16) * 16;
+
+  // pass 1: sizes
+  struct Rec { const uint8_t* w; const uint8_t* b; };
+  std::vector<Rec> recs;
+  size_t arena = 0;
+  const uint8_t* q = p;
+  for (int i = 0; i < n_convs; ++i) {
+    if (q + 32 > end) { delete pl; set_error("fav_load_weights: truncated at conv %d", i); return FAV_E_ARG; }
+    const int32_t* r = reinterpret_cast<const int32_t*>(q);
+    ConvLayer L;
+    L.cout = r[0]; L.cin = r[1]; L.r = r[2]; L.s = r[3]; L.stride = r[4]; L.pad = r[5];
+    if (L.cout <= 0 || L.cin <= 0 || L.r <= 0 || L.s <= 0 || L.stride <= 0 || L.pad < 0) {
+      delete pl; set_error("fav_load_weights: bad conv record %d", i); return FAV_E_ARG;
+    }
+    conv_layer_finalize(L);
+    const size_t wb = ((size_t)L.cout * L.k * 2 + 15) / 16 * 16, bb = ((size_t)L.cout * 4 + 15) / 16 * 16;
+    if (q + 32 + wb + bb > end) { delete pl; set_error("fav_load_weights: truncated weights at conv %d", i); return FAV_E_ARG; }
+    recs.push_back({q + 32, q + 32 + wb});
+    q += 32 + wb + bb;
+    arena += ((size_t)L.cout_pad * L.kpad * 2 + 255) / 256 * 256 + ((size_t)L.cout_pad * 4 + 255) / 256 * 256;
+    pl->convs.push_back(L);
+  }
+  FAV_CUDA_OK(cudaSetDevice(h->device));
+  cudaError_t e = cudaMalloc(&pl->arena, arena);
+  if (e != cudaSuccess) { delete pl; set_error("fav_load_weights: cudaMalloc(%zu) failed: %s", arena, cudaGetErrorString(e)); return FAV_E_CUDA; }
+  pl->arena_bytes = arena;
+  cudaMemset(pl->arena, 0, arena);
+  // pass 2: upload with row padding k -> kpad
+  uint8_t* d = reinterpret_cast<uint8_t*>(pl->arena);
+  for (int i = 0; i < n_convs; ++i) {
+    ConvLayer& L = pl->convs[i];
+    e = cudaMemcpy2D(d, (size_t)L.kpad * 2, recs[i].w, (size_t)L.k * 2, (size_t)L.k * 2, L.cout, cudaMemcpyHostToDevice);
+    L.w = reinterpret_cast<const __nv_bfloat16*>(d);
+    d += ((size_t)L.cout_pad * L.kpad * 2 + 255) / 256 * 256;
+    if (e == cudaSuccess) e = cudaMemcpy(d, recs[i].b, (size_t)L.cout * 4, cudaMemcpyHostToDevice);
+    L.bias = reinterpret_cast<const float*>(d);
+    d += ((size_t)L.cout_pad * 4 + 255) / 256 * 256;
+    int rc = e == cudaSuccess ? conv_layer_finalize(L) : FAV_E_CUDA;
+    if (rc) {
+      if (e != cudaSuccess) set_error("fav_load_weights: upload failed: %s", cudaGetErrorString(e));
+      plan_destroy(pl);
+      return rc;
+    }
+  }
+  const ConvLayer& fc = pl->convs.back();
+  if (fc.r != 1 || fc.s != 1 || fc.cout != num_classes) { plan_destroy(pl); set_error("fav_load_weights: last record must be the 1x1 fc"); return FAV_E_ARG; }
+  if (h->plan) plan_destroy(h->plan);
+  h->plan = pl;
+  if (h->ws) { cudaFree(h->ws); h->ws = nullptr; h->ws_bytes = 0; }
+  return FAV_OK;
+}
+
+extern "C" int fav_reserve(fav_handle h, int max_images, int T) {
+  FAV_REQUIRE(h && h->plan, "fav_reserve: load weights first");
+  FAV_REQUIRE(max_images > 0 && T >= 1, "fav_reserve: bad max_images/T");
+  Plan& pl = *h->plan;
+  size_t mx = 0;
+  walk_activations(pl, max_images, T, [&](size_t b) { if (b > mx) mx = b; });
+  mx = (mx + 1023) / 1024 * 1024;
+  const size_t need = 5 * mx;
+  if (need > h->ws_bytes) {
+    if (h->ws) { FAV_CUDA_OK(cudaFree(h->ws)); h->ws = nullptr; h->ws_bytes = 0; }
+    FAV_CUDA_OK(cudaMalloc(&h->ws, need));
+    h->ws_bytes = need;
+  }
+  pl.buf_bytes = h->ws_bytes / 5 / 1024 * 1024;
+  pl.max_images = max_images; pl.max_T = T;
+  return FAV_OK;
+}
+
+extern "C" int fav_forward_mc(fav_handle h, const void* d_x, float* d_logits, int n, int T, float p_drop, uint64_t seed,
+                              uint64_t first_image, void* stream) {
+  FAV_REQUIRE(h && h->plan, "fav_forward_mc: load weights first");
+  if (!h->plan) return FAV_E_STATE;
+  FAV_REQUIRE(d_x && d_logits && n >= 0 && T >= 1, "fav_forward_mc: bad arguments");
+  FAV_REQUIRE(T == 1 || (p_drop >= 0.f && p_drop < 1.f), "fav_forward_mc: p_drop must be in [0,1)");
+  if (n == 0) return FAV_OK;
+  Plan& pl = *h->plan;
+  size_t mx = 0;
+  walk_activations(pl, n, T, [&](size_t b) { if (b > mx) mx = b; });
+  if (!h->ws || mx > pl.buf_bytes) {
+    int rc = fav_reserve(h, n > pl.max_images ? n : pl.max_images, T > pl.max_T ? T : pl.max_T);
+    if (rc) return rc;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* base = reinterpret_cast<uint8_t*>(h->ws);
+  void* X[2] = {base, base + pl.buf_bytes};
+  void* Y1 = base + 2 * pl.buf_bytes;
+  void* Y2 = base + 3 * pl.buf_bytes;
+  void* DS = base + 4 * pl.buf_bytes;
+  const bool mc = T > 1;
+  const uint32_t k0 = uint32_t(seed), k1 = uint32_t(seed >> 32);
+
+  auto run = [&](const ConvLayer& L, const void* x, void* y, const void* res, int P, int hh, int ww, int relu, int drop,
+                 int rep, int layer_id, int out_f32) -> int {
+    ConvCall c;
+    c.L = &L; c.x = x; c.y = y; c.res = res; c.p = P; c.h = hh; c.w = ww; c.relu = relu; c.out_f32 = out_f32;
+    c.T = T; c.rep = rep; c.drop = drop; c.p_drop = p_drop; c.seed = seed; c.first_image = first_image; c.layer_id = layer_id;
+    return conv_launch(h, c, st);
+  };
+
+  // stem + max-pool (pass-invariant)
+  const ConvLayer& stem = pl.convs[0];
+  int rc = run(stem, d_x, Y1, nullptr, n, pl.in_h, pl.in_w, 1, 0, 1, 0, 0);
+  if (rc) return rc;
+  int hh = conv_out_dim(pl.in_h, stem.r, stem.stride, stem.pad), ww = conv_out_dim(pl.in_w, stem.s, stem.stride, stem.pad);
+  {
+    const int oh = conv_out_dim(hh, 3, 2, 1), ow = conv_out_dim(ww, 3, 2, 1);
+    FAV_REQUIRE((stem.cout & 7) == 0, "stem Cout must be a multiple of 8");
+    const long long work = (long long)n * oh * ow * (stem.cout / 8);
+    k_maxpool3x3s2<<<grid_for(work, 256, h->num_sms), 256, 0, st>>>(reinterpret_cast<const uint4*>(Y1), reinterpret_cast<uint4*>(X[0]),
+                                                                    n, hh, ww, stem.cout / 8, oh, ow);
+    h->launches++;
+    hh = oh; ww = ow;
+  }
+  int cur = 0, P = n, ch = stem.cout;
+  for (size_t b = 0; b < pl.blocks.size(); ++b) {
+    const BlockDesc& bd = pl.blocks[b];
+    const void* ident = X[cur];
+    int oh = hh, ow = ww;
+    if (bd.ds >= 0) {
+      const ConvLayer& D = pl.convs[bd.ds];
+      rc = run(D, X[cur], DS, nullptr, P, hh, ww, 0, 0, 1, 0, 0);
+      if (rc) return rc;
+      ident = DS;
+    }
+    const void* in = X[cur];
+    void* tmp[2] = {Y1, Y2};
+    int ih = hh, iw = ww;
+    for (int k = 0; k < bd.n_convs; ++k) {
+      const ConvLayer& L = pl.convs[bd.conv0 + k];
+      const bool last = k == bd.n_convs - 1;
+      oh = conv_out_dim(ih, L.r, L.stride, L.pad); ow = conv_out_dim(iw, L.s, L.stride, L.pad);
+      if (!last) {
+        rc = run(L, in, tmp[k & 1], nullptr, P, ih, iw, 1, 0, 1, 0, 0);
+        in = tmp[k & 1];
+      } else {
+        const int rep = (mc && b == 0) ? T : 1;
+        rc = run(L, in, X[cur ^ 1], ident, P, ih, iw, 1, mc ? 1 : 0, rep, int(b), 0);
+        ch = L.cout;
+      }
+      if (rc) return rc;
+      ih = oh; iw = ow;
+    }
+    if (mc && b == 0) P *= T;
+    cur ^= 1; hh = oh; ww = ow;
+  }
+  // global average pool + dropout on the pooled feature, then fc as a 1x1 conv with fp32 output [n, T, C]
+  FAV_REQUIRE((ch & 7) == 0, "feature width must be a multiple of 8");
+  {
+    const long long work = (long long)P * (ch / 8);
+    const uint32_t thr = mc ? uint32_t(floor(double(p_drop) * 65536.0)) : 0u;
+    k_pool_dropout<<<grid_for(work, 256, h->num_sms), 256, 0, st>>>(
+        reinterpret_cast<const uint4*>(X[cur]), reinterpret_cast<uint4*>(Y1), P, hh * ww, ch / 8, T, mc ? 1 : 0, thr,
+        1.0f / (1.0f - p_drop), k0, k1, uint32_t(first_image), stream_id(KIND_DROPOUT, 255, 0));
+    h->launches++;
+  }
+  const ConvLayer& fc = pl.convs.back();
+  FAV_REQUIRE(fc.cin == ch, "fc input width %d does not match the trunk (%d)", fc.cin, ch);
+  rc = run(fc, Y1, d_logits, nullptr, P, 1, 1, 0, 0, 1, 0, 1);
+  if (rc) return rc;
+  FAV_CUDA_OK(cudaGetLastError());
+  return FAV_OK;
+}

@@ -1,0 +1,200 @@
+"""CorruptionSweep -- the offline batch driver of the path (15 corruptions x 5 severities).
+
+No reference counterpart: the closest thing is the playground's batch replay loop
+(platform/backend/main.py:340-352), a scalar recurrence.  Results are emitted in the
+reference's style -- plain dicts of rounded floats (trust_engine.py:247-263) and an in-memory
+CSV like session_logger.py:15-51.
+
+Sharding: work items (cell, image block) are dealt round-robin to ranks, weights
+replicated, Philox counters keyed by the GLOBAL image index, and the only exchange is one
+integer all-reduce of the histogram arena at the end -- so metrics are bit-identical on
+1/2/4/8 GPUs.
+"""
+import csv
+import ctypes as C
+import io
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib, spec
+from .classifier import VisionClassifier, _ptr, _stream
+from .spec import CorruptionConfig
+
+HDR = 8
+
+
+@dataclass
+class SweepConfig:
+    model: str = "resnet18"
+    num_classes: int = 10
+    input_hw: tuple = (32, 32)
+    corruptions: tuple = spec.IMPLEMENTED
+    severities: tuple = (1, 2, 3, 4, 5)
+    include_clean: bool = False
+    T: int = 20
+    p_drop: float = 0.2
+    tau: float = 0.9
+    n_bins: int = 15
+    n_buckets: int = 4096
+    seed: int = 0
+    weights_seed: int = 0
+    logit_gain: float = None
+    block: int = 512               # images per launch sequence
+
+    def cells(self):
+        out = [CorruptionConfig(None, 0)] if self.include_clean else []
+        out += [CorruptionConfig(c, s) for c in self.corruptions for s in self.severities]
+        return out
+
+    def to_dict(self):
+        d = dict(self.__dict__)
+        d["corruptions"] = list(self.corruptions)
+        d["severities"] = list(self.severities)
+        d["input_hw"] = list(self.input_hw)
+        return d
+
+
+def partition(n_items, rank, world_size):
+    """Indices of the work items owned by ``rank`` (round-robin: equal FLOPs, cells interleaved)."""
+    return list(range(rank, n_items, world_size))
+
+
+def allreduce_arena(arena):
+    """The path's only exchange: integer sum of the histogram arena over ranks (NCCL on GPUs, gloo in the
+    CPU tests).  Integer payload => the result is independent of reduction order and of the rank count."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(arena, op=dist.ReduceOp.SUM)
+    return arena
+
+
+def finalize(arena, num_classes, n_bins, n_buckets):
+    """int64 arena of one cell -> metrics dict (fp64 on the host)."""
+    a = np.asarray(arena, dtype=np.int64)
+    n = int(a[0])
+    out = {"n": n}
+    if n == 0:
+        return out
+    two32 = 4294967296.0
+    out["accuracy"] = int(a[1]) / n
+    out["failure_rate"] = int(a[2]) / n
+    out["mean_confidence"] = int(a[3]) / two32 / n
+    out["mean_entropy"] = int(a[4]) / two32 / n
+    out["mean_mutual_information"] = int(a[5]) / two32 / n
+    ece = 0.0
+    for b in range(n_bins):
+        cnt, sconf, ncor = (int(v) for v in a[HDR + 3 * b: HDR + 3 * b + 3])
+        if cnt:
+            ece += cnt / n * abs(ncor / cnt - sconf / two32 / cnt)
+    out["ece"] = ece
+    base = HDR + 3 * n_bins
+    for s, name in enumerate(("auroc_msp", "auroc_entropy", "auroc_mi")):
+        bk = a[base + 2 * s * n_buckets: base + 2 * (s + 1) * n_buckets].reshape(n_buckets, 2).astype(np.float64)
+        neg, pos = bk[:, 0], bk[:, 1]
+        P, Nn = pos.sum(), neg.sum()
+        if P == 0 or Nn == 0:
+            out[name] = float("nan")
+        else:
+            below = np.concatenate([[0.0], np.cumsum(neg)[:-1]])
+            out[name] = float((pos * (below + 0.5 * neg)).sum() / (P * Nn))
+    return out
+
+
+class MetricsAccumulator:
+    """Device arena of integer histograms, one row per sweep cell."""
+
+    def __init__(self, clf: VisionClassifier, n_cells, n_bins=15, n_buckets=4096):
+        self.clf, self.n_bins, self.n_buckets = clf, n_bins, n_buckets
+        self.words = int(clf.lib.fav_hist_words(clf.num_classes, n_bins, n_buckets))
+        self.arena = torch.zeros((n_cells, self.words), dtype=torch.int64, device=clf.device)
+
+    def reset(self):
+        self.arena.zero_()
+
+    def add_logits(self, cell, logits, labels, tau, outputs=None):
+        n, T, c = logits.shape
+        o = outputs or {}
+        _lib.check(self.clf.lib.fav_epilogue_accumulate(
+            self.clf.handle.h, _ptr(logits), _ptr(labels), n, T, c, float(tau), self.n_bins, self.n_buckets,
+            C.c_void_p(self.arena[cell].data_ptr()), _ptr(o.get("confidence")), _ptr(o.get("entropy")),
+            _ptr(o.get("mutual_information")), _ptr(o.get("pred")), _ptr(o.get("failure_flag")), _stream()),
+            "fav_epilogue_accumulate")
+
+    def add_scores(self, cell, conf, ent, mi, pred, labels, tau):
+        _lib.check(self.clf.lib.fav_accumulate(
+            self.clf.handle.h, _ptr(conf), _ptr(ent), _ptr(mi), _ptr(pred), _ptr(labels), conf.numel(),
+            self.clf.num_classes, float(tau), self.n_bins, self.n_buckets, C.c_void_p(self.arena[cell].data_ptr()),
+            _stream()), "fav_accumulate")
+
+    def allreduce(self):
+        """The path's only exchange: integer sum over ranks (NCCL on GPUs)."""
+        allreduce_arena(self.arena)
+
+    def results(self):
+        host = self.arena.cpu().numpy()
+        return [finalize(host[i], self.clf.num_classes, self.n_bins, self.n_buckets) for i in range(host.shape[0])]
+
+
+class CorruptionSweep:
+    def __init__(self, cfg: SweepConfig = None, classifier: VisionClassifier = None, device=0):
+        self.cfg = cfg or SweepConfig()
+        self.clf = classifier or VisionClassifier(self.cfg.model, self.cfg.num_classes, self.cfg.input_hw,
+                                                  self.cfg.weights_seed, self.cfg.logit_gain, device=device)
+        self.cells = self.cfg.cells()
+        self.acc = MetricsAccumulator(self.clf, len(self.cells), self.cfg.n_bins, self.cfg.n_buckets)
+        self._x = None
+        self._logits = None
+
+    def reset(self):
+        self.acc.reset()
+
+    def work_items(self, n_images):
+        nblk = (n_images + self.cfg.block - 1) // self.cfg.block
+        return [(ci, b) for b in range(nblk) for ci in range(len(self.cells))]
+
+    def _buffers(self, n):
+        h, w = self.cfg.input_hw
+        if self._x is None or self._x.shape[0] < n:
+            self._x = torch.empty((n, h, w, 3), dtype=torch.bfloat16, device=self.clf.device)
+            self._logits = torch.empty((n, self.cfg.T, self.cfg.num_classes), dtype=torch.float32, device=self.clf.device)
+        return self._x[:n], self._logits[:n]
+
+    def run_item(self, images_dev, labels_dev, item, first_image=0):
+        """One step of the hot path: one image block of one (corruption, severity) cell."""
+        ci, b = item
+        lo = b * self.cfg.block
+        hi = min(lo + self.cfg.block, images_dev.shape[0])
+        x, logits = self._buffers(hi - lo)
+        cfg = self.cfg
+        self.clf.corrupt_normalize(images_dev[lo:hi], self.cells[ci], cfg.seed, first_image + lo, out=x)
+        self.clf.forward_logits(x, cfg.T, cfg.p_drop, cfg.seed, first_image + lo, out=logits)
+        self.acc.add_logits(ci, logits, labels_dev[lo:hi], cfg.tau)
+        return hi - lo
+
+    def run(self, images_u8, labels, rank=0, world_size=1, first_image=0):
+        """images uint8 [N,H,W,3] (numpy or torch, host or device), labels int [N].
+        Returns {(corruption, severity): metrics} after the cross-rank reduction."""
+        images_dev = self.clf._images(images_u8)
+        labels_dev = self.clf._labels(labels)
+        items = self.work_items(images_dev.shape[0])
+        for i in partition(len(items), rank, world_size):
+            self.run_item(images_dev, labels_dev, items[i], first_image)
+        self.acc.allreduce()
+        res = self.acc.results()
+        return {(c.name or "clean", c.severity): r for c, r in zip(self.cells, res)}
+
+    @staticmethod
+    def to_csv(results):
+        """In-memory CSV in the style of session_logger.py:49-51."""
+        cols = ["corruption", "severity", "n", "accuracy", "ece", "mean_confidence", "mean_entropy",
+                "mean_mutual_information", "failure_rate", "auroc_msp", "auroc_entropy", "auroc_mi"]
+        buf = io.StringIO()
+        wr = csv.writer(buf)
+        wr.writerow(cols)
+        for (name, sev), r in results.items():
+            wr.writerow([name, sev] + [round(r[k], 6) if isinstance(r.get(k), float) and not math.isnan(r[k]) else r.get(k, "")
+                                      for k in cols[2:]])
+        return buf.getvalue()

@@ -1,0 +1,166 @@
+/*
+ * fav_b200.h -- C ABI of the B200-native corruption-sweep evaluation path.
+ *
+ * Drop-in boundary.  The reference (Indra-jith/failure-aware-vision) has no
+ * FFI: it composes plain Python objects in platform/backend/main.py:110-118 and duck-types
+ *     analyzer.analyze_frame(frame) -> dict            (main.py:160, signal_analyzer.py:47-143)
+ *     anomaly.compute_anomaly(noise, brightness, st)   (main.py:141-143, anomaly_simulator.py:34-77)
+ *     vision.set_noise/set_brightness/set_mode         (main.py:269-282, vision_simulator.py:25-36)
+ * Each entry point below names the reference call whose work it takes over (or "none" where
+ * the reference only states the intent, README.md:2,15-24).  The Python mirror of those
+ * objects lives in failure-aware-vision_b200/ and calls this library through ctypes
+ * (binding shown in INTEGRATION.md).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer named d_* is a DEVICE pointer owned by the
+ *     caller; the library owns only its weight arena + workspace inside fav_handle.
+ *   - every call enqueues on `stream` (a cudaStream_t passed as void*) and returns; no hidden
+ *     synchronisation unless stated.
+ *   - return 0 on success, negative FAV_E_* on error; message via fav_last_error()
+ *     (thread-local).  There is no CPU fallback: without a usable sm_100 device fav_init fails.
+ *   - images are uint8 NHWC [n,h,w,3]; activations are bf16 NHWC; logits are fp32 [n,T,C].
+ */
+#ifndef FAV_B200_H
+#define FAV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FAV_ABI_VERSION 1
+
+#define FAV_OK 0
+#define FAV_E_ARG (-1)      /* bad argument */
+#define FAV_E_CUDA (-2)     /* CUDA runtime / driver error */
+#define FAV_E_DEVICE (-3)   /* not an sm_100 device */
+#define FAV_E_STATE (-4)    /* call order (e.g. forward before load_weights) */
+#define FAV_E_UNSUPPORTED (-5)
+
+typedef struct fav_ctx* fav_handle;
+
+/* ---- corruption ids (order of Hendrycks & Dietterich's 15; 0 = clean) --------------------- */
+enum {
+  FAV_CLEAN = 0, FAV_GAUSSIAN_NOISE = 1, FAV_SHOT_NOISE = 2, FAV_IMPULSE_NOISE = 3,
+  FAV_DEFOCUS_BLUR = 4, FAV_GLASS_BLUR = 5, FAV_MOTION_BLUR = 6, FAV_ZOOM_BLUR = 7,
+  FAV_SNOW = 8, FAV_FROST = 9, FAV_FOG = 10, FAV_BRIGHTNESS = 11, FAV_CONTRAST = 12,
+  FAV_ELASTIC = 13, FAV_PIXELATE = 14, FAV_JPEG = 15
+};
+
+/* flags for fav_corrupt_normalize */
+#define FAV_SRC_BGR 1u        /* source frames are BGR (reference frames: signal_analyzer.py:51,62) */
+#define FAV_OUT_F32 2u        /* write fp32 instead of bf16 (parity tooling) */
+#define FAV_NO_NORMALIZE 4u   /* write the corrupted [0,1] value, skip (x-mean)/std */
+
+/* model ids for fav_load_weights */
+#define FAV_RESNET18 18
+#define FAV_RESNET50 50
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int fav_abi_version(void);
+const char* fav_last_error(void);
+/* replaces: object construction at main.py:110-118 (one handle per connection / per process). */
+int fav_init(int device, fav_handle* out);
+/* replaces: reset() at signal_analyzer.py:41-45 / main.py:285-290 (drops workspace, keeps weights). */
+int fav_reset(fav_handle h);
+int fav_destroy(fav_handle h);
+
+/* ---- K1: corrupt + normalize ---------------------------------------------------------------
+ * replaces: vision_simulator.py:25-36 (noise / brightness knobs) and the display-only JS
+ * effects (frontend/js/app.js:789-799); the reference has no server-side generator.
+ *
+ * d_src  uint8 [n,h,w,3]; d_dst bf16 (or fp32 with FAV_OUT_F32) [n,h,w,3], RGB order.
+ * fparams / iparams: per-corruption constants chosen by the host from the severity table
+ *   (failure-aware-vision_b200/spec.py); d_table: optional device table (Poisson inverse-CDF,
+ *   stencil taps, resampling ranges); d_scratch: device scratch for two-pass corruptions
+ *   (contrast: 3 uint64 per image; fog: plasma map), may be NULL otherwise.
+ * All randomness is Philox4x32-10 keyed by (seed, first_image + image index, position):
+ *   results do not depend on batch size or GPU count. */
+int fav_corrupt_normalize(fav_handle h, const uint8_t* d_src, void* d_dst, int n, int height,
+                          int width, int corruption, int severity, const float* fparams,
+                          int n_fparams, const int32_t* iparams, int n_iparams,
+                          const void* d_table, size_t table_bytes, void* d_scratch,
+                          size_t scratch_bytes, uint64_t seed, uint64_t first_image,
+                          const float mean[3], const float std[3], unsigned flags, void* stream);
+/* bytes of d_scratch fav_corrupt_normalize needs for (corruption, n, h, w). */
+size_t fav_corrupt_scratch_bytes(int corruption, int n, int height, int width);
+
+/* ---- K2: classifier forward ---------------------------------------------------------------
+ * replaces: nothing in the reference ("image classification", README.md:19; torchvision named in
+ * requirements.txt:2); fills the ML-score slot of anomaly_simulator.py:34-77.
+ *
+ * blob: host memory, format FAVW1 written by failure-aware-vision_b200/weights.py (BN already
+ * folded, weights bf16 [Cout][R][S][Cin], bias fp32).  Copies to the device arena; synchronous. */
+int fav_load_weights(fav_handle h, const void* blob, size_t nbytes, int model_id, int num_classes,
+                     int in_h, int in_w);
+/* max images per fav_forward_mc call for a given T (sizes the workspace; allocates). */
+int fav_reserve(fav_handle h, int max_images, int T);
+/* d_x bf16 [n,h,w,3] -> d_logits fp32 [n,T,C].  T MC-dropout passes in one batched launch
+ * sequence; masks are generated in the conv epilogues from Philox(seed, first_image+i, t, layer).
+ * T == 1 disables dropout. */
+int fav_forward_mc(fav_handle h, const void* d_x, float* d_logits, int n, int T, float p_drop,
+                   uint64_t seed, uint64_t first_image, void* stream);
+/* single convolution (unit-test / tooling entry): y = act(conv(x, w) + bias [+ res]).
+ * x bf16 NHWC [p,h,w,cin]; w bf16 [cout][r][s][cin]; y bf16 (or fp32 if out_f32) NHWC. */
+int fav_conv2d(fav_handle h, const void* d_x, const void* d_w, const float* d_bias,
+               const void* d_res, void* d_y, int p, int height, int width, int cin, int cout,
+               int r, int s, int stride, int pad, int relu, int out_f32, int a_mode,
+               void* stream);
+
+/* ---- K3: uncertainty epilogue ---------------------------------------------------------------
+ * replaces: nothing (README.md:2 "uncertainty estimation"; failure definition README.md:22-24).
+ * d_logits fp32 [n,T,C]; d_labels int32 [n] or NULL; outputs may individually be NULL. */
+int fav_epilogue(fav_handle h, const float* d_logits, const int32_t* d_labels, int n, int T, int C,
+                 float tau, float* d_conf, float* d_entropy, float* d_mi, int32_t* d_pred,
+                 uint8_t* d_flag, void* stream);
+
+/* ---- K4: calibration / detection aggregates --------------------------------------------------
+ * replaces: nothing (nearest: failure_attributor.py:93-108 summary counters).
+ * Arena of int64 words, layout below; counts and Q32 fixed-point sums only, so a plain
+ * integer sum over ranks (one NCCL all-reduce) gives bit-identical metrics on 1/2/4/8 GPUs. */
+#define FAV_HIST_HDR 8
+#define FAV_HIST_N 0
+#define FAV_HIST_NCORRECT 1
+#define FAV_HIST_NFLAG 2
+#define FAV_HIST_SUM_CONF 3
+#define FAV_HIST_SUM_H 4
+#define FAV_HIST_SUM_MI 5
+size_t fav_hist_words(int C, int n_bins, int n_buckets);
+int fav_accumulate(fav_handle h, const float* d_conf, const float* d_entropy, const float* d_mi,
+                   const int32_t* d_pred, const int32_t* d_labels, int n, int C, float tau,
+                   int n_bins, int n_buckets, int64_t* d_hist, void* stream);
+/* fused K3+K4 (what the sweep uses): logits -> arena, per-sample outputs optional. */
+int fav_epilogue_accumulate(fav_handle h, const float* d_logits, const int32_t* d_labels, int n,
+                            int T, int C, float tau, int n_bins, int n_buckets, int64_t* d_hist,
+                            float* d_conf, float* d_entropy, float* d_mi, int32_t* d_pred,
+                            uint8_t* d_flag, void* stream);
+
+/* ---- synthetic inputs on the device (bench / tests; Philox streams "images", "labels") ------ */
+int fav_synth_images(fav_handle h, uint8_t* d_dst, int n, int height, int width, uint64_t seed,
+                     uint64_t first_image, void* stream);
+int fav_synth_labels(fav_handle h, int32_t* d_dst, int n, int C, uint64_t seed,
+                     uint64_t first_image, void* stream);
+
+/* ---- f1: fused SignalAnalyzer statistics -----------------------------------------------------
+ * replaces: SignalAnalyzer.analyze_frame arithmetic, signal_analyzer.py:62-105
+ * (cvtColor BGR2GRAY, Laplacian(CV_64F) sum / sum of squares, mean, absdiff vs previous gray,
+ * 256-bin histogram).  d_frame BGR u8 [h,w,3]; d_prev_gray u8 [h,w] (in: previous, out: current;
+ * first_frame != 0 skips the diff); d_out int64[4 + 256] = {sum_lap, sum_lap_sq, sum_gray,
+ * sum_absdiff, hist[256]} -- all integers, bit-exact vs OpenCV. */
+int fav_frame_stats(fav_handle h, const uint8_t* d_frame, uint8_t* d_prev_gray, int height,
+                    int width, int first_frame, int64_t* d_out, void* stream);
+
+/* counters for bench.py's gpu_launches claim */
+uint64_t fav_launch_count(fav_handle h);
+/* in-situ timing of the tensor-core conv launches (bench.py roofline): while enabled, every conv launch is
+ * bracketed by CUDA events on its stream; fav_conv_timing_read synchronises, returns the summed device time
+ * and the number of launches since the last read, and clears the record. */
+int fav_conv_timing_enable(fav_handle h, int on);
+int fav_conv_timing_read(fav_handle h, float* total_ms, int* n_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FAV_B200_H */

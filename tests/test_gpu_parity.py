@@ -1,0 +1,363 @@
+"""GPU parity tests: every CUDA stage, called through the C ABI, against the CPU oracle on the
+same seeded inputs.  Bars (BASELINE.json north_star): corruption outputs within 1e-3 abs; logits
+within bf16 tolerance; flags and integer histogram counts bit-exact apart from reported near-ties."""
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import corruptions as OC
+from oracle import frame_stats as OFS
+from oracle import metrics as OX
+from oracle import model as OM
+from oracle import philox as px
+from oracle import sweep as OS
+from oracle import uncertainty as OU
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+from make_golden_frames import frame_sequence  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def fav():
+    import fav as _fav
+    return _fav
+
+
+@pytest.fixture(scope="module")
+def clf18(fav):
+    return fav.VisionClassifier("resnet18", 10, (32, 32), weights_seed=0, logit_gain=8.0)
+
+
+@pytest.fixture(scope="module")
+def folded18():
+    return OM.fold_resnet(OM.build_torchvision("resnet18", 10, 0, logit_gain=8.0))
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _s():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ------------------------------------------------------------------------------------------- RNG
+def test_device_philox_streams_match_oracle(fav, clf18):
+    for (n, h, w, first) in ((5, 32, 32, 0), (3, 17, 9, 7), (2, 224, 224, 123456)):
+        d = torch.empty((n, h, w, 3), dtype=torch.uint8, device="cuda")
+        fav._lib.check(clf18.lib.fav_synth_images(clf18.handle.h, _p(d), n, h, w, 42, first, _s()), "synth")
+        assert np.array_equal(d.cpu().numpy(), px.synthetic_images(n, h, w, 42, first))
+    lab = torch.empty(1000, dtype=torch.int32, device="cuda")
+    fav._lib.check(clf18.lib.fav_synth_labels(clf18.handle.h, _p(lab), 1000, 10, 9, 5, _s()), "labels")
+    assert np.array_equal(lab.cpu().numpy(), px.synthetic_labels(1000, 10, 9, 5))
+
+
+# ------------------------------------------------------------------------------------------- K1
+K1_CASES = [(name, s) for name in ("gaussian_noise", "shot_noise", "impulse_noise", "defocus_blur", "motion_blur",
+                                   "zoom_blur", "fog", "brightness", "contrast", "pixelate") for s in (1, 3, 5)]
+
+
+@pytest.mark.parametrize("name,sev", K1_CASES)
+def test_k1_corruption_cifar_shape(fav, clf18, name, sev):
+    n, first, seed = 12, 1000, 3
+    x = px.synthetic_images(n, 32, 32, seed, first)
+    want = OC.corrupt(x, name, sev, seed=seed, first_image=first)
+    cfg = fav.CorruptionConfig(name, sev)
+    got = clf18.corrupt_normalize(x, cfg, seed, first, out_f32=True, normalize=False).cpu().numpy()
+    err = np.abs(got - want)
+    assert err.max() <= 1e-3, f"{name} s{sev}: max abs err {err.max()}"
+    # production output: bf16 of the normalised value (at most 1 bf16 ulp apart where fp32 rounding differs)
+    gotb = clf18.corrupt_normalize(x, cfg, seed, first).float().cpu().numpy()
+    wantn = OC.normalize(want, *OC.MEAN_STD["cifar"])
+    wantb = OC.to_bf16(wantn)
+    assert (gotb == wantb).mean() > 0.99
+    assert np.abs(gotb - wantn).max() <= 2.0 ** -7 * max(1.0, np.abs(wantn).max()) + 1e-3
+
+
+@pytest.mark.parametrize("name,sev", [("gaussian_noise", 5), ("shot_noise", 1), ("defocus_blur", 4), ("motion_blur", 5),
+                                      ("zoom_blur", 2), ("fog", 3), ("contrast", 4), ("pixelate", 3), ("brightness", 2),
+                                      ("impulse_noise", 4)])
+def test_k1_corruption_imagenet_shape(fav, name, sev):
+    clf = _clf_cache(fav, "resnet18", 1000, (224, 224))
+    n, first, seed = 2, 77, 1
+    x = px.synthetic_images(n, 224, 224, seed, first)
+    want = OC.corrupt(x, name, sev, seed=seed, first_image=first)
+    got = clf.corrupt_normalize(x, fav.CorruptionConfig(name, sev), seed, first, out_f32=True, normalize=False).cpu().numpy()
+    assert np.abs(got - want).max() <= 1e-3, f"{name} s{sev}: {np.abs(got - want).max()}"
+
+
+_CLFS = {}
+
+
+def _clf_cache(fav, model, ncls, hw, gain=None):
+    key = (model, ncls, hw, gain)
+    if key not in _CLFS:
+        _CLFS[key] = fav.VisionClassifier(model, ncls, hw, weights_seed=0, logit_gain=gain)
+    return _CLFS[key]
+
+
+def test_k1_bgr_and_ragged_and_clean(fav, clf18):
+    x = px.synthetic_images(3, 32, 32, 5)
+    a = clf18.corrupt_normalize(x, None, out_f32=True, normalize=False).cpu().numpy()
+    assert np.array_equal(a, (x.astype(np.float32) / np.float32(255)))
+    b = clf18.corrupt_normalize(np.ascontiguousarray(x[..., ::-1]), fav.CorruptionConfig("contrast", 3), 0, 0, bgr=True,
+                                out_f32=True, normalize=False).cpu().numpy()
+    assert np.abs(b - OC.corrupt(x, "contrast", 3)).max() <= 1e-6
+    # empty batch is a no-op, bad severity raises
+    clf18.corrupt_normalize(x[:0], fav.CorruptionConfig("gaussian_noise", 1))
+    with pytest.raises(ValueError):
+        fav.CorruptionConfig("gaussian_noise", 6)
+    with pytest.raises(ValueError):
+        fav.CorruptionConfig("no_such_corruption", 1)
+
+
+def test_k1_partition_independence(fav, clf18):
+    x = px.synthetic_images(10, 32, 32, 0)
+    cfg = fav.CorruptionConfig("shot_noise", 2)
+    whole = clf18.corrupt_normalize(x, cfg, 11, 0).cpu()
+    part = clf18.corrupt_normalize(x[6:], cfg, 11, 6).cpu()
+    assert torch.equal(whole[6:], part)
+
+
+# ------------------------------------------------------------------------------------------- K2 conv
+CONV_CASES = [
+    # p, h, w, cin, cout, k, stride, pad, relu, res, modes
+    (4, 8, 8, 64, 64, 3, 1, 1, 1, 1, (0, 1)),
+    (3, 8, 8, 64, 128, 3, 2, 1, 1, 0, (1,)),
+    (3, 8, 8, 64, 128, 1, 2, 0, 0, 0, (1,)),
+    (17, 4, 4, 128, 128, 3, 1, 1, 1, 1, (0, 1)),
+    (40, 2, 2, 256, 256, 3, 1, 1, 1, 0, (0, 1)),
+    (200, 1, 1, 512, 512, 3, 1, 1, 1, 1, (0, 1)),
+    (5, 32, 32, 3, 64, 7, 2, 3, 1, 0, (2,)),
+    (2, 14, 14, 256, 256, 3, 1, 1, 1, 1, (0, 1)),
+    (2, 56, 56, 64, 64, 3, 1, 1, 0, 0, (0, 1)),
+    (3, 7, 7, 512, 2048, 1, 1, 0, 0, 1, (0, 1)),
+    (1, 9, 13, 16, 24, 3, 1, 1, 1, 0, (1, 2)),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_k2_conv_matches_torch_fp32(fav, clf18, case):
+    p, h, w, cin, cout, k, stride, pad, relu, use_res, modes = case
+    g = torch.Generator(device="cpu").manual_seed(hash(case) % (2 ** 31))
+    x = torch.randn((p, h, w, cin), generator=g).to(torch.bfloat16).cuda()
+    wt = (torch.randn((cout, k, k, cin), generator=g) / (k * k * cin) ** 0.5).to(torch.bfloat16).cuda()
+    bias = torch.randn(cout, generator=g).cuda()
+    oh, ow = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    res = torch.randn((p, oh, ow, cout), generator=g).to(torch.bfloat16).cuda() if use_res else None
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), bias, stride, pad)
+    ref = ref.permute(0, 2, 3, 1)
+    if res is not None:
+        ref = ref + res.float()
+    if relu:
+        ref = torch.relu(ref)
+    for mode in modes:
+        for out_f32 in (0, 1):
+            y = torch.full((p, oh, ow, cout), float("nan"), dtype=torch.float32 if out_f32 else torch.bfloat16, device="cuda")
+            rc = clf18.lib.fav_conv2d(clf18.handle.h, _p(x), _p(wt), _p(bias), _p(res), _p(y), p, h, w, cin, cout, k, k,
+                                      stride, pad, relu, out_f32, mode, _s())
+            fav._lib.check(rc, "fav_conv2d")
+            torch.cuda.synchronize()
+            tol = 2e-3 if out_f32 else 2e-2
+            err = (y.float() - ref).abs().max().item()
+            assert not torch.isnan(y.float()).any(), f"mode {mode}: unwritten outputs"
+            assert err <= tol * max(1.0, ref.abs().max().item()), f"mode {mode} f32={out_f32}: err {err}"
+
+
+# ------------------------------------------------------------------------------------------- K2 forward
+@pytest.mark.parametrize("T", [1, 4])
+def test_k2_forward_logits_vs_oracle(fav, clf18, folded18, T):
+    n, seed, first, p = 48, 2, 300, 0.25
+    x = px.synthetic_images(n, 32, 32, seed, first)
+    xc = OC.corrupt(x, "gaussian_noise", 2, seed=seed, first_image=first)
+    xn = OC.to_bf16(OC.normalize(xc, *OC.MEAN_STD["cifar"]))
+    xb = torch.from_numpy(xn).to(torch.bfloat16).cuda()
+    got = clf18.forward_logits(xb, T, p, seed, first).cpu().numpy()
+    assert got.shape == (n, T, 10)
+    emu = OM.forward(folded18, xn, T=T, p=p, seed=seed, first_image=first, emulate_bf16=True)
+    f32 = OM.forward(folded18, xn, T=T, p=p, seed=seed, first_image=first, emulate_bf16=False)
+    scale = np.abs(f32).max()
+    # same rounding points as the device: only fp32 accumulation order differs (rare bf16 rounding flips propagate)
+    assert np.abs(got - emu).max() <= 2e-2 * scale, np.abs(got - emu).max() / scale
+    # bf16 tolerance against the fp32 reference path
+    assert np.abs(got - f32).max() <= 6e-2 * scale, np.abs(got - f32).max() / scale
+    if T > 1:      # passes differ, and a different first_image gives different masks
+        assert np.abs(got[:, 0] - got[:, 1]).max() > 1e-3
+        other = clf18.forward_logits(xb, T, p, seed, first + 1).cpu().numpy()
+        assert np.abs(other - got).max() > 1e-3
+    # argmax agreement apart from near-ties (reported)
+    pb_g, pb_r = OU.softmax(got).mean(1), OU.softmax(f32).mean(1)
+    dis = pb_g.argmax(-1) != pb_r.argmax(-1)
+    gap = OU.top2_gap(pb_r)
+    assert (gap[dis] < 0.05).all(), f"argmax differs on non-tied samples: gaps {gap[dis]}"
+
+
+def test_k2_forward_resnet50_small(fav):
+    clf = _clf_cache(fav, "resnet50", 100, (64, 64), 4.0)
+    folded = OM.fold_resnet(OM.build_torchvision("resnet50", 100, 0, logit_gain=4.0))
+    n, T, p = 6, 3, 0.2
+    xn = OC.to_bf16(np.random.default_rng(0).standard_normal((n, 64, 64, 3)).astype(np.float32))
+    got = clf.forward_logits(torch.from_numpy(xn).to(torch.bfloat16).cuda(), T, p, 5, 0).cpu().numpy()
+    emu = OM.forward(folded, xn, T=T, p=p, seed=5, emulate_bf16=True)
+    assert np.abs(got - emu).max() <= 3e-2 * np.abs(emu).max()
+
+
+# ------------------------------------------------------------------------------------------- K3
+@pytest.mark.parametrize("n,T,Cc", [(257, 20, 10), (64, 1, 10), (33, 1, 1000), (20, 3, 1000), (50, 5, 100), (1, 30, 37)])
+def test_k3_epilogue_vs_oracle(fav, clf18, n, T, Cc):
+    rng = np.random.default_rng(n + T + Cc)
+    z = (rng.standard_normal((n, T, Cc)) * 4).astype(np.float32)
+    z[0, 0, :2] = 50.0            # an exact tie at the top -> lowest index wins
+    y = rng.integers(0, Cc, n).astype(np.int32)
+    out = clf18.epilogue(torch.from_numpy(z).cuda(), torch.from_numpy(y).cuda(), tau=0.3)
+    ref = OU.uncertainty(z, y, 0.3)
+    assert np.abs(out["confidence"].cpu().numpy() - ref["confidence"]).max() <= 2e-6
+    assert np.abs(out["entropy"].cpu().numpy() - ref["entropy"]).max() <= 2e-5
+    assert np.abs(out["mutual_information"].cpu().numpy() - ref["mutual_information"]).max() <= 2e-5
+    pred = out["pred"].cpu().numpy()
+    dis = pred != ref["pred"]
+    assert (OU.top2_gap(ref["pbar"])[dis] < 1e-6).all()
+    if T == 1:
+        assert pred[0] == 0
+    flag = out["failure_flag"].cpu().numpy()
+    conf = out["confidence"].cpu().numpy()
+    assert np.array_equal(flag, ((pred != y) & (conf >= np.float32(0.3))).astype(np.uint8))
+
+
+# ------------------------------------------------------------------------------------------- K4
+@pytest.mark.parametrize("n,Cc", [(10000, 10), (3000, 1000), (1, 10), (777, 100)])
+def test_k4_histograms_bit_exact(fav, clf18, n, Cc):
+    from fav.sweep import MetricsAccumulator, finalize
+    clf = clf18 if Cc == 10 else _clf_cache(fav, "resnet18", Cc, (32, 32))
+    rng = np.random.default_rng(n)
+    conf = rng.uniform(0, 1, n).astype(np.float32)
+    conf[: min(n, 16)] = (np.arange(min(n, 16)) / 15).astype(np.float32)         # exact bin edges
+    H = rng.uniform(0, np.log(Cc), n).astype(np.float32)
+    mi = rng.uniform(0, 1, n).astype(np.float32)
+    y = rng.integers(0, Cc, n).astype(np.int32)
+    pred = np.where(rng.uniform(size=n) < 0.6, y, rng.integers(0, Cc, n)).astype(np.int32)
+    acc = MetricsAccumulator(clf, 2)
+    t = lambda a: torch.from_numpy(a).cuda()
+    acc.add_scores(1, t(conf), t(H), t(mi), t(pred), t(y), 0.7)
+    acc.add_scores(1, t(conf[: n // 2]), t(H[: n // 2]), t(mi[: n // 2]), t(pred[: n // 2]), t(y[: n // 2]), 0.7)
+    ar = np.zeros(OX.arena_words(Cc), np.int64)
+    OX.accumulate(ar, conf, H, mi, pred, y, 0.7, Cc)
+    OX.accumulate(ar, conf[: n // 2], H[: n // 2], mi[: n // 2], pred[: n // 2], y[: n // 2], 0.7, Cc)
+    dev = acc.arena.cpu().numpy()
+    assert np.array_equal(dev[1], ar)
+    assert not dev[0].any()
+    a, b = finalize(dev[1], Cc, 15, 4096), OX.finalize(ar, Cc)
+    for k in b:
+        assert a[k] == b[k] or (np.isnan(a[k]) and np.isnan(b[k]))
+
+
+def test_k34_fused_equals_separate(fav, clf18):
+    from fav.sweep import MetricsAccumulator
+    rng = np.random.default_rng(3)
+    z = torch.from_numpy((rng.standard_normal((5000, 7, 10)) * 3).astype(np.float32)).cuda()
+    y = torch.from_numpy(rng.integers(0, 10, 5000).astype(np.int32)).cuda()
+    u = clf18.epilogue(z, y, 0.6)
+    a = MetricsAccumulator(clf18, 1)
+    a.add_scores(0, u["confidence"], u["entropy"], u["mutual_information"], u["pred"], y, 0.6)
+    b = MetricsAccumulator(clf18, 1)
+    outs = {k: torch.empty_like(v) for k, v in u.items()}
+    b.add_logits(0, z, y, 0.6, outs)
+    assert torch.equal(a.arena, b.arena)
+    for k in u:
+        assert torch.equal(u[k], outs[k])
+    assert int(a.arena[0, 0]) == 5000
+
+
+# ------------------------------------------------------------------------------------------- end to end
+@pytest.mark.parametrize("name,sev,T", [("gaussian_noise", 3, 1), ("contrast", 2, 5), ("shot_noise", 4, 3)])
+def test_cell_end_to_end_vs_oracle(fav, folded18, name, sev, T):
+    from fav.sweep import CorruptionSweep, SweepConfig
+    n, tau, p, seed = 96, 0.5, 0.2, 4
+    x = px.synthetic_images(n, 32, 32, seed)
+    y = px.synthetic_labels(n, 10, seed)
+    cfg = SweepConfig(corruptions=(name,), severities=(sev,), T=T, p_drop=p, tau=tau, seed=seed, logit_gain=8.0, block=40)
+    sw = CorruptionSweep(cfg)
+    res = sw.run(x, y)[(name, sev)]
+    u, ar = OS.eval_cell(folded18, x, y, name, sev, T=T, p=p, tau=tau, seed=seed, emulate_bf16=True)
+    dev = sw.acc.arena[0].cpu().numpy()
+    assert dev[0] == n == ar[0]
+    # samples whose decision could legitimately differ: top-2 gap or distance to tau / bin edge within tolerance
+    tol = 0.03
+    gap = OU.top2_gap(u["pbar"])
+    risky = int((gap < tol).sum())
+    assert abs(int(dev[1]) - int(ar[1])) <= risky, (dev[1], ar[1], risky)
+    near_tau = int((np.abs(u["confidence"] - tau) < tol).sum())
+    assert abs(int(dev[2]) - int(ar[2])) <= risky + near_tau
+    ref = OX.finalize(ar, 10)
+    assert abs(res["mean_confidence"] - ref["mean_confidence"]) < 5e-3
+    assert abs(res["mean_entropy"] - ref["mean_entropy"]) < 5e-3
+    assert abs(res["ece"] - ref["ece"]) < 0.05
+    print(f"[report] {name} s{sev} T={T}: near-tie samples={risky}, near-tau={near_tau}, "
+          f"acc dev/oracle={dev[1]}/{ar[1]}, flags={dev[2]}/{ar[2]}, ece={res['ece']:.4f}/{ref['ece']:.4f}")
+
+
+def test_sweep_partition_is_bit_identical(fav):
+    """Emulated ranks on one GPU: the arenas of a 1-rank run and the sum of a 3-rank split are identical."""
+    from fav.sweep import CorruptionSweep, SweepConfig, partition
+    cfg = SweepConfig(corruptions=("impulse_noise", "brightness"), severities=(1, 4), T=3, logit_gain=8.0, block=32)
+    x = px.synthetic_images(100, 32, 32, 0)
+    y = px.synthetic_labels(100, 10, 0)
+    sw = CorruptionSweep(cfg)
+    sw.run(x, y)
+    whole = sw.acc.arena.clone()
+    total = torch.zeros_like(whole)
+    for r in range(3):
+        sw.reset()
+        xd, yd = sw.clf._images(x), sw.clf._labels(y)
+        items = sw.work_items(100)
+        for i in partition(len(items), r, 3):
+            sw.run_item(xd, yd, items[i])
+        total += sw.acc.arena
+    assert torch.equal(total, whole)
+    assert int(whole[:, 0].sum()) == 100 * 4
+
+
+# ------------------------------------------------------------------------------------------- f1 + gate
+def test_frame_stats_kernel_bit_exact(fav, clf18):
+    for seed, (h, w) in ((0, (240, 320)), (1, (480, 640)), (2, (96, 130)), (3, (2, 2)), (4, (33, 1031))):
+        frames = frame_sequence(seed, h, w)[:4] if h > 2 else [np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8) for _ in range(3)]
+        gray_d = torch.zeros((h, w), dtype=torch.uint8, device="cuda")
+        out = torch.zeros(260, dtype=torch.int64, device="cuda")
+        prev = None
+        for i, f in enumerate(frames):
+            fd = torch.from_numpy(f).cuda()
+            fav._lib.check(clf18.lib.fav_frame_stats(clf18.handle.h, _p(fd), _p(gray_d), h, w, 1 if i == 0 else 0, _p(out), _s()), "stats")
+            want, gray = OFS.frame_stats(f, prev)
+            prev = gray
+            assert np.array_equal(out.cpu().numpy(), want), (seed, i)
+            assert np.array_equal(gray_d.cpu().numpy(), gray)
+
+
+def test_gate_reproduces_reference_signal_analyzer(fav):
+    with open(os.path.join(os.path.dirname(__file__), "golden", "signal_analyzer.json")) as fh:
+        gold = json.load(fh)
+    for case in gold["cases"][:2]:
+        gate = fav.UncertaintyGate(frame_hw=(case["h"], case["w"]), score_source="signal", use_classifier=False)
+        for f, want in zip(frame_sequence(case["seed"], case["h"], case["w"]), case["results"]):
+            got = gate.analyze_frame(f)
+            assert got == want
+
+
+def test_gate_with_classifier_feeds_trust_engine_contract(fav):
+    gate = fav.UncertaintyGate(frame_hw=(96, 128), T=4, num_classes=10, logit_gain=8.0)
+    f = frame_sequence(0, 96, 128)
+    r = gate.analyze_frame(f[1])
+    assert set(r) == {"anomaly_score", "vision_status", "metrics"}
+    assert set(r["metrics"]) >= {"blur", "brightness", "freeze", "entropy", "raw", "uncertainty"}
+    assert 0.0 <= r["anomaly_score"] <= 1.0 and r["vision_status"].startswith("VISION_")
+    u = r["metrics"]["uncertainty"]
+    assert 0 < u["confidence"] <= 1 and u["entropy"] >= 0 and u["mutual_information"] >= 0
+    gate.reset()
+    assert gate.analyze_frame(f[1])["metrics"]["raw"]["frame_diff"] == 10.0
