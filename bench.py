@@ -209,6 +209,7 @@ def main():
 
     cfg = SweepConfig(T=T_PASSES, p_drop=P_DROP, tau=TAU, logit_gain=8.0, block=BLOCK, seed=0)
     sweep = CorruptionSweep(cfg, device=local)
+    sweep.prepare()
     clf = sweep.clf
     lib, h = clf.lib, clf.handle.h
     # synthetic inputs generated on the device from the Philox "images"/"labels" streams; each rank owns a

@@ -61,6 +61,7 @@ extern "C" int fav_conv_timing_enable(fav_handle h, int on) {
   FAV_REQUIRE(h, "null handle");
   h->timing = on != 0;
   h->ev_used = 0;
+  h->ev_gflop.clear();
   return FAV_OK;
 }
 
@@ -76,5 +77,20 @@ extern "C" int fav_conv_timing_read(fav_handle h, float* total_ms, int* n_launch
   *total_ms = tot;
   *n_launches = int(h->ev_used / 2);
   h->ev_used = 0;
+  h->ev_gflop.clear();
+  return FAV_OK;
+}
+
+extern "C" int fav_conv_timing_read_all(fav_handle h, float* ms, float* gflop, int cap, int* n_launches) {
+  FAV_REQUIRE(h && ms && gflop && n_launches, "fav_conv_timing_read_all: null pointer");
+  int n = 0;
+  for (size_t i = 0; i + 1 < h->ev_used && n < cap; i += 2, ++n) {
+    FAV_CUDA_OK(cudaEventSynchronize(h->ev_pool[i + 1]));
+    FAV_CUDA_OK(cudaEventElapsedTime(&ms[n], h->ev_pool[i], h->ev_pool[i + 1]));
+    gflop[n] = n < int(h->ev_gflop.size()) ? h->ev_gflop[n] : 0.f;
+  }
+  *n_launches = n;
+  h->ev_used = 0;
+  h->ev_gflop.clear();
   return FAV_OK;
 }

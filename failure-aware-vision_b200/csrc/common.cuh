@@ -89,6 +89,7 @@ struct Ctx {
   bool timing = false;
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
+  std::vector<float> ev_gflop;
 };
 
 }  // namespace fav

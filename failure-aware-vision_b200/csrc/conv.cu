@@ -484,6 +484,7 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
     }
     e0 = ctx->ev_pool[ctx->ev_used]; e1 = ctx->ev_pool[ctx->ev_used + 1];
     ctx->ev_used += 2;
+    ctx->ev_gflop.push_back(float(2.0 * double(M) * L.k * L.cout * 1e-9));
     FAV_CUDA_OK(cudaEventRecord(e0, st));
   }
   conv_igemm_kernel<<<grid, CONV_THREADS, smem, st>>>(tmA, *reinterpret_cast<const CUtensorMap*>(L.tmap_w), a);

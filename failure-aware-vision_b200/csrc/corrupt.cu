@@ -521,8 +521,9 @@ extern "C" int fav_corrupt_normalize(fav_handle h, const uint8_t* d_src, void* d
                                      const void* d_table, size_t table_bytes, void* d_scratch,
                                      size_t scratch_bytes, uint64_t seed, uint64_t first_image,
                                      const float mean[3], const float std[3], unsigned flags, void* stream) {
-  FAV_REQUIRE(h && d_src && d_dst, "fav_corrupt_normalize: null handle/pointer");
+  FAV_REQUIRE(h, "fav_corrupt_normalize: null handle");
   FAV_REQUIRE(n >= 0 && height > 0 && width > 0, "fav_corrupt_normalize: bad shape n=%d h=%d w=%d", n, height, width);
+  FAV_REQUIRE(n == 0 || (d_src && d_dst), "fav_corrupt_normalize: null image pointer");
   FAV_REQUIRE(corruption == FAV_CLEAN || (severity >= 1 && severity <= 5), "severity must be 1..5 (got %d)", severity);
   FAV_REQUIRE(mean && std, "fav_corrupt_normalize: mean/std required");
   if (n == 0) return FAV_OK;

@@ -241,6 +241,7 @@ static int launch_k34(fav_handle h, const float* d_logits, const int32_t* d_labe
 extern "C" int fav_epilogue(fav_handle h, const float* d_logits, const int32_t* d_labels, int n, int T, int C, float tau,
                             float* d_conf, float* d_entropy, float* d_mi, int32_t* d_pred, uint8_t* d_flag,
                             void* stream) {
+  if (n == 0 && h) return FAV_OK;
   FAV_REQUIRE(d_logits, "fav_epilogue: logits required");
   FAV_REQUIRE(!d_flag || d_labels, "fav_epilogue: failure flags need labels");
   return launch_k34(h, d_logits, d_labels, n, T, C, tau, 0, 0, nullptr, d_conf, d_entropy, d_mi, d_pred, d_flag,
@@ -250,6 +251,7 @@ extern "C" int fav_epilogue(fav_handle h, const float* d_logits, const int32_t* 
 extern "C" int fav_accumulate(fav_handle h, const float* d_conf, const float* d_entropy, const float* d_mi,
                               const int32_t* d_pred, const int32_t* d_labels, int n, int C, float tau, int n_bins,
                               int n_buckets, int64_t* d_hist, void* stream) {
+  if (n == 0 && h) return FAV_OK;
   FAV_REQUIRE(d_conf && d_entropy && d_mi && d_pred && d_labels && d_hist, "fav_accumulate: null pointer");
   return launch_k34(h, nullptr, d_labels, n, 1, C, tau, n_bins, n_buckets, d_hist, nullptr, nullptr, nullptr, nullptr,
                     nullptr, d_conf, d_entropy, d_mi, d_pred, stream);
@@ -258,6 +260,7 @@ extern "C" int fav_accumulate(fav_handle h, const float* d_conf, const float* d_
 extern "C" int fav_epilogue_accumulate(fav_handle h, const float* d_logits, const int32_t* d_labels, int n, int T,
                                        int C, float tau, int n_bins, int n_buckets, int64_t* d_hist, float* d_conf,
                                        float* d_entropy, float* d_mi, int32_t* d_pred, uint8_t* d_flag, void* stream) {
+  if (n == 0 && h) return FAV_OK;
   FAV_REQUIRE(d_logits && d_labels && d_hist, "fav_epilogue_accumulate: null pointer");
   return launch_k34(h, d_logits, d_labels, n, T, C, tau, n_bins, n_buckets, d_hist, d_conf, d_entropy, d_mi, d_pred,
                     d_flag, nullptr, nullptr, nullptr, nullptr, stream);

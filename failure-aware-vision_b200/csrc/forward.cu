@@ -225,7 +225,7 @@ extern "C" int fav_forward_mc(fav_handle h, const void* d_x, float* d_logits, in
                               uint64_t first_image, void* stream) {
   FAV_REQUIRE(h && h->plan, "fav_forward_mc: load weights first");
   if (!h->plan) return FAV_E_STATE;
-  FAV_REQUIRE(d_x && d_logits && n >= 0 && T >= 1, "fav_forward_mc: bad arguments");
+  FAV_REQUIRE(n >= 0 && T >= 1 && (n == 0 || (d_x && d_logits)), "fav_forward_mc: bad arguments");
   FAV_REQUIRE(T == 1 || (p_drop >= 0.f && p_drop < 1.f), "fav_forward_mc: p_drop must be in [0,1)");
   if (n == 0) return FAV_OK;
   Plan& pl = *h->plan;

@@ -151,6 +151,18 @@ class CorruptionSweep:
     def reset(self):
         self.acc.reset()
 
+    def prepare(self, n_images=None):
+        """Build every cell's host table, upload it, size the workspace and touch every kernel once (untimed
+        setup: Poisson / stencil tables take tens of ms each on the host)."""
+        n = min(self.cfg.block, n_images or self.cfg.block)
+        h, w = self.cfg.input_hw
+        x = torch.zeros((min(n, 8), h, w, 3), dtype=torch.uint8, device=self.clf.device)
+        for cell in self.cells:
+            self.clf.corrupt_normalize(x, cell, self.cfg.seed, 0)
+        _lib.check(self.clf.lib.fav_reserve(self.clf.handle.h, n, self.cfg.T), "fav_reserve")
+        self._buffers(n)
+        torch.cuda.synchronize()
+
     def work_items(self, n_images):
         nblk = (n_images + self.cfg.block - 1) // self.cfg.block
         return [(ci, b) for b in range(nblk) for ci in range(len(self.cells))]

@@ -159,6 +159,8 @@ uint64_t fav_launch_count(fav_handle h);
  * and the number of launches since the last read, and clears the record. */
 int fav_conv_timing_enable(fav_handle h, int on);
 int fav_conv_timing_read(fav_handle h, float* total_ms, int* n_launches);
+/* same, but per launch in launch order: ms[i] and the launch's algorithmic GFLOP (2*M*K*N, padded taps counted). */
+int fav_conv_timing_read_all(fav_handle h, float* ms, float* gflop, int cap, int* n_launches);
 
 #ifdef __cplusplus
 }
