@@ -38,6 +38,7 @@ struct ConvArgs {
   int K, num_kb, M, BN, stages;
   int relu, out_f32, a_mode;
   int bw, bh, bn_img, tiles_w, tiles_h, cin_blocks;
+  int s_store;                 // a_mode 3: filter-row slots (S padded to an even count), Cin stored as 4
   int T, rep, drop;
   uint32_t drop_thr16;
   float drop_scale;
@@ -95,6 +96,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tm, uint32
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
@@ -156,8 +163,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto kb_active = [&](int kb) -> bool {
     if (a.a_mode != 0) return true;
     const int tap = kb / a.cin_blocks, r = tap / a.S, s = tap - r * a.S;
-    const int ih_lo = oh0 + r - a.pad, ih_hi = min(oh0 + a.bh, a.OH) - 1 + r - a.pad;
-    const int iw_lo = ow0 + s - a.pad, iw_hi = min(ow0 + a.bw, a.OW) - 1 + s - a.pad;
+    const int ih_lo = oh0 * a.stride + r - a.pad, ih_hi = (min(oh0 + a.bh, a.OH) - 1) * a.stride + r - a.pad;
+    const int iw_lo = ow0 * a.stride + s - a.pad, iw_hi = (min(ow0 + a.bw, a.OW) - 1) * a.stride + s - a.pad;
     return !(ih_hi < 0 || ih_lo >= a.H || iw_hi < 0 || iw_lo >= a.W);
   };
 
@@ -189,7 +196,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t sa = smem_base + s * stage_bytes;
         if (a.a_mode == 0) {
           const int tap = kb / a.cin_blocks, cb = kb - tap * a.cin_blocks, r = tap / a.S, ss = tap - r * a.S;
-          tma_load_4d(sa, &tmA, full_bar(s), cb * 64, ow0 + ss - a.pad, oh0 + r - a.pad, q0);
+          if (a.stride == 1) {
+            tma_load_4d(sa, &tmA, full_bar(s), cb * 64, ow0 + ss - a.pad, oh0 + r - a.pad, q0);
+          } else {
+            // stride 2: input row 2*oh + v (v = r - pad) = 2*(oh + (v >> 1)) + (v & 1); the tensor map views the
+            // activation as (2*Cin [w parity folded into channels], W/2, 2 [h parity], H/2, P)
+            const int v = r - a.pad, u = ss - a.pad;
+            tma_load_5d(sa, &tmA, full_bar(s), (u & 1) * a.Cin + cb * 64, ow0 + (u >> 1), v & 1, oh0 + (v >> 1), q0);
+          }
         }
         tma_load_2d(sa + A_TILE_BYTES, &tmB, full_bar(s), kb * BK, nt * a.BN);
         ++it;
@@ -247,7 +261,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           uint4 v = make_uint4(0, 0, 0, 0);
           const int k = kb * BK + c * 8;
           if (valid && k < a.K) {
-            if (a.a_mode == 1) {
+            if (a.a_mode == 3) {
+              const int pair = k >> 3, half = a.s_store >> 1, r = pair / half, ss = (pair - r * half) * 2;
+              const int ih = ih0 + r, iw = iw0 + ss;
+              if (r < a.R && ih >= 0 && ih < a.H) {
+                const uint2* rowx = reinterpret_cast<const uint2*>(ximg) + (size_t)ih * a.W;
+                if (iw >= 0 && iw < a.W && ss < a.S) { const uint2 t = __ldg(rowx + iw); v.x = t.x; v.y = t.y; }
+                if (iw + 1 >= 0 && iw + 1 < a.W && ss + 1 < a.S) { const uint2 t = __ldg(rowx + iw + 1); v.z = t.x; v.w = t.y; }
+              }
+            } else if (a.a_mode == 1) {
               const int tap = k / a.Cin, ci = k - tap * a.Cin, r = tap / a.S, ss = tap - r * a.S;
               const int ih = ih0 + r, iw = iw0 + ss;
               if (ih >= 0 && ih < a.H && iw >= 0 && iw < a.W)
@@ -392,7 +414,7 @@ int conv_out_dim(int in, int k, int stride, int pad) { return (in + 2 * pad - k)
 int conv_pick_bn(int cout) { return cout <= 16 ? 16 : cout <= 32 ? 32 : cout <= 64 ? 64 : 128; }
 
 int conv_layer_finalize(ConvLayer& L) {
-  L.k = L.r * L.s * L.cin;
+  L.k = L.r * (L.s_store ? L.s_store : L.s) * (L.cin_store ? L.cin_store : L.cin);
   L.kpad = (L.k + BK - 1) / BK * BK;
   L.bn = conv_pick_bn(L.cout);
   L.cout_pad = (L.cout + L.bn - 1) / L.bn * L.bn;
@@ -414,7 +436,8 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   ConvArgs a{};
   a.x = reinterpret_cast<const __nv_bfloat16*>(c.x); a.y = c.y; a.bias = L.bias;
   a.res = reinterpret_cast<const __nv_bfloat16*>(c.res);
-  a.P = c.p; a.H = c.h; a.W = c.w; a.Cin = L.cin; a.Cout = L.cout;
+  a.P = c.p; a.H = c.h; a.W = c.w; a.Cin = L.cin_store ? L.cin_store : L.cin; a.Cout = L.cout;
+  a.s_store = L.s_store;
   a.R = L.r; a.S = L.s; a.stride = L.stride; a.pad = L.pad;
   a.OH = conv_out_dim(c.h, L.r, L.stride, L.pad); a.OW = conv_out_dim(c.w, L.s, L.stride, L.pad);
   FAV_REQUIRE(a.OH > 0 && a.OW > 0, "conv: empty output");
@@ -433,11 +456,15 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
     a.drop_stream = stream_id(KIND_DROPOUT, c.layer_id, 0);
   }
   // operand-A mode
-  const bool tma_ok = L.stride == 1 && (L.cin % 64) == 0 && L.r == L.s && 2 * L.pad == L.r - 1 && a.OW <= 128;
+  const bool tma_s1 = L.stride == 1 && 2 * L.pad == L.r - 1;
+  const bool tma_s2 = L.stride == 2 && (c.h % 2) == 0 && (c.w % 2) == 0;
+  const bool tma_ok = !L.cin_store && (L.cin % 64) == 0 && L.r == L.s && a.OW <= 128 && (tma_s1 || tma_s2);
   int mode = c.a_mode;
+  if (L.cin_store) mode = 3;
   if (mode < 0) mode = tma_ok ? 0 : ((L.cin % 8) == 0 ? 1 : 2);
-  FAV_REQUIRE(mode != 0 || tma_ok, "conv: a_mode 0 (TMA) needs stride 1, Cin %% 64 == 0, 'same' padding");
+  FAV_REQUIRE(mode != 0 || tma_ok, "conv: a_mode 0 (TMA) needs Cin %% 64 == 0 and stride 1 with 'same' padding or stride 2 with even H, W");
   FAV_REQUIRE(mode != 1 || (L.cin % 8) == 0, "conv: a_mode 1 needs Cin %% 8 == 0");
+  FAV_REQUIRE(mode != 3 || (L.cin_store == 4 && (L.s_store % 2) == 0), "conv: a_mode 3 needs the channel-padded stem layout");
   a.a_mode = mode;
   CUtensorMap tmA;
   memset(&tmA, 0, sizeof(tmA));
@@ -450,10 +477,20 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
     const int tiles_n = (c.p + a.bn_img - 1) / a.bn_img;
     a.cin_blocks = L.cin / 64;
     mtiles = a.tiles_w * a.tiles_h * tiles_n;
-    const cuuint64_t dims[4] = {(cuuint64_t)L.cin, (cuuint64_t)c.w, (cuuint64_t)c.h, (cuuint64_t)c.p};
-    const cuuint64_t strides[3] = {(cuuint64_t)L.cin * 2, (cuuint64_t)c.w * L.cin * 2, (cuuint64_t)c.h * c.w * L.cin * 2};
-    const cuuint32_t box[4] = {64, (cuuint32_t)a.bw, (cuuint32_t)a.bh, (cuuint32_t)a.bn_img};
-    int rc = encode_map(&tmA, c.x, 4, dims, strides, box);
+    int rc;
+    if (L.stride == 1) {
+      const cuuint64_t dims[4] = {(cuuint64_t)L.cin, (cuuint64_t)c.w, (cuuint64_t)c.h, (cuuint64_t)c.p};
+      const cuuint64_t strides[3] = {(cuuint64_t)L.cin * 2, (cuuint64_t)c.w * L.cin * 2, (cuuint64_t)c.h * c.w * L.cin * 2};
+      const cuuint32_t box[4] = {64, (cuuint32_t)a.bw, (cuuint32_t)a.bh, (cuuint32_t)a.bn_img};
+      rc = encode_map(&tmA, c.x, 4, dims, strides, box);
+    } else {
+      // parity-split view for stride 2: (2*Cin [w parity folded in], W/2, 2 [h parity], H/2, P)
+      const cuuint64_t dims[5] = {(cuuint64_t)L.cin * 2, (cuuint64_t)c.w / 2, 2, (cuuint64_t)c.h / 2, (cuuint64_t)c.p};
+      const cuuint64_t strides[4] = {(cuuint64_t)L.cin * 4, (cuuint64_t)c.w * L.cin * 2, (cuuint64_t)c.w * L.cin * 4,
+                                     (cuuint64_t)c.h * c.w * L.cin * 2};
+      const cuuint32_t box[5] = {64, (cuuint32_t)a.bw, 1, (cuuint32_t)a.bh, (cuuint32_t)a.bn_img};
+      rc = encode_map(&tmA, c.x, 5, dims, strides, box);
+    }
     if (rc) return rc;
   } else {
     mtiles = int((M + BM - 1) / BM);
@@ -484,7 +521,7 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
     }
     e0 = ctx->ev_pool[ctx->ev_used]; e1 = ctx->ev_pool[ctx->ev_used + 1];
     ctx->ev_used += 2;
-    ctx->ev_gflop.push_back(float(2.0 * double(M) * L.k * L.cout * 1e-9));
+    ctx->ev_gflop.push_back(float(2.0 * double(M) * L.r * L.s * L.cin * L.cout * 1e-9));
     FAV_CUDA_OK(cudaEventRecord(e0, st));
   }
   conv_igemm_kernel<<<grid, CONV_THREADS, smem, st>>>(tmA, *reinterpret_cast<const CUtensorMap*>(L.tmap_w), a);

@@ -8,6 +8,7 @@ struct ConvLayer {          // device-resident, BN folded
   const __nv_bfloat16* w = nullptr;   // [cout_pad][kpad]  (k = (r*S + s)*cin + c), zero padded
   const float* bias = nullptr;        // [cout_pad]
   int cin = 0, cout = 0, r = 0, s = 0, stride = 1, pad = 0;
+  int cin_store = 0, s_store = 0;      // stem layout: channels padded to 4, filter-row slots padded to even (0 = as cin / s)
   int k = 0, kpad = 0, cout_pad = 0, bn = 0;
   alignas(64) unsigned char tmap_w[128];   // CUtensorMap for the weights (box 64 x bn, SWIZZLE_128B)
   bool tmap_ok = false;
@@ -20,7 +21,7 @@ struct ConvCall {
   const void* res = nullptr;      // bf16 NHWC [p, oh, ow, cout] or null
   int p = 0, h = 0, w = 0;
   int relu = 0, out_f32 = 0;
-  int a_mode = -1;                // -1 auto, 0 TMA-tiled, 1 vector gather, 2 scalar gather
+  int a_mode = -1;                // -1 auto, 0 TMA-tiled, 1 vector gather, 2 scalar gather, 3 channel-padded stem gather
   // MC-dropout in the epilogue
   int T = 1;                      // passes; rows of x are pass-images (image = row / T, t = row % T) unless rep > 1
   int rep = 1;                    // rep == T: x holds plain images, each output row is written T times with mask t

@@ -90,6 +90,14 @@ __global__ void __launch_bounds__(256) k_pool_dropout(const uint4* __restrict__ 
   }
 }
 
+// bf16 NHWC3 -> NHWC4 (zero 4th channel): lets the stem gather 8-byte pixels, two filter taps per 16-byte chunk
+__global__ void __launch_bounds__(256) k_pad_c3_c4(const unsigned short* __restrict__ x, uint2* __restrict__ y, long long npix) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned short* p = x + 3 * i;
+    y[i] = make_uint2(uint32_t(p[0]) | (uint32_t(p[1]) << 16), uint32_t(p[2]));
+  }
+}
+
 static inline int grid_for(long long work, int threads, int num_sms) {
   long long b = (work + threads - 1) / threads, cap = (long long)num_sms * 16;
   return int(b < 1 ? 1 : (b > cap ? cap : b));
@@ -101,6 +109,7 @@ static void walk_activations(const Plan& pl, int n, int T, F&& f) {
   const ConvLayer& stem = pl.convs[0];
   int h = conv_out_dim(pl.in_h, stem.r, stem.stride, stem.pad), w = conv_out_dim(pl.in_w, stem.s, stem.stride, stem.pad);
   f((size_t)n * h * w * stem.cout * 2);
+  f((size_t)n * pl.in_h * pl.in_w * 8);
   h = conv_out_dim(h, 3, 2, 1); w = conv_out_dim(w, 3, 2, 1);
   f((size_t)n * h * w * stem.cout * 2);
   long long P = n;
@@ -165,8 +174,10 @@ extern "C" int fav_load_weights(fav_handle h, const void* blob, size_t nbytes, i
     if (L.cout <= 0 || L.cin <= 0 || L.r <= 0 || L.s <= 0 || L.stride <= 0 || L.pad < 0) {
       delete pl; set_error("fav_load_weights: bad conv record %d", i); return FAV_E_ARG;
     }
+    const int k_blob = L.r * L.s * L.cin;
+    if (i == 0 && L.cin == 3) { L.cin_store = 4; L.s_store = (L.s + 1) & ~1; }   // stem: channel-padded layout
     conv_layer_finalize(L);
-    const size_t wb = ((size_t)L.cout * L.k * 2 + 15) / 16 * 16, bb = ((size_t)L.cout * 4 + 15) / 16 * 16;
+    const size_t wb = ((size_t)L.cout * k_blob * 2 + 15) / 16 * 16, bb = ((size_t)L.cout * 4 + 15) / 16 * 16;
     if (q + 32 + wb + bb > end) { delete pl; set_error("fav_load_weights: truncated weights at conv %d", i); return FAV_E_ARG; }
     recs.push_back({q + 32, q + 32 + wb});
     q += 32 + wb + bb;
@@ -182,7 +193,19 @@ extern "C" int fav_load_weights(fav_handle h, const void* blob, size_t nbytes, i
   uint8_t* d = reinterpret_cast<uint8_t*>(pl->arena);
   for (int i = 0; i < n_convs; ++i) {
     ConvLayer& L = pl->convs[i];
-    e = cudaMemcpy2D(d, (size_t)L.kpad * 2, recs[i].w, (size_t)L.k * 2, (size_t)L.k * 2, L.cout, cudaMemcpyHostToDevice);
+    if (L.cin_store) {
+      // [cout][r][s][3] -> [cout][r][s_store][4], zero filled
+      std::vector<uint16_t> tmp((size_t)L.cout * L.k, 0);
+      const uint16_t* src = reinterpret_cast<const uint16_t*>(recs[i].w);
+      for (int co = 0; co < L.cout; ++co)
+        for (int rr = 0; rr < L.r; ++rr)
+          for (int ss = 0; ss < L.s; ++ss)
+            for (int c = 0; c < L.cin; ++c)
+              tmp[((size_t)co * L.r + rr) * L.s_store * 4 + ss * 4 + c] = src[(((size_t)co * L.r + rr) * L.s + ss) * L.cin + c];
+      e = cudaMemcpy2D(d, (size_t)L.kpad * 2, tmp.data(), (size_t)L.k * 2, (size_t)L.k * 2, L.cout, cudaMemcpyHostToDevice);
+    } else {
+      e = cudaMemcpy2D(d, (size_t)L.kpad * 2, recs[i].w, (size_t)L.k * 2, (size_t)L.k * 2, L.cout, cudaMemcpyHostToDevice);
+    }
     L.w = reinterpret_cast<const __nv_bfloat16*>(d);
     d += ((size_t)L.cout_pad * L.kpad * 2 + 255) / 256 * 256;
     if (e == cudaSuccess) e = cudaMemcpy(d, recs[i].b, (size_t)L.cout * 4, cudaMemcpyHostToDevice);
@@ -254,7 +277,16 @@ extern "C" int fav_forward_mc(fav_handle h, const void* d_x, float* d_logits, in
 
   // stem + max-pool (pass-invariant)
   const ConvLayer& stem = pl.convs[0];
-  int rc = run(stem, d_x, Y1, nullptr, n, pl.in_h, pl.in_w, 1, 0, 1, 0, 0);
+  const void* stem_in = d_x;
+  if (stem.cin_store == 4) {
+    const long long npix = (long long)n * pl.in_h * pl.in_w;
+    FAV_REQUIRE((size_t)npix * 8 <= pl.buf_bytes, "workspace too small for the padded input");
+    k_pad_c3_c4<<<grid_for(npix, 256, h->num_sms), 256, 0, st>>>(reinterpret_cast<const unsigned short*>(d_x),
+                                                                 reinterpret_cast<uint2*>(DS), npix);
+    h->launches++;
+    stem_in = DS;
+  }
+  int rc = run(stem, stem_in, Y1, nullptr, n, pl.in_h, pl.in_w, 1, 0, 1, 0, 0);
   if (rc) return rc;
   int hh = conv_out_dim(pl.in_h, stem.r, stem.stride, stem.pad), ww = conv_out_dim(pl.in_w, stem.s, stem.stride, stem.pad);
   {

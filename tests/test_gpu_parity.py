@@ -130,8 +130,11 @@ def test_k1_partition_independence(fav, clf18):
 CONV_CASES = [
     # p, h, w, cin, cout, k, stride, pad, relu, res, modes
     (4, 8, 8, 64, 64, 3, 1, 1, 1, 1, (0, 1)),
-    (3, 8, 8, 64, 128, 3, 2, 1, 1, 0, (1,)),
-    (3, 8, 8, 64, 128, 1, 2, 0, 0, 0, (1,)),
+    (3, 8, 8, 64, 128, 3, 2, 1, 1, 0, (0, 1)),
+    (3, 8, 8, 64, 128, 1, 2, 0, 0, 0, (0, 1)),
+    (5, 28, 28, 128, 256, 3, 2, 1, 1, 1, (0, 1)),
+    (2, 56, 56, 256, 512, 1, 2, 0, 0, 0, (0, 1)),
+    (9, 2, 2, 256, 512, 3, 2, 1, 1, 0, (0, 1)),
     (17, 4, 4, 128, 128, 3, 1, 1, 1, 1, (0, 1)),
     (40, 2, 2, 256, 256, 3, 1, 1, 1, 0, (0, 1)),
     (200, 1, 1, 512, 512, 3, 1, 1, 1, 1, (0, 1)),
