@@ -15,8 +15,9 @@
 //   D       128 lanes x BN fp32 columns in TMEM, one tcgen05.mma (M=128, N=BN, K=16) per 32 bytes of K
 //   epilogue: tcgen05.ld -> +bias (+residual) -> ReLU -> MC-dropout mask from Philox (optionally T masked
 //             replicas of a pass-invariant tile) -> bf16 NHWC (or fp32 logits)
-// Warp roles (192 threads): warps 0-3 gather producers + epilogue, warp 4 TMA issuer, warp 5 MMA issuer + TMEM
-// allocator.  smem ring of `stages` {A,B} slots with full/empty mbarriers; tcgen05.commit frees slots.
+// Persistent CTAs, warp-specialised (TMA issuer, MMA issuer, 8 epilogue warps, 4 optional gather warps); smem ring of
+// `stages` {A,B} slots with full/empty mbarriers, tcgen05.commit frees slots; two TMEM accumulators so the epilogue of
+// one tile overlaps the MMAs of the next.
 #include <cuda.h>
 #include <cstdio>
 #include <mutex>
@@ -26,7 +27,6 @@ namespace fav {
 
 constexpr int BM = 128, BK = 64;
 constexpr int A_TILE_BYTES = BM * BK * 2;          // 16 KiB
-constexpr int CONV_THREADS = 192;
 
 struct ConvArgs {
   const __nv_bfloat16* x;
@@ -38,6 +38,7 @@ struct ConvArgs {
   int K, num_kb, M, BN, stages;
   int relu, out_f32, a_mode;
   int bw, bh, bn_img, tiles_w, tiles_h, cin_blocks;
+  int ntiles, total_tiles;     // N tiles per M tile, all tiles (persistent scheduler)
   int s_store;                 // a_mode 3: filter-row slots (S padded to an even count), Cin stored as 4
   int T, rep, drop;
   uint32_t drop_thr16;
@@ -136,122 +137,151 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
 }
 
 // ------------------------------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(CONV_THREADS)
-conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs a) {
+// Persistent, warp-specialised: each CTA walks tiles (tile = blockIdx.x + i * gridDim.x; N-tile fastest so CTAs
+// running side by side share the activation tile in L2).  Two TMEM accumulators let the epilogue of tile i overlap
+// the MMAs of tile i+1.
+//   warp 0      TMA issuer (one lane)            warp 1      MMA issuer (one lane) + TMEM alloc/dealloc
+//   warps 2-9   epilogue: TMEM lane quarter = warp % 4, the two warps of a quarter split the 16-column chunks
+//   warps 10-13 gather producers (a_mode 1/2/3 only; not launched in a_mode 0)
+constexpr int EPI_WARP0 = 2, EPI_WARPS = 8, GATHER_WARP0 = 10;
+constexpr int THREADS_TMA = 32 * GATHER_WARP0, THREADS_GATHER = 32 * (GATHER_WARP0 + 4);
+
+struct Tile { int mt, nt, q0, oh0, ow0; };
+
+__device__ __forceinline__ Tile decode_tile(const ConvArgs& a, int tile) {
+  Tile t;
+  t.nt = tile % a.ntiles; t.mt = tile / a.ntiles;
+  t.q0 = 0; t.oh0 = 0; t.ow0 = 0;
+  if (a.a_mode == 0) {
+    const int tw = t.mt % a.tiles_w, th = (t.mt / a.tiles_w) % a.tiles_h, tn = t.mt / (a.tiles_w * a.tiles_h);
+    t.q0 = tn * a.bn_img; t.oh0 = th * a.bh; t.ow0 = tw * a.bw;
+  }
+  return t;
+}
+// a k-block is skipped when its filter tap only sees padding for this whole tile (a_mode 0)
+__device__ __forceinline__ bool kb_active(const ConvArgs& a, const Tile& t, int kb) {
+  if (a.a_mode != 0) return true;
+  const int tap = kb / a.cin_blocks, r = tap / a.S, s = tap - r * a.S;
+  const int ih_lo = t.oh0 * a.stride + r - a.pad, ih_hi = (min(t.oh0 + a.bh, a.OH) - 1) * a.stride + r - a.pad;
+  const int iw_lo = t.ow0 * a.stride + s - a.pad, iw_hi = (min(t.ow0 + a.bw, a.OW) - 1) * a.stride + s - a.pad;
+  return !(ih_hi < 0 || ih_lo >= a.H || iw_hi < 0 || iw_lo >= a.W);
+}
+// output pixel owned by A-tile row `row` of tile t
+__device__ __forceinline__ bool decode_row(const ConvArgs& a, const Tile& t, int row, int& q, int& oh, int& ow) {
+  if (a.a_mode == 0) {
+    const int per_img = a.bw * a.bh;
+    const int nl = row / per_img, rem = row - nl * per_img, hl = rem / a.bw, wl = rem - hl * a.bw;
+    q = t.q0 + nl; oh = t.oh0 + hl; ow = t.ow0 + wl;
+    return nl < a.bn_img && q < a.P && oh < a.OH && ow < a.OW;
+  }
+  const long long m = (long long)t.mt * BM + row;
+  q = 0; oh = 0; ow = 0;
+  if (m >= a.M) return false;
+  q = int(m / (a.OH * a.OW));
+  const int rem = int(m - (long long)q * (a.OH * a.OW));
+  oh = rem / a.OW; ow = rem - oh * a.OW;
+  return true;
+}
+
+template <bool GATHER>
+__device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvArgs& a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t pad_to_1k = ((raw + 1023u) & ~1023u) - raw;
   uint8_t* smem = smem_raw + pad_to_1k;
   const int stage_bytes = A_TILE_BYTES + a.BN * 128;
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t bars = smem_base + a.stages * stage_bytes;                 // full[s], empty[s], tmem_full
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + a.stages * stage_bytes + (2 * a.stages + 1) * 8);
+  const uint32_t bars = smem_base + a.stages * stage_bytes;      // full[s], empty[s], tmem_full[2], tmem_empty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + a.stages * stage_bytes + (2 * a.stages + 4) * 8);
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (a.stages + s); };
-  const uint32_t tmem_full_bar = bars + 8u * (2 * a.stages);
+  auto tfull_bar = [&](int i) { return bars + 8u * (2 * a.stages + i); };
+  auto tempty_bar = [&](int i) { return bars + 8u * (2 * a.stages + 2 + i); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = blockIdx.x, nt = blockIdx.y;
 
-  // tile origin
-  int q0 = 0, oh0 = 0, ow0 = 0;
-  if (a.a_mode == 0) {
-    const int tw = mt % a.tiles_w, th = (mt / a.tiles_w) % a.tiles_h, tn = mt / (a.tiles_w * a.tiles_h);
-    q0 = tn * a.bn_img; oh0 = th * a.bh; ow0 = tw * a.bw;
-  }
-  // a k-block is skipped when its filter tap only sees padding for this whole tile (a_mode 0)
-  auto kb_active = [&](int kb) -> bool {
-    if (a.a_mode != 0) return true;
-    const int tap = kb / a.cin_blocks, r = tap / a.S, s = tap - r * a.S;
-    const int ih_lo = oh0 * a.stride + r - a.pad, ih_hi = (min(oh0 + a.bh, a.OH) - 1) * a.stride + r - a.pad;
-    const int iw_lo = ow0 * a.stride + s - a.pad, iw_hi = (min(ow0 + a.bw, a.OW) - 1) * a.stride + s - a.pad;
-    return !(ih_hi < 0 || ih_lo >= a.H || iw_hi < 0 || iw_lo >= a.W);
-  };
-
-  if (warp == 4 && lane == 0) {
+  if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmB);
     if (a.a_mode == 0) tma_prefetch_desc(&tmA);
     const uint32_t full_count = a.a_mode == 0 ? 1u : 1u + 128u;
     for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), full_count); mbar_init(empty_bar(s), 1u); }
-    mbar_init(tmem_full_bar, 1u);
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1u); mbar_init(tempty_bar(i), EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(smem_u32(tmem_slot), a.tmem_cols);
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), a.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 0) {
     // ================================================================= TMA issuer
     if (lane == 0) {
       const uint32_t a_bytes = a.a_mode == 0 ? uint32_t(a.bn_img * a.bh * a.bw) * 128u : 0u;
       const uint32_t tx = a_bytes + uint32_t(a.BN) * 128u;
       int it = 0;
-      for (int kb = 0; kb < a.num_kb; ++kb) {
-        if (!kb_active(kb)) continue;
-        const int s = it % a.stages, ph = (it / a.stages) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
-        mbar_arrive_expect_tx(full_bar(s), tx);
-        const uint32_t sa = smem_base + s * stage_bytes;
-        if (a.a_mode == 0) {
-          const int tap = kb / a.cin_blocks, cb = kb - tap * a.cin_blocks, r = tap / a.S, ss = tap - r * a.S;
-          if (a.stride == 1) {
-            tma_load_4d(sa, &tmA, full_bar(s), cb * 64, ow0 + ss - a.pad, oh0 + r - a.pad, q0);
-          } else {
-            // stride 2: input row 2*oh + v (v = r - pad) = 2*(oh + (v >> 1)) + (v & 1); the tensor map views the
-            // activation as (2*Cin [w parity folded into channels], W/2, 2 [h parity], H/2, P)
-            const int v = r - a.pad, u = ss - a.pad;
-            tma_load_5d(sa, &tmA, full_bar(s), (u & 1) * a.Cin + cb * 64, ow0 + (u >> 1), v & 1, oh0 + (v >> 1), q0);
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const Tile t = decode_tile(a, tile);
+        for (int kb = 0; kb < a.num_kb; ++kb) {
+          if (!kb_active(a, t, kb)) continue;
+          const int s = it % a.stages, ph = (it / a.stages) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_arrive_expect_tx(full_bar(s), tx);
+          const uint32_t sa = smem_base + s * stage_bytes;
+          if (a.a_mode == 0) {
+            const int tap = kb / a.cin_blocks, cb = kb - tap * a.cin_blocks, r = tap / a.S, ss = tap - r * a.S;
+            if (a.stride == 1) {
+              tma_load_4d(sa, &tmA, full_bar(s), cb * 64, t.ow0 + ss - a.pad, t.oh0 + r - a.pad, t.q0);
+            } else {
+              // stride 2: input row 2*oh + v (v = r - pad) = 2*(oh + (v >> 1)) + (v & 1); the tensor map views the
+              // activation as (2*Cin [w parity folded into channels], W/2, 2 [h parity], H/2, P)
+              const int v = r - a.pad, u = ss - a.pad;
+              tma_load_5d(sa, &tmA, full_bar(s), (u & 1) * a.Cin + cb * 64, t.ow0 + (u >> 1), v & 1, t.oh0 + (v >> 1), t.q0);
+            }
           }
+          tma_load_2d(sa + A_TILE_BYTES, &tmB, full_bar(s), kb * BK, t.nt * a.BN);
+          ++it;
         }
-        tma_load_2d(sa + A_TILE_BYTES, &tmB, full_bar(s), kb * BK, nt * a.BN);
-        ++it;
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 1) {
     // ================================================================= MMA issuer
     if (lane == 0) {
-      int it = 0;
-      for (int kb = 0; kb < a.num_kb; ++kb) {
-        if (!kb_active(kb)) continue;
-        const int s = it % a.stages, ph = (it / a.stages) & 1;
-        mbar_wait(full_bar(s), ph);
+      int it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
+        const Tile t = decode_tile(a, tile);
+        const int acc = ti & 1;
+        mbar_wait(tempty_bar(acc), ((ti >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_base + s * stage_bytes;
-        const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sa + A_TILE_BYTES);
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * a.BN);
+        bool first = true;
+        for (int kb = 0; kb < a.num_kb; ++kb) {
+          if (!kb_active(a, t, kb)) continue;
+          const int s = it % a.stages, ph = (it / a.stages) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * stage_bytes;
+          const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sa + A_TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)          // 32 bytes of K per MMA: +2 in the (addr >> 4) field
-          umma_f16(tmem_base, da + 2u * k, db + 2u * k, a.idesc, (it > 0 || k > 0) ? 1u : 0u);
-        umma_commit(empty_bar(s));
-        ++it;
-      }
-      umma_commit(tmem_full_bar);
-    }
-  } else {
-    // ================================================================= warps 0-3: gather producers, then epilogue
-    const int row = threadIdx.x;                    // 0..127 = A-tile row = TMEM lane
-    int q = 0, oh = 0, ow = 0;
-    bool valid;
-    if (a.a_mode == 0) {
-      const int per_img = a.bw * a.bh;
-      const int nl = row / per_img, rem = row - nl * per_img, hl = rem / a.bw, wl = rem - hl * a.bw;
-      q = q0 + nl; oh = oh0 + hl; ow = ow0 + wl;
-      valid = nl < a.bn_img && q < a.P && oh < a.OH && ow < a.OW;
-    } else {
-      const long long m = (long long)mt * BM + row;
-      valid = m < a.M;
-      if (valid) {
-        q = int(m / (a.OH * a.OW));
-        const int rem = int(m - (long long)q * (a.OH * a.OW));
-        oh = rem / a.OW; ow = rem - oh * a.OW;
+          for (int k = 0; k < BK / 16; ++k)          // 32 bytes of K per MMA: +2 in the (addr >> 4) field
+            umma_f16(d_tmem, da + 2u * k, db + 2u * k, a.idesc, (!first || k > 0) ? 1u : 0u);
+          first = false;
+          umma_commit(empty_bar(s));
+          ++it;
+        }
+        umma_commit(tfull_bar(acc));
       }
     }
-
-    if (a.a_mode != 0) {
+  } else if (GATHER && warp >= GATHER_WARP0) {
+    // ================================================================= gather producers (a_mode 1/2/3)
+    const int row = threadIdx.x - 32 * GATHER_WARP0;      // 0..127 = A-tile row
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      const Tile t = decode_tile(a, tile);
+      int q, oh, ow;
+      const bool valid = decode_row(a, t, row, q, oh, ow);
       const int ih0 = oh * a.stride - a.pad, iw0 = ow * a.stride - a.pad;
       const __nv_bfloat16* ximg = a.x + (size_t)q * a.H * a.W * a.Cin;
-      int it = 0;
       for (int kb = 0; kb < a.num_kb; ++kb, ++it) {
         const int s = it % a.stages, ph = (it / a.stages) & 1;
         mbar_wait(empty_bar(s), ph ^ 1);
@@ -266,8 +296,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const int ih = ih0 + r, iw = iw0 + ss;
               if (r < a.R && ih >= 0 && ih < a.H) {
                 const uint2* rowx = reinterpret_cast<const uint2*>(ximg) + (size_t)ih * a.W;
-                if (iw >= 0 && iw < a.W && ss < a.S) { const uint2 t = __ldg(rowx + iw); v.x = t.x; v.y = t.y; }
-                if (iw + 1 >= 0 && iw + 1 < a.W && ss + 1 < a.S) { const uint2 t = __ldg(rowx + iw + 1); v.z = t.x; v.w = t.y; }
+                if (iw >= 0 && iw < a.W && ss < a.S) { const uint2 u = __ldg(rowx + iw); v.x = u.x; v.y = u.y; }
+                if (iw + 1 >= 0 && iw + 1 < a.W && ss + 1 < a.S) { const uint2 u = __ldg(rowx + iw + 1); v.z = u.x; v.w = u.y; }
               }
             } else if (a.a_mode == 1) {
               const int tap = k / a.Cin, ci = k - tap * a.Cin, r = tap / a.S, ss = tap - r * a.S;
@@ -297,88 +327,119 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_arrive(full_bar(s));
       }
     }
-
-    // ----------------------------------------------------------------- epilogue
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const uint32_t trow = tmem_base + (uint32_t(warp * 32) << 16);
-    const int hw = oh * a.OW + ow, ohw = a.OH * a.OW;
-    const size_t res_off = ((size_t)q * ohw + hw) * a.Cout;
-    const int n_rep = a.rep > 1 ? a.rep : 1;
-    for (int j = 0; j < a.BN / 16; ++j) {
-      uint32_t acc[16];
-      tmem_ld16(trow + uint32_t(j * 16), acc);       // warp-collective: executed by every lane, valid or not
-      tmem_ld_wait();
-      const int c0 = nt * a.BN + j * 16;
-      if (!valid || c0 >= a.Cout) continue;
-      float v[16];
+  } else {
+    // ================================================================= epilogue warps
+    const int quarter = warp & 3;                        // TMEM lanes 32*quarter .. +31 (hardware: warp id % 4)
+    const int half = (warp - EPI_WARP0) >> 2;            // which of the two warps of this quarter
+    const int row = quarter * 32 + lane;
+    const int ohw = a.OH * a.OW, n_rep = a.rep > 1 ? a.rep : 1;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
+      const Tile t = decode_tile(a, tile);
+      int q, oh, ow;
+      const bool valid = decode_row(a, t, row, q, oh, ow);
+      const int acc_i = ti & 1;
+      mbar_wait(tfull_bar(acc_i), (ti >> 1) & 1);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc_i * a.BN);
+      const int hw = oh * a.OW + ow;
+      const size_t res_off = ((size_t)q * ohw + hw) * a.Cout;
+      for (int j = half; j < a.BN / 16; j += 2) {
+        uint32_t acc[16];
+        tmem_ld16(trow + uint32_t(j * 16), acc);       // warp-collective: executed by every lane, valid or not
+        tmem_ld_wait();
+        const int c0 = t.nt * a.BN + j * 16;
+        if (!valid || c0 >= a.Cout) continue;
+        float v[16];
+        {
+          const float4* bp = reinterpret_cast<const float4*>(a.bias + c0);     // bias is padded to cout_pad
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]) + __ldg(a.bias + c0 + i);
-      if (a.res) {
-        if ((a.Cout & 7) == 0) {
-          const uint4* rp = reinterpret_cast<const uint4*>(a.res + res_off + c0);
-#pragma unroll
-          for (int hseg = 0; hseg < 2; ++hseg) {
-            if (c0 + 8 * hseg >= a.Cout) break;
-            const uint4 rv = __ldg(rp + hseg);
-            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { v[8 * hseg + 2 * i] += bf16_lo(rw[i]); v[8 * hseg + 2 * i + 1] += bf16_hi(rw[i]); }
+          for (int i = 0; i < 4; ++i) {
+            const float4 b = __ldg(bp + i);
+            v[4 * i] = __uint_as_float(acc[4 * i]) + b.x; v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + b.y;
+            v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b.z; v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b.w;
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (c0 + i < a.Cout) v[i] += __bfloat162float(a.res[res_off + c0 + i]);
         }
-      }
-      if (a.relu) {
+        if (a.res) {
+          if ((a.Cout & 7) == 0) {
+            const uint4* rp = reinterpret_cast<const uint4*>(a.res + res_off + c0);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-      }
-      for (int rp = 0; rp < n_rep; ++rp) {
-        const int p_out = a.rep > 1 ? q * a.rep + rp : q;
-        const size_t off = ((size_t)p_out * ohw + hw) * a.Cout + c0;
-        float o[16];
+            for (int hseg = 0; hseg < 2; ++hseg) {
+              if (c0 + 8 * hseg >= a.Cout) break;
+              const uint4 rv = __ldg(rp + hseg);
+              const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
-        for (int i = 0; i < 16; ++i) o[i] = v[i];
-        if (a.drop) {
-          const int n_img = a.rep > 1 ? q : q / a.T;
-          const int t = a.rep > 1 ? rp : q - n_img * a.T;
-          const uint32_t e8 = uint32_t((size_t)hw * a.Cout + c0) >> 3;
+              for (int i = 0; i < 4; ++i) { v[8 * hseg + 2 * i] += bf16_lo(rw[i]); v[8 * hseg + 2 * i + 1] += bf16_hi(rw[i]); }
+            }
+          } else {
 #pragma unroll
-          for (int hseg = 0; hseg < 2; ++hseg) {
-            const uint4 r = philox4x32_10(e8 + hseg, a.first_image + uint32_t(n_img), uint32_t(t), a.drop_stream, a.k0, a.k1);
-            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+            for (int i = 0; i < 16; ++i)
+              if (c0 + i < a.Cout) v[i] += __bfloat162float(a.res[res_off + c0 + i]);
+          }
+        }
+        if (a.relu) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              o[8 * hseg + 2 * i] = (rw[i] & 0xFFFFu) >= a.drop_thr16 ? o[8 * hseg + 2 * i] * a.drop_scale : 0.f;
-              o[8 * hseg + 2 * i + 1] = (rw[i] >> 16) >= a.drop_thr16 ? o[8 * hseg + 2 * i + 1] * a.drop_scale : 0.f;
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        for (int rp = 0; rp < n_rep; ++rp) {
+          const int p_out = a.rep > 1 ? q * a.rep + rp : q;
+          const size_t off = ((size_t)p_out * ohw + hw) * a.Cout + c0;
+          float o[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = v[i];
+          if (a.drop) {
+            const int n_img = a.rep > 1 ? q : q / a.T;
+            const int tt = a.rep > 1 ? rp : q - n_img * a.T;
+            const uint32_t e8 = uint32_t((size_t)hw * a.Cout + c0) >> 3;
+#pragma unroll
+            for (int hseg = 0; hseg < 2; ++hseg) {
+              const uint4 r = philox4x32_10(e8 + hseg, a.first_image + uint32_t(n_img), uint32_t(tt), a.drop_stream, a.k0, a.k1);
+              const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                o[8 * hseg + 2 * i] = (rw[i] & 0xFFFFu) >= a.drop_thr16 ? o[8 * hseg + 2 * i] * a.drop_scale : 0.f;
+                o[8 * hseg + 2 * i + 1] = (rw[i] >> 16) >= a.drop_thr16 ? o[8 * hseg + 2 * i + 1] * a.drop_scale : 0.f;
+              }
             }
           }
-        }
-        if (a.out_f32) {
-          float* yp = reinterpret_cast<float*>(a.y) + off;
+          if (a.out_f32) {
+            float* yp = reinterpret_cast<float*>(a.y) + off;
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (c0 + i < a.Cout) yp[i] = o[i];
-        } else if ((a.Cout & 7) == 0) {
-          uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + off);
-          yp[0] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-          if (c0 + 8 < a.Cout)
-            yp[1] = make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
-        } else {
-          __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + off;
+            for (int i = 0; i < 16; ++i)
+              if (c0 + i < a.Cout) yp[i] = o[i];
+          } else if ((a.Cout & 7) == 0) {
+            uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + off);
+            yp[0] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+            if (c0 + 8 < a.Cout)
+              yp[1] = make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
+          } else {
+            __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + off;
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (c0 + i < a.Cout) yp[i] = __float2bfloat16_rn(o[i]);
+            for (int i = 0; i < 16; ++i)
+              if (c0 + i < a.Cout) yp[i] = __float2bfloat16_rn(o[i]);
+          }
         }
       }
+      // this warp has finished reading the accumulator: hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc_i));
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, a.tmem_cols);
+  if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+// TMA-fed variant: 320 threads, two CTAs per SM (register budget 102); gather variant: 448 threads, one CTA per SM.
+__global__ void __launch_bounds__(THREADS_TMA, 2)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs a) {
+  conv_igemm_body<false>(tmA, tmB, a);
+}
+__global__ void __launch_bounds__(THREADS_GATHER, 1)
+conv_igemm_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs a) {
+  conv_igemm_body<true>(tmA, tmB, a);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -500,8 +561,10 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   stages = stages < 2 ? 2 : (stages > 6 ? 6 : stages);
   a.stages = stages;
   uint32_t cols = 32;
-  while (cols < uint32_t(a.BN)) cols *= 2;
+  while (cols < uint32_t(2 * a.BN)) cols *= 2;           // two accumulators (double-buffered epilogue)
   a.tmem_cols = cols;
+  a.ntiles = L.cout_pad / a.BN;
+  a.total_tiles = mtiles * a.ntiles;
   // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128
   a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(a.BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
@@ -509,9 +572,13 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
     attr_err = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(conv_igemm_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   FAV_CUDA_OK(attr_err);
-  dim3 grid(mtiles, L.cout_pad / a.BN);
+  const int threads = mode == 0 ? THREADS_TMA : THREADS_GATHER;
+  const int ctas_per_sm = (mode == 0 && cols <= 256) ? 2 : 1;
+  const int grid = a.total_tiles < ctas_per_sm * ctx->num_sms ? a.total_tiles : ctas_per_sm * ctx->num_sms;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx->timing) {
     while (ctx->ev_pool.size() < ctx->ev_used + 2) {
@@ -524,7 +591,10 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
     ctx->ev_gflop.push_back(float(2.0 * double(M) * L.r * L.s * L.cin * L.cout * 1e-9));
     FAV_CUDA_OK(cudaEventRecord(e0, st));
   }
-  conv_igemm_kernel<<<grid, CONV_THREADS, smem, st>>>(tmA, *reinterpret_cast<const CUtensorMap*>(L.tmap_w), a);
+  if (mode == 0)
+    conv_igemm_kernel<<<grid, threads, smem, st>>>(tmA, *reinterpret_cast<const CUtensorMap*>(L.tmap_w), a);
+  else
+    conv_igemm_gather_kernel<<<grid, threads, smem, st>>>(tmA, *reinterpret_cast<const CUtensorMap*>(L.tmap_w), a);
   if (e1) FAV_CUDA_OK(cudaEventRecord(e1, st));
   ctx->launches++;
   FAV_CUDA_OK(cudaGetLastError());
