@@ -51,6 +51,7 @@ extern "C" int fav_destroy(fav_handle h) {
   if (h->ws) cudaFree(h->ws);
   if (h->plan) plan_destroy(h->plan);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  if (h->stats_buf) cudaFree(h->stats_buf);
   delete h;
   return FAV_OK;
 }
@@ -92,5 +93,20 @@ extern "C" int fav_conv_timing_read_all(fav_handle h, float* ms, float* gflop, i
   *n_launches = n;
   h->ev_used = 0;
   h->ev_gflop.clear();
+  return FAV_OK;
+}
+
+// per-launch role counters (cycles summed over CTAs): {tma wait-empty, tma total, mma wait-full, mma wait-tmem-empty,
+// mma total, epilogue wait-tmem-full, epilogue total, #CTAs}; valid for launches made while timing is enabled, must be
+// read BEFORE fav_conv_timing_read* (which resets the launch index).
+extern "C" int fav_conv_stats_read(fav_handle h, uint64_t* out, int cap_launches, int* n_launches) {
+  FAV_REQUIRE(h && out && n_launches, "fav_conv_stats_read: null pointer");
+  int n = int(h->ev_used / 2);
+  if (n > cap_launches) n = cap_launches;
+  if (n > 512) n = 512;
+  *n_launches = n;
+  if (n == 0 || !h->stats_buf) return FAV_OK;
+  FAV_CUDA_OK(cudaDeviceSynchronize());
+  FAV_CUDA_OK(cudaMemcpy(out, h->stats_buf, (size_t)n * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   return FAV_OK;
 }

@@ -90,6 +90,7 @@ struct Ctx {
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
   std::vector<float> ev_gflop;
+  void* stats_buf = nullptr;      // 512 launches x 8 role counters (cycles)
 };
 
 }  // namespace fav

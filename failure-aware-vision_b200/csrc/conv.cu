@@ -20,6 +20,7 @@
 // one tile overlaps the MMAs of the next.
 #include <cuda.h>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include "conv.cuh"
 
@@ -38,13 +39,16 @@ struct ConvArgs {
   int K, num_kb, M, BN, stages;
   int relu, out_f32, a_mode;
   int bw, bh, bn_img, tiles_w, tiles_h, cin_blocks;
-  int ntiles, total_tiles;     // N tiles per M tile, all tiles (persistent scheduler)
+  int ntiles, total_tiles;     // N tiles per M tile, all CTA tiles (persistent scheduler)
+  int mt_per_tile, mtiles;     // 128-row M tiles per CTA tile (1 or 2), number of 128-row M tiles
   int s_store;                 // a_mode 3: filter-row slots (S padded to an even count), Cin stored as 4
   int T, rep, drop;
   uint32_t drop_thr16;
   float drop_scale;
   uint32_t k0, k1, first_image, drop_stream;
   uint32_t tmem_cols, idesc;
+  int kb2, stride2, Cin2;      // fused second source (the block's 1x1 downsample branch): extra k-blocks after the main taps
+  unsigned long long* stats;   // optional per-launch role timing (8 counters), see fav_conv_stats_read
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -79,6 +83,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, long long& acc, bool on) {
+  if (on) { const long long c0 = clock64(); mbar_wait(bar, parity); acc += clock64() - c0; }
+  else mbar_wait(bar, parity);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -143,14 +151,18 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
 //   warp 0      TMA issuer (one lane)            warp 1      MMA issuer (one lane) + TMEM alloc/dealloc
 //   warps 2-9   epilogue: TMEM lane quarter = warp % 4, the two warps of a quarter split the 16-column chunks
 //   warps 10-13 gather producers (a_mode 1/2/3 only; not launched in a_mode 0)
-constexpr int EPI_WARP0 = 2, EPI_WARPS = 8, GATHER_WARP0 = 10;
-constexpr int THREADS_TMA = 32 * GATHER_WARP0, THREADS_GATHER = 32 * (GATHER_WARP0 + 4);
+//   MT = 2: each CTA tile is 256 output pixels (two A tiles sharing one W tile per k-block, two accumulators) --
+//           1.36x fewer L2->smem bytes per FLOP; the conv kernels are L2-bandwidth-bound, so this is the main lever.
+constexpr int EPI_WARP0 = 2;
+constexpr int THREADS_TMA1 = 32 * (2 + 8);        // MT = 1: 8 epilogue warps, two CTAs per SM
+constexpr int THREADS_TMA2 = 32 * (2 + 16);       // MT = 2: 16 epilogue warps, one CTA per SM
+constexpr int THREADS_GATHER = 32 * (2 + 8 + 4);  // gather variant: 8 epilogue + 4 gather warps
 
-struct Tile { int mt, nt, q0, oh0, ow0; };
+struct Tile { int mt, nt, q0, oh0, ow0; };   // mt = index of the 128-row M tile
 
-__device__ __forceinline__ Tile decode_tile(const ConvArgs& a, int tile) {
+__device__ __forceinline__ Tile decode_tile(const ConvArgs& a, int tile, int u = 0) {
   Tile t;
-  t.nt = tile % a.ntiles; t.mt = tile / a.ntiles;
+  t.nt = tile % a.ntiles; t.mt = (tile / a.ntiles) * a.mt_per_tile + u;
   t.q0 = 0; t.oh0 = 0; t.ow0 = 0;
   if (a.a_mode == 0) {
     const int tw = t.mt % a.tiles_w, th = (t.mt / a.tiles_w) % a.tiles_h, tn = t.mt / (a.tiles_w * a.tiles_h);
@@ -158,14 +170,25 @@ __device__ __forceinline__ Tile decode_tile(const ConvArgs& a, int tile) {
   }
   return t;
 }
-// a k-block is skipped when its filter tap only sees padding for this whole tile (a_mode 0)
-__device__ __forceinline__ bool kb_active(const ConvArgs& a, const Tile& t, int kb) {
-  if (a.a_mode != 0) return true;
-  const int tap = kb / a.cin_blocks, r = tap / a.S, s = tap - r * a.S;
-  const int ih_lo = t.oh0 * a.stride + r - a.pad, ih_hi = (min(t.oh0 + a.bh, a.OH) - 1) * a.stride + r - a.pad;
-  const int iw_lo = t.ow0 * a.stride + s - a.pad, iw_hi = (min(t.ow0 + a.bw, a.OW) - 1) * a.stride + s - a.pad;
-  return !(ih_hi < 0 || ih_lo >= a.H || iw_hi < 0 || iw_lo >= a.W);
+// Division-free walk over the k-blocks of a tile: f(kb, r, s, cb).  In a_mode 0 the filter taps whose shifted window
+// only sees padding for the whole tile are skipped (row / column tests hoisted out of the channel-block loop).
+template <class F>
+__device__ __forceinline__ void for_each_kb(const ConvArgs& a, const Tile& t, F&& f) {
+  if (a.a_mode != 0) {
+    for (int kb = 0; kb < a.num_kb; ++kb) f(kb, 0, 0, 0);
+    return;
+  }
+  const int oh_last = min(t.oh0 + a.bh, a.OH) - 1, ow_last = min(t.ow0 + a.bw, a.OW) - 1;
+  int kb = 0;
+  for (int r = 0; r < a.R; ++r) {
+    const bool row_ok = !(oh_last * a.stride + r - a.pad < 0 || t.oh0 * a.stride + r - a.pad >= a.H);
+    for (int ss = 0; ss < a.S; ++ss, kb += a.cin_blocks) {
+      if (!row_ok || ow_last * a.stride + ss - a.pad < 0 || t.ow0 * a.stride + ss - a.pad >= a.W) continue;
+      for (int cb = 0; cb < a.cin_blocks; ++cb) f(kb + cb, r, ss, cb);
+    }
+  }
 }
+
 // output pixel owned by A-tile row `row` of tile t
 __device__ __forceinline__ bool decode_row(const ConvArgs& a, const Tile& t, int row, int& q, int& oh, int& ow) {
   if (a.a_mode == 0) {
@@ -183,13 +206,15 @@ __device__ __forceinline__ bool decode_row(const ConvArgs& a, const Tile& t, int
   return true;
 }
 
-template <bool GATHER>
-__device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvArgs& a) {
+template <bool GATHER, int MT, int EPI_WARPS>
+__device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2,
+                                                const ConvArgs& a) {
+  constexpr int GATHER_WARP0 = EPI_WARP0 + EPI_WARPS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t pad_to_1k = ((raw + 1023u) & ~1023u) - raw;
   uint8_t* smem = smem_raw + pad_to_1k;
-  const int stage_bytes = A_TILE_BYTES + a.BN * 128;
+  const int stage_bytes = MT * A_TILE_BYTES + a.BN * 128;
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bars = smem_base + a.stages * stage_bytes;      // full[s], empty[s], tmem_full[2], tmem_empty[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + a.stages * stage_bytes + (2 * a.stages + 4) * 8);
@@ -203,9 +228,10 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmB);
     if (a.a_mode == 0) tma_prefetch_desc(&tmA);
+    if (a.kb2 > 0) tma_prefetch_desc(&tmA2);
     const uint32_t full_count = a.a_mode == 0 ? 1u : 1u + 128u;
     for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), full_count); mbar_init(empty_bar(s), 1u); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1u); mbar_init(tempty_bar(i), EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1u); mbar_init(tempty_bar(i), uint32_t(EPI_WARPS)); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), a.tmem_cols);
@@ -218,94 +244,154 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
     // ================================================================= TMA issuer
     if (lane == 0) {
       const uint32_t a_bytes = a.a_mode == 0 ? uint32_t(a.bn_img * a.bh * a.bw) * 128u : 0u;
-      const uint32_t tx = a_bytes + uint32_t(a.BN) * 128u;
-      int it = 0;
+      int stage = 0, phase = 0;
+      long long w_empty = 0;
+      const long long t_begin = clock64();
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-        const Tile t = decode_tile(a, tile);
-        for (int kb = 0; kb < a.num_kb; ++kb) {
-          if (!kb_active(a, t, kb)) continue;
-          const int s = it % a.stages, ph = (it / a.stages) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1);
-          mbar_arrive_expect_tx(full_bar(s), tx);
-          const uint32_t sa = smem_base + s * stage_bytes;
+        Tile t[MT];
+        int n_sub = 0;
+#pragma unroll
+        for (int u = 0; u < MT; ++u) { t[u] = decode_tile(a, tile, u); if (t[u].mt < a.mtiles) n_sub = u + 1; }
+        const uint32_t tx = a_bytes * n_sub + uint32_t(a.BN) * 128u;
+        const int n_col = t[0].nt * a.BN;
+        for_each_kb(a, t[0], [&](int kb, int r, int ss, int cb) {
+          mbar_wait_timed(empty_bar(stage), phase ^ 1, w_empty, a.stats != nullptr);
+          mbar_arrive_expect_tx(full_bar(stage), tx);
+          const uint32_t sa = smem_base + stage * stage_bytes;
           if (a.a_mode == 0) {
-            const int tap = kb / a.cin_blocks, cb = kb - tap * a.cin_blocks, r = tap / a.S, ss = tap - r * a.S;
-            if (a.stride == 1) {
-              tma_load_4d(sa, &tmA, full_bar(s), cb * 64, t.ow0 + ss - a.pad, t.oh0 + r - a.pad, t.q0);
-            } else {
-              // stride 2: input row 2*oh + v (v = r - pad) = 2*(oh + (v >> 1)) + (v & 1); the tensor map views the
-              // activation as (2*Cin [w parity folded into channels], W/2, 2 [h parity], H/2, P)
-              const int v = r - a.pad, u = ss - a.pad;
-              tma_load_5d(sa, &tmA, full_bar(s), (u & 1) * a.Cin + cb * 64, t.ow0 + (u >> 1), v & 1, t.oh0 + (v >> 1), t.q0);
+#pragma unroll
+            for (int u = 0; u < MT; ++u) {
+              if (u >= n_sub) break;
+              if (a.stride == 1) {
+                tma_load_4d(sa + u * A_TILE_BYTES, &tmA, full_bar(stage), cb * 64, t[u].ow0 + ss - a.pad, t[u].oh0 + r - a.pad, t[u].q0);
+              } else {
+                // stride 2: input row 2*oh + v (v = r - pad) = 2*(oh + (v >> 1)) + (v & 1); the tensor map views the
+                // activation as (2*Cin [w parity folded into channels], W/2, 2 [h parity], H/2, P)
+                const int v = r - a.pad, w = ss - a.pad;
+                tma_load_5d(sa + u * A_TILE_BYTES, &tmA, full_bar(stage), (w & 1) * a.Cin + cb * 64, t[u].ow0 + (w >> 1), v & 1,
+                            t[u].oh0 + (v >> 1), t[u].q0);
+              }
             }
           }
-          tma_load_2d(sa + A_TILE_BYTES, &tmB, full_bar(s), kb * BK, t.nt * a.BN);
-          ++it;
+          tma_load_2d(sa + MT * A_TILE_BYTES, &tmB, full_bar(stage), kb * BK, n_col);
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        });
+        for (int cb = 0; cb < a.kb2; ++cb) {        // fused downsample branch: 1x1 taps of the block input, same output tile
+          mbar_wait_timed(empty_bar(stage), phase ^ 1, w_empty, a.stats != nullptr);
+          mbar_arrive_expect_tx(full_bar(stage), tx);
+          const uint32_t sa = smem_base + stage * stage_bytes;
+#pragma unroll
+          for (int u = 0; u < MT; ++u) {
+            if (u >= n_sub) break;
+            if (a.stride2 == 1) tma_load_4d(sa + u * A_TILE_BYTES, &tmA2, full_bar(stage), cb * 64, t[u].ow0, t[u].oh0, t[u].q0);
+            else tma_load_5d(sa + u * A_TILE_BYTES, &tmA2, full_bar(stage), cb * 64, t[u].ow0, 0, t[u].oh0, t[u].q0);
+          }
+          tma_load_2d(sa + MT * A_TILE_BYTES, &tmB, full_bar(stage), (a.num_kb + cb) * BK, n_col);
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
+      }
+      if (a.stats) {
+        atomicAdd(&a.stats[0], (unsigned long long)w_empty);
+        atomicAdd(&a.stats[1], (unsigned long long)(clock64() - t_begin));
+        atomicAdd(&a.stats[7], 1ull);
       }
     }
   } else if (warp == 1) {
     // ================================================================= MMA issuer
     if (lane == 0) {
-      int it = 0, ti = 0;
+      int stage = 0, phase = 0, ti = 0;
+      const uint64_t desc0 = make_sw128_desc(smem_base);
+      const uint64_t desc_stage = uint64_t(stage_bytes >> 4);      // descriptor address field is in 16-byte units
+      long long w_full = 0, w_tempty = 0;
+      const long long t_begin = clock64();
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
-        const Tile t = decode_tile(a, tile);
+        const Tile t = decode_tile(a, tile, 0);
+        const int n_sub = (MT == 2 && decode_tile(a, tile, 1).mt < a.mtiles) ? 2 : 1;
         const int acc = ti & 1;
-        mbar_wait(tempty_bar(acc), ((ti >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+        mbar_wait_timed(tempty_bar(acc), ((ti >> 1) & 1) ^ 1, w_tempty, a.stats != nullptr);   // epilogue drained this accumulator set
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + uint32_t(acc * a.BN);
-        bool first = true;
-        for (int kb = 0; kb < a.num_kb; ++kb) {
-          if (!kb_active(a, t, kb)) continue;
-          const int s = it % a.stages, ph = (it / a.stages) & 1;
-          mbar_wait(full_bar(s), ph);
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * MT * a.BN);
+        uint32_t accumulate = 0;
+        auto issue_stage = [&]() {
+          mbar_wait_timed(full_bar(stage), phase, w_full, a.stats != nullptr);
           tc_fence_after();
-          const uint32_t sa = smem_base + s * stage_bytes;
-          const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sa + A_TILE_BYTES);
+          const uint64_t da0 = desc0 + uint64_t(stage) * desc_stage, db = da0 + uint64_t(MT * (A_TILE_BYTES >> 4));
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)          // 32 bytes of K per MMA: +2 in the (addr >> 4) field
-            umma_f16(d_tmem, da + 2u * k, db + 2u * k, a.idesc, (!first || k > 0) ? 1u : 0u);
-          first = false;
-          umma_commit(empty_bar(s));
-          ++it;
-        }
+          for (int u = 0; u < MT; ++u) {
+            if (u >= n_sub) break;
+            const uint64_t da = da0 + uint64_t(u * (A_TILE_BYTES >> 4));
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)          // 32 bytes of K per MMA: +2 in the (addr >> 4) field
+              umma_f16(d_tmem + uint32_t(u * a.BN), da + 2u * k, db + 2u * k, a.idesc, k > 0 ? 1u : accumulate);
+          }
+          accumulate = 1;
+          umma_commit(empty_bar(stage));
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        };
+        for_each_kb(a, t, [&](int, int, int, int) { issue_stage(); });
+        for (int cb = 0; cb < a.kb2; ++cb) issue_stage();
         umma_commit(tfull_bar(acc));
+      }
+      if (a.stats) {
+        atomicAdd(&a.stats[2], (unsigned long long)w_full);
+        atomicAdd(&a.stats[3], (unsigned long long)w_tempty);
+        atomicAdd(&a.stats[4], (unsigned long long)(clock64() - t_begin));
       }
     }
   } else if (GATHER && warp >= GATHER_WARP0) {
     // ================================================================= gather producers (a_mode 1/2/3)
     const int row = threadIdx.x - 32 * GATHER_WARP0;      // 0..127 = A-tile row
-    int it = 0;
+    int stage = 0, phase = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
       const Tile t = decode_tile(a, tile);
       int q, oh, ow;
       const bool valid = decode_row(a, t, row, q, oh, ow);
       const int ih0 = oh * a.stride - a.pad, iw0 = ow * a.stride - a.pad;
       const __nv_bfloat16* ximg = a.x + (size_t)q * a.H * a.W * a.Cin;
-      for (int kb = 0; kb < a.num_kb; ++kb, ++it) {
-        const int s = it % a.stages, ph = (it / a.stages) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
-        uint8_t* rowp = smem + s * stage_bytes + row * 128;
+      for (int kb = 0; kb < a.num_kb; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        uint8_t* rowp = smem + stage * stage_bytes + row * 128;
+        if (a.a_mode == 3) {
+          // channel-padded stem: a 16-byte chunk = two horizontally adjacent filter taps x 4 channels.  All 16 loads of
+          // the k-block are issued before any store (clamped addresses + predicated zeroing: no branches in between).
+          uint2 lo[8], hi[8];
+          const int half = a.s_store >> 1;
+          const uint2* xi = reinterpret_cast<const uint2*>(ximg);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          uint4 v = make_uint4(0, 0, 0, 0);
-          const int k = kb * BK + c * 8;
-          if (valid && k < a.K) {
-            if (a.a_mode == 3) {
-              const int pair = k >> 3, half = a.s_store >> 1, r = pair / half, ss = (pair - r * half) * 2;
-              const int ih = ih0 + r, iw = iw0 + ss;
-              if (r < a.R && ih >= 0 && ih < a.H) {
-                const uint2* rowx = reinterpret_cast<const uint2*>(ximg) + (size_t)ih * a.W;
-                if (iw >= 0 && iw < a.W && ss < a.S) { const uint2 u = __ldg(rowx + iw); v.x = u.x; v.y = u.y; }
-                if (iw + 1 >= 0 && iw + 1 < a.W && ss + 1 < a.S) { const uint2 u = __ldg(rowx + iw + 1); v.z = u.x; v.w = u.y; }
-              }
-            } else if (a.a_mode == 1) {
-              const int tap = k / a.Cin, ci = k - tap * a.Cin, r = tap / a.S, ss = tap - r * a.S;
-              const int ih = ih0 + r, iw = iw0 + ss;
-              if (ih >= 0 && ih < a.H && iw >= 0 && iw < a.W)
-                v = __ldg(reinterpret_cast<const uint4*>(ximg + ((size_t)ih * a.W + iw) * a.Cin + ci));
-            } else {
-              uint32_t w4[4] = {0, 0, 0, 0};
+          for (int c = 0; c < 8; ++c) {
+            const int pair = (kb * BK + c * 8) >> 3, r = pair / half, ss = (pair - r * half) * 2;
+            const int ih = ih0 + r, iw = iw0 + ss;
+            const bool okr = valid && r < a.R && ih >= 0 && ih < a.H;
+            const bool ok0 = okr && iw >= 0 && iw < a.W && ss < a.S, ok1 = okr && iw + 1 >= 0 && iw + 1 < a.W && ss + 1 < a.S;
+            const size_t base = (size_t)min(max(ih, 0), a.H - 1) * a.W;
+            lo[c] = __ldg(xi + base + min(max(iw, 0), a.W - 1));
+            hi[c] = __ldg(xi + base + min(max(iw + 1, 0), a.W - 1));
+            if (!ok0) lo[c] = make_uint2(0, 0);
+            if (!ok1) hi[c] = make_uint2(0, 0);
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(rowp + ((c ^ (row & 7)) << 4)) = make_uint4(lo[c].x, lo[c].y, hi[c].x, hi[c].y);
+        } else if (a.a_mode == 1) {
+          uint4 v[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int k = kb * BK + c * 8;
+            const int tap = k / a.Cin, ci = k - tap * a.Cin, r = tap / a.S, ss = tap - r * a.S;
+            const int ih = ih0 + r, iw = iw0 + ss;
+            const bool ok = valid && k < a.K && ih >= 0 && ih < a.H && iw >= 0 && iw < a.W;
+            const size_t off = ((size_t)min(max(ih, 0), a.H - 1) * a.W + min(max(iw, 0), a.W - 1)) * a.Cin + min(ci, a.Cin - 8);
+            v[c] = __ldg(reinterpret_cast<const uint4*>(ximg + off));
+            if (!ok) v[c] = make_uint4(0, 0, 0, 0);
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(rowp + ((c ^ (row & 7)) << 4)) = v[c];
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int k = kb * BK + c * 8;
+            uint32_t w4[4] = {0, 0, 0, 0};
+            if (valid && k < a.K) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 const int kk = k + e;
@@ -318,33 +404,39 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
                   }
                 }
               }
-              v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
             }
+            *reinterpret_cast<uint4*>(rowp + ((c ^ (row & 7)) << 4)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);      // 128B swizzle: chunk ^= row % 8
           }
-          *reinterpret_cast<uint4*>(rowp + ((c ^ (row & 7)) << 4)) = v;      // 128B swizzle: chunk ^= row % 8
         }
         fence_proxy_async();                        // generic-proxy writes -> visible to the tensor core (async proxy)
-        mbar_arrive(full_bar(s));
+        mbar_arrive(full_bar(stage));
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
     // ================================================================= epilogue warps
     const int quarter = warp & 3;                        // TMEM lanes 32*quarter .. +31 (hardware: warp id % 4)
-    const int half = (warp - EPI_WARP0) >> 2;            // which of the two warps of this quarter
+    const int sub_w = (warp - EPI_WARP0) >> 2;           // which of the EPI_WARPS/4 warps of this quarter
+    constexpr int WPQ = EPI_WARPS / 4;
     const int row = quarter * 32 + lane;
     const int ohw = a.OH * a.OW, n_rep = a.rep > 1 ? a.rep : 1;
     int ti = 0;
+    long long w_tfull = 0;
+    const long long t_begin = clock64();
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
-      const Tile t = decode_tile(a, tile);
+      const int acc_i = ti & 1;
+      mbar_wait_timed(tfull_bar(acc_i), (ti >> 1) & 1, w_tfull, a.stats != nullptr);
+      tc_fence_after();
+#pragma unroll 1
+      for (int u = 0; u < MT; ++u) {
+      const Tile t = decode_tile(a, tile, u);
+      if (t.mt >= a.mtiles) break;
       int q, oh, ow;
       const bool valid = decode_row(a, t, row, q, oh, ow);
-      const int acc_i = ti & 1;
-      mbar_wait(tfull_bar(acc_i), (ti >> 1) & 1);
-      tc_fence_after();
-      const uint32_t trow = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc_i * a.BN);
+      const uint32_t trow = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t((acc_i * MT + u) * a.BN);
       const int hw = oh * a.OW + ow;
       const size_t res_off = ((size_t)q * ohw + hw) * a.Cout;
-      for (int j = half; j < a.BN / 16; j += 2) {
+      for (int j = sub_w; j < a.BN / 16; j += WPQ) {
         uint32_t acc[16];
         tmem_ld16(trow + uint32_t(j * 16), acc);       // warp-collective: executed by every lane, valid or not
         tmem_ld_wait();
@@ -420,10 +512,15 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
           }
         }
       }
-      // this warp has finished reading the accumulator: hand it back to the MMA issuer
+      }   // sub-tiles
+      // this warp has finished reading the accumulators: hand them back to the MMA issuer
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc_i));
+    }
+    if (a.stats && warp == EPI_WARP0 && lane == 0) {
+      atomicAdd(&a.stats[5], (unsigned long long)w_tfull);
+      atomicAdd(&a.stats[6], (unsigned long long)(clock64() - t_begin));
     }
   }
 
@@ -432,14 +529,21 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
   if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
 }
 
-// TMA-fed variant: 320 threads, two CTAs per SM (register budget 102); gather variant: 448 threads, one CTA per SM.
-__global__ void __launch_bounds__(THREADS_TMA, 2)
-conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs a) {
-  conv_igemm_body<false>(tmA, tmB, a);
+// TMA-fed variants: MT=1 (320 threads, two CTAs per SM) and MT=2 (576 threads, one CTA per SM); gather variant.
+__global__ void __launch_bounds__(THREADS_TMA1, 2)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmA2, const ConvArgs a) {
+  conv_igemm_body<false, 1, 8>(tmA, tmB, tmA2, a);
+}
+__global__ void __launch_bounds__(THREADS_TMA2, 1)
+conv_igemm_m256_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ CUtensorMap tmA2, const ConvArgs a) {
+  conv_igemm_body<false, 2, 16>(tmA, tmB, tmA2, a);
 }
 __global__ void __launch_bounds__(THREADS_GATHER, 1)
-conv_igemm_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs a) {
-  conv_igemm_body<true>(tmA, tmB, a);
+conv_igemm_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmA2, const ConvArgs a) {
+  conv_igemm_body<true, 1, 8>(tmA, tmB, tmA2, a);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -480,8 +584,8 @@ int conv_layer_finalize(ConvLayer& L) {
   L.bn = conv_pick_bn(L.cout);
   L.cout_pad = (L.cout + L.bn - 1) / L.bn * L.bn;
   if (L.w) {
-    const cuuint64_t dims[2] = {(cuuint64_t)L.kpad, (cuuint64_t)L.cout_pad};
-    const cuuint64_t strides[1] = {(cuuint64_t)L.kpad * 2};
+    const cuuint64_t dims[2] = {(cuuint64_t)(L.kpad + L.k2pad), (cuuint64_t)L.cout_pad};
+    const cuuint64_t strides[1] = {(cuuint64_t)(L.kpad + L.k2pad) * 2};
     const cuuint32_t box[2] = {BK, (cuuint32_t)L.bn};
     int rc = encode_map(reinterpret_cast<CUtensorMap*>(L.tmap_w), L.w, 2, dims, strides, box);
     if (rc) return rc;
@@ -556,15 +660,49 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   } else {
     mtiles = int((M + BM - 1) / BM);
   }
-  const int stage_bytes = A_TILE_BYTES + a.BN * 128;
-  int stages = (100 * 1024) / stage_bytes;
-  stages = stages < 2 ? 2 : (stages > 6 ? 6 : stages);
+  // fused downsample branch (second A source): 1x1 conv of the block input onto the same output tile
+  CUtensorMap tmA2;
+  memset(&tmA2, 0, sizeof(tmA2));
+  if (L.k2pad > 0) {
+    FAV_REQUIRE(mode == 0 && c.x2, "conv: the fused downsample branch needs the TMA path and its input");
+    FAV_REQUIRE((L.cin2 % 64) == 0 && (L.stride2 == 1 || (L.stride2 == 2 && (c.h2 % 2) == 0 && (c.w2 % 2) == 0)),
+                "conv: unsupported downsample geometry");
+    FAV_REQUIRE(conv_out_dim(c.h2, 1, L.stride2, 0) == a.OH && conv_out_dim(c.w2, 1, L.stride2, 0) == a.OW,
+                "conv: downsample branch output does not match the main branch");
+    a.kb2 = L.k2pad / BK; a.stride2 = L.stride2; a.Cin2 = L.cin2;
+    int rc;
+    if (L.stride2 == 1) {
+      const cuuint64_t dims[4] = {(cuuint64_t)L.cin2, (cuuint64_t)c.w2, (cuuint64_t)c.h2, (cuuint64_t)c.p};
+      const cuuint64_t strides[3] = {(cuuint64_t)L.cin2 * 2, (cuuint64_t)c.w2 * L.cin2 * 2, (cuuint64_t)c.h2 * c.w2 * L.cin2 * 2};
+      const cuuint32_t box[4] = {64, (cuuint32_t)a.bw, (cuuint32_t)a.bh, (cuuint32_t)a.bn_img};
+      rc = encode_map(&tmA2, c.x2, 4, dims, strides, box);
+    } else {
+      const cuuint64_t dims[5] = {(cuuint64_t)L.cin2 * 2, (cuuint64_t)c.w2 / 2, 2, (cuuint64_t)c.h2 / 2, (cuuint64_t)c.p};
+      const cuuint64_t strides[4] = {(cuuint64_t)L.cin2 * 4, (cuuint64_t)c.w2 * L.cin2 * 2, (cuuint64_t)c.w2 * L.cin2 * 4,
+                                     (cuuint64_t)c.h2 * c.w2 * L.cin2 * 2};
+      const cuuint32_t box[5] = {64, (cuuint32_t)a.bw, 1, (cuuint32_t)a.bh, (cuuint32_t)a.bn_img};
+      rc = encode_map(&tmA2, c.x2, 5, dims, strides, box);
+    }
+    if (rc) return rc;
+  }
+  a.ntiles = L.cout_pad / a.BN;
+  a.mtiles = mtiles;
+  // M = 256 per CTA when there is enough work to fill the machine twice over with one CTA per SM
+  const int pair_tiles = ((mtiles + 1) / 2) * a.ntiles;
+  static const int env_mt = [] { const char* e = getenv("FAV_FORCE_MT"); return e ? atoi(e) : 0; }();   // tuning aid
+  const int force_mt = c.force_mt ? c.force_mt : env_mt;
+  (void)pair_tiles;   // measured on B200: two CTAs x 128-pixel tiles beat one CTA x 256-pixel tiles on every ResNet-18 layer
+  const int MT = (mode == 0 && force_mt == 2) ? 2 : 1;
+  a.mt_per_tile = MT;
+  a.total_tiles = ((mtiles + MT - 1) / MT) * a.ntiles;
+  const int stage_bytes = MT * A_TILE_BYTES + a.BN * 128;
+  const int ctas_per_sm = (mode == 0 && MT == 1) ? 2 : 1;
+  int stages = ((ctas_per_sm == 2 ? 100 : 200) * 1024) / stage_bytes;
+  stages = stages < 2 ? 2 : (stages > 8 ? 8 : stages);
   a.stages = stages;
   uint32_t cols = 32;
-  while (cols < uint32_t(2 * a.BN)) cols *= 2;           // two accumulators (double-buffered epilogue)
+  while (cols < uint32_t(2 * MT * a.BN)) cols *= 2;       // two accumulator sets (double-buffered epilogue)
   a.tmem_cols = cols;
-  a.ntiles = L.cout_pad / a.BN;
-  a.total_tiles = mtiles * a.ntiles;
   // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128
   a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(a.BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
@@ -573,11 +711,12 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   std::call_once(attr_once, [] {
     attr_err = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(conv_igemm_m256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
       attr_err = cudaFuncSetAttribute(conv_igemm_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   FAV_CUDA_OK(attr_err);
-  const int threads = mode == 0 ? THREADS_TMA : THREADS_GATHER;
-  const int ctas_per_sm = (mode == 0 && cols <= 256) ? 2 : 1;
+  const int threads = mode != 0 ? THREADS_GATHER : (MT == 2 ? THREADS_TMA2 : THREADS_TMA1);
   const int grid = a.total_tiles < ctas_per_sm * ctx->num_sms ? a.total_tiles : ctas_per_sm * ctx->num_sms;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx->timing) {
@@ -588,13 +727,23 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
     }
     e0 = ctx->ev_pool[ctx->ev_used]; e1 = ctx->ev_pool[ctx->ev_used + 1];
     ctx->ev_used += 2;
-    ctx->ev_gflop.push_back(float(2.0 * double(M) * L.r * L.s * L.cin * L.cout * 1e-9));
+    ctx->ev_gflop.push_back(float(2.0 * double(M) * (L.r * L.s * L.cin + L.cin2) * L.cout * 1e-9));
+    if (!ctx->stats_buf) {
+      FAV_CUDA_OK(cudaMalloc(&ctx->stats_buf, 512 * 8 * sizeof(unsigned long long)));
+    }
+    const size_t li = ctx->ev_used / 2 - 1;
+    if (li < 512) {
+      a.stats = reinterpret_cast<unsigned long long*>(ctx->stats_buf) + 8 * li;
+      FAV_CUDA_OK(cudaMemsetAsync(a.stats, 0, 8 * sizeof(unsigned long long), st));
+    }
     FAV_CUDA_OK(cudaEventRecord(e0, st));
   }
-  if (mode == 0)
-    conv_igemm_kernel<<<grid, threads, smem, st>>>(tmA, *reinterpret_cast<const CUtensorMap*>(L.tmap_w), a);
+  if (mode == 0 && MT == 2)
+    conv_igemm_m256_kernel<<<grid, threads, smem, st>>>(tmA, *reinterpret_cast<const CUtensorMap*>(L.tmap_w), tmA2, a);
+  else if (mode == 0)
+    conv_igemm_kernel<<<grid, threads, smem, st>>>(tmA, *reinterpret_cast<const CUtensorMap*>(L.tmap_w), tmA2, a);
   else
-    conv_igemm_gather_kernel<<<grid, threads, smem, st>>>(tmA, *reinterpret_cast<const CUtensorMap*>(L.tmap_w), a);
+    conv_igemm_gather_kernel<<<grid, threads, smem, st>>>(tmA, *reinterpret_cast<const CUtensorMap*>(L.tmap_w), tmA2, a);
   if (e1) FAV_CUDA_OK(cudaEventRecord(e1, st));
   ctx->launches++;
   FAV_CUDA_OK(cudaGetLastError());
@@ -629,7 +778,9 @@ extern "C" int fav_conv2d(fav_handle h, const void* d_x, const void* d_w, const 
   if (rc == FAV_OK) {
     ConvCall c;
     c.L = &L; c.x = d_x; c.y = d_y; c.res = d_res; c.p = p; c.h = height; c.w = width;
-    c.relu = relu; c.out_f32 = out_f32; c.a_mode = a_mode;
+    c.relu = relu; c.out_f32 = out_f32;
+    c.a_mode = a_mode < 0 ? -1 : (a_mode & 0xFF);          // bits 8-9: force the CTA tile height (1 -> 128, 2 -> 256 pixels)
+    c.force_mt = a_mode < 0 ? 0 : ((a_mode >> 8) & 3);
     rc = conv_launch(h, c, st);
   }
   cudaError_t e = cudaStreamSynchronize(st);

@@ -10,6 +10,7 @@ struct ConvLayer {          // device-resident, BN folded
   int cin = 0, cout = 0, r = 0, s = 0, stride = 1, pad = 0;
   int cin_store = 0, s_store = 0;      // stem layout: channels padded to 4, filter-row slots padded to even (0 = as cin / s)
   int k = 0, kpad = 0, cout_pad = 0, bn = 0;
+  int k2pad = 0, cin2 = 0, stride2 = 1;   // fused 1x1 downsample branch: extra K columns [kpad, kpad + k2pad) of w, its Cin and stride
   alignas(64) unsigned char tmap_w[128];   // CUtensorMap for the weights (box 64 x bn, SWIZZLE_128B)
   bool tmap_ok = false;
 };
@@ -19,8 +20,11 @@ struct ConvCall {
   const void* x = nullptr;        // bf16 NHWC [p, h, w, cin]
   void* y = nullptr;              // bf16 / fp32 NHWC [p*rep, oh, ow, cout]
   const void* res = nullptr;      // bf16 NHWC [p, oh, ow, cout] or null
+  const void* x2 = nullptr;       // input of the fused downsample branch, bf16 NHWC [p, h2, w2, cin2]
+  int h2 = 0, w2 = 0;
   int p = 0, h = 0, w = 0;
   int relu = 0, out_f32 = 0;
+  int force_mt = 0;               // 0 auto, 1 / 2: 128- or 256-pixel CTA tiles (a_mode 0 only)
   int a_mode = -1;                // -1 auto, 0 TMA-tiled, 1 vector gather, 2 scalar gather, 3 channel-padded stem gather
   // MC-dropout in the epilogue
   int T = 1;                      // passes; rows of x are pass-images (image = row / T, t = row % T) unless rep > 1

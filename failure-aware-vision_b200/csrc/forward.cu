@@ -10,7 +10,7 @@
 
 namespace fav {
 
-struct BlockDesc { int n_convs; int ds; int conv0; };   // conv0 = index of the block's first conv; ds = index or -1
+struct BlockDesc { int n_convs; int ds; int conv0; bool fused_ds = false; };   // conv0 = index of the block's first conv; ds = index or -1
 
 struct Plan {
   int model_id = 0, num_classes = 0, in_h = 0, in_w = 0;
@@ -181,9 +181,21 @@ extern "C" int fav_load_weights(fav_handle h, const void* blob, size_t nbytes, i
     if (q + 32 + wb + bb > end) { delete pl; set_error("fav_load_weights: truncated weights at conv %d", i); return FAV_E_ARG; }
     recs.push_back({q + 32, q + 32 + wb});
     q += 32 + wb + bb;
-    arena += ((size_t)L.cout_pad * L.kpad * 2 + 255) / 256 * 256 + ((size_t)L.cout_pad * 4 + 255) / 256 * 256;
     pl->convs.push_back(L);
   }
+  // fuse every TMA-able 1x1 downsample conv into the last conv of its block: its weights become extra K columns
+  for (BlockDesc& bd : pl->blocks) {
+    if (bd.ds < 0) continue;
+    const ConvLayer& D = pl->convs[bd.ds];
+    ConvLayer& last = pl->convs[bd.conv0 + bd.n_convs - 1];
+    if (D.r == 1 && D.s == 1 && D.pad == 0 && (D.cin % 64) == 0 && D.cout == last.cout && (D.stride == 1 || D.stride == 2) &&
+        (last.cin % 64) == 0 && last.stride == 1) {
+      last.k2pad = D.kpad; last.cin2 = D.cin; last.stride2 = D.stride;
+      bd.fused_ds = true;
+    }
+  }
+  for (const ConvLayer& L : pl->convs)
+    arena += ((size_t)L.cout_pad * (L.kpad + L.k2pad) * 2 + 255) / 256 * 256 + ((size_t)L.cout_pad * 4 + 255) / 256 * 256;
   FAV_CUDA_OK(cudaSetDevice(h->device));
   cudaError_t e = cudaMalloc(&pl->arena, arena);
   if (e != cudaSuccess) { delete pl; set_error("fav_load_weights: cudaMalloc(%zu) failed: %s", arena, cudaGetErrorString(e)); return FAV_E_CUDA; }
@@ -204,19 +216,36 @@ extern "C" int fav_load_weights(fav_handle h, const void* blob, size_t nbytes, i
               tmp[((size_t)co * L.r + rr) * L.s_store * 4 + ss * 4 + c] = src[(((size_t)co * L.r + rr) * L.s + ss) * L.cin + c];
       e = cudaMemcpy2D(d, (size_t)L.kpad * 2, tmp.data(), (size_t)L.k * 2, (size_t)L.k * 2, L.cout, cudaMemcpyHostToDevice);
     } else {
-      e = cudaMemcpy2D(d, (size_t)L.kpad * 2, recs[i].w, (size_t)L.k * 2, (size_t)L.k * 2, L.cout, cudaMemcpyHostToDevice);
+      e = cudaMemcpy2D(d, (size_t)(L.kpad + L.k2pad) * 2, recs[i].w, (size_t)L.k * 2, (size_t)L.k * 2, L.cout, cudaMemcpyHostToDevice);
     }
     L.w = reinterpret_cast<const __nv_bfloat16*>(d);
-    d += ((size_t)L.cout_pad * L.kpad * 2 + 255) / 256 * 256;
+    d += ((size_t)L.cout_pad * (L.kpad + L.k2pad) * 2 + 255) / 256 * 256;
     if (e == cudaSuccess) e = cudaMemcpy(d, recs[i].b, (size_t)L.cout * 4, cudaMemcpyHostToDevice);
     L.bias = reinterpret_cast<const float*>(d);
     d += ((size_t)L.cout_pad * 4 + 255) / 256 * 256;
-    int rc = e == cudaSuccess ? conv_layer_finalize(L) : FAV_E_CUDA;
-    if (rc) {
-      if (e != cudaSuccess) set_error("fav_load_weights: upload failed: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+      set_error("fav_load_weights: upload failed: %s", cudaGetErrorString(e));
       plan_destroy(pl);
-      return rc;
+      return FAV_E_CUDA;
     }
+  }
+  for (const BlockDesc& bd : pl->blocks) {
+    if (!bd.fused_ds) continue;
+    const ConvLayer& D = pl->convs[bd.ds];
+    ConvLayer& last = pl->convs[bd.conv0 + bd.n_convs - 1];
+    // extra K columns of the last conv <- downsample weights (device to device); bias <- bias + downsample bias
+    e = cudaMemcpy2D(const_cast<__nv_bfloat16*>(last.w) + last.kpad, (size_t)(last.kpad + last.k2pad) * 2, D.w, (size_t)D.kpad * 2,
+                     (size_t)D.kpad * 2, D.cout, cudaMemcpyDeviceToDevice);
+    std::vector<float> b0(last.cout), b1(D.cout);
+    if (e == cudaSuccess) e = cudaMemcpy(b0.data(), last.bias, (size_t)last.cout * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(b1.data(), D.bias, (size_t)D.cout * 4, cudaMemcpyDeviceToHost);
+    for (int i = 0; i < last.cout; ++i) b0[i] += b1[i];
+    if (e == cudaSuccess) e = cudaMemcpy(const_cast<float*>(last.bias), b0.data(), (size_t)last.cout * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { set_error("fav_load_weights: downsample fusion failed: %s", cudaGetErrorString(e)); plan_destroy(pl); return FAV_E_CUDA; }
+  }
+  for (ConvLayer& L : pl->convs) {
+    int rc = conv_layer_finalize(L);
+    if (rc) { plan_destroy(pl); return rc; }
   }
   const ConvLayer& fc = pl->convs.back();
   if (fc.r != 1 || fc.s != 1 || fc.cout != num_classes) { plan_destroy(pl); set_error("fav_load_weights: last record must be the 1x1 fc"); return FAV_E_ARG; }
@@ -268,9 +297,10 @@ extern "C" int fav_forward_mc(fav_handle h, const void* d_x, float* d_logits, in
   const uint32_t k0 = uint32_t(seed), k1 = uint32_t(seed >> 32);
 
   auto run = [&](const ConvLayer& L, const void* x, void* y, const void* res, int P, int hh, int ww, int relu, int drop,
-                 int rep, int layer_id, int out_f32) -> int {
+                 int rep, int layer_id, int out_f32, const void* x2 = nullptr, int h2 = 0, int w2 = 0) -> int {
     ConvCall c;
     c.L = &L; c.x = x; c.y = y; c.res = res; c.p = P; c.h = hh; c.w = ww; c.relu = relu; c.out_f32 = out_f32;
+    c.x2 = x2; c.h2 = h2; c.w2 = w2;
     c.T = T; c.rep = rep; c.drop = drop; c.p_drop = p_drop; c.seed = seed; c.first_image = first_image; c.layer_id = layer_id;
     return conv_launch(h, c, st);
   };
@@ -303,7 +333,7 @@ extern "C" int fav_forward_mc(fav_handle h, const void* d_x, float* d_logits, in
     const BlockDesc& bd = pl.blocks[b];
     const void* ident = X[cur];
     int oh = hh, ow = ww;
-    if (bd.ds >= 0) {
+    if (bd.ds >= 0 && !bd.fused_ds) {
       const ConvLayer& D = pl.convs[bd.ds];
       rc = run(D, X[cur], DS, nullptr, P, hh, ww, 0, 0, 1, 0, 0);
       if (rc) return rc;
@@ -321,7 +351,8 @@ extern "C" int fav_forward_mc(fav_handle h, const void* d_x, float* d_logits, in
         in = tmp[k & 1];
       } else {
         const int rep = (mc && b == 0) ? T : 1;
-        rc = run(L, in, X[cur ^ 1], ident, P, ih, iw, 1, mc ? 1 : 0, rep, int(b), 0);
+        if (bd.fused_ds) rc = run(L, in, X[cur ^ 1], nullptr, P, ih, iw, 1, mc ? 1 : 0, rep, int(b), 0, X[cur], hh, ww);
+        else rc = run(L, in, X[cur ^ 1], ident, P, ih, iw, 1, mc ? 1 : 0, rep, int(b), 0);
         ch = L.cout;
       }
       if (rc) return rc;

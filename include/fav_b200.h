@@ -103,7 +103,8 @@ int fav_reserve(fav_handle h, int max_images, int T);
 int fav_forward_mc(fav_handle h, const void* d_x, float* d_logits, int n, int T, float p_drop,
                    uint64_t seed, uint64_t first_image, void* stream);
 /* single convolution (unit-test / tooling entry): y = act(conv(x, w) + bias [+ res]).
- * x bf16 NHWC [p,h,w,cin]; w bf16 [cout][r][s][cin]; y bf16 (or fp32 if out_f32) NHWC. */
+ * x bf16 NHWC [p,h,w,cin]; w bf16 [cout][r][s][cin]; y bf16 (or fp32 if out_f32) NHWC.
+ * a_mode: -1 auto; low byte 0 TMA / 1 vector gather / 2 scalar gather; bits 8-9 force 128- (1) or 256-pixel (2) CTA tiles. */
 int fav_conv2d(fav_handle h, const void* d_x, const void* d_w, const float* d_bias,
                const void* d_res, void* d_y, int p, int height, int width, int cin, int cout,
                int r, int s, int stride, int pad, int relu, int out_f32, int a_mode,
@@ -161,6 +162,8 @@ int fav_conv_timing_enable(fav_handle h, int on);
 int fav_conv_timing_read(fav_handle h, float* total_ms, int* n_launches);
 /* same, but per launch in launch order: ms[i] and the launch's algorithmic GFLOP (2*M*K*N, padded taps counted). */
 int fav_conv_timing_read_all(fav_handle h, float* ms, float* gflop, int cap, int* n_launches);
+/* tuning aid: per-launch role wait counters (cycles summed over CTAs, 8 per launch; layout in api.cu). */
+int fav_conv_stats_read(fav_handle h, uint64_t* out, int cap_launches, int* n_launches);
 
 #ifdef __cplusplus
 }

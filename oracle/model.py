@@ -132,7 +132,9 @@ def forward(folded, x_nhwc, T=1, p=0.2, seed=0, first_image=0, emulate_bf16=Fals
             if bi == 0 and "b0" in cache:
                 y = cache["b0"]
             else:
-                ident = h if blk["ds"] is None else q(conv(blk["ds"], h, False))
+                # device: the 1x1 downsample branch is fused into the last conv as extra K-blocks of the same fp32
+                # accumulator, so its result is never rounded to bf16 on its own
+                ident = h if blk["ds"] is None else conv(blk["ds"], h, False)
                 y = h
                 for k, ci in enumerate(blk["convs"]):
                     last = k == len(blk["convs"]) - 1

@@ -161,6 +161,7 @@ def test_k2_conv_matches_torch_fp32(fav, clf18, case):
         ref = ref + res.float()
     if relu:
         ref = torch.relu(ref)
+    modes = tuple(modes) + ((0x200, 0x100) if 0 in modes else ())      # also force 256- and 128-pixel CTA tiles
     for mode in modes:
         for out_f32 in (0, 1):
             y = torch.full((p, oh, ow, cout), float("nan"), dtype=torch.float32 if out_f32 else torch.bfloat16, device="cuda")

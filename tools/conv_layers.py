@@ -30,6 +30,9 @@ reps = 5
 acc = None
 for _ in range(reps):
     sw.run_item(x, y, (0, 0))
+    st = (C.c_uint64 * (256 * 8))(); ns = C.c_int()
+    _lib.check(lib.fav_conv_stats_read(h, st, 256, C.byref(ns)), "stats")
+    stats = [list(st[8 * i: 8 * i + 8]) for i in range(ns.value)]
     ms = (C.c_float * 256)(); gf = (C.c_float * 256)(); n = C.c_int()
     _lib.check(lib.fav_conv_timing_read_all(h, ms, gf, 256, C.byref(n)), "read_all")
     row = [(ms[i], gf[i]) for i in range(n.value)]
@@ -40,7 +43,12 @@ tot_gf = sum(a[1] for a in acc)
 print(f"{model} {hw}x{hw} block={block} T={T}: {len(acc)} conv launches, {tot_ms:.3f} ms, {tot_gf / tot_ms:.1f} TFLOP/s nominal")
 for i, (m, g) in enumerate(acc):
     m /= reps
-    print(f"  conv[{i:2d}] {m * 1e3:9.1f} us  {g:9.2f} GFLOP  {g / m if m > 0 else 0:8.1f} TFLOP/s  {100 * m / tot_ms:5.1f}%")
+    s8 = stats[i] if i < len(stats) else [0] * 8
+    nc = max(1, s8[7])
+    pct = lambda a, b: 100.0 * a / b if b else 0.0
+    print(f"  conv[{i:2d}] {m * 1e3:9.1f} us  {g:9.2f} GFLOP  {g / m if m > 0 else 0:8.1f} TFLOP/s  {100 * m / tot_ms:5.1f}%"
+          f"  | ctas {nc:4d} tma: wait-empty {pct(s8[0], s8[1]):4.0f}%  mma: wait-full {pct(s8[2], s8[4]):4.0f}% wait-tmem {pct(s8[3], s8[4]):4.0f}%"
+          f"  epi: wait-acc {pct(s8[5], s8[6]):4.0f}%  cyc/cta {s8[4] / nc:9.0f}")
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(10):
