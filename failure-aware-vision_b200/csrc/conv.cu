@@ -48,6 +48,7 @@ struct ConvArgs {
   uint32_t k0, k1, first_image, drop_stream;
   uint32_t tmem_cols, idesc;
   int kb2, stride2, Cin2;      // fused second source (the block's 1x1 downsample branch): extra k-blocks after the main taps
+  int ablate;                  // tuning aid (env FAV_CONV_ABLATE): 1 skip A loads, 2 skip B loads, 4 skip MMAs, 8 skip epilogue math
   unsigned long long* stats;   // optional per-launch role timing (8 counters), see fav_conv_stats_read
 };
 
@@ -252,13 +253,13 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
         int n_sub = 0;
 #pragma unroll
         for (int u = 0; u < MT; ++u) { t[u] = decode_tile(a, tile, u); if (t[u].mt < a.mtiles) n_sub = u + 1; }
-        const uint32_t tx = a_bytes * n_sub + uint32_t(a.BN) * 128u;
+        const uint32_t tx = ((a.ablate & 1) ? 0u : a_bytes * n_sub) + ((a.ablate & 2) ? 0u : uint32_t(a.BN) * 128u);
         const int n_col = t[0].nt * a.BN;
         for_each_kb(a, t[0], [&](int kb, int r, int ss, int cb) {
           mbar_wait_timed(empty_bar(stage), phase ^ 1, w_empty, a.stats != nullptr);
           mbar_arrive_expect_tx(full_bar(stage), tx);
           const uint32_t sa = smem_base + stage * stage_bytes;
-          if (a.a_mode == 0) {
+          if (a.a_mode == 0 && !(a.ablate & 1)) {
 #pragma unroll
             for (int u = 0; u < MT; ++u) {
               if (u >= n_sub) break;
@@ -273,7 +274,7 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
               }
             }
           }
-          tma_load_2d(sa + MT * A_TILE_BYTES, &tmB, full_bar(stage), kb * BK, n_col);
+          if (!(a.ablate & 2)) tma_load_2d(sa + MT * A_TILE_BYTES, &tmB, full_bar(stage), kb * BK, n_col);
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         });
         for (int cb = 0; cb < a.kb2; ++cb) {        // fused downsample branch: 1x1 taps of the block input, same output tile
@@ -322,7 +323,7 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
             const uint64_t da = da0 + uint64_t(u * (A_TILE_BYTES >> 4));
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)          // 32 bytes of K per MMA: +2 in the (addr >> 4) field
-              umma_f16(d_tmem + uint32_t(u * a.BN), da + 2u * k, db + 2u * k, a.idesc, k > 0 ? 1u : accumulate);
+              if (!(a.ablate & 4)) umma_f16(d_tmem + uint32_t(u * a.BN), da + 2u * k, db + 2u * k, a.idesc, k > 0 ? 1u : accumulate);
           }
           accumulate = 1;
           umma_commit(empty_bar(stage));
@@ -441,7 +442,7 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
         tmem_ld16(trow + uint32_t(j * 16), acc);       // warp-collective: executed by every lane, valid or not
         tmem_ld_wait();
         const int c0 = t.nt * a.BN + j * 16;
-        if (!valid || c0 >= a.Cout) continue;
+        if (!valid || c0 >= a.Cout || (a.ablate & 8)) continue;
         float v[16];
         {
           const float4* bp = reinterpret_cast<const float4*>(a.bias + c0);     // bias is padded to cout_pad
@@ -685,6 +686,8 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
     }
     if (rc) return rc;
   }
+  static const int env_ablate = [] { const char* e = getenv("FAV_CONV_ABLATE"); return e ? atoi(e) : 0; }();
+  a.ablate = env_ablate;
   a.ntiles = L.cout_pad / a.BN;
   a.mtiles = mtiles;
   // M = 256 per CTA when there is enough work to fill the machine twice over with one CTA per SM
@@ -727,7 +730,9 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
     }
     e0 = ctx->ev_pool[ctx->ev_used]; e1 = ctx->ev_pool[ctx->ev_used + 1];
     ctx->ev_used += 2;
-    ctx->ev_gflop.push_back(float(2.0 * double(M) * (L.r * L.s * L.cin + L.cin2) * L.cout * 1e-9));
+    // nominal (stock PyTorch) FLOPs, padded taps counted; a folded 2x2 conv is 4 pixels x 9 taps of the original layer
+    ctx->ev_gflop.push_back(L.fold ? float(2.0 * double(M) * 36.0 * (L.cin / 4) * (L.cout / 4) * 1e-9)
+                                   : float(2.0 * double(M) * (L.r * L.s * L.cin + L.cin2) * L.cout * 1e-9));
     if (!ctx->stats_buf) {
       FAV_CUDA_OK(cudaMalloc(&ctx->stats_buf, 512 * 8 * sizeof(unsigned long long)));
     }

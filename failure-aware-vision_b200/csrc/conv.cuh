@@ -10,6 +10,7 @@ struct ConvLayer {          // device-resident, BN folded
   int cin = 0, cout = 0, r = 0, s = 0, stride = 1, pad = 0;
   int cin_store = 0, s_store = 0;      // stem layout: channels padded to 4, filter-row slots padded to even (0 = as cin / s)
   int k = 0, kpad = 0, cout_pad = 0, bn = 0;
+  int fold = 0;                           // 4: a 3x3/s1/p1 conv on 2x2 images folded into a dense 1x1 GEMM (cin, cout already x4)
   int k2pad = 0, cin2 = 0, stride2 = 1;   // fused 1x1 downsample branch: extra K columns [kpad, kpad + k2pad) of w, its Cin and stride
   alignas(64) unsigned char tmap_w[128];   // CUtensorMap for the weights (box 64 x bn, SWIZZLE_128B)
   bool tmap_ok = false;

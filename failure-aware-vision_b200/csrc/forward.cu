@@ -121,7 +121,7 @@ static void walk_activations(const Plan& pl, int n, int T, F&& f) {
       hh = conv_out_dim(hh, L.r, L.stride, L.pad); ww = conv_out_dim(ww, L.s, L.stride, L.pad);
       const bool last = k == bd.n_convs - 1;
       const long long Pout = (last && b == 0 && T > 1) ? P * T : P;
-      f((size_t)Pout * hh * ww * L.cout * 2);
+      f((size_t)Pout * hh * ww * (L.cout / (L.fold ? L.fold : 1)) * 2);
     }
     if (bd.ds >= 0) f((size_t)P * hh * ww * pl.convs[bd.ds].cout * 2);
     if (b == 0 && T > 1) P *= T;
@@ -194,6 +194,27 @@ extern "C" int fav_load_weights(fav_handle h, const void* blob, size_t nbytes, i
       bd.fused_ds = true;
     }
   }
+  // 3x3 / stride 1 / pad 1 convs whose input is 2x2: every output pixel sees every input pixel through exactly one tap,
+  // so the conv is a dense GEMM [P, 4*Cin] x [4*Cin, 4*Cout] on the NHWC image itself (no im2col redundancy, no padding MACs)
+  std::vector<int> fold_src(n_convs, 0);
+  {
+    const ConvLayer& stem0 = pl->convs[0];
+    int gh = conv_out_dim(in_h, stem0.r, stem0.stride, stem0.pad), gw = conv_out_dim(in_w, stem0.s, stem0.stride, stem0.pad);
+    gh = conv_out_dim(gh, 3, 2, 1); gw = conv_out_dim(gw, 3, 2, 1);
+    for (BlockDesc& bd : pl->blocks) {
+      for (int k = 0; k < bd.n_convs; ++k) {
+        ConvLayer& L = pl->convs[bd.conv0 + k];
+        if (gh == 2 && gw == 2 && L.r == 3 && L.s == 3 && L.stride == 1 && L.pad == 1 && L.k2pad == 0 && (L.cin % 16) == 0 &&
+            (L.cout % 16) == 0) {
+          fold_src[bd.conv0 + k] = 1;
+          L.fold = 4; L.cin *= 4; L.cout *= 4; L.r = 1; L.s = 1; L.pad = 0;
+          conv_layer_finalize(L);
+        } else {
+          gh = conv_out_dim(gh, L.r, L.stride, L.pad); gw = conv_out_dim(gw, L.s, L.stride, L.pad);
+        }
+      }
+    }
+  }
   for (const ConvLayer& L : pl->convs)
     arena += ((size_t)L.cout_pad * (L.kpad + L.k2pad) * 2 + 255) / 256 * 256 + ((size_t)L.cout_pad * 4 + 255) / 256 * 256;
   FAV_CUDA_OK(cudaSetDevice(h->device));
@@ -205,7 +226,19 @@ extern "C" int fav_load_weights(fav_handle h, const void* blob, size_t nbytes, i
   uint8_t* d = reinterpret_cast<uint8_t*>(pl->arena);
   for (int i = 0; i < n_convs; ++i) {
     ConvLayer& L = pl->convs[i];
-    if (L.cin_store) {
+    if (fold_src[i]) {
+      // W2[(po*cout0 + co)][(pi*cin0 + ci)] = W[co][yi - yo + 1][xi - xo + 1][ci]   (po = yo*2 + xo, pi = yi*2 + xi)
+      const int cin0 = L.cin / 4, cout0 = L.cout / 4;
+      std::vector<uint16_t> tmp((size_t)L.cout * L.k);
+      const uint16_t* src = reinterpret_cast<const uint16_t*>(recs[i].w);
+      for (int po = 0; po < 4; ++po)
+        for (int co = 0; co < cout0; ++co)
+          for (int pi = 0; pi < 4; ++pi) {
+            const int rr = (pi >> 1) - (po >> 1) + 1, ss = (pi & 1) - (po & 1) + 1;
+            memcpy(&tmp[((size_t)po * cout0 + co) * L.k + (size_t)pi * cin0], &src[(((size_t)co * 3 + rr) * 3 + ss) * cin0], (size_t)cin0 * 2);
+          }
+      e = cudaMemcpy2D(d, (size_t)L.kpad * 2, tmp.data(), (size_t)L.k * 2, (size_t)L.k * 2, L.cout, cudaMemcpyHostToDevice);
+    } else if (L.cin_store) {
       // [cout][r][s][3] -> [cout][r][s_store][4], zero filled
       std::vector<uint16_t> tmp((size_t)L.cout * L.k, 0);
       const uint16_t* src = reinterpret_cast<const uint16_t*>(recs[i].w);
@@ -220,7 +253,15 @@ extern "C" int fav_load_weights(fav_handle h, const void* blob, size_t nbytes, i
     }
     L.w = reinterpret_cast<const __nv_bfloat16*>(d);
     d += ((size_t)L.cout_pad * (L.kpad + L.k2pad) * 2 + 255) / 256 * 256;
-    if (e == cudaSuccess) e = cudaMemcpy(d, recs[i].b, (size_t)L.cout * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+      if (fold_src[i]) {
+        const int cout0 = L.cout / 4;
+        for (int po = 0; po < 4 && e == cudaSuccess; ++po)
+          e = cudaMemcpy(d + (size_t)po * cout0 * 4, recs[i].b, (size_t)cout0 * 4, cudaMemcpyHostToDevice);
+      } else {
+        e = cudaMemcpy(d, recs[i].b, (size_t)L.cout * 4, cudaMemcpyHostToDevice);
+      }
+    }
     L.bias = reinterpret_cast<const float*>(d);
     d += ((size_t)L.cout_pad * 4 + 255) / 256 * 256;
     if (e != cudaSuccess) {
@@ -346,14 +387,15 @@ extern "C" int fav_forward_mc(fav_handle h, const void* d_x, float* d_logits, in
       const ConvLayer& L = pl.convs[bd.conv0 + k];
       const bool last = k == bd.n_convs - 1;
       oh = conv_out_dim(ih, L.r, L.stride, L.pad); ow = conv_out_dim(iw, L.s, L.stride, L.pad);
+      const int ch_ = L.fold ? 1 : ih, cw_ = L.fold ? 1 : iw;      // folded: the whole 2x2 image is one GEMM row
       if (!last) {
-        rc = run(L, in, tmp[k & 1], nullptr, P, ih, iw, 1, 0, 1, 0, 0);
+        rc = run(L, in, tmp[k & 1], nullptr, P, ch_, cw_, 1, 0, 1, 0, 0);
         in = tmp[k & 1];
       } else {
         const int rep = (mc && b == 0) ? T : 1;
         if (bd.fused_ds) rc = run(L, in, X[cur ^ 1], nullptr, P, ih, iw, 1, mc ? 1 : 0, rep, int(b), 0, X[cur], hh, ww);
-        else rc = run(L, in, X[cur ^ 1], ident, P, ih, iw, 1, mc ? 1 : 0, rep, int(b), 0);
-        ch = L.cout;
+        else rc = run(L, in, X[cur ^ 1], ident, P, ch_, cw_, 1, mc ? 1 : 0, rep, int(b), 0);
+        ch = L.cout / (L.fold ? L.fold : 1);
       }
       if (rc) return rc;
       ih = oh; iw = ow;
