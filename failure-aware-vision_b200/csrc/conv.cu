@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <mutex>
 #include "conv.cuh"
+#include "tc_ptx.cuh"
 
 namespace fav {
 
@@ -51,99 +52,6 @@ struct ConvArgs {
   int ablate;                  // tuning aid (env FAV_CONV_ABLATE): 1 skip A loads, 2 skip B loads, 4 skip MMAs, 8 skip epilogue math
   unsigned long long* stats;   // optional per-launch role timing (8 counters), see fav_conv_stats_read
 };
-
-// ------------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-// bounded wait: a protocol bug traps (sticky CUDA error) instead of hanging the GPU box
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("fav conv: mbarrier timeout block (%d,%d) thread %d bar %u parity %u\n", blockIdx.x, blockIdx.y,
-             threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, long long& acc, bool on) {
-  if (on) { const long long c0 = clock64(); mbar_wait(bar, parity); acc += clock64() - c0; }
-  else mbar_wait(bar, parity);
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_prefetch_desc(const void* tm) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tm, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 covers bf16 inputs with fp32 accumulation
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"): 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
 
 // ------------------------------------------------------------------------------------------ the kernel
 // Persistent, warp-specialised: each CTA walks tiles (tile = blockIdx.x + i * gridDim.x; N-tile fastest so CTAs
@@ -242,8 +150,8 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ================================================================= TMA issuer
-    if (lane == 0) {
+    // ================================================================= TMA issuer (warp converged, one elected lane issues)
+    {
       const uint32_t a_bytes = a.a_mode == 0 ? uint32_t(a.bn_img * a.bh * a.bw) * 128u : 0u;
       int stage = 0, phase = 0;
       long long w_empty = 0;
@@ -257,8 +165,9 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
         const int n_col = t[0].nt * a.BN;
         for_each_kb(a, t[0], [&](int kb, int r, int ss, int cb) {
           mbar_wait_timed(empty_bar(stage), phase ^ 1, w_empty, a.stats != nullptr);
-          mbar_arrive_expect_tx(full_bar(stage), tx);
           const uint32_t sa = smem_base + stage * stage_bytes;
+          if (elect_one()) {
+          mbar_arrive_expect_tx(full_bar(stage), tx);
           if (a.a_mode == 0 && !(a.ablate & 1)) {
 #pragma unroll
             for (int u = 0; u < MT; ++u) {
@@ -275,12 +184,15 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
             }
           }
           if (!(a.ablate & 2)) tma_load_2d(sa + MT * A_TILE_BYTES, &tmB, full_bar(stage), kb * BK, n_col);
+          }
+          __syncwarp();
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         });
         for (int cb = 0; cb < a.kb2; ++cb) {        // fused downsample branch: 1x1 taps of the block input, same output tile
           mbar_wait_timed(empty_bar(stage), phase ^ 1, w_empty, a.stats != nullptr);
-          mbar_arrive_expect_tx(full_bar(stage), tx);
           const uint32_t sa = smem_base + stage * stage_bytes;
+          if (elect_one()) {
+          mbar_arrive_expect_tx(full_bar(stage), tx);
 #pragma unroll
           for (int u = 0; u < MT; ++u) {
             if (u >= n_sub) break;
@@ -288,18 +200,20 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
             else tma_load_5d(sa + u * A_TILE_BYTES, &tmA2, full_bar(stage), cb * 64, t[u].ow0, 0, t[u].oh0, t[u].q0);
           }
           tma_load_2d(sa + MT * A_TILE_BYTES, &tmB, full_bar(stage), (a.num_kb + cb) * BK, n_col);
+          }
+          __syncwarp();
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
       }
-      if (a.stats) {
+      if (a.stats && lane == 0) {
         atomicAdd(&a.stats[0], (unsigned long long)w_empty);
         atomicAdd(&a.stats[1], (unsigned long long)(clock64() - t_begin));
         atomicAdd(&a.stats[7], 1ull);
       }
     }
   } else if (warp == 1) {
-    // ================================================================= MMA issuer
-    if (lane == 0) {
+    // ================================================================= MMA issuer (warp converged, one elected lane issues)
+    {
       int stage = 0, phase = 0, ti = 0;
       const uint64_t desc0 = make_sw128_desc(smem_base);
       const uint64_t desc_stage = uint64_t(stage_bytes >> 4);      // descriptor address field is in 16-byte units
@@ -317,6 +231,7 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
           mbar_wait_timed(full_bar(stage), phase, w_full, a.stats != nullptr);
           tc_fence_after();
           const uint64_t da0 = desc0 + uint64_t(stage) * desc_stage, db = da0 + uint64_t(MT * (A_TILE_BYTES >> 4));
+          if (elect_one()) {
 #pragma unroll
           for (int u = 0; u < MT; ++u) {
             if (u >= n_sub) break;
@@ -325,15 +240,18 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
             for (int k = 0; k < BK / 16; ++k)          // 32 bytes of K per MMA: +2 in the (addr >> 4) field
               if (!(a.ablate & 4)) umma_f16(d_tmem + uint32_t(u * a.BN), da + 2u * k, db + 2u * k, a.idesc, k > 0 ? 1u : accumulate);
           }
-          accumulate = 1;
           umma_commit(empty_bar(stage));
+          }
+          __syncwarp();
+          accumulate = 1;
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         };
         for_each_kb(a, t, [&](int, int, int, int) { issue_stage(); });
         for (int cb = 0; cb < a.kb2; ++cb) issue_stage();
-        umma_commit(tfull_bar(acc));
+        if (elect_one()) umma_commit(tfull_bar(acc));
+        __syncwarp();
       }
-      if (a.stats) {
+      if (a.stats && lane == 0) {
         atomicAdd(&a.stats[2], (unsigned long long)w_full);
         atomicAdd(&a.stats[3], (unsigned long long)w_tempty);
         atomicAdd(&a.stats[4], (unsigned long long)(clock64() - t_begin));
@@ -437,70 +355,85 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
       const uint32_t trow = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t((acc_i * MT + u) * a.BN);
       const int hw = oh * a.OW + ow;
       const size_t res_off = ((size_t)q * ohw + hw) * a.Cout;
+      const bool vec_io = (a.Cout & 7) == 0;
+      const int n_img = a.rep > 1 ? q : q / a.T;
+      const int tt0 = a.rep > 1 ? 0 : q - n_img * a.T;
+      // dropout keep-mask of the 16 channels starting at c0 (bit i = channel c0 + i kept); independent of the accumulator
+      auto keep_mask = [&](int c0, int tt) -> uint32_t {
+        const uint32_t e8 = uint32_t((size_t)hw * a.Cout + c0) >> 3;
+        const uint4 ra = philox4x32_10(e8, a.first_image + uint32_t(n_img), uint32_t(tt), a.drop_stream, a.k0, a.k1);
+        const uint4 rb = philox4x32_10(e8 + 1, a.first_image + uint32_t(n_img), uint32_t(tt), a.drop_stream, a.k0, a.k1);
+        const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+        uint32_t m = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          m |= ((rw[i] & 0xFFFFu) >= a.drop_thr16 ? 1u : 0u) << (2 * i);
+          m |= ((rw[i] >> 16) >= a.drop_thr16 ? 1u : 0u) << (2 * i + 1);
+        }
+        return m;
+      };
+      // residual of chunk j (two 16-byte vectors), prefetched one chunk ahead so its L2 latency overlaps the previous chunk
+      auto load_res = [&](int j, uint4& r0, uint4& r1) {
+        r0 = make_uint4(0, 0, 0, 0); r1 = r0;
+        const int c0 = t.nt * a.BN + j * 16;
+        if (a.res && vec_io && valid && j < a.BN / 16 && c0 < a.Cout) {
+          const uint4* rp = reinterpret_cast<const uint4*>(a.res + res_off + c0);
+          r0 = __ldg(rp);
+          if (c0 + 8 < a.Cout) r1 = __ldg(rp + 1);
+        }
+      };
+      uint4 rn0, rn1;
+      load_res(sub_w, rn0, rn1);
       for (int j = sub_w; j < a.BN / 16; j += WPQ) {
+        const int c0 = t.nt * a.BN + j * 16;
+        const uint4 rv0 = rn0, rv1 = rn1;
+        load_res(j + WPQ, rn0, rn1);
+        uint32_t mask = 0xFFFFu;
+        if (a.drop && valid && c0 < a.Cout) mask = keep_mask(c0, tt0);
         uint32_t acc[16];
         tmem_ld16(trow + uint32_t(j * 16), acc);       // warp-collective: executed by every lane, valid or not
         tmem_ld_wait();
-        const int c0 = t.nt * a.BN + j * 16;
         if (!valid || c0 >= a.Cout || (a.ablate & 8)) continue;
         float v[16];
         {
           const float4* bp = reinterpret_cast<const float4*>(a.bias + c0);     // bias is padded to cout_pad
+          const uint32_t rw[8] = {rv0.x, rv0.y, rv0.z, rv0.w, rv1.x, rv1.y, rv1.z, rv1.w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 b = __ldg(bp + i);
-            v[4 * i] = __uint_as_float(acc[4 * i]) + b.x; v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + b.y;
-            v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b.z; v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b.w;
+            v[4 * i] = __uint_as_float(acc[4 * i]) + b.x + bf16_lo(rw[2 * i]);
+            v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + b.y + bf16_hi(rw[2 * i]);
+            v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b.z + bf16_lo(rw[2 * i + 1]);
+            v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b.w + bf16_hi(rw[2 * i + 1]);
           }
         }
-        if (a.res) {
-          if ((a.Cout & 7) == 0) {
-            const uint4* rp = reinterpret_cast<const uint4*>(a.res + res_off + c0);
+        if (a.res && !vec_io) {
 #pragma unroll
-            for (int hseg = 0; hseg < 2; ++hseg) {
-              if (c0 + 8 * hseg >= a.Cout) break;
-              const uint4 rv = __ldg(rp + hseg);
-              const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) { v[8 * hseg + 2 * i] += bf16_lo(rw[i]); v[8 * hseg + 2 * i + 1] += bf16_hi(rw[i]); }
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (c0 + i < a.Cout) v[i] += __bfloat162float(a.res[res_off + c0 + i]);
-          }
+          for (int i = 0; i < 16; ++i)
+            if (c0 + i < a.Cout) v[i] += __bfloat162float(a.res[res_off + c0 + i]);
         }
         if (a.relu) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
         }
+        if (a.drop) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= a.drop_scale;
+        }
         for (int rp = 0; rp < n_rep; ++rp) {
           const int p_out = a.rep > 1 ? q * a.rep + rp : q;
           const size_t off = ((size_t)p_out * ohw + hw) * a.Cout + c0;
+          const uint32_t next_mask = (a.drop && rp + 1 < n_rep) ? keep_mask(c0, rp + 1) : 0u;   // overlaps this replica's stores
           float o[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = v[i];
-          if (a.drop) {
-            const int n_img = a.rep > 1 ? q : q / a.T;
-            const int tt = a.rep > 1 ? rp : q - n_img * a.T;
-            const uint32_t e8 = uint32_t((size_t)hw * a.Cout + c0) >> 3;
-#pragma unroll
-            for (int hseg = 0; hseg < 2; ++hseg) {
-              const uint4 r = philox4x32_10(e8 + hseg, a.first_image + uint32_t(n_img), uint32_t(tt), a.drop_stream, a.k0, a.k1);
-              const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                o[8 * hseg + 2 * i] = (rw[i] & 0xFFFFu) >= a.drop_thr16 ? o[8 * hseg + 2 * i] * a.drop_scale : 0.f;
-                o[8 * hseg + 2 * i + 1] = (rw[i] >> 16) >= a.drop_thr16 ? o[8 * hseg + 2 * i + 1] * a.drop_scale : 0.f;
-              }
-            }
-          }
+          for (int i = 0; i < 16; ++i) o[i] = ((mask >> i) & 1u) ? v[i] : 0.f;
+          mask = next_mask;
           if (a.out_f32) {
             float* yp = reinterpret_cast<float*>(a.y) + off;
 #pragma unroll
             for (int i = 0; i < 16; ++i)
               if (c0 + i < a.Cout) yp[i] = o[i];
-          } else if ((a.Cout & 7) == 0) {
+          } else if (vec_io) {
             uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + off);
             yp[0] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
             if (c0 + 8 < a.Cout)
@@ -564,8 +497,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                      const cuuint32_t* box) {
+int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+               const cuuint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return FAV_E_CUDA; }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -573,6 +506,31 @@ static int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint6
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", int(r), rank); return FAV_E_CUDA; }
+  return FAV_OK;
+}
+
+// optional per-launch timing (bench roofline / tuning): records the start event, returns the stop event to record after
+// the launch and a zeroed 8-counter stats slot for the kernel's role timers
+int conv_timing_begin(Ctx* ctx, cudaStream_t st, float gflop, cudaEvent_t* stop, unsigned long long** stats) {
+  *stop = nullptr;
+  *stats = nullptr;
+  if (!ctx->timing) return FAV_OK;
+  while (ctx->ev_pool.size() < ctx->ev_used + 2) {
+    cudaEvent_t e;
+    FAV_CUDA_OK(cudaEventCreate(&e));
+    ctx->ev_pool.push_back(e);
+  }
+  cudaEvent_t e0 = ctx->ev_pool[ctx->ev_used];
+  *stop = ctx->ev_pool[ctx->ev_used + 1];
+  ctx->ev_used += 2;
+  ctx->ev_gflop.push_back(gflop);
+  if (!ctx->stats_buf) FAV_CUDA_OK(cudaMalloc(&ctx->stats_buf, 512 * 8 * sizeof(unsigned long long)));
+  const size_t li = ctx->ev_used / 2 - 1;
+  if (li < 512) {
+    *stats = reinterpret_cast<unsigned long long*>(ctx->stats_buf) + 8 * li;
+    FAV_CUDA_OK(cudaMemsetAsync(*stats, 0, 8 * sizeof(unsigned long long), st));
+  }
+  FAV_CUDA_OK(cudaEventRecord(e0, st));
   return FAV_OK;
 }
 
@@ -599,6 +557,8 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   const ConvLayer& L = *c.L;
   FAV_REQUIRE(L.tmap_ok, "conv: layer not finalized");
   FAV_REQUIRE(c.p > 0 && c.h > 0 && c.w > 0, "conv: bad shape p=%d h=%d w=%d", c.p, c.h, c.w);
+  if (conv_flat_applicable(c)) return conv_flat_launch(ctx, c, st);
+  FAV_REQUIRE(c.a_mode != 4, "conv: a_mode 4 (flat-padded 3x3) needs 3x3/s1/p1, Cin = Cout = 64 and (H+1)(W+1) <= 256");
   ConvArgs a{};
   a.x = reinterpret_cast<const __nv_bfloat16*>(c.x); a.y = c.y; a.bias = L.bias;
   a.res = reinterpret_cast<const __nv_bfloat16*>(c.res);
@@ -721,27 +681,12 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   FAV_CUDA_OK(attr_err);
   const int threads = mode != 0 ? THREADS_GATHER : (MT == 2 ? THREADS_TMA2 : THREADS_TMA1);
   const int grid = a.total_tiles < ctas_per_sm * ctx->num_sms ? a.total_tiles : ctas_per_sm * ctx->num_sms;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (ctx->timing) {
-    while (ctx->ev_pool.size() < ctx->ev_used + 2) {
-      cudaEvent_t e;
-      FAV_CUDA_OK(cudaEventCreate(&e));
-      ctx->ev_pool.push_back(e);
-    }
-    e0 = ctx->ev_pool[ctx->ev_used]; e1 = ctx->ev_pool[ctx->ev_used + 1];
-    ctx->ev_used += 2;
-    // nominal (stock PyTorch) FLOPs, padded taps counted; a folded 2x2 conv is 4 pixels x 9 taps of the original layer
-    ctx->ev_gflop.push_back(L.fold ? float(2.0 * double(M) * 36.0 * (L.cin / 4) * (L.cout / 4) * 1e-9)
-                                   : float(2.0 * double(M) * (L.r * L.s * L.cin + L.cin2) * L.cout * 1e-9));
-    if (!ctx->stats_buf) {
-      FAV_CUDA_OK(cudaMalloc(&ctx->stats_buf, 512 * 8 * sizeof(unsigned long long)));
-    }
-    const size_t li = ctx->ev_used / 2 - 1;
-    if (li < 512) {
-      a.stats = reinterpret_cast<unsigned long long*>(ctx->stats_buf) + 8 * li;
-      FAV_CUDA_OK(cudaMemsetAsync(a.stats, 0, 8 * sizeof(unsigned long long), st));
-    }
-    FAV_CUDA_OK(cudaEventRecord(e0, st));
+  cudaEvent_t e1 = nullptr;
+  {
+    const float gf = L.fold ? float(2.0 * double(M) * 36.0 * (L.cin / 4) * (L.cout / 4) * 1e-9)   // nominal (stock PyTorch) FLOPs
+                            : float(2.0 * double(M) * (L.r * L.s * L.cin + L.cin2) * L.cout * 1e-9);
+    int rc = conv_timing_begin(ctx, st, gf, &e1, &a.stats);
+    if (rc) return rc;
   }
   if (mode == 0 && MT == 2)
     conv_igemm_m256_kernel<<<grid, threads, smem, st>>>(tmA, *reinterpret_cast<const CUtensorMap*>(L.tmap_w), tmA2, a);

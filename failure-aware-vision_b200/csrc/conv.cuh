@@ -26,7 +26,8 @@ struct ConvCall {
   int p = 0, h = 0, w = 0;
   int relu = 0, out_f32 = 0;
   int force_mt = 0;               // 0 auto, 1 / 2: 128- or 256-pixel CTA tiles (a_mode 0 only)
-  int a_mode = -1;                // -1 auto, 0 TMA-tiled, 1 vector gather, 2 scalar gather, 3 channel-padded stem gather
+  int a_mode = -1;                // -1 auto, 0 TMA-tiled, 1 vector gather, 2 scalar gather, 3 channel-padded stem gather,
+                                  // 4 flat-padded resident 3x3 (conv_flat.cu)
   // MC-dropout in the epilogue
   int T = 1;                      // passes; rows of x are pass-images (image = row / T, t = row % T) unless rep > 1
   int rep = 1;                    // rep == T: x holds plain images, each output row is written T times with mask t
@@ -41,5 +42,10 @@ int conv_pick_bn(int cout);
 // fills k/kpad/cout_pad/bn and encodes the weight tensor map (weights must already be on the device)
 int conv_layer_finalize(ConvLayer& L);
 int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st);
+int conv_timing_begin(Ctx* ctx, cudaStream_t st, float gflop, cudaEvent_t* stop, unsigned long long** stats);
+// conv_flat.cu: 3x3 / stride 1 / pad 1, Cin = Cout = 64 on small images: activations resident in shared memory as a
+// flat zero-padded pixel list, weights resident, filter taps = shifted UMMA descriptors
+bool conv_flat_applicable(const ConvCall& c);
+int conv_flat_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st);
 
 }  // namespace fav
