@@ -58,11 +58,14 @@ __device__ __forceinline__ float u32_to_uniform(uint32_t x) {
 
 // Box-Muller: two u32 -> (r cos th, r sin th)
 __device__ __forceinline__ float2 box_muller(uint32_t xa, uint32_t xb) {
+  // MUFU-based fast math (abs error ~1e-6, far inside the 1e-3 parity bar): r = sqrt(-2 ln u1) and the angle is
+  // evaluated on (-pi, pi] where __sinf / __cosf are most accurate, using cos(t + pi) = -cos t, sin(t + pi) = -sin t
   const float u1 = u32_to_uniform(xa), u2 = u32_to_uniform(xb);
-  const float r = sqrtf(-2.0f * logf(u1));
-  float s, c;
-  sincosf(6.283185307179586f * u2, &s, &c);
-  return make_float2(r * c, r * s);
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
+  r = -r;
+  const float t = fmaf(6.283185307179586f, u2, -3.141592653589793f);
+  return make_float2(r * __cosf(t), r * __sinf(t));
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -24,7 +24,7 @@ struct PointwiseArgs {
   uint32_t stream;            // Philox c3
   float f0, f1;               // corruption constants
   uint32_t u0, u1;            // integer constants (thresholds / table width)
-  const void* table;          // shot: int32 kmin[256] then uint32 thr[256][width]
+  const void* table;          // shot: int32 kmin[256], uint32 thr[256][width], uint16 jump[256][256]
   const void* scratch;        // contrast: uint64 sums[n][3]; fog: float stats[n][4] + maps
   int hw, width, mapsize;     // fog geometry
   size_t map_offset;          // bytes from scratch to the plasma maps
@@ -32,7 +32,14 @@ struct PointwiseArgs {
   unsigned flags;
 };
 
-__device__ __forceinline__ float u8f(uint32_t b) { return __fdiv_rn(float(b), 255.0f); }
+// b / 255 for an integer b in [0,255], correctly rounded (== __fdiv_rn(b, 255)) in three FMA-pipe instructions:
+// q = b*r, residual e = fma(-q, 255, b), q' = fma(e, r, q).  Verified exhaustively for all 256 inputs (tests/test_host.py).
+__device__ __forceinline__ float div255(float b) {
+  const float r = 0.003921568859368563f;      // RN(1/255)
+  const float q = __fmul_rn(b, r);
+  return __fmaf_rn(__fmaf_rn(-q, 255.0f, b), r, q);
+}
+__device__ __forceinline__ float u8f(uint32_t b) { return div255(float(b)); }
 
 template <int MODE>
 __global__ void __launch_bounds__(256) k1_pointwise(const PointwiseArgs a) {
@@ -80,15 +87,16 @@ __global__ void __launch_bounds__(256) k1_pointwise(const PointwiseArgs a) {
       for (int j = 0; j < 12; ++j) {
         const uint4 r = philox4x32_10(uint32_t(e0 / 4 + j), gimg, 0u, a.stream, a.k0, a.k1);
         const float2 za = box_muller(r.x, r.y), zb = box_muller(r.z, r.w);
-        x[4 * j + 0] = __fdiv_rn(x[4 * j + 0], 255.0f) + a.f0 * za.x;
-        x[4 * j + 1] = __fdiv_rn(x[4 * j + 1], 255.0f) + a.f0 * za.y;
-        x[4 * j + 2] = __fdiv_rn(x[4 * j + 2], 255.0f) + a.f0 * zb.x;
-        x[4 * j + 3] = __fdiv_rn(x[4 * j + 3], 255.0f) + a.f0 * zb.y;
+        x[4 * j + 0] = div255(x[4 * j + 0]) + a.f0 * za.x;
+        x[4 * j + 1] = div255(x[4 * j + 1]) + a.f0 * za.y;
+        x[4 * j + 2] = div255(x[4 * j + 2]) + a.f0 * zb.x;
+        x[4 * j + 3] = div255(x[4 * j + 3]) + a.f0 * zb.y;
       }
     } else if (MODE == PW_SHOT) {
       const int* kmin = reinterpret_cast<const int*>(a.table);
       const uint32_t* thr = reinterpret_cast<const uint32_t*>(a.table) + 256;
       const int width = int(a.u0);
+      const unsigned short* jump = reinterpret_cast<const unsigned short*>(thr + 256 * (size_t)width);
 #pragma unroll
       for (int j = 0; j < 12; ++j) {
         const uint4 r = philox4x32_10(uint32_t(e0 / 4 + j), gimg, 0u, a.stream, a.k0, a.k1);
@@ -97,10 +105,18 @@ __global__ void __launch_bounds__(256) k1_pointwise(const PointwiseArgs a) {
         for (int q = 0; q < 4; ++q) {
           const int v = int(x[4 * j + q]);
           const uint32_t* row = thr + (size_t)v * width;
-          int lo = 0, hi = width;                       // first index with row[idx] > u
-          while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (__ldg(row + mid) <= rr[q]) lo = mid + 1; else hi = mid;
+          // first index with row[idx] > u: start from the per-(value, top byte of u) lower bound, then probe linearly
+          int lo;
+          if (width <= 160) {
+            lo = int(__ldg(jump + v * 256 + (rr[q] >> 24)));
+            while (lo < width && __ldg(row + lo) <= rr[q]) ++lo;
+          } else {                                       // large lambda: the tables spill L1, plain binary search does fewer probes
+            lo = 0;
+            int hi = width;
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              if (__ldg(row + mid) <= rr[q]) lo = mid + 1; else hi = mid;
+            }
           }
           x[4 * j + q] = __fdiv_rn(float(__ldg(kmin + v) + lo), a.f0);
         }
@@ -112,7 +128,7 @@ __global__ void __launch_bounds__(256) k1_pointwise(const PointwiseArgs a) {
         const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          float v = __fdiv_rn(x[4 * j + q], 255.0f);
+          float v = div255(x[4 * j + q]);
           if (rr[q] < a.u1) v = 1.0f;
           if (rr[q] < a.u0) v = 0.0f;
           x[4 * j + q] = v;
@@ -121,7 +137,7 @@ __global__ void __launch_bounds__(256) k1_pointwise(const PointwiseArgs a) {
     } else if (MODE == PW_BRIGHT) {
 #pragma unroll
       for (int p = 0; p < 16; ++p) {
-        const float r = u8f(x[3 * p]), gg = u8f(x[3 * p + 1]), b = u8f(x[3 * p + 2]);
+        const float r = div255(x[3 * p]), gg = div255(x[3 * p + 1]), b = div255(x[3 * p + 2]);
         const float v = fmaxf(r, fmaxf(gg, b));
         const float v2 = fminf(__fadd_rn(v, a.f0), 1.0f);
         if (v > 0.0f) {
@@ -138,7 +154,7 @@ __global__ void __launch_bounds__(256) k1_pointwise(const PointwiseArgs a) {
       for (int c = 0; c < 3; ++c) mu[c] = __fdiv_rn(__ull2float_rn(sums[bgr ? 2 - c : c]), 255.0f * float(a.hw));
 #pragma unroll
       for (int i = 0; i < 48; ++i)
-        x[i] = __fadd_rn(__fmul_rn(__fsub_rn(u8f(x[i]), mu[i % 3]), a.f0), mu[i % 3]);
+        x[i] = __fadd_rn(__fmul_rn(__fsub_rn(div255(x[i]), mu[i % 3]), a.f0), mu[i % 3]);
     } else if (MODE == PW_FOG) {
       const float* st = reinterpret_cast<const float*>(a.scratch) + 4 * (size_t)img;
       const float* map = reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.scratch) + a.map_offset) +
@@ -155,11 +171,11 @@ __global__ void __launch_bounds__(256) k1_pointwise(const PointwiseArgs a) {
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c)
-          x[3 * p + c] = __fmul_rn(__fadd_rn(u8f(x[3 * p + c]), __fmul_rn(a.f0, pl)), gain);
+          x[3 * p + c] = __fmul_rn(__fadd_rn(div255(x[3 * p + c]), __fmul_rn(a.f0, pl)), gain);
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < 48; ++i) x[i] = u8f(x[i]);
+      for (int i = 0; i < 48; ++i) x[i] = div255(x[i]);
     }
 
     // clip + normalize + store
@@ -198,12 +214,23 @@ __global__ void __launch_bounds__(256) k1_pointwise(const PointwiseArgs a) {
 // ---------------------------------------------------------------- per-image channel sums (contrast)
 __global__ void __launch_bounds__(256) k1_channel_sums(const uint8_t* __restrict__ src, int per,
                                                        unsigned long long* __restrict__ sums) {
-  const int img = blockIdx.y;
+  const int img = blockIdx.x;
   const uint8_t* p = src + (size_t)img * per;
   unsigned int s[3] = {0, 0, 0};
-  // each thread walks whole pixels so channel = position % 3 is static
-  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix * 3 < per; pix += gridDim.x * blockDim.x) {
-    s[0] += p[3 * pix]; s[1] += p[3 * pix + 1]; s[2] += p[3 * pix + 2];
+  const bool vec = (per % 48) == 0 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
+  if (vec) {   // 16 whole pixels = three 128-bit loads per thread; byte j of the group belongs to channel j % 3
+    for (int g = blockIdx.y * blockDim.x + threadIdx.x; g * 48 < per; g += gridDim.y * blockDim.x) {
+      const uint4* q = reinterpret_cast<const uint4*>(p + (size_t)g * 48);
+      uint32_t w[12];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { const uint4 v = __ldg(q + i); w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
+#pragma unroll
+      for (int j = 0; j < 48; ++j) s[j % 3] += (w[j >> 2] >> (8 * (j & 3))) & 0xFF;
+    }
+  } else {
+    for (int pix = blockIdx.y * blockDim.x + threadIdx.x; pix * 3 < per; pix += gridDim.y * blockDim.x) {
+      s[0] += p[3 * pix]; s[1] += p[3 * pix + 1]; s[2] += p[3 * pix + 2];
+    }
   }
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -342,8 +369,8 @@ __global__ void __launch_bounds__(256) k1_taps(const TapArgs a) {
   extern __shared__ uint32_t s_tile[];
   const int SW = TAP_TILE + a.dx_max - a.dx_min, SH = TAP_TILE + a.dy_max - a.dy_min;
   uint2* s_taps = reinterpret_cast<uint2*>(s_tile + SW * SH);
-  const int img = blockIdx.y;
-  const int ty = blockIdx.x / a.tiles_x, tx = blockIdx.x - ty * a.tiles_x;
+  const int img = blockIdx.x;
+  const int ty = blockIdx.y / a.tiles_x, tx = blockIdx.y - ty * a.tiles_x;
   const int y0 = ty * TAP_TILE, x0 = tx * TAP_TILE;
   int entry = 0;
   if (a.n_entries > 1) {
@@ -556,7 +583,7 @@ extern "C" int fav_corrupt_normalize(fav_handle h, const uint8_t* d_src, void* d
       k1_pointwise<PW_GAUSS><<<grid, 256, 0, st>>>(a); h->launches++; break;
     case FAV_SHOT_NOISE:
       FAV_REQUIRE(need_f(1) && need_i(1) && d_table, "shot_noise needs fparams[0]=c, iparams[0]=width, table");
-      FAV_REQUIRE(table_bytes >= 1024 + (size_t)iparams[0] * 1024, "shot_noise table too small");
+      FAV_REQUIRE(table_bytes >= 1024 + (size_t)iparams[0] * 1024 + 256 * 256 * 2, "shot_noise table too small");
       a.f0 = fparams[0]; a.u0 = uint32_t(iparams[0]);
       k1_pointwise<PW_SHOT><<<grid, 256, 0, st>>>(a); h->launches++; break;
     case FAV_IMPULSE_NOISE:
@@ -573,8 +600,8 @@ extern "C" int fav_corrupt_normalize(fav_handle h, const uint8_t* d_src, void* d
                   "contrast needs %zu scratch bytes", fav_corrupt_scratch_bytes(corruption, n, height, width));
       a.f0 = fparams[0];
       FAV_CUDA_OK(cudaMemsetAsync(d_scratch, 0, (size_t)n * 24, st));
-      const int bx = max(1, min(64, (height * width + 1023) / 1024));
-      k1_channel_sums<<<dim3(bx, n), 256, 0, st>>>(d_src, per, reinterpret_cast<unsigned long long*>(d_scratch));
+      const int bx = max(1, min(64, (height * width + 4095) / 4096));
+      k1_channel_sums<<<dim3(n, bx), 256, 0, st>>>(d_src, per, reinterpret_cast<unsigned long long*>(d_scratch));
       k1_pointwise<PW_CONTRAST><<<grid, 256, 0, st>>>(a); h->launches += 2; break;
     }
     case FAV_FOG: {
@@ -608,7 +635,7 @@ extern "C" int fav_corrupt_normalize(fav_handle h, const uint8_t* d_src, void* d
       const size_t smem = (size_t)(TAP_TILE + t.dx_max - t.dx_min) * (TAP_TILE + t.dy_max - t.dy_min) * 4 + (size_t)t.max_taps * 8;
       FAV_REQUIRE(smem <= 200 * 1024, "tap stencil halo too large (%zu B of shared memory)", smem);
       if (smem > 48 * 1024) FAV_CUDA_OK(cudaFuncSetAttribute(k1_taps, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-      k1_taps<<<dim3(t.tiles_x * t.tiles_y, n), 256, smem, st>>>(t); h->launches++; break;
+      k1_taps<<<dim3(n, t.tiles_x * t.tiles_y), 256, smem, st>>>(t); h->launches++; break;
     }
     case FAV_ZOOM_BLUR: {
       FAV_REQUIRE(need_i(1) && d_table, "zoom_blur needs iparams[0]=nz and a table");

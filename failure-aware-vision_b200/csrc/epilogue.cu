@@ -48,18 +48,20 @@ __device__ __forceinline__ SampleOut sample_uncertainty(const float* __restrict_
       m = fmaxf(m, v[i]);
     }
     m = warp_max(m);
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < NC; ++i) { v[i] = expf(v[i] - m); s += v[i]; }   // exp(-inf) = 0 for padding lanes
-    s = warp_sum(s);
-    float h = 0.f;
+    float s = 0.f, w = 0.f;
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
-      const float p = __fdiv_rn(v[i], s);
-      pbar[i] += p;
-      if (p > 0.f) h -= p * logf(p);
+      const float d = v[i] - m;                      // -inf for padding lanes
+      v[i] = expf(d);                                // exp(-inf) = 0
+      s += v[i];
+      w += v[i] > 0.f ? v[i] * d : 0.f;
     }
-    hsum += warp_sum(h);
+    s = warp_sum(s);
+    w = warp_sum(w);
+    const float inv_s = __fdiv_rn(1.0f, s);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) pbar[i] += v[i] * inv_s;
+    hsum += logf(s) - w * inv_s;                     // H(p_t) = ln S - sum_i e_i (z_i - m) / S   (no per-class log)
   }
   const float invT = 1.0f / float(T);
   float best = -1.f;
@@ -80,6 +82,50 @@ __device__ __forceinline__ SampleOut sample_uncertainty(const float* __restrict_
     const float ob = __shfl_xor_sync(0xffffffffu, best, o);
     const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
     if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+  }
+  SampleOut r;
+  r.conf = best; r.pred = arg; r.H = H;
+  r.mi = fmaxf(H - hsum * invT, 0.f);
+  return r;
+}
+
+// C <= 16: lanes run over the MC passes (lane t owns pass t, t + 32, ...), each lane does its softmax serially in
+// registers; only the pass-mean needs cross-lane reductions.  ~3x fewer shuffles than lanes-over-classes at C = 10.
+__device__ __forceinline__ SampleOut sample_uncertainty_small(const float* __restrict__ z, int T, int C, int lane) {
+  float pbar[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) pbar[c] = 0.f;
+  float hsum = 0.f;
+  for (int t = lane; t < T; t += 32) {
+    const float* zt = z + (size_t)t * C;
+    float v[16];
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { v[c] = c < C ? zt[c] : -INFINITY; m = fmaxf(m, v[c]); }
+    float s = 0.f, w = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float d = v[c] - m;
+      v[c] = expf(d);
+      s += v[c];
+      w += v[c] > 0.f ? v[c] * d : 0.f;
+    }
+    const float inv_s = __fdiv_rn(1.0f, s);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) pbar[c] += v[c] * inv_s;
+    hsum += logf(s) - w * inv_s;
+  }
+  const float invT = 1.0f / float(T);
+  hsum = warp_sum(hsum);
+  float best = -1.f, H = 0.f;
+  int arg = 0;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const float p = warp_sum(pbar[c]) * invT;       // identical in every lane
+    if (c < C) {
+      if (p > best) { best = p; arg = c; }          // ascending c: lowest index wins ties
+      if (p > 0.f) H -= p * logf(p);
+    }
   }
   SampleOut r;
   r.conf = best; r.pred = arg; r.H = H;
@@ -151,7 +197,8 @@ __global__ void __launch_bounds__(256) k34_kernel(const float* __restrict__ logi
   unsigned long long my[6] = {0, 0, 0, 0, 0, 0};
   if (logits) {
     for (int i = blockIdx.x * warps_per_block + (threadIdx.x >> 5); i < n; i += gridDim.x * warps_per_block) {
-      const SampleOut r = sample_uncertainty<NC>(logits + (size_t)i * T * g.C, T, g.C, lane);
+      const SampleOut r = NC == 0 ? sample_uncertainty_small(logits + (size_t)i * T * g.C, T, g.C, lane)
+                                  : sample_uncertainty<(NC > 0 ? NC : 1)>(logits + (size_t)i * T * g.C, T, g.C, lane);
       if (lane == 0) {
         const int label = labels ? labels[i] : -1;
         const bool flag = labels && r.pred != label && r.conf >= g.tau;
@@ -219,7 +266,7 @@ static int launch_k34(fav_handle h, const float* d_logits, const int32_t* d_labe
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   unsigned long long* hist = reinterpret_cast<unsigned long long*>(d_hist);
-  const int nc = C <= 32 ? 1 : (C <= 128 ? 4 : 32);
+  const int nc = C <= 16 ? 0 : (C <= 32 ? 1 : (C <= 128 ? 4 : 32));
   const int warps = 8;
   long long blocks = d_logits ? (n + warps - 1) / warps : (n + 255) / 256;
   const long long cap = (long long)h->num_sms * (smem > 64 * 1024 ? 2 : 4);
@@ -231,7 +278,7 @@ static int launch_k34(fav_handle h, const float* d_logits, const int32_t* d_labe
     k34_kernel<NC, true><<<int(blocks), 256, smem, st>>>(d_logits, d_labels, n, T, g, hist, d_conf, d_entropy, d_mi,  \
                                                          d_pred, d_flag, i_conf, i_H, i_mi, i_pred);          \
   } while (0)
-  if (nc == 1) FAV_K34(1); else if (nc == 4) FAV_K34(4); else FAV_K34(32);
+  if (nc == 0) FAV_K34(0); else if (nc == 1) FAV_K34(1); else if (nc == 4) FAV_K34(4); else FAV_K34(32);
 #undef FAV_K34
   h->launches++;
   FAV_CUDA_OK(cudaGetLastError());

@@ -183,15 +183,27 @@ extern "C" int fav_load_weights(fav_handle h, const void* blob, size_t nbytes, i
     q += 32 + wb + bb;
     pl->convs.push_back(L);
   }
-  // fuse every TMA-able 1x1 downsample conv into the last conv of its block: its weights become extra K columns
-  for (BlockDesc& bd : pl->blocks) {
-    if (bd.ds < 0) continue;
-    const ConvLayer& D = pl->convs[bd.ds];
-    ConvLayer& last = pl->convs[bd.conv0 + bd.n_convs - 1];
-    if (D.r == 1 && D.s == 1 && D.pad == 0 && (D.cin % 64) == 0 && D.cout == last.cout && (D.stride == 1 || D.stride == 2) &&
-        (last.cin % 64) == 0 && last.stride == 1) {
-      last.k2pad = D.kpad; last.cin2 = D.cin; last.stride2 = D.stride;
-      bd.fused_ds = true;
+  // fuse every TMA-able 1x1 downsample conv into the last conv of its block: its weights become extra K columns.
+  // (stride-2 branches need even input dims for the parity-split tensor map, so the geometry is walked here)
+  {
+    const ConvLayer& stem0 = pl->convs[0];
+    int gh = conv_out_dim(in_h, stem0.r, stem0.stride, stem0.pad), gw = conv_out_dim(in_w, stem0.s, stem0.stride, stem0.pad);
+    gh = conv_out_dim(gh, 3, 2, 1); gw = conv_out_dim(gw, 3, 2, 1);
+    for (BlockDesc& bd : pl->blocks) {
+      const int bh = gh, bw = gw;               // block input size = input of the downsample branch
+      for (int k = 0; k < bd.n_convs; ++k) {
+        const ConvLayer& L = pl->convs[bd.conv0 + k];
+        gh = conv_out_dim(gh, L.r, L.stride, L.pad); gw = conv_out_dim(gw, L.s, L.stride, L.pad);
+      }
+      if (bd.ds < 0) continue;
+      const ConvLayer& D = pl->convs[bd.ds];
+      ConvLayer& last = pl->convs[bd.conv0 + bd.n_convs - 1];
+      const bool dims_ok = D.stride == 1 || (D.stride == 2 && (bh % 2) == 0 && (bw % 2) == 0);
+      const bool last_tma = (last.cin % 64) == 0 && last.stride == 1 && last.r == last.s && 2 * last.pad == last.r - 1 && gw <= 128;
+      if (D.r == 1 && D.s == 1 && D.pad == 0 && (D.cin % 64) == 0 && D.cout == last.cout && dims_ok && last_tma) {
+        last.k2pad = D.kpad; last.cin2 = D.cin; last.stride2 = D.stride;
+        bd.fused_ds = true;
+      }
     }
   }
   // 3x3 / stride 1 / pad 1 convs whose input is 2x2: every output pixel sees every input pixel through exactly one tap,

@@ -259,7 +259,10 @@ def kernel_params(cfg: CorruptionConfig, h, w, profile=None):
         return [float(c)], [], None
     if n == "shot_noise":
         kmin, width, thr = poisson_table(c)
-        tab = np.concatenate([kmin.view(np.uint8), thr.view(np.uint8).ravel()])
+        # jump[v][b] = #{j : thr[v][j] < b << 24}: where the linear probe for a draw with top byte b starts
+        edges = (np.arange(256, dtype=np.uint64) << np.uint64(24))
+        jump = (thr[:, None, :].astype(np.uint64) < edges[None, :, None]).sum(-1).astype(np.uint16)
+        tab = np.concatenate([kmin.view(np.uint8), thr.view(np.uint8).ravel(), jump.view(np.uint8).ravel()])
         return [float(c)], [width], tab
     if n == "impulse_noise":
         tp, ts = int(math.floor(c / 2 * 2.0 ** 32)), int(math.floor(c * 2.0 ** 32))

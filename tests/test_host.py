@@ -182,3 +182,25 @@ def test_trust_engine_golden_transcript_is_recorded():
         tr = json.load(fh)["transcript"]
     assert [round(r[1], 6) for r in tr] == [1.0, 0.5149, 0.0, 0.0, 0.501721]
     assert [r[2] for r in tr] == ["VISION_ALLOWED", "VISION_DEGRADED", "VISION_BLOCKED", "VISION_BLOCKED", "VISION_DEGRADED"]
+
+
+def test_div255_fma_correction_is_exact():
+    """corrupt.cu::div255 claims b*r + FMA residual correction == correctly rounded b/255 for every byte."""
+    from fractions import Fraction
+    f32 = np.float32
+
+    def fma(a, b, c):
+        x = Fraction(float(a)) * Fraction(float(b)) + Fraction(float(c))
+        cand = f32(float(x))
+        best = None
+        for d in (np.nextafter(cand, f32(-np.inf)), cand, np.nextafter(cand, f32(np.inf))):
+            err = abs(Fraction(float(d)) - x)
+            if best is None or err < best[0] or (err == best[0] and (int(f32(d).view(np.uint32)) & 1) == 0):
+                best = (err, d)
+        return f32(best[1])
+
+    r = f32(0.003921568859368563)
+    assert r == f32(1.0) / f32(255.0)
+    for b in range(256):
+        q = f32(b) * r
+        assert fma(fma(-q, f32(255.0), f32(b)), r, q) == f32(b) / f32(255.0)
