@@ -12,7 +12,7 @@
 
 namespace fav {
 
-enum { PW_CLEAN = 0, PW_GAUSS, PW_SHOT, PW_IMPULSE, PW_BRIGHT, PW_CONTRAST, PW_FOG };
+enum { PW_CLEAN = 0, PW_GAUSS, PW_SHOT, PW_IMPULSE, PW_BRIGHT, PW_CONTRAST, PW_FOG, PW_FROST };
 
 struct PointwiseArgs {
   const uint8_t* src;
@@ -23,6 +23,7 @@ struct PointwiseArgs {
   uint32_t first_image;
   uint32_t stream;            // Philox c3
   float f0, f1;               // corruption constants
+  float tint[3];              // frost texture colour
   uint32_t u0, u1;            // integer constants (thresholds / table width)
   const void* table;          // shot: int32 kmin[256], uint32 thr[256][width], uint16 jump[256][256]
   const void* scratch;        // contrast: uint64 sums[n][3]; fog: float stats[n][4] + maps
@@ -172,6 +173,26 @@ __global__ void __launch_bounds__(256) k1_pointwise(const PointwiseArgs a) {
 #pragma unroll
         for (int c = 0; c < 3; ++c)
           x[3 * p + c] = __fmul_rn(__fadd_rn(div255(x[3 * p + c]), __fmul_rn(a.f0, pl)), gain);
+      }
+    } else if (MODE == PW_FROST) {
+      // procedural frost (the ImageNet-C frost photographs are not available): texture = plasma through a contrast curve,
+      // tinted; out = c0 * x + c1 * texture
+      const float* st = reinterpret_cast<const float*>(a.scratch) + 4 * (size_t)img;
+      const float* map = reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.scratch) + a.map_offset) +
+                         (size_t)img * a.mapsize * a.mapsize;
+      const float mn = st[0], pmx = st[1];
+#pragma unroll
+      for (int p = 0; p < 16; ++p) {
+        const int pix = e0 / 3 + p;
+        float f = 0.f;
+        if (pix < a.hw) {
+          const int yy = pix / a.width, xx = pix - yy * a.width;
+          const float pl = __fdiv_rn(__fsub_rn(map[yy * a.mapsize + xx], mn), pmx);
+          f = fminf(fmaxf(__fsub_rn(__fmul_rn(1.35f, pl), 0.1f), 0.f), 1.f);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          x[3 * p + c] = __fadd_rn(__fmul_rn(a.f0, div255(x[3 * p + c])), __fmul_rn(a.f1, __fmul_rn(f, a.tint[c])));
       }
     } else {
 #pragma unroll
@@ -496,6 +517,184 @@ __global__ void __launch_bounds__(256) k1_pixelate(const PixArgs a) {
   }
 }
 
+// ---------------------------------------------------------------- jpeg_compression: integer baseline-JPEG round trip
+// One CTA = one 16x16 MCU (4:2:0): JFIF colour transform in libjpeg's 16-bit fixed point, 2x2 chroma mean, six 8x8 blocks
+// through a 13-bit fixed-point orthonormal DCT, Annex-K quantisation, inverse, chroma replication.  All integer:
+// bit-exact against oracle/jpeg.py.  table: int32 lum[64], chr[64], T[64].
+struct JpegArgs {
+  const uint8_t* src;
+  OutArgs out;
+  int n, h, w, mcu_x, mcu_y;
+  const int* table;
+  unsigned src_bgr;
+};
+__global__ void __launch_bounds__(256) k1_jpeg(const JpegArgs a) {
+  __shared__ int sQ[128], sT[64];
+  __shared__ int blk[6][64];        // Y00, Y01, Y10, Y11, Cb, Cr   (level-shifted samples, then coefficients, then samples)
+  __shared__ int tmp[6][64];
+  __shared__ int sc[2][256];        // full-resolution Cb, Cr before subsampling
+  const int img = blockIdx.x, my = blockIdx.y / a.mcu_x, mx = blockIdx.y - my * a.mcu_x;
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  if (t < 128) sQ[t] = a.table[t];
+  if (t < 64) sT[t] = a.table[128 + t];
+  const int y = min(my * 16 + ty, a.h - 1), x = min(mx * 16 + tx, a.w - 1);       // edge replication
+  const uint8_t* p = a.src + (((size_t)img * a.h + y) * a.w + x) * 3;
+  int R = p[0], G = p[1], B = p[2];
+  if (a.src_bgr) { const int q = R; R = B; B = q; }
+  const int Y = (19595 * R + 38470 * G + 7471 * B + 32768) >> 16;
+  sc[0][t] = (-11059 * R - 21709 * G + 32768 * B + 8388608 + 32767) >> 16;
+  sc[1][t] = (32768 * R - 27439 * G - 5329 * B + 8388608 + 32767) >> 16;
+  blk[(ty >> 3) * 2 + (tx >> 3)][(ty & 7) * 8 + (tx & 7)] = Y - 128;
+  __syncthreads();
+  if (t < 128) {
+    const int c = t >> 6, i = t & 63, cy = i >> 3, cx = i & 7;
+    const int* q = sc[c] + (2 * cy) * 16 + 2 * cx;
+    blk[4 + c][i] = ((q[0] + q[1] + q[16] + q[17] + 2) >> 2) - 128;
+  }
+  __syncthreads();
+  // forward rows: t1[y][u] = (sum_x T[u][x] f[y][x] + 512) >> 10
+  for (int i = t; i < 384; i += 256) {
+    const int b = i >> 6, yy = (i >> 3) & 7, u = i & 7;
+    int acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += sT[u * 8 + k] * blk[b][yy * 8 + k];
+    tmp[b][yy * 8 + u] = (acc + 512) >> 10;
+  }
+  __syncthreads();
+  // forward cols + quantise + dequantise: F[v][u] = (sum_y T[v][y] t1[y][u] + 4096) >> 13 (= 8 F_true)
+  for (int i = t; i < 384; i += 256) {
+    const int b = i >> 6, v = (i >> 3) & 7, u = i & 7;
+    int acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += sT[v * 8 + k] * tmp[b][k * 8 + u];
+    const int F = (acc + 4096) >> 13;
+    const int Q = sQ[(b < 4 ? 0 : 64) + v * 8 + u], Q8 = Q * 8;
+    const int qa = (abs(F) + Q8 / 2) / Q8;
+    blk[b][v * 8 + u] = (F < 0 ? -qa : qa) * Q;
+  }
+  __syncthreads();
+  // inverse cols: t[y][u] = (sum_v T[v][y] F'[v][u] + 1024) >> 11
+  for (int i = t; i < 384; i += 256) {
+    const int b = i >> 6, yy = (i >> 3) & 7, u = i & 7;
+    int acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += sT[k * 8 + yy] * blk[b][k * 8 + u];
+    tmp[b][yy * 8 + u] = (acc + 1024) >> 11;
+  }
+  __syncthreads();
+  // inverse rows: f'[y][x] = (sum_u T[u][x] t[y][u] + 16384) >> 15, + 128, clamp
+  for (int i = t; i < 384; i += 256) {
+    const int b = i >> 6, yy = (i >> 3) & 7, xx = i & 7;
+    int acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += sT[k * 8 + xx] * tmp[b][yy * 8 + k];
+    blk[b][yy * 8 + xx] = min(max(((acc + 16384) >> 15) + 128, 0), 255);
+  }
+  __syncthreads();
+  const int oy = my * 16 + ty, ox = mx * 16 + tx;
+  if (oy < a.h && ox < a.w) {
+    const int Yr = blk[(ty >> 3) * 2 + (tx >> 3)][(ty & 7) * 8 + (tx & 7)];
+    const int cb = blk[4][(ty >> 1) * 8 + (tx >> 1)] - 128, cr = blk[5][(ty >> 1) * 8 + (tx >> 1)] - 128;
+    const int r = min(max(Yr + ((91881 * cr + 32768) >> 16), 0), 255);
+    const int g = min(max(Yr + ((-22554 * cb - 46802 * cr + 32768) >> 16), 0), 255);
+    const int b = min(max(Yr + ((116130 * cb + 32768) >> 16), 0), 255);
+    store_pixel(a.out, ((size_t)img * a.h + oy) * a.w + ox, div255(float(r)), div255(float(g)), div255(float(b)));
+  }
+}
+
+// ---------------------------------------------------------------- glass_blur: blur -> sequential local swaps -> blur
+// One CTA per image, the whole image resident in shared memory as packed RGBX words.  Stage 1: exact fixed-point Gaussian
+// (bit-exact bytes).  Stage 2: the scan-order swap chain is inherently sequential -- thread 0 walks it while the other
+// threads pre-compute the Philox offsets chunk by chunk.  Stage 3: fp32 Gaussian + normalize.
+// table: int32 q16[2r+1], float k[2r+1]
+struct GlassArgs {
+  const uint8_t* src;
+  OutArgs out;
+  int n, h, w, delta, iters, radius;
+  const int* table;
+  uint32_t k0, k1, first_image, stream;
+  unsigned src_bgr;
+};
+constexpr int GLASS_CHUNK = 2048;
+__global__ void __launch_bounds__(256) k1_glass(const GlassArgs a) {
+  extern __shared__ uint32_t g_img[];                       // h*w RGBX words, then GLASS_CHUNK packed offsets, then taps
+  const int hw = a.h * a.w, nt = 2 * a.radius + 1;
+  short2* s_off = reinterpret_cast<short2*>(g_img + hw);
+  int* s_q = reinterpret_cast<int*>(s_off + GLASS_CHUNK);
+  float* s_k = reinterpret_cast<float*>(s_q + nt);
+  const int img = blockIdx.x;
+  const uint8_t* p = a.src + (size_t)img * hw * 3;
+  for (int i = threadIdx.x; i < nt; i += blockDim.x) { s_q[i] = a.table[i]; s_k[i] = reinterpret_cast<const float*>(a.table)[nt + i]; }
+  __syncthreads();
+  // stage 1: exact integer blur, (sum_y q[y] * ((sum_x q[x] * u8 + 128) >> 8) + 2^23) >> 24
+  for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+    const int y = i / a.w, x = i - y * a.w;
+    unsigned acc[3] = {0, 0, 0};
+    for (int dy = -a.radius; dy <= a.radius; ++dy) {
+      const uint8_t* row = p + (size_t)min(max(y + dy, 0), a.h - 1) * a.w * 3;
+      unsigned h3[3] = {0, 0, 0};
+      for (int dx = -a.radius; dx <= a.radius; ++dx) {
+        const uint8_t* q = row + min(max(x + dx, 0), a.w - 1) * 3;
+        const unsigned wq = unsigned(s_q[dx + a.radius]);
+        h3[0] += wq * q[0]; h3[1] += wq * q[1]; h3[2] += wq * q[2];
+      }
+      const unsigned wy = unsigned(s_q[dy + a.radius]);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[c] += wy * ((h3[c] + 128u) >> 8);
+    }
+    unsigned b[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) b[c] = min((acc[c] + (1u << 23)) >> 24, 255u);
+    if (a.src_bgr) { const unsigned q = b[0]; b[0] = b[2]; b[2] = q; }
+    g_img[i] = b[0] | (b[1] << 8) | (b[2] << 16);
+  }
+  __syncthreads();
+  // stage 2: swaps.  step j of iteration it visits (hh, ww) descending; offsets d in [-delta, delta-1]
+  const int sh = a.h - 2 * a.delta, sw = a.w - 2 * a.delta;
+  const int per_iter = sh * sw, steps = a.iters * per_iter;
+  const uint32_t gimg = a.first_image + uint32_t(img), m = uint32_t(2 * a.delta);
+  for (int base = 0; base < steps; base += GLASS_CHUNK) {
+    const int cnt = min(GLASS_CHUNK, steps - base);
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const uint4 r = philox4x32_10(uint32_t(base + i), gimg, 0u, a.stream, a.k0, a.k1);
+      s_off[i] = make_short2(short(int(r.y % m) - a.delta), short(int(r.x % m) - a.delta));     // (dy, dx)
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < cnt; ++i) {
+        const int j = (base + i) % per_iter;
+        const int hh = a.h - a.delta - j / sw, ww = a.w - a.delta - j % sw;
+        const short2 d = s_off[i];
+        const int i0 = hh * a.w + ww, i1 = (hh + d.x) * a.w + (ww + d.y);
+        const uint32_t t0 = g_img[i0];
+        g_img[i0] = g_img[i1];
+        g_img[i1] = t0;
+      }
+    }
+    __syncthreads();
+  }
+  // stage 3: fp32 Gaussian (x then y, accumulated in tap order like the oracle) -- done directly in 2-D from shared memory
+  for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+    const int y = i / a.w, x = i - y * a.w;
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int dy = -a.radius; dy <= a.radius; ++dy) {
+      const uint32_t* row = g_img + min(max(y + dy, 0), a.h - 1) * a.w;
+      float h3[3] = {0.f, 0.f, 0.f};
+      for (int dx = -a.radius; dx <= a.radius; ++dx) {
+        const uint32_t v = row[min(max(x + dx, 0), a.w - 1)];
+        const float wk = s_k[dx + a.radius];
+        h3[0] = fmaf(wk, div255(float(v & 0xFF)), h3[0]);
+        h3[1] = fmaf(wk, div255(float((v >> 8) & 0xFF)), h3[1]);
+        h3[2] = fmaf(wk, div255(float((v >> 16) & 0xFF)), h3[2]);
+      }
+      const float wy = s_k[dy + a.radius];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[c] = fmaf(wy, h3[c], acc[c]);
+    }
+    store_pixel(a.out, (size_t)img * hw + i, acc[0], acc[1], acc[2]);
+  }
+}
+
 // ---------------------------------------------------------------- synthetic inputs
 __global__ void k_synth_images(uint8_t* dst, int n, int per, uint32_t k0, uint32_t k1, uint32_t first_image) {
   const int nch = (per + 15) / 16;
@@ -533,7 +732,7 @@ using namespace fav;
 
 extern "C" size_t fav_corrupt_scratch_bytes(int corruption, int n, int height, int width) {
   if (corruption == FAV_CONTRAST) return (size_t)n * 3 * sizeof(unsigned long long);
-  if (corruption == FAV_FOG) {
+  if (corruption == FAV_FOG || corruption == FAV_FROST) {
     int m = 1;
     while (m < (height > width ? height : width)) m *= 2;
     const size_t stats = (((size_t)n * 16) + 255) / 256 * 256;
@@ -616,6 +815,43 @@ extern "C" int fav_corrupt_normalize(fav_handle h, const uint8_t* d_src, void* d
       float* maps = reinterpret_cast<float*>(reinterpret_cast<char*>(d_scratch) + a.map_offset);
       k1_plasma<<<n, 1024, 0, st>>>(d_src, per, m, fparams[1], k0, k1, uint32_t(first_image), a.stream, stats, maps);
       k1_pointwise<PW_FOG><<<grid, 256, 0, st>>>(a); h->launches += 2; break;
+    }
+    case FAV_FROST: {
+      FAV_REQUIRE(need_f(6), "frost needs fparams = c0, c1, plasma decay, tint r, g, b");
+      FAV_REQUIRE(d_scratch && scratch_bytes >= fav_corrupt_scratch_bytes(corruption, n, height, width),
+                  "frost needs %zu scratch bytes", fav_corrupt_scratch_bytes(corruption, n, height, width));
+      int m = 1;
+      while (m < max(height, width)) m *= 2;
+      a.f0 = fparams[0]; a.f1 = fparams[1]; a.mapsize = m;
+      a.tint[0] = fparams[3]; a.tint[1] = fparams[4]; a.tint[2] = fparams[5];
+      a.map_offset = (((size_t)n * 16) + 255) / 256 * 256;
+      float* stats = reinterpret_cast<float*>(d_scratch);
+      float* maps = reinterpret_cast<float*>(reinterpret_cast<char*>(d_scratch) + a.map_offset);
+      k1_plasma<<<n, 1024, 0, st>>>(d_src, per, m, fparams[2], k0, k1, uint32_t(first_image), a.stream, stats, maps);
+      k1_pointwise<PW_FROST><<<grid, 256, 0, st>>>(a); h->launches += 2; break;
+    }
+    case FAV_JPEG: {
+      FAV_REQUIRE(d_table && table_bytes >= 192 * 4, "jpeg_compression needs the 192-int quantisation / DCT table");
+      JpegArgs j{};
+      j.src = d_src; j.out = out; j.n = n; j.h = height; j.w = width;
+      j.mcu_x = (width + 15) / 16; j.mcu_y = (height + 15) / 16;
+      FAV_REQUIRE(j.mcu_x * j.mcu_y <= 65535, "jpeg_compression: frame too large");
+      j.table = reinterpret_cast<const int*>(d_table); j.src_bgr = flags & FAV_SRC_BGR;
+      k1_jpeg<<<dim3(n, j.mcu_x * j.mcu_y), 256, 0, st>>>(j); h->launches++; break;
+    }
+    case FAV_GLASS_BLUR: {
+      FAV_REQUIRE(need_i(3) && d_table, "glass_blur needs iparams = delta, iterations, radius and the tap table");
+      GlassArgs g{};
+      g.src = d_src; g.out = out; g.n = n; g.h = height; g.w = width;
+      g.delta = iparams[0]; g.iters = iparams[1]; g.radius = iparams[2];
+      FAV_REQUIRE(g.delta >= 1 && g.iters >= 1 && g.radius >= 0 && 2 * g.delta < min(height, width), "glass_blur: bad parameters");
+      FAV_REQUIRE(table_bytes >= (size_t)(2 * g.radius + 1) * 8, "glass_blur tap table too small");
+      g.table = reinterpret_cast<const int*>(d_table);
+      g.k0 = k0; g.k1 = k1; g.first_image = uint32_t(first_image); g.stream = a.stream; g.src_bgr = flags & FAV_SRC_BGR;
+      const size_t smem = (size_t)height * width * 4 + GLASS_CHUNK * 4 + (size_t)(2 * g.radius + 1) * 8;
+      FAV_REQUIRE(smem <= 226 * 1024, "glass_blur keeps the image in shared memory: %dx%d is too large", height, width);
+      if (smem > 48 * 1024) FAV_CUDA_OK(cudaFuncSetAttribute(k1_glass, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      k1_glass<<<n, 256, smem, st>>>(g); h->launches++; break;
     }
     case FAV_DEFOCUS_BLUR:
     case FAV_MOTION_BLUR: {

@@ -17,8 +17,8 @@ CORRUPTIONS = (
 )
 CORRUPTION_ID = {name: i + 1 for i, name in enumerate(CORRUPTIONS)}
 # corruptions with a device kernel in this build; the sweep reports the rest as unavailable
-IMPLEMENTED = ("gaussian_noise", "shot_noise", "impulse_noise", "defocus_blur", "motion_blur",
-               "zoom_blur", "fog", "brightness", "contrast", "pixelate")
+IMPLEMENTED = ("gaussian_noise", "shot_noise", "impulse_noise", "defocus_blur", "glass_blur", "motion_blur",
+               "zoom_blur", "frost", "fog", "brightness", "contrast", "pixelate", "jpeg_compression")
 
 SEVERITY = {
     "imagenet": {
@@ -32,6 +32,9 @@ SEVERITY = {
         "brightness": [.1, .2, .3, .4, .5],
         "contrast": [.4, .3, .2, .1, .05],
         "pixelate": [.6, .5, .4, .3, .25],
+        "jpeg_compression": [25, 18, 15, 10, 7],
+        "glass_blur": [(.7, 1, 2), (.9, 2, 1), (1, 2, 3), (1.1, 3, 2), (1.5, 4, 2)],
+        "frost": [(1, .4), (.8, .6), (.7, .7), (.65, .7), (.6, .75)],
     },
     "cifar": {
         "gaussian_noise": [.04, .06, .08, .09, .10],
@@ -44,6 +47,9 @@ SEVERITY = {
         "brightness": [.05, .1, .15, .2, .3],
         "contrast": [.75, .5, .4, .3, .15],
         "pixelate": [.95, .9, .85, .75, .65],
+        "jpeg_compression": [80, 65, 58, 50, 40],
+        "glass_blur": [(.05, 1, 1), (.25, 1, 1), (.4, 1, 1), (.25, 1, 2), (.4, 1, 2)],
+        "frost": [(1, .2), (1, .3), (.9, .4), (.85, .4), (.75, .45)],
     },
 }
 
@@ -247,6 +253,40 @@ def pixelate_table(c, h, w):
     return tab.view(np.uint8)
 
 
+# ---- jpeg: Annex-K tables scaled by the libjpeg quality rule, 13-bit fixed-point orthonormal DCT matrix
+_JPEG_LUM = [16, 11, 10, 16, 24, 40, 51, 61, 12, 12, 14, 19, 26, 58, 60, 55, 14, 13, 16, 24, 40, 57, 69, 56, 14, 17, 22, 29, 51, 87,
+             80, 62, 18, 22, 37, 56, 68, 109, 103, 77, 24, 35, 55, 64, 81, 104, 113, 92, 49, 64, 78, 87, 103, 121, 120, 101, 72, 92,
+             95, 98, 112, 100, 103, 99]
+_JPEG_CHR = [17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99, 24, 26, 56, 99, 99, 99, 99, 99, 47, 66, 99, 99, 99, 99,
+             99, 99] + [99] * 32
+
+
+def jpeg_table(quality):
+    """int32[192]: luminance table, chrominance table (row-major v,u), DCT matrix T[u][x]."""
+    q = int(min(max(quality, 1), 100))
+    scale = 5000 // q if q < 50 else 200 - 2 * q
+    tabs = [np.clip((np.asarray(b, dtype=np.int64) * scale + 50) // 100, 1, 255) for b in (_JPEG_LUM, _JPEG_CHR)]
+    u = np.arange(8, dtype=np.float64)[:, None]
+    x = np.arange(8, dtype=np.float64)[None, :]
+    t = np.rint(8192.0 * np.where(u == 0, math.sqrt(0.125), 0.5) * np.cos((2 * x + 1) * u * math.pi / 16.0))
+    return np.concatenate([tabs[0], tabs[1], t.ravel()]).astype(np.int32)
+
+
+FROST_TINT = (0.85, 0.92, 1.0)
+FROST_DECAY = 2.0
+
+
+def glass_table(sigma):
+    """radius, uint8 table = int32 fixed-point taps (sum 65536) followed by fp32 taps."""
+    r = int(4.0 * float(sigma) + 0.5)
+    xs = np.arange(-r, r + 1, dtype=np.float64)
+    k = np.exp(-0.5 * (xs / float(sigma)) ** 2)
+    k = k / k.sum()
+    q = np.rint(k * 65536.0).astype(np.int64)
+    q[r] += 65536 - q.sum()
+    return r, np.concatenate([q.astype(np.int32).view(np.uint8), k.astype(np.float32).view(np.uint8)])
+
+
 def kernel_params(cfg: CorruptionConfig, h, w, profile=None):
     """-> (fparams list, iparams list, table uint8 ndarray or None) for fav_corrupt_normalize."""
     if cfg.name is None:
@@ -282,6 +322,13 @@ def kernel_params(cfg: CorruptionConfig, h, w, profile=None):
         return [], [nz], buf
     if n == "pixelate":
         return [], [], pixelate_table(c, h, w)
+    if n == "jpeg_compression":
+        return [], [int(c)], jpeg_table(c).view(np.uint8)
+    if n == "frost":
+        return [float(c[0]), float(c[1]), FROST_DECAY] + [float(t) for t in FROST_TINT], [], None
+    if n == "glass_blur":
+        r, tab = glass_table(c[0])
+        return [], [int(c[1]), int(c[2]), r], tab
     raise AssertionError(n)
 
 

@@ -320,11 +320,11 @@ def fog_mapsize(h, w):
     return m
 
 
-def plasma_fractal(n, mapsize, wibbledecay, severity, seed=0, first_image=0):
+def plasma_fractal(n, mapsize, wibbledecay, severity, seed=0, first_image=0, name="fog"):
     """Diamond-square plasma on a torus, fp32, noise from Philox keyed by the written cell."""
     img = np.arange(first_image, first_image + n, dtype=np.uint64)[:, None]
     cell = np.arange(mapsize * mapsize, dtype=np.uint64)[None, :]
-    x0, _, _, _ = px.philox4x32_10(cell, img, 0, _stream("fog", severity), seed)
+    x0, _, _, _ = px.philox4x32_10(cell, img, 0, _stream(name, severity), seed)
     u = px.u32_to_uniform(x0).reshape(n, mapsize, mapsize)
     noise = (np.float32(2.0) * u - np.float32(1.0)).astype(np.float32)       # U(-1,1)
     M = np.zeros((n, mapsize, mapsize), dtype=np.float32)
@@ -397,10 +397,97 @@ def pixelate(x_u8, severity, seed=0, first_image=0, profile=None):
     return (v.astype(np.float32) / np.float32(255.0)).astype(np.float32)
 
 
+# ----------------------------------------------------------------------------- f2 corruptions
+def jpeg_compression(x_u8, severity, seed=0, first_image=0, profile=None):
+    """Integer JPEG round trip (oracle/jpeg.py) at quality c."""
+    from . import jpeg as J
+    n, h, w, _ = x_u8.shape
+    q = CONSTANTS[profile or profile_for(h, w)]["jpeg_compression"][severity - 1]
+    return _to_float(J.jpeg_roundtrip_u8(x_u8, q))
+
+
+FROST_TINT = (0.85, 0.92, 1.0)
+FROST_DECAY = 2.0
+
+
+def frost(x_u8, severity, seed=0, first_image=0, profile=None):
+    """Procedural substitute (documented deviation: the six frost photographs of ImageNet-C are not available):
+    frost texture = diamond-square plasma (decay 2.0) through a contrast curve, tinted icy blue;
+    out = clip(c0 * x + c1 * frost)."""
+    n, h, w, _ = x_u8.shape
+    c0, c1 = CONSTANTS[profile or profile_for(h, w)]["frost"][severity - 1]
+    c0, c1 = np.float32(c0), np.float32(c1)
+    pl = plasma_fractal(n, fog_mapsize(h, w), FROST_DECAY, severity, seed, first_image, name="frost")[:, :h, :w, None]
+    f = np.clip(np.float32(1.35) * pl - np.float32(0.1), 0, 1).astype(np.float32)
+    tex = (f * np.asarray(FROST_TINT, dtype=np.float32)).astype(np.float32)
+    return np.clip(c0 * _to_float(x_u8) + c1 * tex, 0, 1).astype(np.float32)
+
+
+def gaussian_taps(sigma):
+    """scipy / skimage style 1-D Gaussian: radius int(4 sigma + 0.5), normalised."""
+    r = int(4.0 * float(sigma) + 0.5)
+    xs = np.arange(-r, r + 1, dtype=np.float64)
+    k = np.exp(-0.5 * (xs / float(sigma)) ** 2)
+    return r, k / k.sum()
+
+
+def gaussian_taps_q16(sigma):
+    """Fixed-point taps (sum exactly 65536) for the exact integer first blur of glass_blur."""
+    r, k = gaussian_taps(sigma)
+    q = np.rint(k * 65536.0).astype(np.int64)
+    q[r] += 65536 - q.sum()
+    return r, q
+
+
+def glass_swaps(n, h, w, delta, iters, severity, seed, first_image):
+    """(dy, dx) int arrays [n, iters * (h - 2 delta) * (w - 2 delta)] in scan order (h, w descending)."""
+    steps = iters * (h - 2 * delta) * (w - 2 * delta)
+    img = np.arange(first_image, first_image + n, dtype=np.uint64)[:, None]
+    j = np.arange(steps, dtype=np.uint64)[None, :]
+    x0, x1, _, _ = px.philox4x32_10(j, img, 0, _stream("glass_blur", severity), seed)
+    m = np.uint32(2 * delta)
+    return (x1 % m).astype(np.int64) - delta, (x0 % m).astype(np.int64) - delta
+
+
+def glass_blur(x_u8, severity, seed=0, first_image=0, profile=None):
+    """gaussian(sigma) -> uint8 -> `iters` passes of local pixel swaps within +-delta (scan order, sequential) ->
+    gaussian(sigma).  First blur is exact fixed-point integer (so the bytes being swapped are bit-exact on any device),
+    second blur is fp32; borders clamp ('nearest')."""
+    n, h, w, _ = x_u8.shape
+    sigma, delta, iters = CONSTANTS[profile or profile_for(h, w)]["glass_blur"][severity - 1]
+    r, q = gaussian_taps_q16(sigma)
+    xi = x_u8.astype(np.int64)
+    idx = lambda size: np.clip(np.arange(size)[:, None] + np.arange(-r, r + 1)[None, :], 0, size - 1)
+    a1 = ((xi[:, :, idx(w)] * q[None, None, None, :, None]).sum(3) + 128) >> 8                  # along x, 8 fractional bits
+    a2 = (a1[:, idx(h)] * q[None, None, :, None, None]).sum(2)                                  # along y
+    b = np.clip((a2 + (1 << 23)) >> 24, 0, 255).astype(np.uint8)
+    dy, dx = glass_swaps(n, h, w, delta, iters, severity, seed, first_image)
+    for i in range(n):
+        j = 0
+        img = b[i]
+        for _ in range(iters):
+            for hh in range(h - delta, delta, -1):
+                for ww in range(w - delta, delta, -1):
+                    h2, w2 = hh + int(dy[i, j]), ww + int(dx[i, j])
+                    j += 1
+                    t = img[hh, ww].copy(); img[hh, ww] = img[h2, w2]; img[h2, w2] = t
+    _, k = gaussian_taps(sigma)
+    k = k.astype(np.float32)
+    y = _to_float(b)
+    y1 = np.zeros_like(y)
+    for t in range(2 * r + 1):
+        y1 += k[t] * y[:, :, np.clip(np.arange(w) + t - r, 0, w - 1)]
+    y2 = np.zeros_like(y)
+    for t in range(2 * r + 1):
+        y2 += k[t] * y1[:, np.clip(np.arange(h) + t - r, 0, h - 1)]
+    return np.clip(y2, 0, 1).astype(np.float32)
+
+
 GENERATORS = {
     "gaussian_noise": gaussian_noise, "shot_noise": shot_noise, "impulse_noise": impulse_noise,
     "defocus_blur": defocus_blur, "motion_blur": motion_blur, "zoom_blur": zoom_blur,
     "brightness": brightness, "contrast": contrast, "fog": fog, "pixelate": pixelate,
+    "jpeg_compression": jpeg_compression, "frost": frost, "glass_blur": glass_blur,
 }
 
 
