@@ -184,8 +184,8 @@ def run_reference(args, rank, world):
 def workload_config(n_gpus, block):
     import fav
     return {"workload": "C2: ResNet-18 random-init (torchvision, logit-gain fixture 8.0), 32x32 CIFAR-shape, "
-                        f"MC-dropout T={T_PASSES} p={P_DROP}, sweep over {len(fav.IMPLEMENTED)} corruptions x 5 severities "
-                        f"({len(fav.IMPLEMENTED) * 5} of 75 cells have device kernels), ECE(15 bins)+entropy+MI+AUROC(4096 buckets)",
+                        f"MC-dropout T={T_PASSES} p={P_DROP}, sweep over all {len(fav.IMPLEMENTED)} corruptions x 5 severities "
+                        f"({len(fav.IMPLEMENTED) * 5} cells), ECE(15 bins)+entropy+MI+AUROC(4096 buckets)",
             "images_per_step": block, "passes": T_PASSES, "num_classes": 10,
             "corruptions": list(fav.IMPLEMENTED), "parallelism": f"image-block x cell sharding over {n_gpus} GPU(s)",
             "l2": "working set (5 activation buffers x 84 MB per step) exceeds the 126 MB L2; image blocks rotate"}

@@ -12,7 +12,7 @@
 
 namespace fav {
 
-enum { PW_CLEAN = 0, PW_GAUSS, PW_SHOT, PW_IMPULSE, PW_BRIGHT, PW_CONTRAST, PW_FOG, PW_FROST };
+enum { PW_CLEAN = 0, PW_GAUSS, PW_SHOT, PW_IMPULSE, PW_BRIGHT, PW_CONTRAST, PW_FOG, PW_FROST, PW_SNOW };
 
 struct PointwiseArgs {
   const uint8_t* src;
@@ -173,6 +173,24 @@ __global__ void __launch_bounds__(256) k1_pointwise(const PointwiseArgs a) {
 #pragma unroll
         for (int c = 0; c < 3; ++c)
           x[3 * p + c] = __fmul_rn(__fadd_rn(div255(x[3 * p + c]), __fmul_rn(a.f0, pl)), gain);
+      }
+    } else if (MODE == PW_SNOW) {
+      // x' = blend x + (1 - blend) max(x, 1.5 gray + 0.5);  out = x' + B[y,x] + B[H-1-y, W-1-x]   (B = blurred snow layer)
+      const float* B = reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.scratch) + a.map_offset) + (size_t)img * a.hw;
+#pragma unroll
+      for (int p = 0; p < 16; ++p) {
+        const int pix = e0 / 3 + p;
+        const float r = div255(x[3 * p]), gg = div255(x[3 * p + 1]), b = div255(x[3 * p + 2]);
+        const float gray = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, r), __fmul_rn(0.587f, gg)), __fmul_rn(0.114f, b));
+        const float lift = __fadd_rn(__fmul_rn(gray, 1.5f), 0.5f);
+        float s0 = 0.f, s1 = 0.f;
+        if (pix < a.hw) { s0 = B[pix]; s1 = B[a.hw - 1 - pix]; }
+        const float c3[3] = {r, gg, b};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float xb = __fadd_rn(__fmul_rn(a.f0, c3[c]), __fmul_rn(a.f1, fmaxf(c3[c], lift)));
+          x[3 * p + c] = __fadd_rn(__fadd_rn(xb, s0), s1);
+        }
       }
     } else if (MODE == PW_FROST) {
       // procedural frost (the ImageNet-C frost photographs are not available): texture = plasma through a contrast curve,
@@ -517,6 +535,179 @@ __global__ void __launch_bounds__(256) k1_pixelate(const PixArgs a) {
   }
 }
 
+// ---------------------------------------------------------------- snow: layer generation and its motion blur
+// Layer: 8-term Irwin-Hall field (one Philox call per pixel, integer sum -> bit-exact) -> clipped bilinear zoom ->
+// hard threshold -> clip.  Blur: per-image tap list (integer angle -135..-45), clamp border.
+struct SnowArgs {
+  int n, h, w;
+  float loc, scale, thresh, ih_scale;
+  const uint2* ztab;                       // (h + w) x {i0 | i1 << 16, frac}
+  const uint8_t* taps;                     // tap table (k1_taps format)
+  int n_entries, max_taps;
+  uint32_t k0, k1, first_image, stream, aux_stream;
+  float* layer;                            // [n, h, w]
+  float* blurred;                          // [n, h, w]
+};
+__device__ __forceinline__ float snow_field_at(const SnowArgs& a, uint32_t gimg, int yy, int xx) {
+  const uint4 r = philox4x32_10(uint32_t(yy * a.w + xx), gimg, 0u, a.stream, a.k0, a.k1);
+  const int ssum = int((r.x & 0xFFFFu) + (r.x >> 16) + (r.y & 0xFFFFu) + (r.y >> 16) + (r.z & 0xFFFFu) + (r.z >> 16) +
+                       (r.w & 0xFFFFu) + (r.w >> 16)) - 4 * 65535;
+  return __fadd_rn(a.loc, __fmul_rn(a.scale, __fmul_rn(float(ssum), a.ih_scale)));
+}
+__global__ void __launch_bounds__(256) k1_snow_layer(const SnowArgs a) {
+  const long long total = (long long)a.n * a.h * a.w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int img = int(i / (a.h * a.w));
+    const int rem = int(i - (long long)img * a.h * a.w);
+    const int y = rem / a.w, x = rem - y * a.w;
+    const uint32_t gimg = a.first_image + uint32_t(img);
+    const uint2 ry = __ldg(a.ztab + y), rx = __ldg(a.ztab + a.h + x);
+    const int y0 = int(ry.x & 0xFFFF), y1 = int(ry.x >> 16), x0 = int(rx.x & 0xFFFF), x1 = int(rx.x >> 16);
+    const float fy = __uint_as_float(ry.y), fx = __uint_as_float(rx.y);
+    const float v00 = snow_field_at(a, gimg, y0, x0), v01 = snow_field_at(a, gimg, y0, x1);
+    const float v10 = snow_field_at(a, gimg, y1, x0), v11 = snow_field_at(a, gimg, y1, x1);
+    const float top = __fadd_rn(__fmul_rn(v00, __fsub_rn(1.0f, fx)), __fmul_rn(v01, fx));
+    const float bot = __fadd_rn(__fmul_rn(v10, __fsub_rn(1.0f, fx)), __fmul_rn(v11, fx));
+    float v = __fadd_rn(__fmul_rn(top, __fsub_rn(1.0f, fy)), __fmul_rn(bot, fy));
+    if (v < a.thresh) v = 0.f;
+    a.layer[i] = fminf(fmaxf(v, 0.f), 1.f);
+  }
+}
+__global__ void __launch_bounds__(256) k1_snow_blur(const SnowArgs a) {
+  const long long total = (long long)a.n * a.h * a.w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int img = int(i / (a.h * a.w));
+    const int rem = int(i - (long long)img * a.h * a.w);
+    const int y = rem / a.w, x = rem - y * a.w;
+    const uint4 r = philox4x32_10(0u, a.first_image + uint32_t(img), 0u, a.aux_stream, a.k0, a.k1);
+    const uint8_t* ent = a.taps + (size_t)(r.x % uint32_t(a.n_entries)) * (16 + 8 * (size_t)a.max_taps);
+    const int ntaps = *reinterpret_cast<const int*>(ent);
+    const uint2* tp = reinterpret_cast<const uint2*>(ent + 16);
+    const float* L = a.layer + (size_t)img * a.h * a.w;
+    float acc = 0.f;
+    for (int t = 0; t < ntaps; ++t) {
+      const uint2 q = __ldg(tp + t);
+      const int dy = int(short(q.x & 0xFFFF)), dx = int(short(q.x >> 16));
+      acc = fmaf(__uint_as_float(q.y), L[min(max(y + dy, 0), a.h - 1) * a.w + min(max(x + dx, 0), a.w - 1)], acc);
+    }
+    a.blurred[i] = acc;
+  }
+}
+
+// ---------------------------------------------------------------- elastic_transform
+// (1) random affine warp (bilinear, reflect-101) + raw U(-1,1) displacement fields, (2) Gaussian x-pass, (3) Gaussian y-pass,
+// scale by alpha, bilinear sample of the warped image with symmetric reflection, normalize.  scratch planes (fp32, n*h*w
+// each): warped R,G,B | U0,U1 | P0,P1.
+struct ElasticArgs {
+  const uint8_t* src;
+  OutArgs out;
+  int n, h, w, radius;
+  float alpha, mag, c0, c1, sq;
+  const float* taps;
+  uint32_t k0, k1, first_image, stream, aux_stream;
+  float* scratch;
+  unsigned src_bgr;
+};
+__device__ __forceinline__ int reflect_sym(int i, int n) {
+  i %= 2 * n;
+  if (i < 0) i += 2 * n;
+  return i >= n ? 2 * n - 1 - i : i;
+}
+__device__ __forceinline__ int reflect101_clamped(int i, int n) {
+  i = min(max(i, -(n - 1)), 2 * (n - 1));
+  i = abs(i);
+  if (i >= n) i = 2 * (n - 1) - i;
+  return min(max(i, 0), n - 1);
+}
+__global__ void __launch_bounds__(256) k1_elastic_prep(const ElasticArgs a) {
+  const long long hw = (long long)a.h * a.w, total = a.n * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int img = int(i / hw);
+    const int rem = int(i - img * hw);
+    const int y = rem / a.w, x = rem - y * a.w;
+    const uint32_t gimg = a.first_image + uint32_t(img);
+    // inverse affine map dst -> src from the three jittered control points
+    const uint4 ja = philox4x32_10(0u, gimg, 0u, a.aux_stream, a.k0, a.k1);
+    const uint4 jb = philox4x32_10(1u, gimg, 0u, a.aux_stream, a.k0, a.k1);
+    const uint32_t jw[6] = {ja.x, ja.y, ja.z, ja.w, jb.x, jb.y};
+    float jit[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) jit[k] = (2.0f * u32_to_uniform(jw[k]) - 1.0f) * a.mag;
+    const float p[3][2] = {{a.c0 + a.sq, a.c1 + a.sq}, {a.c0 + a.sq, a.c1 - a.sq}, {a.c0 - a.sq, a.c1 - a.sq}};
+    float q[3][2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { q[k][0] = p[k][0] + jit[2 * k]; q[k][1] = p[k][1] + jit[2 * k + 1]; }
+    const float e1x = q[1][0] - q[0][0], e1y = q[1][1] - q[0][1], e2x = q[2][0] - q[0][0], e2y = q[2][1] - q[0][1];
+    const float d1x = p[1][0] - p[0][0], d1y = p[1][1] - p[0][1], d2x = p[2][0] - p[0][0], d2y = p[2][1] - p[0][1];
+    const float inv = 1.0f / (e1x * e2y - e2x * e1y);
+    const float qi00 = e2y * inv, qi01 = -e2x * inv, qi10 = -e1y * inv, qi11 = e1x * inv;
+    const float A00 = d1x * qi00 + d2x * qi10, A01 = d1x * qi01 + d2x * qi11;
+    const float A10 = d1y * qi00 + d2y * qi10, A11 = d1y * qi01 + d2y * qi11;
+    const float dx = float(x) - q[0][0], dy = float(y) - q[0][1];
+    const float sx = p[0][0] + (A00 * dx + A01 * dy), sy = p[0][1] + (A10 * dx + A11 * dy);
+    const float fx0 = floorf(sx), fy0 = floorf(sy), fx = sx - fx0, fy = sy - fy0;
+    const int xa = reflect101_clamped(int(fx0), a.w), xb = reflect101_clamped(int(fx0) + 1, a.w);
+    const int ya = reflect101_clamped(int(fy0), a.h), yb = reflect101_clamped(int(fy0) + 1, a.h);
+    const uint8_t* im = a.src + (size_t)img * hw * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int cs = a.src_bgr ? 2 - c : c;
+      const float v00 = u8f(im[((size_t)ya * a.w + xa) * 3 + cs]), v01 = u8f(im[((size_t)ya * a.w + xb) * 3 + cs]);
+      const float v10 = u8f(im[((size_t)yb * a.w + xa) * 3 + cs]), v11 = u8f(im[((size_t)yb * a.w + xb) * 3 + cs]);
+      const float top = v00 * (1.0f - fx) + v01 * fx, bot = v10 * (1.0f - fx) + v11 * fx;
+      a.scratch[(size_t)c * total + i] = top * (1.0f - fy) + bot * fy;
+    }
+    const uint4 r = philox4x32_10(uint32_t(rem), gimg, 0u, a.stream, a.k0, a.k1);
+    a.scratch[3 * (size_t)total + i] = 2.0f * u32_to_uniform(r.x) - 1.0f;
+    a.scratch[4 * (size_t)total + i] = 2.0f * u32_to_uniform(r.y) - 1.0f;
+  }
+}
+__global__ void __launch_bounds__(256) k1_elastic_xpass(const ElasticArgs a) {
+  const long long hw = (long long)a.h * a.w, total = a.n * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int rem = int(i % hw), x = rem % a.w;
+    const float* u0 = a.scratch + 3 * (size_t)total + (i - x);
+    const float* u1 = a.scratch + 4 * (size_t)total + (i - x);
+    float s0 = 0.f, s1 = 0.f;
+    for (int t = -a.radius; t <= a.radius; ++t) {
+      const int xx = reflect_sym(x + t, a.w);
+      const float k = __ldg(a.taps + t + a.radius);
+      s0 = fmaf(k, u0[xx], s0); s1 = fmaf(k, u1[xx], s1);
+    }
+    a.scratch[5 * (size_t)total + i] = s0;
+    a.scratch[6 * (size_t)total + i] = s1;
+  }
+}
+__global__ void __launch_bounds__(256) k1_elastic_final(const ElasticArgs a) {
+  const long long hw = (long long)a.h * a.w, total = a.n * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int img = int(i / hw);
+    const int rem = int(i - img * hw);
+    const int y = rem / a.w, x = rem - y * a.w;
+    const float* p0 = a.scratch + 5 * (size_t)total + (size_t)img * hw + x;
+    const float* p1 = a.scratch + 6 * (size_t)total + (size_t)img * hw + x;
+    float d0 = 0.f, d1 = 0.f;
+    for (int t = -a.radius; t <= a.radius; ++t) {
+      const int yy = reflect_sym(y + t, a.h);
+      const float k = __ldg(a.taps + t + a.radius);
+      d0 = fmaf(k, p0[(size_t)yy * a.w], d0); d1 = fmaf(k, p1[(size_t)yy * a.w], d1);
+    }
+    const float sx = float(x) + d0 * a.alpha, sy = float(y) + d1 * a.alpha;
+    const float fx0 = floorf(sx), fy0 = floorf(sy), fx = sx - fx0, fy = sy - fy0;
+    const int xa = reflect_sym(int(fx0), a.w), xb = reflect_sym(int(fx0) + 1, a.w);
+    const int ya = reflect_sym(int(fy0), a.h), yb = reflect_sym(int(fy0) + 1, a.h);
+    float o[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* im = a.scratch + (size_t)c * total + (size_t)img * hw;
+      const float top = im[ya * a.w + xa] * (1.0f - fx) + im[ya * a.w + xb] * fx;
+      const float bot = im[yb * a.w + xa] * (1.0f - fx) + im[yb * a.w + xb] * fx;
+      o[c] = top * (1.0f - fy) + bot * fy;
+    }
+    store_pixel(a.out, (size_t)i, o[0], o[1], o[2]);
+  }
+}
+
 // ---------------------------------------------------------------- jpeg_compression: integer baseline-JPEG round trip
 // One CTA = one 16x16 MCU (4:2:0): JFIF colour transform in libjpeg's 16-bit fixed point, 2x2 chroma mean, six 8x8 blocks
 // through a 13-bit fixed-point orthonormal DCT, Annex-K quantisation, inverse, chroma replication.  All integer:
@@ -732,6 +923,8 @@ using namespace fav;
 
 extern "C" size_t fav_corrupt_scratch_bytes(int corruption, int n, int height, int width) {
   if (corruption == FAV_CONTRAST) return (size_t)n * 3 * sizeof(unsigned long long);
+  if (corruption == FAV_SNOW) return 2 * (size_t)n * height * width * sizeof(float);
+  if (corruption == FAV_ELASTIC) return 7 * (size_t)n * height * width * sizeof(float);
   if (corruption == FAV_FOG || corruption == FAV_FROST) {
     int m = 1;
     while (m < (height > width ? height : width)) m *= 2;
@@ -829,6 +1022,46 @@ extern "C" int fav_corrupt_normalize(fav_handle h, const uint8_t* d_src, void* d
       float* maps = reinterpret_cast<float*>(reinterpret_cast<char*>(d_scratch) + a.map_offset);
       k1_plasma<<<n, 1024, 0, st>>>(d_src, per, m, fparams[2], k0, k1, uint32_t(first_image), a.stream, stats, maps);
       k1_pointwise<PW_FROST><<<grid, 256, 0, st>>>(a); h->launches += 2; break;
+    }
+    case FAV_ELASTIC: {
+      FAV_REQUIRE(need_f(5) && need_i(1) && d_table, "elastic_transform needs fparams[5], iparams[0]=radius and the Gaussian taps");
+      FAV_REQUIRE(d_scratch && scratch_bytes >= fav_corrupt_scratch_bytes(corruption, n, height, width),
+                  "elastic_transform needs %zu scratch bytes", fav_corrupt_scratch_bytes(corruption, n, height, width));
+      ElasticArgs e{};
+      e.src = d_src; e.out = out; e.n = n; e.h = height; e.w = width; e.radius = iparams[0];
+      FAV_REQUIRE(e.radius >= 0 && table_bytes >= (size_t)(2 * e.radius + 1) * 4, "elastic_transform tap table too small");
+      e.alpha = fparams[0]; e.mag = fparams[1]; e.c0 = fparams[2]; e.c1 = fparams[3]; e.sq = fparams[4];
+      e.taps = reinterpret_cast<const float*>(d_table);
+      e.k0 = k0; e.k1 = k1; e.first_image = uint32_t(first_image);
+      e.stream = a.stream; e.aux_stream = stream_id(KIND_AUX, corruption, severity);
+      e.scratch = reinterpret_cast<float*>(d_scratch); e.src_bgr = flags & FAV_SRC_BGR;
+      const int g2 = grid_for((long long)n * height * width, 256, h->num_sms, 16);
+      k1_elastic_prep<<<g2, 256, 0, st>>>(e);
+      k1_elastic_xpass<<<g2, 256, 0, st>>>(e);
+      k1_elastic_final<<<g2, 256, 0, st>>>(e);
+      h->launches += 3; break;
+    }
+    case FAV_SNOW: {
+      FAV_REQUIRE(need_f(6) && need_i(8) && d_table, "snow needs fparams[6], iparams[8] and the tap + zoom tables");
+      FAV_REQUIRE(d_scratch && scratch_bytes >= fav_corrupt_scratch_bytes(corruption, n, height, width),
+                  "snow needs %zu scratch bytes", fav_corrupt_scratch_bytes(corruption, n, height, width));
+      SnowArgs sn{};
+      sn.n = n; sn.h = height; sn.w = width;
+      sn.loc = fparams[0]; sn.scale = fparams[1]; sn.thresh = fparams[2]; sn.ih_scale = fparams[5];
+      sn.n_entries = iparams[0]; sn.max_taps = iparams[1];
+      FAV_REQUIRE(table_bytes >= (size_t)iparams[7] + (size_t)(height + width) * 8, "snow table too small");
+      sn.taps = reinterpret_cast<const uint8_t*>(d_table);
+      sn.ztab = reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(d_table) + iparams[7]);
+      sn.k0 = k0; sn.k1 = k1; sn.first_image = uint32_t(first_image);
+      sn.stream = a.stream; sn.aux_stream = stream_id(KIND_AUX, corruption, severity);
+      sn.layer = reinterpret_cast<float*>(d_scratch);
+      sn.blurred = sn.layer + (size_t)n * height * width;
+      const int g2 = grid_for((long long)n * height * width, 256, h->num_sms, 16);
+      k1_snow_layer<<<g2, 256, 0, st>>>(sn);
+      k1_snow_blur<<<g2, 256, 0, st>>>(sn);
+      a.f0 = fparams[3]; a.f1 = fparams[4];
+      a.map_offset = (size_t)n * height * width * sizeof(float);       // pointwise reads the blurred plane
+      k1_pointwise<PW_SNOW><<<grid, 256, 0, st>>>(a); h->launches += 3; break;
     }
     case FAV_JPEG: {
       FAV_REQUIRE(d_table && table_bytes >= 192 * 4, "jpeg_compression needs the 192-int quantisation / DCT table");

@@ -17,8 +17,7 @@ CORRUPTIONS = (
 )
 CORRUPTION_ID = {name: i + 1 for i, name in enumerate(CORRUPTIONS)}
 # corruptions with a device kernel in this build; the sweep reports the rest as unavailable
-IMPLEMENTED = ("gaussian_noise", "shot_noise", "impulse_noise", "defocus_blur", "glass_blur", "motion_blur",
-               "zoom_blur", "frost", "fog", "brightness", "contrast", "pixelate", "jpeg_compression")
+IMPLEMENTED = CORRUPTIONS      # all 15 have device kernels
 
 SEVERITY = {
     "imagenet": {
@@ -35,6 +34,9 @@ SEVERITY = {
         "jpeg_compression": [25, 18, 15, 10, 7],
         "glass_blur": [(.7, 1, 2), (.9, 2, 1), (1, 2, 3), (1.1, 3, 2), (1.5, 4, 2)],
         "frost": [(1, .4), (.8, .6), (.7, .7), (.65, .7), (.6, .75)],
+        "snow": [(.1, .3, 3, .5, 10, 4, .8), (.2, .3, 2, .5, 12, 4, .7), (.55, .3, 4, .9, 12, 8, .7),
+                 (.55, .3, 4.5, .85, 12, 8, .65), (.55, .3, 2.5, .85, 12, 12, .55)],
+        "elastic_transform": [(2., .7, .1), (2., .08, .2), (.05, .01, .02), (.07, .01, .02), (.12, .01, .02)],
     },
     "cifar": {
         "gaussian_noise": [.04, .06, .08, .09, .10],
@@ -50,6 +52,9 @@ SEVERITY = {
         "jpeg_compression": [80, 65, 58, 50, 40],
         "glass_blur": [(.05, 1, 1), (.25, 1, 1), (.4, 1, 1), (.25, 1, 2), (.4, 1, 2)],
         "frost": [(1, .2), (1, .3), (.9, .4), (.85, .4), (.75, .45)],
+        "snow": [(.1, .2, 1, .6, 8, 3, .95), (.1, .2, 1, .5, 10, 4, .9), (.15, .3, 1.75, .55, 10, 4, .9),
+                 (.25, .3, 2.25, .6, 12, 6, .85), (.3, .3, 1.25, .65, 14, 12, .8)],
+        "elastic_transform": [(0, 0, .08), (.05, .2, .07), (.08, .06, .06), (.1, .04, .05), (.1, .03, .03)],
     },
 }
 
@@ -178,6 +183,7 @@ def defocus_table(radius, alias_blur):
 
 
 MOTION_ANGLES = 91        # integer degrees -45..45, chosen per image by a Philox draw
+SNOW_ANGLES = 91          # integer degrees -135..-45 for the snow layer's motion blur
 
 
 def motion_taps(radius, sigma, angle_deg, h, w):
@@ -291,8 +297,6 @@ def kernel_params(cfg: CorruptionConfig, h, w, profile=None):
     """-> (fparams list, iparams list, table uint8 ndarray or None) for fav_corrupt_normalize."""
     if cfg.name is None:
         return [], [], None
-    if cfg.name not in IMPLEMENTED:
-        raise NotImplementedError(f"corruption '{cfg.name}' has no device kernel in this build")
     c = SEVERITY[profile or profile_for(h, w)][cfg.name][cfg.severity - 1]
     n = cfg.name
     if n == "gaussian_noise":
@@ -329,6 +333,31 @@ def kernel_params(cfg: CorruptionConfig, h, w, profile=None):
     if n == "glass_blur":
         r, tab = glass_table(c[0])
         return [], [int(c[1]), int(c[2]), r], tab
+    if n == "elastic_transform":
+        S = min(h, w)
+        alpha, sigma, mag = float(c[0]) * S, float(c[1]) * S, float(c[2]) * S
+        r = int(3.0 * sigma + 0.5)
+        if sigma <= 1e-6:
+            r, k = 0, np.ones(1, dtype=np.float32)
+        else:
+            xs = np.arange(-r, r + 1, dtype=np.float64)
+            k = np.exp(-0.5 * (xs / sigma) ** 2)
+            k = (k / k.sum()).astype(np.float32)
+        return [alpha, mag, float(h // 2), float(w // 2), float(min(h, w) // 3)], [r], k.view(np.uint8)
+    if n == "snow":
+        loc, scale, zoom, thresh, mb_r, mb_s, blend = c
+        geom, taps = _pack_taps([motion_taps(int(mb_r), float(mb_s), a - 135, h, w) for a in range(SNOW_ANGLES)])
+        geom[2] = 1                                    # clamp border
+        ztab = np.zeros((h + w, 2), dtype=np.uint32)
+        for off, size in ((0, h), (h, w)):
+            i0, i1, fr = _zoom_axis(size, float(zoom))
+            ztab[off:off + size, 0] = i0.astype(np.uint32) | (i1.astype(np.uint32) << 16)
+            ztab[off:off + size, 1] = fr.view(np.uint32)
+        pad = (-len(taps)) % 16
+        tab = np.concatenate([taps, np.zeros(pad, np.uint8), ztab.view(np.uint8).ravel()])
+        irwin_hall = float(np.float32(1.0 / (65536.0 * math.sqrt(8.0 / 12.0))))
+        return ([float(loc), float(scale), float(thresh), float(blend), float(np.float32(1 - blend)), irwin_hall],
+                geom + [len(taps) + pad], tab)
     raise AssertionError(n)
 
 

@@ -483,11 +483,155 @@ def glass_blur(x_u8, severity, seed=0, first_image=0, profile=None):
     return np.clip(y2, 0, 1).astype(np.float32)
 
 
+SNOW_ANGLES = 91            # integer degrees -135..-45
+
+
+def snow_field(n, h, w, loc, scale, severity, seed, first_image):
+    """Bit-exact stand-in for N(loc, scale^2): 8-term Irwin-Hall on the eight 16-bit lanes of one Philox call per pixel
+    (documented deviation; integer sum -> identical on CPU and GPU, so the hard threshold below cannot flip)."""
+    img = np.arange(first_image, first_image + n, dtype=np.uint64)[:, None]
+    pix = np.arange(h * w, dtype=np.uint64)[None, :]
+    xs = px.philox4x32_10(pix, img, 0, _stream("snow", severity), seed)
+    ssum = px.u16_lanes(*xs).astype(np.int64).sum(-1) - 4 * 65535                    # exact integer, |.| <= 262140
+    z = (ssum.astype(np.float32) * np.float32(1.0 / (65536.0 * math.sqrt(8.0 / 12.0)))).astype(np.float32)
+    return (np.float32(loc) + np.float32(scale) * z).astype(np.float32).reshape(n, h, w)
+
+
+def snow(x_u8, severity, seed=0, first_image=0, profile=None):
+    n, h, w, _ = x_u8.shape
+    loc, scale, zoom, thresh, mb_r, mb_s, blend = CONSTANTS[profile or profile_for(h, w)]["snow"][severity - 1]
+    L = snow_field(n, h, w, loc, scale, severity, seed, first_image)
+    # clipped zoom (bilinear, same geometry and op order as zoom_blur), then hard threshold and clip
+    y0, y1, fy = _zoom_sample_axis(h, float(zoom))
+    x0, x1, fx = _zoom_sample_axis(w, float(zoom))
+    fy_, fx_ = fy[None, :, None], fx[None, None, :]
+    top = L[:, y0][:, :, x0] * (1 - fx_) + L[:, y0][:, :, x1] * fx_
+    bot = L[:, y1][:, :, x0] * (1 - fx_) + L[:, y1][:, :, x1] * fx_
+    L = (top * (1 - fy_) + bot * fy_).astype(np.float32)
+    L = np.where(L < np.float32(thresh), np.float32(0), L)
+    L = np.clip(L, 0, 1).astype(np.float32)
+    # motion blur of the layer, one integer angle in [-135, -45] per image
+    img = np.arange(first_image, first_image + n, dtype=np.uint64)
+    a0, _, _, _ = px.philox4x32_10(0, img, 0, _stream("snow", severity, px.KIND_AUX), seed)
+    aidx = (a0 % np.uint32(SNOW_ANGLES)).astype(np.int64)
+    B = np.empty_like(L)
+    for i in range(n):
+        dys, dxs, ws = motion_taps(int(mb_r), float(mb_s), int(aidx[i]) - 135)
+        keep = len(ws)
+        for j, (dy, dx) in enumerate(zip(dys, dxs)):
+            if abs(dy) >= h or abs(dx) >= w:
+                keep = j
+                break
+        B[i] = _apply_taps(L[i:i + 1, :, :, None], dys[:keep], dxs[:keep], ws[:keep], "clamp")[0, :, :, 0]
+    x = _to_float(x_u8)
+    gray = (np.float32(0.299) * x[..., 0] + np.float32(0.587) * x[..., 1] + np.float32(0.114) * x[..., 2]).astype(np.float32)
+    lift = (gray * np.float32(1.5) + np.float32(0.5))[..., None]
+    x = np.float32(blend) * x + np.float32(1 - blend) * np.maximum(x, lift)
+    return np.clip(x + B[..., None] + B[:, ::-1, ::-1, None], 0, 1).astype(np.float32)
+
+
+def _reflect_sym(i, n):
+    """scipy 'reflect' (half-sample symmetric): ... c b a | a b c ... valid for any integer i."""
+    i = np.mod(i, 2 * n)
+    return np.where(i >= n, 2 * n - 1 - i, i)
+
+
+def elastic_gauss_taps(sigma):
+    r = int(3.0 * float(sigma) + 0.5)
+    if sigma <= 1e-6:
+        return 0, np.ones(1, dtype=np.float32)
+    xs = np.arange(-r, r + 1, dtype=np.float64)
+    k = np.exp(-0.5 * (xs / float(sigma)) ** 2)
+    return r, (k / k.sum()).astype(np.float32)
+
+
+def elastic_params(h, w, c):
+    S = min(h, w)
+    return float(c[0]) * S, float(c[1]) * S, float(c[2]) * S          # alpha, sigma, affine magnitude
+
+
+def elastic_affine(n, h, w, mag, severity, seed, first_image):
+    """Per image the INVERSE map dst -> src as (p0 [2], q0 [2], A [2,2]): src = p0 + A (dst - q0), all fp32.
+    pts1 -> pts2 = pts1 + U(-mag, mag) as in make_imagenet_c.elastic_transform."""
+    img = np.arange(first_image, first_image + n, dtype=np.uint64)
+    a = px.philox4x32_10(0, img, 0, _stream("elastic_transform", severity, px.KIND_AUX), seed)
+    b = px.philox4x32_10(1, img, 0, _stream("elastic_transform", severity, px.KIND_AUX), seed)
+    u = np.stack([px.u32_to_uniform(v) for v in (a[0], a[1], a[2], a[3], b[0], b[1])], -1)          # [n, 6]
+    jit = ((np.float32(2.0) * u - np.float32(1.0)) * np.float32(mag)).astype(np.float32).reshape(n, 3, 2)
+    c0, c1, sq = np.float32(h // 2), np.float32(w // 2), np.float32(min(h, w) // 3)
+    p = np.array([[c0 + sq, c1 + sq], [c0 + sq, c1 - sq], [c0 - sq, c1 - sq]], dtype=np.float32)        # (x, y) points
+    q = (p[None] + jit).astype(np.float32)
+    e1, e2 = q[:, 1] - q[:, 0], q[:, 2] - q[:, 0]                        # columns of Q
+    d1, d2 = p[1] - p[0], p[2] - p[0]                                    # columns of P
+    det = (e1[:, 0] * e2[:, 1] - e2[:, 0] * e1[:, 1]).astype(np.float32)
+    inv = np.float32(1.0) / det
+    # Q^-1 = 1/det [[e2y, -e2x], [-e1y, e1x]];  A = P Q^-1
+    qi00, qi01 = e2[:, 1] * inv, -e2[:, 0] * inv
+    qi10, qi11 = -e1[:, 1] * inv, e1[:, 0] * inv
+    A = np.empty((n, 2, 2), dtype=np.float32)
+    A[:, 0, 0] = d1[0] * qi00 + d2[0] * qi10
+    A[:, 0, 1] = d1[0] * qi01 + d2[0] * qi11
+    A[:, 1, 0] = d1[1] * qi00 + d2[1] * qi10
+    A[:, 1, 1] = d1[1] * qi01 + d2[1] * qi11
+    return p[0], q[:, 0], A
+
+
+def elastic_transform(x_u8, severity, seed=0, first_image=0, profile=None):
+    """Random affine warp (bilinear, reflect-101) followed by a Gaussian-smoothed random displacement field sampled
+    bilinearly with symmetric reflection; own float formulation of make_imagenet_c.elastic_transform."""
+    n, h, w, _ = x_u8.shape
+    alpha, sigma, mag = elastic_params(h, w, CONSTANTS[profile or profile_for(h, w)]["elastic_transform"][severity - 1])
+    x = _to_float(x_u8)
+    p0, q0, A = elastic_affine(n, h, w, mag, severity, seed, first_image)
+    X, Y = np.meshgrid(np.arange(w, dtype=np.float32), np.arange(h, dtype=np.float32))
+    warped = np.empty_like(x)
+    for i in range(n):
+        dxs, dys = X - q0[i, 0], Y - q0[i, 1]
+        sx = (p0[0] + (A[i, 0, 0] * dxs + A[i, 0, 1] * dys)).astype(np.float32)
+        sy = (p0[1] + (A[i, 1, 0] * dxs + A[i, 1, 1] * dys)).astype(np.float32)
+        x0, y0 = np.floor(sx), np.floor(sy)
+        fx, fy = (sx - x0)[..., None], (sy - y0)[..., None]
+        x0i, y0i = x0.astype(np.int64), y0.astype(np.int64)
+        r101 = lambda v, m: _reflect101(np.clip(v, -(m - 1), 2 * (m - 1)), m)          # far-off coordinates clamp to one reflection
+        xa, xb, ya, yb = r101(x0i, w), r101(x0i + 1, w), r101(y0i, h), r101(y0i + 1, h)
+        im = x[i]
+        top = im[ya, xa] * (1 - fx) + im[ya, xb] * fx
+        bot = im[yb, xa] * (1 - fx) + im[yb, xb] * fx
+        warped[i] = (top * (1 - fy) + bot * fy).astype(np.float32)
+    # displacement fields
+    img = np.arange(first_image, first_image + n, dtype=np.uint64)[:, None]
+    pix = np.arange(h * w, dtype=np.uint64)[None, :]
+    r0, r1, _, _ = px.philox4x32_10(pix, img, 0, _stream("elastic_transform", severity), seed)
+    U = np.stack([px.u32_to_uniform(r0), px.u32_to_uniform(r1)], 1).reshape(n, 2, h, w)
+    U = (np.float32(2.0) * U - np.float32(1.0)).astype(np.float32)
+    r, k = elastic_gauss_taps(sigma)
+    P1 = np.zeros_like(U)
+    for t in range(2 * r + 1):
+        P1 += k[t] * U[:, :, :, _reflect_sym(np.arange(w) + t - r, w)]
+    D = np.zeros_like(U)
+    for t in range(2 * r + 1):
+        D += k[t] * P1[:, :, _reflect_sym(np.arange(h) + t - r, h)]
+    D = (D * np.float32(alpha)).astype(np.float32)
+    out = np.empty_like(x)
+    for i in range(n):
+        sx, sy = (X + D[i, 0]).astype(np.float32), (Y + D[i, 1]).astype(np.float32)
+        x0, y0 = np.floor(sx), np.floor(sy)
+        fx, fy = (sx - x0)[..., None], (sy - y0)[..., None]
+        x0i, y0i = x0.astype(np.int64), y0.astype(np.int64)
+        xa, xb, ya, yb = _reflect_sym(x0i, w), _reflect_sym(x0i + 1, w), _reflect_sym(y0i, h), _reflect_sym(y0i + 1, h)
+        im = warped[i]
+        top = im[ya, xa] * (1 - fx) + im[ya, xb] * fx
+        bot = im[yb, xa] * (1 - fx) + im[yb, xb] * fx
+        out[i] = (top * (1 - fy) + bot * fy).astype(np.float32)
+    return np.clip(out, 0, 1).astype(np.float32)
+
+
 GENERATORS = {
     "gaussian_noise": gaussian_noise, "shot_noise": shot_noise, "impulse_noise": impulse_noise,
     "defocus_blur": defocus_blur, "motion_blur": motion_blur, "zoom_blur": zoom_blur,
     "brightness": brightness, "contrast": contrast, "fog": fog, "pixelate": pixelate,
-    "jpeg_compression": jpeg_compression, "frost": frost, "glass_blur": glass_blur,
+    "jpeg_compression": jpeg_compression, "frost": frost, "glass_blur": glass_blur, "snow": snow,
+    "elastic_transform": elastic_transform,
 }
 
 

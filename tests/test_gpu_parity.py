@@ -62,7 +62,7 @@ def test_device_philox_streams_match_oracle(fav, clf18):
 # ------------------------------------------------------------------------------------------- K1
 K1_CASES = [(name, s) for name in ("gaussian_noise", "shot_noise", "impulse_noise", "defocus_blur", "motion_blur",
                                    "zoom_blur", "fog", "brightness", "contrast", "pixelate", "jpeg_compression", "frost",
-                                   "glass_blur") for s in (1, 3, 5)]
+                                   "glass_blur", "snow", "elastic_transform") for s in (1, 3, 5)]
 
 
 @pytest.mark.parametrize("name,sev", K1_CASES)
@@ -84,7 +84,7 @@ def test_k1_corruption_cifar_shape(fav, clf18, name, sev):
 
 @pytest.mark.parametrize("name,sev", [("gaussian_noise", 5), ("shot_noise", 1), ("defocus_blur", 4), ("motion_blur", 5),
                                       ("zoom_blur", 2), ("fog", 3), ("contrast", 4), ("pixelate", 3), ("brightness", 2),
-                                      ("impulse_noise", 4), ("jpeg_compression", 2), ("frost", 5), ("glass_blur", 1)])
+                                      ("impulse_noise", 4), ("jpeg_compression", 2), ("frost", 5), ("glass_blur", 1), ("snow", 4), ("elastic_transform", 1), ("elastic_transform", 4)])
 def test_k1_corruption_imagenet_shape(fav, name, sev):
     clf = _clf_cache(fav, "resnet18", 1000, (224, 224))
     n, first, seed = 2, 77, 1

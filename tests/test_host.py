@@ -85,7 +85,7 @@ def test_config_objects():
         with pytest.raises(ValueError):
             fav.CorruptionConfig(*bad)
     cfg = SweepConfig(include_clean=True)
-    assert len(cfg.cells()) == 1 + 5 * len(fav.IMPLEMENTED)
+    assert len(cfg.cells()) == 1 + 5 * len(fav.IMPLEMENTED) == 76          # the full 15 x 5 grid + clean
     json.dumps(cfg.to_dict())             # trivially serialisable, like the reference's JSON actions
 
 

