@@ -372,3 +372,37 @@ def test_gate_with_classifier_feeds_trust_engine_contract(fav):
     assert 0 < u["confidence"] <= 1 and u["entropy"] >= 0 and u["mutual_information"] >= 0
     gate.reset()
     assert gate.analyze_frame(f[1])["metrics"]["raw"]["frame_diff"] == 10.0
+
+
+# ------------------------------------------------------------------------------------------- full BASELINE sizes
+def test_c2_full_size_properties(fav):
+    """Config C2 at its full size (N = 10 000 CIFAR-shape images, T = 20) on a few cells: size-independent properties of the
+    aggregates -- every histogram family sums to N, integer sums are consistent, and the result does not depend on the block
+    size used to walk the images (Philox counters are keyed by the global image index)."""
+    from fav.sweep import CorruptionSweep, SweepConfig, HDR
+    N, T = 10_000, 20
+    cells = (("gaussian_noise",), (2, 5))
+    arenas = []
+    for block in (512, 384):
+        cfg = SweepConfig(corruptions=cells[0], severities=cells[1], T=T, logit_gain=8.0, block=block, seed=11)
+        sw = CorruptionSweep(cfg)
+        h, st = sw.clf.handle.h, C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        x = torch.empty((N, 32, 32, 3), dtype=torch.uint8, device="cuda")
+        y = torch.empty(N, dtype=torch.int32, device="cuda")
+        fav._lib.check(sw.clf.lib.fav_synth_images(h, _p(x), N, 32, 32, 11, 0, st), "synth")
+        fav._lib.check(sw.clf.lib.fav_synth_labels(h, _p(y), N, 10, 11, 0, st), "synth")
+        res = sw.run(x, y)
+        arenas.append(sw.acc.arena.cpu().numpy())
+        for (name, sev), r in res.items():
+            assert r["n"] == N and 0 <= r["ece"] <= 1 and 0 <= r["accuracy"] <= 1
+    a = arenas[0]
+    assert np.array_equal(a, arenas[1]), "aggregates depend on the block size"
+    for row in a:
+        assert row[0] == N
+        bins = row[HDR:HDR + 45].reshape(15, 3)
+        assert bins[:, 0].sum() == N and bins[:, 2].sum() == row[1] and bins[:, 1].sum() == row[3]
+        buckets = row[HDR + 45:HDR + 45 + 6 * 4096].reshape(3, 4096, 2)
+        assert (buckets.sum(axis=(1, 2)) == N).all() and (buckets[:, :, 0].sum(1) == row[1]).all()
+        conf = row[HDR + 45 + 6 * 4096:].reshape(10, 10)
+        assert conf.sum() == N and np.trace(conf) == row[1]
+        assert row[2] <= N - row[1]                       # flags are a subset of the misclassified samples
