@@ -148,6 +148,10 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail;
+  // from here on we touch activations it produced (and buffers it may still be reading)
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ================================================================= TMA issuer (warp converged, one elected lane issues)
@@ -688,12 +692,18 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
     int rc = conv_timing_begin(ctx, st, gf, &e1, &a.stats);
     if (rc) return rc;
   }
-  if (mode == 0 && MT == 2)
-    conv_igemm_m256_kernel<<<grid, threads, smem, st>>>(tmA, *reinterpret_cast<const CUtensorMap*>(L.tmap_w), tmA2, a);
-  else if (mode == 0)
-    conv_igemm_kernel<<<grid, threads, smem, st>>>(tmA, *reinterpret_cast<const CUtensorMap*>(L.tmap_w), tmA2, a);
-  else
-    conv_igemm_gather_kernel<<<grid, threads, smem, st>>>(tmA, *reinterpret_cast<const CUtensorMap*>(L.tmap_w), tmA2, a);
+  {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const CUtensorMap& tmW = *reinterpret_cast<const CUtensorMap*>(L.tmap_w);
+    if (mode == 0 && MT == 2) FAV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm_m256_kernel, tmA, tmW, tmA2, a));
+    else if (mode == 0) FAV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm_kernel, tmA, tmW, tmA2, a));
+    else FAV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm_gather_kernel, tmA, tmW, tmA2, a));
+  }
   if (e1) FAV_CUDA_OK(cudaEventRecord(e1, st));
   ctx->launches++;
   FAV_CUDA_OK(cudaGetLastError());

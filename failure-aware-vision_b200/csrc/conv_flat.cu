@@ -72,6 +72,8 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto tempty = [&](int i) { return bars + 8u * (1 + 2 * FL_NSLAB + FL_NACC + i); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ float s_bias[64];
+  if (threadIdx.x < 64) s_bias[threadIdx.x] = a.bias[threadIdx.x];
 
   // zero the margins and every slab's tail rows [slab_rows, 256): they act as the zero halo below the last image of a slab
   {
@@ -92,7 +94,7 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmW);
     mbar_init(w_full, 1u);
     for (int s = 0; s < FL_NSLAB; ++s) { mbar_init(slab_full(s), 1u); mbar_init(slab_empty(s), 1u); }
-    for (int i = 0; i < FL_NACC; ++i) { mbar_init(tfull(i), 1u); mbar_init(tempty(i), uint32_t(FL_EPI_WARPS)); }
+    for (int i = 0; i < FL_NACC; ++i) { mbar_init(tfull(i), 1u); mbar_init(tempty(i), uint32_t(FL_EPI_WARPS / 2)); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 64 * FL_NACC);
@@ -100,6 +102,10 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail;
+  // from here on we touch activations it produced (and buffers it may still be reading)
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ================================================================= TMA issuer: weights once, then one box per slab
@@ -173,91 +179,95 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    // ================================================================= epilogue: 16 warps, 4 per TMEM lane quarter
-    const int quarter = warp & 3;
-    const int sub_w = (warp - 2) >> 2;                  // 0..3 -> 16-column chunk of the 64-wide tile
+    // ================================================================= epilogue: two groups of 8 warps take alternate tiles;
+    // inside a group, warp = (TMEM lane quarter, 32-column half).  Two independent 16-column chunks per warp give the
+    // residual loads / Philox chains of a tile some ILP, and the other group's tile overlaps them further.
+    const int ew = warp - 2, group = ew >> 3, quarter = warp & 3, half = (ew >> 2) & 1;
     const int row = quarter * 32 + lane;
     const int hw_img = a.H * a.W, n_rep = a.rep > 1 ? a.rep : 1, Cout = 64;
+    const int cbase = half * 32;
     long long w_tfull = 0;
     const long long t_begin = clock64();
-    int ai = 0, aph = 0;
-    const int c0 = sub_w * 16;
-    float bias_v[16];
-    {
-      const float4* bp = reinterpret_cast<const float4*>(a.bias + c0);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 b = __ldg(bp + i);
-        bias_v[4 * i] = b.x; bias_v[4 * i + 1] = b.y; bias_v[4 * i + 2] = b.z; bias_v[4 * i + 3] = b.w;
-      }
-    }
+    int tc = 0;                                         // tile sequence number inside this CTA (accumulator = tc % 4)
     for (int slab = blockIdx.x; slab < a.n_slabs; slab += gridDim.x) {
-      for (int tile = 0; tile < a.n_tiles; ++tile) {
+      for (int tile = 0; tile < a.n_tiles; ++tile, ++tc) {
+        if ((tc & 1) != group) continue;
+        const int ai = tc & (FL_NACC - 1), aph = (tc / FL_NACC) & 1;
         // everything that does not depend on the accumulator happens BEFORE the wait: row decode, residual loads,
-        // the first replica's dropout mask -- so their latency overlaps the MMAs of this tile
+        // the first replica's dropout masks -- so their latency overlaps the MMAs of this tile
         const int pi = tile * 128 + row;
         const int g = pi / a.rows_img, rem = pi - g * a.rows_img, ph_ = rem / a.Wp, pw_ = rem - ph_ * a.Wp;
         const int q = slab * a.G + g;
         const bool valid = pi < a.slab_rows && ph_ != 0 && pw_ != 0 && q < a.P;
         const int hw = (ph_ - 1) * a.W + (pw_ - 1);
-        uint4 rv0 = make_uint4(0, 0, 0, 0), rv1 = rv0;
+        uint4 rv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rv[i] = make_uint4(0, 0, 0, 0);
         if (valid && a.res) {
-          const uint4* rp = reinterpret_cast<const uint4*>(a.res + ((size_t)q * hw_img + hw) * Cout + c0);
-          rv0 = __ldg(rp); rv1 = __ldg(rp + 1);
+          const uint4* rp = reinterpret_cast<const uint4*>(a.res + ((size_t)q * hw_img + hw) * Cout + cbase);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rv[i] = __ldg(rp + i);
         }
         const int n_img = a.rep > 1 ? q : q / a.T;
-        const uint32_t e8 = uint32_t(hw * Cout + c0) >> 3;
-        auto keep_mask = [&](int tt) -> uint32_t {          // bit i set = channel c0 + i kept
-          const uint4 ra = philox4x32_10(e8, a.first_image + uint32_t(n_img), uint32_t(tt), a.drop_stream, a.k0, a.k1);
-          const uint4 rb = philox4x32_10(e8 + 1, a.first_image + uint32_t(n_img), uint32_t(tt), a.drop_stream, a.k0, a.k1);
-          const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+        const uint32_t e8 = uint32_t(hw * Cout + cbase) >> 3;
+        auto keep_mask32 = [&](int tt) -> uint32_t {        // bit i set = channel cbase + i kept (four Philox calls)
           uint32_t m = 0;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            m |= ((rw[i] & 0xFFFFu) >= a.drop_thr16 ? 1u : 0u) << (2 * i);
-            m |= ((rw[i] >> 16) >= a.drop_thr16 ? 1u : 0u) << (2 * i + 1);
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const uint4 r = philox4x32_10(e8 + c4, a.first_image + uint32_t(n_img), uint32_t(tt), a.drop_stream, a.k0, a.k1);
+            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              m |= ((rw[i] & 0xFFFFu) >= a.drop_thr16 ? 1u : 0u) << (8 * c4 + 2 * i);
+              m |= ((rw[i] >> 16) >= a.drop_thr16 ? 1u : 0u) << (8 * c4 + 2 * i + 1);
+            }
           }
           return m;
         };
-        uint32_t mask = 0xFFFFu;
-        if (valid && a.drop) mask = keep_mask(a.rep > 1 ? 0 : q - n_img * a.T);
+        uint32_t mask = 0xFFFFFFFFu;
+        if (valid && a.drop) mask = keep_mask32(a.rep > 1 ? 0 : q - n_img * a.T);
 
         mbar_wait_timed(tfull(ai), aph, w_tfull, a.stats != nullptr);
         tc_fence_after();
-        uint32_t acc[16];
-        tmem_ld16(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(ai * 64 + sub_w * 16), acc);
+        uint32_t acc[32];
+        {
+          uint32_t (&lo)[16] = *reinterpret_cast<uint32_t (*)[16]>(&acc[0]);
+          uint32_t (&hi)[16] = *reinterpret_cast<uint32_t (*)[16]>(&acc[16]);
+          const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(ai * 64 + cbase);
+          tmem_ld16(taddr, lo);
+          tmem_ld16(taddr + 16, hi);
+        }
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty(ai));          // accumulator is in registers: release it right away
-        if (++ai == FL_NACC) { ai = 0; aph ^= 1; }
         if (!valid) continue;
-        float v[16];
-        {
-          const uint32_t rw[8] = {rv0.x, rv0.y, rv0.z, rv0.w, rv1.x, rv1.y, rv1.z, rv1.w};
+        float v[32];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            v[2 * i] = __uint_as_float(acc[2 * i]) + bias_v[2 * i] + bf16_lo(rw[i]);
-            v[2 * i + 1] = __uint_as_float(acc[2 * i + 1]) + bias_v[2 * i + 1] + bf16_hi(rw[i]);
-          }
+        for (int i = 0; i < 16; ++i) {
+          const uint32_t rw = reinterpret_cast<const uint32_t*>(rv)[i];
+          v[2 * i] = __uint_as_float(acc[2 * i]) + s_bias[cbase + 2 * i] + bf16_lo(rw);
+          v[2 * i + 1] = __uint_as_float(acc[2 * i + 1]) + s_bias[cbase + 2 * i + 1] + bf16_hi(rw);
         }
         if (a.relu) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         }
         if (a.drop) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] *= a.drop_scale;
+          for (int i = 0; i < 32; ++i) v[i] *= a.drop_scale;
         }
         for (int rp = 0; rp < n_rep; ++rp) {
           const int p_out = a.rep > 1 ? q * a.rep + rp : q;
-          const uint32_t next_mask = (a.drop && rp + 1 < n_rep) ? keep_mask(rp + 1) : 0u;     // overlaps this replica's stores
-          float o[16];
+          const uint32_t next_mask = (a.drop && rp + 1 < n_rep) ? keep_mask32(rp + 1) : 0u;     // overlaps this replica's stores
+          uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + ((size_t)p_out * hw_img + hw) * Cout + cbase);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = ((mask >> i) & 1u) ? v[i] : 0.f;
-          uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + ((size_t)p_out * hw_img + hw) * Cout + c0);
-          yp[0] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-          yp[1] = make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
+          for (int k = 0; k < 4; ++k) {
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = ((mask >> (8 * k + i)) & 1u) ? v[8 * k + i] : 0.f;
+            yp[k] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+          }
           mask = next_mask;
         }
       }
@@ -329,7 +339,7 @@ int conv_flat_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv3x3_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(conv3x3_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);   // + 256 B static
   });
   FAV_CUDA_OK(attr_err);
   const int grid = a.n_slabs < ctx->num_sms ? a.n_slabs : ctx->num_sms;
@@ -339,7 +349,15 @@ int conv_flat_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
     int rc = conv_timing_begin(ctx, st, float(2.0 * double(M) * 576.0 * 64.0 * 1e-9), &e1, &a.stats);
     if (rc) return rc;
   }
-  conv3x3_flat_kernel<<<grid, FL_THREADS, smem, st>>>(tmA, *reinterpret_cast<const CUtensorMap*>(L.tmap_w), a);
+  {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(FL_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    FAV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv3x3_flat_kernel, tmA, *reinterpret_cast<const CUtensorMap*>(L.tmap_w), a));
+  }
   if (e1) FAV_CUDA_OK(cudaEventRecord(e1, st));
   ctx->launches++;
   FAV_CUDA_OK(cudaGetLastError());
