@@ -22,36 +22,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
-#include "conv.cuh"
-#include "tc_ptx.cuh"
+#include "conv_dev.cuh"
 
 namespace fav {
 
-constexpr int BM = 128, BK = 64;
-constexpr int A_TILE_BYTES = BM * BK * 2;          // 16 KiB
-
-struct ConvArgs {
-  const __nv_bfloat16* x;
-  void* y;
-  const float* bias;
-  const __nv_bfloat16* res;
-  int P, H, W, Cin, OH, OW, Cout;
-  int R, S, stride, pad;
-  int K, num_kb, M, BN, stages;
-  int relu, out_f32, a_mode;
-  int bw, bh, bn_img, tiles_w, tiles_h, cin_blocks;
-  int ntiles, total_tiles;     // N tiles per M tile, all CTA tiles (persistent scheduler)
-  int mt_per_tile, mtiles;     // 128-row M tiles per CTA tile (1 or 2), number of 128-row M tiles
-  int s_store;                 // a_mode 3: filter-row slots (S padded to an even count), Cin stored as 4
-  int T, rep, drop;
-  uint32_t drop_thr16;
-  float drop_scale;
-  uint32_t k0, k1, first_image, drop_stream;
-  uint32_t tmem_cols, idesc;
-  int kb2, stride2, Cin2;      // fused second source (the block's 1x1 downsample branch): extra k-blocks after the main taps
-  int ablate;                  // tuning aid (env FAV_CONV_ABLATE): 1 skip A loads, 2 skip B loads, 4 skip MMAs, 8 skip epilogue math
-  unsigned long long* stats;   // optional per-launch role timing (8 counters), see fav_conv_stats_read
-};
+bool conv_pair_applicable(const ConvLayer& L, const ConvArgs& a, int force);
+int conv_pair_launch(Ctx* ctx, const ConvLayer& L, ConvArgs a, const CUtensorMap& tmA, const CUtensorMap& tmA2, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------ the kernel
 // Persistent, warp-specialised: each CTA walks tiles (tile = blockIdx.x + i * gridDim.x; N-tile fastest so CTAs
@@ -62,59 +38,6 @@ struct ConvArgs {
 //   warps 10-13 gather producers (a_mode 1/2/3 only; not launched in a_mode 0)
 //   MT = 2: each CTA tile is 256 output pixels (two A tiles sharing one W tile per k-block, two accumulators) --
 //           1.36x fewer L2->smem bytes per FLOP; the conv kernels are L2-bandwidth-bound, so this is the main lever.
-constexpr int EPI_WARP0 = 2;
-constexpr int THREADS_TMA1 = 32 * (2 + 8);        // MT = 1: 8 epilogue warps, two CTAs per SM
-constexpr int THREADS_TMA2 = 32 * (2 + 16);       // MT = 2: 16 epilogue warps, one CTA per SM
-constexpr int THREADS_GATHER = 32 * (2 + 8 + 4);  // gather variant: 8 epilogue + 4 gather warps
-
-struct Tile { int mt, nt, q0, oh0, ow0; };   // mt = index of the 128-row M tile
-
-__device__ __forceinline__ Tile decode_tile(const ConvArgs& a, int tile, int u = 0) {
-  Tile t;
-  t.nt = tile % a.ntiles; t.mt = (tile / a.ntiles) * a.mt_per_tile + u;
-  t.q0 = 0; t.oh0 = 0; t.ow0 = 0;
-  if (a.a_mode == 0) {
-    const int tw = t.mt % a.tiles_w, th = (t.mt / a.tiles_w) % a.tiles_h, tn = t.mt / (a.tiles_w * a.tiles_h);
-    t.q0 = tn * a.bn_img; t.oh0 = th * a.bh; t.ow0 = tw * a.bw;
-  }
-  return t;
-}
-// Division-free walk over the k-blocks of a tile: f(kb, r, s, cb).  In a_mode 0 the filter taps whose shifted window
-// only sees padding for the whole tile are skipped (row / column tests hoisted out of the channel-block loop).
-template <class F>
-__device__ __forceinline__ void for_each_kb(const ConvArgs& a, const Tile& t, F&& f) {
-  if (a.a_mode != 0) {
-    for (int kb = 0; kb < a.num_kb; ++kb) f(kb, 0, 0, 0);
-    return;
-  }
-  const int oh_last = min(t.oh0 + a.bh, a.OH) - 1, ow_last = min(t.ow0 + a.bw, a.OW) - 1;
-  int kb = 0;
-  for (int r = 0; r < a.R; ++r) {
-    const bool row_ok = !(oh_last * a.stride + r - a.pad < 0 || t.oh0 * a.stride + r - a.pad >= a.H);
-    for (int ss = 0; ss < a.S; ++ss, kb += a.cin_blocks) {
-      if (!row_ok || ow_last * a.stride + ss - a.pad < 0 || t.ow0 * a.stride + ss - a.pad >= a.W) continue;
-      for (int cb = 0; cb < a.cin_blocks; ++cb) f(kb + cb, r, ss, cb);
-    }
-  }
-}
-
-// output pixel owned by A-tile row `row` of tile t
-__device__ __forceinline__ bool decode_row(const ConvArgs& a, const Tile& t, int row, int& q, int& oh, int& ow) {
-  if (a.a_mode == 0) {
-    const int per_img = a.bw * a.bh;
-    const int nl = row / per_img, rem = row - nl * per_img, hl = rem / a.bw, wl = rem - hl * a.bw;
-    q = t.q0 + nl; oh = t.oh0 + hl; ow = t.ow0 + wl;
-    return nl < a.bn_img && q < a.P && oh < a.OH && ow < a.OW;
-  }
-  const long long m = (long long)t.mt * BM + row;
-  q = 0; oh = 0; ow = 0;
-  if (m >= a.M) return false;
-  q = int(m / (a.OH * a.OW));
-  const int rem = int(m - (long long)q * (a.OH * a.OW));
-  oh = rem / a.OW; ow = rem - oh * a.OW;
-  return true;
-}
-
 template <bool GATHER, int MT, int EPI_WARPS>
 __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2,
                                                 const ConvArgs& a) {
@@ -342,7 +265,6 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
     const int sub_w = (warp - EPI_WARP0) >> 2;           // which of the EPI_WARPS/4 warps of this quarter
     constexpr int WPQ = EPI_WARPS / 4;
     const int row = quarter * 32 + lane;
-    const int ohw = a.OH * a.OW, n_rep = a.rep > 1 ? a.rep : 1;
     int ti = 0;
     long long w_tfull = 0;
     const long long t_begin = clock64();
@@ -354,102 +276,7 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
       for (int u = 0; u < MT; ++u) {
       const Tile t = decode_tile(a, tile, u);
       if (t.mt >= a.mtiles) break;
-      int q, oh, ow;
-      const bool valid = decode_row(a, t, row, q, oh, ow);
-      const uint32_t trow = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t((acc_i * MT + u) * a.BN);
-      const int hw = oh * a.OW + ow;
-      const size_t res_off = ((size_t)q * ohw + hw) * a.Cout;
-      const bool vec_io = (a.Cout & 7) == 0;
-      const int n_img = a.rep > 1 ? q : q / a.T;
-      const int tt0 = a.rep > 1 ? 0 : q - n_img * a.T;
-      // dropout keep-mask of the 16 channels starting at c0 (bit i = channel c0 + i kept); independent of the accumulator
-      auto keep_mask = [&](int c0, int tt) -> uint32_t {
-        const uint32_t e8 = uint32_t((size_t)hw * a.Cout + c0) >> 3;
-        const uint4 ra = philox4x32_10(e8, a.first_image + uint32_t(n_img), uint32_t(tt), a.drop_stream, a.k0, a.k1);
-        const uint4 rb = philox4x32_10(e8 + 1, a.first_image + uint32_t(n_img), uint32_t(tt), a.drop_stream, a.k0, a.k1);
-        const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-        uint32_t m = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          m |= ((rw[i] & 0xFFFFu) >= a.drop_thr16 ? 1u : 0u) << (2 * i);
-          m |= ((rw[i] >> 16) >= a.drop_thr16 ? 1u : 0u) << (2 * i + 1);
-        }
-        return m;
-      };
-      // residual of chunk j (two 16-byte vectors), prefetched one chunk ahead so its L2 latency overlaps the previous chunk
-      auto load_res = [&](int j, uint4& r0, uint4& r1) {
-        r0 = make_uint4(0, 0, 0, 0); r1 = r0;
-        const int c0 = t.nt * a.BN + j * 16;
-        if (a.res && vec_io && valid && j < a.BN / 16 && c0 < a.Cout) {
-          const uint4* rp = reinterpret_cast<const uint4*>(a.res + res_off + c0);
-          r0 = __ldg(rp);
-          if (c0 + 8 < a.Cout) r1 = __ldg(rp + 1);
-        }
-      };
-      uint4 rn0, rn1;
-      load_res(sub_w, rn0, rn1);
-      for (int j = sub_w; j < a.BN / 16; j += WPQ) {
-        const int c0 = t.nt * a.BN + j * 16;
-        const uint4 rv0 = rn0, rv1 = rn1;
-        load_res(j + WPQ, rn0, rn1);
-        uint32_t mask = 0xFFFFu;
-        if (a.drop && valid && c0 < a.Cout) mask = keep_mask(c0, tt0);
-        uint32_t acc[16];
-        tmem_ld16(trow + uint32_t(j * 16), acc);       // warp-collective: executed by every lane, valid or not
-        tmem_ld_wait();
-        if (!valid || c0 >= a.Cout || (a.ablate & 8)) continue;
-        float v[16];
-        {
-          const float4* bp = reinterpret_cast<const float4*>(a.bias + c0);     // bias is padded to cout_pad
-          const uint32_t rw[8] = {rv0.x, rv0.y, rv0.z, rv0.w, rv1.x, rv1.y, rv1.z, rv1.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 b = __ldg(bp + i);
-            v[4 * i] = __uint_as_float(acc[4 * i]) + b.x + bf16_lo(rw[2 * i]);
-            v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + b.y + bf16_hi(rw[2 * i]);
-            v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b.z + bf16_lo(rw[2 * i + 1]);
-            v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b.w + bf16_hi(rw[2 * i + 1]);
-          }
-        }
-        if (a.res && !vec_io) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (c0 + i < a.Cout) v[i] += __bfloat162float(a.res[res_off + c0 + i]);
-        }
-        if (a.relu) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-        }
-        if (a.drop) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] *= a.drop_scale;
-        }
-        for (int rp = 0; rp < n_rep; ++rp) {
-          const int p_out = a.rep > 1 ? q * a.rep + rp : q;
-          const size_t off = ((size_t)p_out * ohw + hw) * a.Cout + c0;
-          const uint32_t next_mask = (a.drop && rp + 1 < n_rep) ? keep_mask(c0, rp + 1) : 0u;   // overlaps this replica's stores
-          float o[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = ((mask >> i) & 1u) ? v[i] : 0.f;
-          mask = next_mask;
-          if (a.out_f32) {
-            float* yp = reinterpret_cast<float*>(a.y) + off;
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (c0 + i < a.Cout) yp[i] = o[i];
-          } else if (vec_io) {
-            uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + off);
-            yp[0] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-            if (c0 + 8 < a.Cout)
-              yp[1] = make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
-          } else {
-            __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + off;
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (c0 + i < a.Cout) yp[i] = __float2bfloat16_rn(o[i]);
-          }
-        }
-      }
+      conv_epilogue_subtile(a, t, tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t((acc_i * MT + u) * a.BN), row, sub_w, WPQ);
       }   // sub-tiles
       // this warp has finished reading the accumulators: hand them back to the MMA issuer
       tc_fence_before();
@@ -553,6 +380,12 @@ int conv_layer_finalize(ConvLayer& L) {
     int rc = encode_map(reinterpret_cast<CUtensorMap*>(L.tmap_w), L.w, 2, dims, strides, box);
     if (rc) return rc;
     L.tmap_ok = true;
+    if (L.bn == 128 && L.cout_pad == 128) {
+      const cuuint32_t box64[2] = {BK, 64};
+      rc = encode_map(reinterpret_cast<CUtensorMap*>(L.tmap_w64), L.w, 2, dims, strides, box64);
+      if (rc) return rc;
+      L.tmap64_ok = true;
+    }
   }
   return FAV_OK;
 }
@@ -692,7 +525,10 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
     int rc = conv_timing_begin(ctx, st, gf, &e1, &a.stats);
     if (rc) return rc;
   }
-  {
+  if (MT == 1 && conv_pair_applicable(L, a, c.force_mt == 3 ? 1 : 0) && c.force_mt != 1) {
+    int rc = conv_pair_launch(ctx, L, a, tmA, tmA2, st);
+    if (rc) return rc;
+  } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];

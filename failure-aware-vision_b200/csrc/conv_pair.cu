@@ -1,0 +1,225 @@
+// conv_pair.cu -- K2, 2-SM variant for 128-output-channel convolutions (ResNet-18 layer2).
+//
+// The generic kernel streams a 16 KB activation tile AND a 16 KB weight tile per k-block per CTA and is bound by the
+// 64 B/clk/SM L2->SM port (<= 50 % tensor pipe for 128x128 tiles).  Here two CTAs on one TPC form a cluster and issue
+// tcgen05.mma.cta_group::2 with M = 256 (128 output pixels per CTA), N = 128: each CTA loads only HALF of every weight
+// tile (64 of the 128 output channels), i.e. 24 KB instead of 32 KB per k-block, in a 9-deep ring.  MEASURED: correct but not
+// faster -- the leader's M=256 MMAs issue at ~119 cycles each (role timers), so one CTA pair does less per SM than two
+// independent 128x128 CTAs; kept as an opt-in variant (FAV_PAIR=1) and as the tested base for N=256 tiles.  (A weights-
+// stationary layout -- the 147 KB half resident, activations only streaming -- was measured slower: it leaves room for
+// just four 16 KB activation slots, too few bytes in flight to cover the L2 latency.)  The leader CTA issues the MMAs;
+// tcgen05.commit multicasts completion to both CTAs; each CTA drains its own 128 TMEM lanes in the shared epilogue.
+//
+// Replaces (reference): nothing executable (see conv.cu header); oracle twin oracle/model.py.
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include "conv_dev.cuh"
+
+namespace fav {
+
+int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+               const cuuint32_t* box);
+
+constexpr int PAIR_THREADS = 32 * (2 + 8);
+constexpr int PAIR_EPI_WARPS = 8;
+constexpr int PAIR_BKB_BYTES = 64 * 128;          // one resident W k-block per CTA: 64 output channels x 64 k
+
+__global__ void __launch_bounds__(PAIR_THREADS, 1)
+conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmA2, const ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t pad_to_1k = ((raw + 1023u) & ~1023u) - raw;
+  uint8_t* smem = smem_raw + pad_to_1k;
+  const uint32_t smem_base = smem_u32(smem);
+  // [ring: stages x {A 16 KB, W half 8 KB}][barriers]
+  constexpr int STAGE = A_TILE_BYTES + PAIR_BKB_BYTES;
+  const uint32_t bars = smem_base + a.stages * STAGE;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (bars - smem_base) + (2 * a.stages + 4) * 8);
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (a.stages + s); };
+  auto tfull_bar = [&](int i) { return bars + 8u * (2 * a.stages + i); };
+  auto tempty_bar = [&](int i) { return bars + 8u * (2 * a.stages + 2 + i); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cr = cluster_ctarank();
+  const bool leader = cr == 0;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (a.kb2 > 0) tma_prefetch_desc(&tmA2);
+    for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 2u); mbar_init(empty_bar(s), 1u); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1u); mbar_init(tempty_bar(i), uint32_t(2 * PAIR_EPI_WARPS)); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(smem_u32(tmem_slot), a.tmem_cols);
+  tc_fence_before();
+  cluster_sync_all();                         // both CTAs' barriers are initialised before any remote arrive / multicast
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  const uint32_t a_bytes = uint32_t(a.bn_img * a.bh * a.bw) * 128u;
+
+  if (warp == 0) {
+    // ================================================================= TMA issuer (both CTAs)
+    int stage = 0, phase = 0;
+    long long w_empty = 0;
+    const long long t_begin = clock64();
+    for (int pt = pair; pt < a.pair_tiles; pt += n_pairs) {
+      const Tile t = decode_tile(a, 2 * pt + int(cr));
+      auto arm = [&]() {
+        if (leader) mbar_arrive_expect_tx(full_bar(stage), 2u * (a_bytes + PAIR_BKB_BYTES));
+        else mbar_arrive_remote(full_bar(stage), 0);
+      };
+      for_each_kb(a, t, [&](int kb, int r, int ss, int cb) {
+        mbar_wait_timed(empty_bar(stage), phase ^ 1, w_empty, a.stats != nullptr);
+        if (elect_one()) {
+          arm();
+          const uint32_t sa = smem_base + stage * STAGE;
+          tma_load_2d_2sm(sa + A_TILE_BYTES, &tmB, full_bar(stage), kb * BK, int(cr) * 64);      // this CTA's 64 of the 128 W rows
+          if (a.stride == 1) {
+            tma_load_4d_2sm(sa, &tmA, full_bar(stage), cb * 64, t.ow0 + ss - a.pad, t.oh0 + r - a.pad, t.q0);
+          } else {
+            const int v = r - a.pad, w = ss - a.pad;
+            tma_load_5d_2sm(sa, &tmA, full_bar(stage), (w & 1) * a.Cin + cb * 64, t.ow0 + (w >> 1), v & 1, t.oh0 + (v >> 1), t.q0);
+          }
+        }
+        __syncwarp();
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+      });
+      for (int cb = 0; cb < a.kb2; ++cb) {
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        if (elect_one()) {
+          arm();
+          const uint32_t sa = smem_base + stage * STAGE;
+          tma_load_2d_2sm(sa + A_TILE_BYTES, &tmB, full_bar(stage), (a.num_kb + cb) * BK, int(cr) * 64);
+          if (a.stride2 == 1) tma_load_4d_2sm(sa, &tmA2, full_bar(stage), cb * 64, t.ow0, t.oh0, t.q0);
+          else tma_load_5d_2sm(sa, &tmA2, full_bar(stage), cb * 64, t.ow0, 0, t.oh0, t.q0);
+        }
+        __syncwarp();
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+    if (a.stats && lane == 0 && leader) {
+      atomicAdd(&a.stats[0], (unsigned long long)w_empty);
+      atomicAdd(&a.stats[1], (unsigned long long)(clock64() - t_begin));
+      atomicAdd(&a.stats[7], 1ull);
+    }
+  } else if (warp == 1) {
+    // ================================================================= MMA issuer (leader CTA only)
+    if (leader) {
+      int stage = 0, phase = 0, ti = 0;
+      long long w_full = 0, w_tempty = 0;
+      const long long t_begin = clock64();
+      const uint64_t desc_a0 = make_sw128_desc(smem_base);
+      for (int pt = pair; pt < a.pair_tiles; pt += n_pairs, ++ti) {
+        const Tile t = decode_tile(a, 2 * pt);
+        const int acc = ti & 1;
+        mbar_wait_timed(tempty_bar(acc), ((ti >> 1) & 1) ^ 1, w_tempty, a.stats != nullptr);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * a.BN);
+        uint32_t accumulate = 0;
+        auto issue = [&]() {
+          mbar_wait_timed(full_bar(stage), phase, w_full, a.stats != nullptr);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t da = desc_a0 + uint64_t(stage) * (STAGE >> 4);
+            const uint64_t db = da + uint64_t(A_TILE_BYTES >> 4);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_f16_2sm(d_tmem, da + 2u * k, db + 2u * k, a.idesc, k > 0 ? 1u : accumulate);
+            umma_commit_2sm_mc(empty_bar(stage), 3);
+          }
+          __syncwarp();
+          accumulate = 1;
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        };
+        for_each_kb(a, t, [&](int, int, int, int) { issue(); });
+        for (int cb = 0; cb < a.kb2; ++cb) issue();
+        if (elect_one()) umma_commit_2sm_mc(tfull_bar(acc), 3);
+        __syncwarp();
+      }
+      if (a.stats && lane == 0) {
+        atomicAdd(&a.stats[2], (unsigned long long)w_full);
+        atomicAdd(&a.stats[3], (unsigned long long)w_tempty);
+        atomicAdd(&a.stats[4], (unsigned long long)(clock64() - t_begin));
+      }
+    }
+  } else {
+    // ================================================================= epilogue warps (both CTAs, own 128 TMEM lanes)
+    const int quarter = warp & 3, sub_w = (warp - EPI_WARP0) >> 2;
+    const int row = quarter * 32 + lane;
+    int ti = 0;
+    long long w_tfull = 0;
+    const long long t_begin = clock64();
+    for (int pt = pair; pt < a.pair_tiles; pt += n_pairs, ++ti) {
+      const int acc = ti & 1;
+      const Tile t = decode_tile(a, 2 * pt + int(cr));
+      mbar_wait_timed(tfull_bar(acc), (ti >> 1) & 1, w_tfull, a.stats != nullptr);
+      tc_fence_after();
+      conv_epilogue_subtile(a, t, tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * a.BN), row, sub_w, PAIR_EPI_WARPS / 4);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(tempty_bar(acc));
+        else mbar_arrive_remote(tempty_bar(acc), 0);
+      }
+    }
+    if (a.stats && warp == EPI_WARP0 && lane == 0 && leader) {
+      atomicAdd(&a.stats[5], (unsigned long long)w_tfull);
+      atomicAdd(&a.stats[6], (unsigned long long)(clock64() - t_begin));
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, a.tmem_cols);
+}
+
+static int pair_env() {
+  // opt-in: measured on B200 (profiles/r01k_pair_vs_generic.txt) the 2-SM variant is ~15 % slower than two independent
+  // 128x128 CTAs per SM on ResNet-18 layer2, so the dispatcher only uses it when FAV_PAIR=1 (or when a test forces it)
+  static const int v = [] { const char* e = getenv("FAV_PAIR"); return e ? atoi(e) : 0; }();
+  return v;
+}
+
+// a: fully prepared ConvArgs of the generic TMA path (a_mode 0); returns false if the shape does not fit the pair variant
+bool conv_pair_applicable(const ConvLayer& L, const ConvArgs& a, int force) {
+  if (force == 0 && pair_env() == 0) return false;
+  if (a.a_mode != 0 || L.bn != 128 || L.cout_pad != 128 || !L.tmap64_ok || a.tiles_w != 1 || a.tiles_h != 1) return false;
+  return true;
+}
+
+int conv_pair_launch(Ctx* ctx, const ConvLayer& L, ConvArgs a, const CUtensorMap& tmA, const CUtensorMap& tmA2, cudaStream_t st) {
+  a.nkb_tot = a.num_kb + a.kb2;
+  a.pair_tiles = (a.mtiles + 1) / 2;
+  a.stages = (227 * 1024 - 1024 - 512) / (A_TILE_BYTES + PAIR_BKB_BYTES);          // 9 slots of 24 KB
+  a.tmem_cols = 256;                                                       // two accumulators of 128 columns
+  a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(128 >> 3) << 17) | (uint32_t(256 >> 4) << 24);   // M = 256, N = 128
+  a.ntiles = 1; a.mt_per_tile = 1;
+  const size_t smem = (size_t)a.stages * (A_TILE_BYTES + PAIR_BKB_BYTES) + 1024 + 512;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  FAV_CUDA_OK(attr_err);
+  const int max_pairs = ctx->num_sms / 2;
+  const int n_pairs = a.pair_tiles < max_pairs ? a.pair_tiles : max_pairs;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * n_pairs); cfg.blockDim = dim3(PAIR_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 2;
+  FAV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_pair_kernel, tmA, *reinterpret_cast<const CUtensorMap*>(L.tmap_w64), tmA2, a));
+  return FAV_OK;
+}
+
+}  // namespace fav

@@ -141,6 +141,7 @@ CONV_CASES = [
     (2, 56, 56, 256, 512, 1, 2, 0, 0, 0, (0, 1)),
     (9, 2, 2, 256, 512, 3, 2, 1, 1, 0, (0, 1)),
     (17, 4, 4, 128, 128, 3, 1, 1, 1, 1, (0, 1)),
+    (700, 4, 4, 128, 128, 3, 1, 1, 1, 1, (0,)),
     (40, 2, 2, 256, 256, 3, 1, 1, 1, 0, (0, 1)),
     (200, 1, 1, 512, 512, 3, 1, 1, 1, 1, (0, 1)),
     (5, 32, 32, 3, 64, 7, 2, 3, 1, 0, (2,)),
@@ -167,6 +168,8 @@ def test_k2_conv_matches_torch_fp32(fav, clf18, case):
     if relu:
         ref = torch.relu(ref)
     modes = tuple(modes) + ((0x200, 0x100) if 0 in modes else ())      # also force 256- and 128-pixel CTA tiles
+    if 0 in modes and cout == 128 and oh * ow <= 128:
+        modes += (0x300,)                                               # 2-SM (cta_group::2) weights-stationary variant
     for mode in modes:
         for out_f32 in (0, 1):
             if mode == 4 and out_f32:
