@@ -186,15 +186,21 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
     }
   } else if (GATHER && warp >= GATHER_WARP0) {
     // ================================================================= gather producers (a_mode 1/2/3)
-    const int row = threadIdx.x - 32 * GATHER_WARP0;      // 0..127 = A-tile row
-    int stage = 0, phase = 0;
+    // two groups of 4 warps take alternate k-blocks, so the load latency of one k-block overlaps the stores of the other
+    const int gtid = threadIdx.x - 32 * GATHER_WARP0;
+    const int row = gtid & 127, group = gtid >> 7;        // row = A-tile row
+    int stage = 0, phase = 0, it = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
       const Tile t = decode_tile(a, tile);
       int q, oh, ow;
       const bool valid = decode_row(a, t, row, q, oh, ow);
       const int ih0 = oh * a.stride - a.pad, iw0 = ow * a.stride - a.pad;
       const __nv_bfloat16* ximg = a.x + (size_t)q * a.H * a.W * a.Cin;
-      for (int kb = 0; kb < a.num_kb; ++kb) {
+      for (int kb = 0; kb < a.num_kb; ++kb, ++it) {
+        if ((it & 1) != group) {
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+          continue;
+        }
         mbar_wait(empty_bar(stage), phase ^ 1);
         uint8_t* rowp = smem + stage * stage_bytes + row * 128;
         if (a.a_mode == 3) {

@@ -36,7 +36,7 @@ struct ConvArgs {
 constexpr int EPI_WARP0 = 2;
 constexpr int THREADS_TMA1 = 32 * (2 + 8);        // MT = 1: 8 epilogue warps, two CTAs per SM
 constexpr int THREADS_TMA2 = 32 * (2 + 16);       // MT = 2: 16 epilogue warps, one CTA per SM
-constexpr int THREADS_GATHER = 32 * (2 + 8 + 4);  // gather variant: 8 epilogue + 4 gather warps
+constexpr int THREADS_GATHER = 32 * (2 + 8 + 8);  // gather variant: 8 epilogue + 8 gather warps (two groups on alternate k-blocks)
 
 struct Tile { int mt, nt, q0, oh0, ow0; };   // mt = index of the 128-row M tile
 
