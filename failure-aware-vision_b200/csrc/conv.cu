@@ -99,7 +99,11 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
 #pragma unroll
             for (int u = 0; u < MT; ++u) {
               if (u >= n_sub) break;
-              if (a.stride == 1) {
+              if (a.stem_tma) {
+                // space-to-depth input viewed as (64 = 4 taps x 16 ch, tap row, ow [32-byte step], oh, image):
+                // k-block kb = tap row kb -> 128 contiguous bytes per output pixel, no bounds handling needed
+                tma_load_5d(sa + u * A_TILE_BYTES, &tmA, full_bar(stage), 0, kb, t[u].ow0, t[u].oh0, t[u].q0);
+              } else if (a.stride == 1) {
                 tma_load_4d(sa + u * A_TILE_BYTES, &tmA, full_bar(stage), cb * 64, t[u].ow0 + ss - a.pad, t[u].oh0 + r - a.pad, t[u].q0);
               } else {
                 // stride 2: input row 2*oh + v (v = r - pad) = 2*(oh + (v >> 1)) + (v & 1); the tensor map views the
@@ -374,8 +378,23 @@ int conv_timing_begin(Ctx* ctx, cudaStream_t st, float gflop, cudaEvent_t* stop,
 int conv_out_dim(int in, int k, int stride, int pad) { return (in + 2 * pad - k) / stride + 1; }
 int conv_pick_bn(int cout) { return cout <= 16 ? 16 : cout <= 32 ? 32 : cout <= 64 ? 64 : 128; }
 
+// a_mode 5 (stride-2 stem, R, S <= 8): the zero-padded image is stored 2x2 space-to-depth, x = [p][hp][wp][16] bf16 with
+// channel (dy*2 + dx)*4 + c of pixel (Y, X) = padded image (2Y + dy, 2X + dx, c).  The conv becomes 4x4 / stride 1 over
+// 16 channels: one k-block = one row of 4 taps x 16 channels = 128 contiguous bytes starting at pixel (oh + r', ow), so
+// A is one 5-D TMA box per k-block with no bounds handling (windows of neighbouring pixels overlap, 32-byte step).
+// A SWIZZLE_128B box narrower than 128 bytes faults on sm_100 (tools/probe/tma_probe.cu), which rules out feeding
+// 8-tap NHWC4 rows directly.
+bool conv_stem_padded_dims(const ConvLayer& L, int h, int w, int* hp, int* wp) {
+  if (!L.s2d) return false;
+  const int oh = conv_out_dim(h, L.r, L.stride, L.pad), ow = conv_out_dim(w, L.s, L.stride, L.pad);
+  if (oh <= 0 || ow <= 0) return false;
+  *hp = oh + 3;
+  *wp = ow + 3;
+  return true;
+}
+
 int conv_layer_finalize(ConvLayer& L) {
-  L.k = L.r * (L.s_store ? L.s_store : L.s) * (L.cin_store ? L.cin_store : L.cin);
+  L.k = L.s2d ? 256 : L.r * (L.s_store ? L.s_store : L.s) * (L.cin_store ? L.cin_store : L.cin);
   L.kpad = (L.k + BK - 1) / BK * BK;
   L.bn = conv_pick_bn(L.cout);
   L.cout_pad = (L.cout + L.bn - 1) / L.bn * L.bn;
@@ -429,17 +448,36 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   const bool tma_s2 = L.stride == 2 && (c.h % 2) == 0 && (c.w % 2) == 0;
   const bool tma_ok = !L.cin_store && (L.cin % 64) == 0 && L.r == L.s && a.OW <= 128 && (tma_s1 || tma_s2);
   int mode = c.a_mode;
-  if (L.cin_store) mode = 3;
+  const bool stem_tma = c.a_mode == 5;
+  if (stem_tma) {
+    int hp, wp;
+    FAV_REQUIRE(conv_stem_padded_dims(L, c.h, c.w, &hp, &wp), "conv: a_mode 5 needs the space-to-depth stem layout (stride 2, R, S <= 8)");
+    mode = 0;
+  } else if (L.cin_store) {
+    FAV_REQUIRE(!L.s2d, "conv: a space-to-depth stem runs in a_mode 5 only");
+    mode = 3;
+  }
   if (mode < 0) mode = tma_ok ? 0 : ((L.cin % 8) == 0 ? 1 : 2);
-  FAV_REQUIRE(mode != 0 || tma_ok, "conv: a_mode 0 (TMA) needs Cin %% 64 == 0 and stride 1 with 'same' padding or stride 2 with even H, W");
+  FAV_REQUIRE(mode != 0 || tma_ok || stem_tma, "conv: a_mode 0 (TMA) needs Cin %% 64 == 0 and stride 1 with 'same' padding or stride 2 with even H, W");
   FAV_REQUIRE(mode != 1 || (L.cin % 8) == 0, "conv: a_mode 1 needs Cin %% 8 == 0");
   FAV_REQUIRE(mode != 3 || (L.cin_store == 4 && (L.s_store % 2) == 0), "conv: a_mode 3 needs the channel-padded stem layout");
   a.a_mode = mode;
   CUtensorMap tmA;
   memset(&tmA, 0, sizeof(tmA));
   int mtiles;
+  a.stem_tma = stem_tma ? 1 : 0;
   if (mode == 0) {
     if (a.OH * a.OW <= BM) { a.bw = a.OW; a.bh = a.OH; a.bn_img = BM / (a.OH * a.OW); }
+    else if (stem_tma) {
+      // any OW: the (bw x bh <= 128) pixel rectangle that covers the output with the fewest tiles
+      long long best = -1;
+      for (int bw = 1; bw <= (a.OW < BM ? a.OW : BM); ++bw) {
+        const int bh = (BM / bw) < a.OH ? (BM / bw) : a.OH;
+        const long long tiles = (long long)((a.OW + bw - 1) / bw) * ((a.OH + bh - 1) / bh);
+        if (best < 0 || tiles <= best) { best = tiles; a.bw = bw; a.bh = bh; }
+      }
+      a.bn_img = 1;
+    }
     else { a.bw = a.OW; a.bh = BM / a.OW; a.bn_img = 1; }
     if (a.bn_img > c.p) a.bn_img = c.p;
     a.tiles_w = (a.OW + a.bw - 1) / a.bw; a.tiles_h = (a.OH + a.bh - 1) / a.bh;
@@ -447,7 +485,15 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
     a.cin_blocks = L.cin / 64;
     mtiles = a.tiles_w * a.tiles_h * tiles_n;
     int rc;
-    if (L.stride == 1) {
+    if (stem_tma) {
+      int hp, wp;
+      conv_stem_padded_dims(L, c.h, c.w, &hp, &wp);
+      const cuuint64_t row = (cuuint64_t)wp * 32;      // bytes per space-to-depth row (16 bf16 per pixel)
+      const cuuint64_t dims[5] = {64, (cuuint64_t)a.num_kb, (cuuint64_t)a.OW, (cuuint64_t)a.OH, (cuuint64_t)c.p};
+      const cuuint64_t strides[4] = {row, 32, row, (cuuint64_t)hp * row};
+      const cuuint32_t box[5] = {64, 1, (cuuint32_t)a.bw, (cuuint32_t)a.bh, (cuuint32_t)a.bn_img};
+      rc = encode_map(&tmA, c.x, 5, dims, strides, box);
+    } else if (L.stride == 1) {
       const cuuint64_t dims[4] = {(cuuint64_t)L.cin, (cuuint64_t)c.w, (cuuint64_t)c.h, (cuuint64_t)c.p};
       const cuuint64_t strides[3] = {(cuuint64_t)L.cin * 2, (cuuint64_t)c.w * L.cin * 2, (cuuint64_t)c.h * c.w * L.cin * 2};
       const cuuint32_t box[4] = {64, (cuuint32_t)a.bw, (cuuint32_t)a.bh, (cuuint32_t)a.bn_img};

@@ -9,6 +9,7 @@ struct ConvLayer {          // device-resident, BN folded
   const float* bias = nullptr;        // [cout_pad]
   int cin = 0, cout = 0, r = 0, s = 0, stride = 1, pad = 0;
   int cin_store = 0, s_store = 0;      // stem layout: channels padded to 4, filter-row slots padded to even (0 = as cin / s)
+  int s2d = 0;                         // stem as a 4x4/s1 conv over the 2x2 space-to-depth input (16 ch): k = (r'*4 + s')*16 + (dy*2 + dx)*4 + c
   int k = 0, kpad = 0, cout_pad = 0, bn = 0;
   int fold = 0;                           // 4: a 3x3/s1/p1 conv on 2x2 images folded into a dense 1x1 GEMM (cin, cout already x4)
   int k2pad = 0, cin2 = 0, stride2 = 1;   // fused 1x1 downsample branch: extra K columns [kpad, kpad + k2pad) of w, its Cin and stride
@@ -29,7 +30,8 @@ struct ConvCall {
   int relu = 0, out_f32 = 0;
   int force_mt = 0;               // 0 auto, 1 / 2: 128- or 256-pixel CTA tiles (a_mode 0 only)
   int a_mode = -1;                // -1 auto, 0 TMA-tiled, 1 vector gather, 2 scalar gather, 3 channel-padded stem gather,
-                                  // 4 flat-padded resident 3x3 (conv_flat.cu)
+                                  // 4 flat-padded resident 3x3 (conv_flat.cu), 5 TMA on the space-to-depth stem input
+                                  // (x = [p][hp][wp][16], see conv_stem_padded_dims)
   // MC-dropout in the epilogue
   int T = 1;                      // passes; rows of x are pass-images (image = row / T, t = row % T) unless rep > 1
   int rep = 1;                    // rep == T: x holds plain images, each output row is written T times with mask t
@@ -44,6 +46,7 @@ int conv_pick_bn(int cout);
 // fills k/kpad/cout_pad/bn and encodes the weight tensor map (weights must already be on the device)
 int conv_layer_finalize(ConvLayer& L);
 int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st);
+bool conv_stem_padded_dims(const ConvLayer& L, int h, int w, int* hp, int* wp);
 int conv_timing_begin(Ctx* ctx, cudaStream_t st, float gflop, cudaEvent_t* stop, unsigned long long** stats);
 // conv_flat.cu: 3x3 / stride 1 / pad 1, Cin = Cout = 64 on small images: activations resident in shared memory as a
 // flat zero-padded pixel list, weights resident, filter taps = shifted UMMA descriptors

@@ -22,6 +22,7 @@ struct ConvArgs {
   int ntiles, total_tiles;     // N tiles per M tile, all CTA tiles (persistent scheduler)
   int mt_per_tile, mtiles;     // 128-row M tiles per CTA tile (1 or 2), number of 128-row M tiles
   int s_store;                 // a_mode 3: filter-row slots (S padded to an even count), Cin stored as 4
+  int stem_tma;                // a_mode 0 on the pre-padded NHWC4 stem input: one 5-D TMA box = one filter row x 16 taps x 4 ch per k-block
   int T, rep, drop;
   uint32_t drop_thr16;
   float drop_scale;
@@ -54,7 +55,7 @@ __device__ __forceinline__ Tile decode_tile(const ConvArgs& a, int tile, int u =
 // only sees padding for the whole tile are skipped (row / column tests hoisted out of the channel-block loop).
 template <class F>
 __device__ __forceinline__ void for_each_kb(const ConvArgs& a, const Tile& t, F&& f) {
-  if (a.a_mode != 0) {
+  if (a.a_mode != 0 || a.stem_tma) {
     for (int kb = 0; kb < a.num_kb; ++kb) f(kb, 0, 0, 0);
     return;
   }

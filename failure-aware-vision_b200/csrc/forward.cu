@@ -90,6 +90,29 @@ __global__ void __launch_bounds__(256) k_pool_dropout(const uint4* __restrict__ 
   }
 }
 
+// bf16 NHWC3 -> 2x2 space-to-depth of the zero-padded image, [n][hp][wp][16]: channel (dy*2 + dx)*4 + c of pixel (Y, X) is
+// image pixel (2Y + dy - pad, 2X + dx - pad), zero outside the image and for c = 3 (conv_stem_padded_dims)
+__global__ void __launch_bounds__(256) k_stem_s2d(const unsigned short* __restrict__ x, uint4* __restrict__ y, int n, int h, int w,
+                                                  int hp, int wp, int pad) {
+  const long long total = (long long)n * hp * wp * 2;          // one thread per (pixel, dy): 16 bytes
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int dy = int(i & 1);
+    const long long pix = i >> 1;
+    const int X = int(pix % wp);
+    const long long row = pix / wp;
+    const int Y = int(row % hp);
+    const long long img = row / hp;
+    const int yy = 2 * Y + dy - pad, x0 = 2 * X - pad;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (yy >= 0 && yy < h) {
+      const unsigned short* p = x + 3 * ((img * h + yy) * (long long)w + x0);
+      if (x0 >= 0 && x0 < w) { v.x = uint32_t(p[0]) | (uint32_t(p[1]) << 16); v.y = uint32_t(p[2]); }
+      if (x0 + 1 >= 0 && x0 + 1 < w) { v.z = uint32_t(p[3]) | (uint32_t(p[4]) << 16); v.w = uint32_t(p[5]); }
+    }
+    y[i] = v;
+  }
+}
+
 // bf16 NHWC3 -> NHWC4 (zero 4th channel): lets the stem gather 8-byte pixels, two filter taps per 16-byte chunk
 __global__ void __launch_bounds__(256) k_pad_c3_c4(const unsigned short* __restrict__ x, uint2* __restrict__ y, long long npix) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
@@ -109,7 +132,10 @@ static void walk_activations(const Plan& pl, int n, int T, F&& f) {
   const ConvLayer& stem = pl.convs[0];
   int h = conv_out_dim(pl.in_h, stem.r, stem.stride, stem.pad), w = conv_out_dim(pl.in_w, stem.s, stem.stride, stem.pad);
   f((size_t)n * h * w * stem.cout * 2);
-  f((size_t)n * pl.in_h * pl.in_w * 8);
+  {
+    int hp = pl.in_h, wp = pl.in_w;
+    f(conv_stem_padded_dims(stem, pl.in_h, pl.in_w, &hp, &wp) ? (size_t)n * hp * wp * 32 : (size_t)n * pl.in_h * pl.in_w * 8);
+  }
   h = conv_out_dim(h, 3, 2, 1); w = conv_out_dim(w, 3, 2, 1);
   f((size_t)n * h * w * stem.cout * 2);
   long long P = n;
@@ -175,7 +201,13 @@ extern "C" int fav_load_weights(fav_handle h, const void* blob, size_t nbytes, i
       delete pl; set_error("fav_load_weights: bad conv record %d", i); return FAV_E_ARG;
     }
     const int k_blob = L.r * L.s * L.cin;
-    if (i == 0 && L.cin == 3) { L.cin_store = 4; L.s_store = (L.s + 1) & ~1; }   // stem: channel-padded layout
+    if (i == 0 && L.cin == 3) {
+      // stem: stride 2 with R, S <= 8 -> 4x4/s1 conv over the space-to-depth input, A by TMA (conv a_mode 5); anything else
+      // -> channels padded to 4 and S rounded up to even for the gather path (a_mode 3)
+      static const int env_stem_tma = [] { const char* e = getenv("FAV_STEM_TMA"); return e ? atoi(e) : 1; }();   // 0: gather path
+      if (env_stem_tma && L.stride == 2 && L.r <= 8 && L.s <= 8) { L.s2d = 1; L.cin_store = 16; L.s_store = 4; }
+      else { L.cin_store = 4; L.s_store = (L.s + 1) & ~1; }
+    }
     conv_layer_finalize(L);
     const size_t wb = ((size_t)L.cout * k_blob * 2 + 15) / 16 * 16, bb = ((size_t)L.cout * 4 + 15) / 16 * 16;
     if (q + 32 + wb + bb > end) { delete pl; set_error("fav_load_weights: truncated weights at conv %d", i); return FAV_E_ARG; }
@@ -249,6 +281,17 @@ extern "C" int fav_load_weights(fav_handle h, const void* blob, size_t nbytes, i
             const int rr = (pi >> 1) - (po >> 1) + 1, ss = (pi & 1) - (po & 1) + 1;
             memcpy(&tmp[((size_t)po * cout0 + co) * L.k + (size_t)pi * cin0], &src[(((size_t)co * 3 + rr) * 3 + ss) * cin0], (size_t)cin0 * 2);
           }
+      e = cudaMemcpy2D(d, (size_t)L.kpad * 2, tmp.data(), (size_t)L.k * 2, (size_t)L.k * 2, L.cout, cudaMemcpyHostToDevice);
+    } else if (L.s2d) {
+      // [cout][r][s][3] -> [cout][r' = r/2][s' = s/2][dy = r%2][dx = s%2][4], zero filled
+      std::vector<uint16_t> tmp((size_t)L.cout * L.k, 0);
+      const uint16_t* src = reinterpret_cast<const uint16_t*>(recs[i].w);
+      for (int co = 0; co < L.cout; ++co)
+        for (int rr = 0; rr < L.r; ++rr)
+          for (int ss = 0; ss < L.s; ++ss)
+            for (int c = 0; c < L.cin; ++c)
+              tmp[(size_t)co * L.k + ((rr >> 1) * 4 + (ss >> 1)) * 16 + ((rr & 1) * 2 + (ss & 1)) * 4 + c] =
+                  src[(((size_t)co * L.r + rr) * L.s + ss) * L.cin + c];
       e = cudaMemcpy2D(d, (size_t)L.kpad * 2, tmp.data(), (size_t)L.k * 2, (size_t)L.k * 2, L.cout, cudaMemcpyHostToDevice);
     } else if (L.cin_store) {
       // [cout][r][s][3] -> [cout][r][s_store][4], zero filled
@@ -350,10 +393,10 @@ extern "C" int fav_forward_mc(fav_handle h, const void* d_x, float* d_logits, in
   const uint32_t k0 = uint32_t(seed), k1 = uint32_t(seed >> 32);
 
   auto run = [&](const ConvLayer& L, const void* x, void* y, const void* res, int P, int hh, int ww, int relu, int drop,
-                 int rep, int layer_id, int out_f32, const void* x2 = nullptr, int h2 = 0, int w2 = 0) -> int {
+                 int rep, int layer_id, int out_f32, const void* x2 = nullptr, int h2 = 0, int w2 = 0, int a_mode = -1) -> int {
     ConvCall c;
     c.L = &L; c.x = x; c.y = y; c.res = res; c.p = P; c.h = hh; c.w = ww; c.relu = relu; c.out_f32 = out_f32;
-    c.x2 = x2; c.h2 = h2; c.w2 = w2;
+    c.x2 = x2; c.h2 = h2; c.w2 = w2; c.a_mode = a_mode;
     c.T = T; c.rep = rep; c.drop = drop; c.p_drop = p_drop; c.seed = seed; c.first_image = first_image; c.layer_id = layer_id;
     return conv_launch(h, c, st);
   };
@@ -361,7 +404,17 @@ extern "C" int fav_forward_mc(fav_handle h, const void* d_x, float* d_logits, in
   // stem + max-pool (pass-invariant)
   const ConvLayer& stem = pl.convs[0];
   const void* stem_in = d_x;
-  if (stem.cin_store == 4) {
+  int stem_mode = -1, hp = 0, wp = 0;
+  if (conv_stem_padded_dims(stem, pl.in_h, pl.in_w, &hp, &wp)) {
+    const long long npix = (long long)n * hp * wp;
+    FAV_REQUIRE((size_t)npix * 32 <= pl.buf_bytes, "workspace too small for the space-to-depth input");
+    k_stem_s2d<<<grid_for(npix * 2, 256, h->num_sms), 256, 0, st>>>(reinterpret_cast<const unsigned short*>(d_x),
+                                                                    reinterpret_cast<uint4*>(DS), n, pl.in_h, pl.in_w, hp, wp, stem.pad);
+    FAV_CUDA_OK(cudaGetLastError());
+    h->launches++;
+    stem_in = DS;
+    stem_mode = 5;
+  } else if (stem.cin_store == 4) {
     const long long npix = (long long)n * pl.in_h * pl.in_w;
     FAV_REQUIRE((size_t)npix * 8 <= pl.buf_bytes, "workspace too small for the padded input");
     k_pad_c3_c4<<<grid_for(npix, 256, h->num_sms), 256, 0, st>>>(reinterpret_cast<const unsigned short*>(d_x),
@@ -369,7 +422,7 @@ extern "C" int fav_forward_mc(fav_handle h, const void* d_x, float* d_logits, in
     h->launches++;
     stem_in = DS;
   }
-  int rc = run(stem, stem_in, Y1, nullptr, n, pl.in_h, pl.in_w, 1, 0, 1, 0, 0);
+  int rc = run(stem, stem_in, Y1, nullptr, n, pl.in_h, pl.in_w, 1, 0, 1, 0, 0, nullptr, 0, 0, stem_mode);
   if (rc) return rc;
   int hh = conv_out_dim(pl.in_h, stem.r, stem.stride, stem.pad), ww = conv_out_dim(pl.in_w, stem.s, stem.stride, stem.pad);
   {
