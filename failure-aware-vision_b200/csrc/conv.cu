@@ -40,7 +40,7 @@ int conv_pair_launch(Ctx* ctx, const ConvLayer& L, ConvArgs a, const CUtensorMap
 //           1.36x fewer L2->smem bytes per FLOP; the conv kernels are L2-bandwidth-bound, so this is the main lever.
 template <bool GATHER, int MT, int EPI_WARPS>
 __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2,
-                                                const ConvArgs& a) {
+                                                const CUtensorMap& tmY, const CUtensorMap& tmR, const ConvArgs& a) {
   constexpr int GATHER_WARP0 = EPI_WARP0 + EPI_WARPS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -48,8 +48,9 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
   uint8_t* smem = smem_raw + pad_to_1k;
   const int stage_bytes = MT * A_TILE_BYTES + a.BN * 128;
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t bars = smem_base + a.stages * stage_bytes;      // full[s], empty[s], tmem_full[2], tmem_empty[2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + a.stages * stage_bytes + (2 * a.stages + 4) * 8);
+  uint8_t* stg = smem + a.stages * stage_bytes;                  // staged epilogue: two 16 KB output slabs (a.stg_bytes, may be 0)
+  const uint32_t bars = smem_base + a.stages * stage_bytes + a.stg_bytes;      // full[s], empty[s], tmem_full[2], tmem_empty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + a.stages * stage_bytes + a.stg_bytes + (2 * a.stages + 4) * 8);
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (a.stages + s); };
   auto tfull_bar = [&](int i) { return bars + 8u * (2 * a.stages + i); };
@@ -61,6 +62,8 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
     tma_prefetch_desc(&tmB);
     if (a.a_mode == 0) tma_prefetch_desc(&tmA);
     if (a.kb2 > 0) tma_prefetch_desc(&tmA2);
+    if (a.stg_bytes) tma_prefetch_desc(&tmY);
+    if (a.res_prefetch) tma_prefetch_desc(&tmR);
     const uint32_t full_count = a.a_mode == 0 ? 1u : 1u + 128u;
     for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), full_count); mbar_init(empty_bar(s), 1u); }
     for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1u); mbar_init(tempty_bar(i), uint32_t(EPI_WARPS)); }
@@ -90,6 +93,14 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
         for (int u = 0; u < MT; ++u) { t[u] = decode_tile(a, tile, u); if (t[u].mt < a.mtiles) n_sub = u + 1; }
         const uint32_t tx = ((a.ablate & 1) ? 0u : a_bytes * n_sub) + ((a.ablate & 2) ? 0u : uint32_t(a.BN) * 128u);
         const int n_col = t[0].nt * a.BN;
+        if (a.res_prefetch && elect_one()) {
+          // the epilogue reads this tile's residual rows a whole tile later: pull them from HBM into L2 now
+#pragma unroll
+          for (int u = 0; u < MT; ++u)
+            if (u < n_sub)
+              for (int hf = 0; hf < a.BN / 64; ++hf) tma_prefetch_l2_4d(&tmR, n_col + hf * 64, t[u].ow0, t[u].oh0, t[u].q0);
+        }
+        __syncwarp();
         for_each_kb(a, t[0], [&](int kb, int r, int ss, int cb) {
           mbar_wait_timed(empty_bar(stage), phase ^ 1, w_empty, a.stats != nullptr);
           const uint32_t sa = smem_base + stage * stage_bytes;
@@ -275,7 +286,8 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
     const int sub_w = (warp - EPI_WARP0) >> 2;           // which of the EPI_WARPS/4 warps of this quarter
     constexpr int WPQ = EPI_WARPS / 4;
     const int row = quarter * 32 + lane;
-    int ti = 0;
+    int ti = 0, seq = 0;
+    const bool leader = warp == EPI_WARP0 && lane == 0;      // issues the staged epilogue's TMA stores
     long long w_tfull = 0;
     const long long t_begin = clock64();
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
@@ -286,13 +298,16 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
       for (int u = 0; u < MT; ++u) {
       const Tile t = decode_tile(a, tile, u);
       if (t.mt >= a.mtiles) break;
-      conv_epilogue_subtile(a, t, tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t((acc_i * MT + u) * a.BN), row, sub_w, WPQ);
+      const uint32_t trow = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t((acc_i * MT + u) * a.BN);
+      if (!GATHER && a.stg_bytes) conv_epilogue_staged<WPQ>(a, &tmY, t, trow, row, sub_w, stg, seq, leader);
+      else conv_epilogue_subtile(a, t, trow, row, sub_w, WPQ);
       }   // sub-tiles
       // this warp has finished reading the accumulators: hand them back to the MMA issuer
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc_i));
     }
+    if (leader && a.stg_bytes) bulk_wait_all();              // shared memory must outlive the last store's reads
     if (a.stats && warp == EPI_WARP0 && lane == 0) {
       atomicAdd(&a.stats[5], (unsigned long long)w_tfull);
       atomicAdd(&a.stats[6], (unsigned long long)(clock64() - t_begin));
@@ -307,18 +322,21 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
 // TMA-fed variants: MT=1 (320 threads, two CTAs per SM) and MT=2 (576 threads, one CTA per SM); gather variant.
 __global__ void __launch_bounds__(THREADS_TMA1, 2)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmA2, const ConvArgs a) {
-  conv_igemm_body<false, 1, 8>(tmA, tmB, tmA2, a);
+                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmY,
+                  const __grid_constant__ CUtensorMap tmR, const ConvArgs a) {
+  conv_igemm_body<false, 1, 8>(tmA, tmB, tmA2, tmY, tmR, a);
 }
 __global__ void __launch_bounds__(THREADS_TMA2, 1)
 conv_igemm_m256_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                       const __grid_constant__ CUtensorMap tmA2, const ConvArgs a) {
-  conv_igemm_body<false, 2, 16>(tmA, tmB, tmA2, a);
+                       const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmY,
+                  const __grid_constant__ CUtensorMap tmR, const ConvArgs a) {
+  conv_igemm_body<false, 2, 16>(tmA, tmB, tmA2, tmY, tmR, a);
 }
 __global__ void __launch_bounds__(THREADS_GATHER, 1)
 conv_igemm_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmA2, const ConvArgs a) {
-  conv_igemm_body<true, 1, 8>(tmA, tmB, tmA2, a);
+                         const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmY,
+                  const __grid_constant__ CUtensorMap tmR, const ConvArgs a) {
+  conv_igemm_body<true, 1, 8>(tmA, tmB, tmA2, tmY, tmR, a);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -549,7 +567,37 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   a.total_tiles = ((mtiles + MT - 1) / MT) * a.ntiles;
   const int stage_bytes = MT * A_TILE_BYTES + a.BN * 128;
   const int ctas_per_sm = (mode == 0 && MT == 1) ? 2 : 1;
-  int stages = ((ctas_per_sm == 2 ? 100 : 200) * 1024) / stage_bytes;
+  // staged epilogue (TMA stores from two shared-memory slabs): bf16 NHWC output of the TMA-tiled modes.  The default
+  // keeps it for the layers whose epilogue is the bottleneck (few k-blocks per tile, or T masked replicas per tile).
+  static const int env_stg = [] { const char* e = getenv("FAV_EPI_TMA"); return e ? atoi(e) : -1; }();   // -1 auto, 0 off, 1 all eligible
+  const bool stg_ok = mode == 0 && !c.out_f32 && (L.cout % 64) == 0;
+  const bool stg_auto = (a.num_kb + a.kb2) <= 8 || a.rep > 1 || a.BN == 64;
+  a.stg_bytes = (stg_ok && env_stg != 0 && (env_stg > 0 || stg_auto)) ? 2 * STG_SLAB_BYTES : 0;
+  CUtensorMap tmY;
+  memset(&tmY, 0, sizeof(tmY));
+  if (a.stg_bytes) {
+    const cuuint64_t px = (cuuint64_t)L.cout * 2;
+    const cuuint64_t dims[5] = {(cuuint64_t)L.cout, (cuuint64_t)a.OW, (cuuint64_t)a.OH, (cuuint64_t)a.rep, (cuuint64_t)c.p};
+    const cuuint64_t strides[4] = {px, px * a.OW, px * a.OW * a.OH, px * a.OW * a.OH * a.rep};
+    const cuuint32_t box[5] = {64, (cuuint32_t)a.bw, (cuuint32_t)a.bh, 1, (cuuint32_t)a.bn_img};
+    int rc = encode_map(&tmY, c.y, 5, dims, strides, box);
+    if (rc) return rc;
+  }
+  // residual rows of a tile are prefetched into L2 by the TMA issuer (same pixel rectangle as the A tile)
+  static const int env_rpf = [] { const char* e = getenv("FAV_RES_PREFETCH"); return e ? atoi(e) : 1; }();
+  CUtensorMap tmR;
+  memset(&tmR, 0, sizeof(tmR));
+  a.res_prefetch = (env_rpf && mode == 0 && c.res && !c.out_f32 && (L.cout % 64) == 0) ? 1 : 0;
+  if (a.res_prefetch) {
+    const cuuint64_t px = (cuuint64_t)L.cout * 2;
+    const cuuint64_t dims[4] = {(cuuint64_t)L.cout, (cuuint64_t)a.OW, (cuuint64_t)a.OH, (cuuint64_t)c.p};
+    const cuuint64_t strides[3] = {px, px * a.OW, px * a.OW * a.OH};
+    const cuuint32_t box[4] = {64, (cuuint32_t)a.bw, (cuuint32_t)a.bh, (cuuint32_t)a.bn_img};
+    int rc = encode_map(&tmR, c.res, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  // two CTAs per SM: (228 KB - 2 x 1 KB reserved) / 2 = 113 KB each, minus 1 KB alignment slack and the barrier block
+  int stages = ((ctas_per_sm == 2 ? 113 * 1024 - 1280 : 200 * 1024) - a.stg_bytes) / stage_bytes;
   stages = stages < 2 ? 2 : (stages > 8 ? 8 : stages);
   a.stages = stages;
   uint32_t cols = 32;
@@ -557,7 +605,7 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   a.tmem_cols = cols;
   // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128
   a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(a.BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  const size_t smem = (size_t)stages * stage_bytes + a.stg_bytes + 1024 + 256;
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
@@ -588,9 +636,9 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     const CUtensorMap& tmW = *reinterpret_cast<const CUtensorMap*>(L.tmap_w);
-    if (mode == 0 && MT == 2) FAV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm_m256_kernel, tmA, tmW, tmA2, a));
-    else if (mode == 0) FAV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm_kernel, tmA, tmW, tmA2, a));
-    else FAV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm_gather_kernel, tmA, tmW, tmA2, a));
+    if (mode == 0 && MT == 2) FAV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm_m256_kernel, tmA, tmW, tmA2, tmY, tmR, a));
+    else if (mode == 0) FAV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm_kernel, tmA, tmW, tmA2, tmY, tmR, a));
+    else FAV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm_gather_kernel, tmA, tmW, tmA2, tmY, tmR, a));
   }
   if (e1) FAV_CUDA_OK(cudaEventRecord(e1, st));
   ctx->launches++;

@@ -30,11 +30,14 @@ struct ConvArgs {
   uint32_t tmem_cols, idesc;
   int pair_tiles, nkb_tot;     // 2-SM variant: CTA-pair tiles (two 128-row M tiles each), resident W k-blocks (main + fused branch)
   int kb2, stride2, Cin2;      // fused second source (the block's 1x1 downsample branch): extra k-blocks after the main taps
+  int stg_bytes;               // > 0: epilogue stages bf16 output in shared memory (two 128 x 64 slabs) and writes it with TMA stores
+  int res_prefetch;            // the TMA issuer prefetches each tile's residual rows into L2 (tmR) when it starts the tile
   int ablate;                  // tuning aid (env FAV_CONV_ABLATE): 1 skip A loads, 2 skip B loads, 4 skip MMAs, 8 skip epilogue math
   unsigned long long* stats;   // optional per-launch role timing (8 counters), see fav_conv_stats_read
 };
 
 constexpr int EPI_WARP0 = 2;
+constexpr int STG_SLAB_BYTES = 128 * 128;         // staged epilogue: 128 pixels x 64 bf16 channels
 constexpr int THREADS_TMA1 = 32 * (2 + 8);        // MT = 1: 8 epilogue warps, two CTAs per SM
 constexpr int THREADS_TMA2 = 32 * (2 + 16);       // MT = 2: 16 epilogue warps, one CTA per SM
 constexpr int THREADS_GATHER = 32 * (2 + 8 + 8);  // gather variant: 8 epilogue + 8 gather warps (two groups on alternate k-blocks)
@@ -184,6 +187,108 @@ __device__ __forceinline__ void conv_epilogue_subtile(const ConvArgs& a, const T
 #pragma unroll
         for (int i = 0; i < 16; ++i)
           if (c0 + i < a.Cout) yp[i] = __float2bfloat16_rn(o[i]);
+      }
+    }
+  }
+}
+
+// Staged epilogue (a.stg_bytes > 0): as above, but the bf16 results go to a SWIZZLE_128B shared-memory slab of 128 pixels x
+// 64 channels and one thread writes the slab with a 5-D TMA store (Cout, OW, OH, replica, image) -- whole 128-byte lines
+// per pixel instead of 16 bytes per lane at a Cout*2-byte stride (32 L1 wavefronts per store instruction).  The box is the
+// A-tile's pixel rectangle, so rows outside the image or beyond P are clipped by the tensor bounds.  Two slabs alternate:
+// the leader waits for the previous store to finish reading before the barrier that releases the next slab's writers.
+template <int WPQ>
+__device__ __forceinline__ void conv_epilogue_staged(const ConvArgs& a, const CUtensorMap* tmY, const Tile& t, uint32_t trow, int row,
+                                                     int sub_w, uint8_t* stg, int& seq, bool leader) {
+  constexpr int NCH = 4 / WPQ;                         // 16-column chunks of a 64-channel slab per warp
+  const int ohw = a.OH * a.OW, n_rep = a.rep > 1 ? a.rep : 1;
+  int q, oh, ow;
+  const bool valid = decode_row(a, t, row, q, oh, ow);
+  const int hw = oh * a.OW + ow;
+  const size_t res_off = ((size_t)q * ohw + hw) * a.Cout;
+  const int n_img = a.rep > 1 ? q : q / a.T;
+  const int tt0 = a.rep > 1 ? 0 : q - n_img * a.T;
+  auto keep_mask = [&](int c0, int tt) -> uint32_t {
+    const uint32_t e8 = uint32_t((size_t)hw * a.Cout + c0) >> 3;
+    const uint4 ra = philox4x32_10(e8, a.first_image + uint32_t(n_img), uint32_t(tt), a.drop_stream, a.k0, a.k1);
+    const uint4 rb = philox4x32_10(e8 + 1, a.first_image + uint32_t(n_img), uint32_t(tt), a.drop_stream, a.k0, a.k1);
+    const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      m |= ((rw[i] & 0xFFFFu) >= a.drop_thr16 ? 1u : 0u) << (2 * i);
+      m |= ((rw[i] >> 16) >= a.drop_thr16 ? 1u : 0u) << (2 * i + 1);
+    }
+    return m;
+  };
+  const uint32_t stg_u32 = smem_u32(stg);
+  for (int hf = 0; hf < a.BN / 64; ++hf) {
+    uint32_t pk[NCH][8];                               // finished values (bias, residual, ReLU, dropout scale) as bf16 pairs
+    uint32_t mask[NCH];
+    uint4 rv[NCH][2];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {               // residual loads of all chunks first: their latency overlaps the TMEM loads
+      const int c0 = t.nt * a.BN + hf * 64 + (sub_w + ch * WPQ) * 16;
+      rv[ch][0] = make_uint4(0, 0, 0, 0); rv[ch][1] = rv[ch][0];
+      if (a.res && valid && !(a.ablate & 16)) {
+        const uint4* rp = reinterpret_cast<const uint4*>(a.res + res_off + c0);
+        rv[ch][0] = __ldg(rp); rv[ch][1] = __ldg(rp + 1);
+      }
+    }
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int jj = sub_w + ch * WPQ, c0 = t.nt * a.BN + hf * 64 + jj * 16;
+      mask[ch] = 0xFFFFu;
+      if (a.drop && valid) mask[ch] = keep_mask(c0, tt0);
+      uint32_t acc[16];
+      tmem_ld16(trow + uint32_t(hf * 64 + jj * 16), acc);       // warp-collective: executed by every lane, valid or not
+      tmem_ld_wait();
+      const float4* bp = reinterpret_cast<const float4*>(a.bias + c0);
+      const uint32_t rw[8] = {rv[ch][0].x, rv[ch][0].y, rv[ch][0].z, rv[ch][0].w, rv[ch][1].x, rv[ch][1].y, rv[ch][1].z, rv[ch][1].w};
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 b = __ldg(bp + i);
+        v[4 * i] = __uint_as_float(acc[4 * i]) + b.x + bf16_lo(rw[2 * i]);
+        v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + b.y + bf16_hi(rw[2 * i]);
+        v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b.z + bf16_lo(rw[2 * i + 1]);
+        v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b.w + bf16_hi(rw[2 * i + 1]);
+      }
+      if (a.relu) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+      if (a.drop) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= a.drop_scale;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pk[ch][i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    }
+    for (int rp = 0; rp < n_rep; ++rp) {             // one slab (and one TMA store) per masked replica
+      uint8_t* rowp = stg + (seq & 1) * STG_SLAB_BYTES + row * 128;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int jj = sub_w + ch * WPQ;
+        uint32_t o[8];                                 // dropped channels -> +0.0 (the dropout product of the direct path)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          o[i] = pk[ch][i] & (((mask[ch] >> (2 * i)) & 1u) * 0xFFFFu | ((mask[ch] >> (2 * i + 1)) & 1u) * 0xFFFF0000u);
+        *reinterpret_cast<uint4*>(rowp + (((2 * jj) ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(rowp + (((2 * jj + 1) ^ (row & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+      }
+      fence_proxy_async();                             // generic-proxy smem writes -> visible to the TMA store
+      if (leader) bulk_wait_read_all();                // the store that last used the OTHER slab has drained it
+      named_bar_sync(1, 128 * WPQ);
+      if (leader && !(a.ablate & 32)) {
+        tma_store_5d(tmY, stg_u32 + uint32_t((seq & 1) * STG_SLAB_BYTES), t.nt * a.BN + hf * 64, t.ow0, t.oh0, rp, t.q0);
+        bulk_commit_group();
+      }
+      ++seq;
+      if (a.drop && rp + 1 < n_rep) {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch)
+          mask[ch] = valid ? keep_mask(t.nt * a.BN + hf * 64 + (sub_w + ch * WPQ) * 16, rp + 1) : 0u;
       }
     }
   }

@@ -196,6 +196,7 @@ bool conv_pair_applicable(const ConvLayer& L, const ConvArgs& a, int force) {
 
 int conv_pair_launch(Ctx* ctx, const ConvLayer& L, ConvArgs a, const CUtensorMap& tmA, const CUtensorMap& tmA2, cudaStream_t st) {
   a.nkb_tot = a.num_kb + a.kb2;
+  a.stg_bytes = 0; a.res_prefetch = 0;
   a.pair_tiles = (a.mtiles + 1) / 2;
   a.stages = (227 * 1024 - 1024 - 512) / (A_TILE_BYTES + PAIR_BKB_BYTES);          // 9 slots of 24 KB
   a.tmem_cols = 256;                                                       // two accumulators of 128 columns
