@@ -21,9 +21,8 @@ namespace fav {
 int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                const cuuint32_t* box);
 
-constexpr int PAIR_THREADS = 32 * (2 + 8);
-constexpr int PAIR_EPI_WARPS = 8;
-constexpr int PAIR_BKB_BYTES = 64 * 128;          // one resident W k-block per CTA: 64 output channels x 64 k
+constexpr int PAIR_EPI_WARPS = 16;
+constexpr int PAIR_THREADS = 32 * (2 + PAIR_EPI_WARPS);
 
 __global__ void __launch_bounds__(PAIR_THREADS, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -33,8 +32,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t pad_to_1k = ((raw + 1023u) & ~1023u) - raw;
   uint8_t* smem = smem_raw + pad_to_1k;
   const uint32_t smem_base = smem_u32(smem);
-  // [ring: stages x {A 16 KB, W half 8 KB}][barriers]
-  constexpr int STAGE = A_TILE_BYTES + PAIR_BKB_BYTES;
+  // [ring: stages x {A 16 KB, this CTA's half of the W tile: BN/2 output channels x 64 k}][barriers]
+  const int w_half_bytes = (a.BN / 2) * 128;
+  const int STAGE = A_TILE_BYTES + w_half_bytes;
   const uint32_t bars = smem_base + a.stages * STAGE;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (bars - smem_base) + (2 * a.stages + 4) * 8);
   auto full_bar = [&](int s) { return bars + 8u * s; };
@@ -46,6 +46,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t cr = cluster_ctarank();
   const bool leader = cr == 0;
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  // pair tile pt -> (pair of M tiles, N tile), N fastest so the CTA pairs running side by side share the A tiles in L2
+  auto pair_tile = [&](int pt, int which) { return decode_tile(a, (2 * (pt / a.ntiles) + which) * a.ntiles + pt % a.ntiles); };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -71,9 +73,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     long long w_empty = 0;
     const long long t_begin = clock64();
     for (int pt = pair; pt < a.pair_tiles; pt += n_pairs) {
-      const Tile t = decode_tile(a, 2 * pt + int(cr));
+      const Tile t = pair_tile(pt, int(cr));
+      const int w_row = t.nt * a.BN + int(cr) * (a.BN / 2);          // this CTA's half of the W tile's rows
       auto arm = [&]() {
-        if (leader) mbar_arrive_expect_tx(full_bar(stage), 2u * (a_bytes + PAIR_BKB_BYTES));
+        if (leader) mbar_arrive_expect_tx(full_bar(stage), 2u * (a_bytes + uint32_t(w_half_bytes)));
         else mbar_arrive_remote(full_bar(stage), 0);
       };
       for_each_kb(a, t, [&](int kb, int r, int ss, int cb) {
@@ -81,7 +84,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (elect_one()) {
           arm();
           const uint32_t sa = smem_base + stage * STAGE;
-          tma_load_2d_2sm(sa + A_TILE_BYTES, &tmB, full_bar(stage), kb * BK, int(cr) * 64);      // this CTA's 64 of the 128 W rows
+          tma_load_2d_2sm(sa + A_TILE_BYTES, &tmB, full_bar(stage), kb * BK, w_row);
           if (a.stride == 1) {
             tma_load_4d_2sm(sa, &tmA, full_bar(stage), cb * 64, t.ow0 + ss - a.pad, t.oh0 + r - a.pad, t.q0);
           } else {
@@ -97,7 +100,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (elect_one()) {
           arm();
           const uint32_t sa = smem_base + stage * STAGE;
-          tma_load_2d_2sm(sa + A_TILE_BYTES, &tmB, full_bar(stage), (a.num_kb + cb) * BK, int(cr) * 64);
+          tma_load_2d_2sm(sa + A_TILE_BYTES, &tmB, full_bar(stage), (a.num_kb + cb) * BK, w_row);
           if (a.stride2 == 1) tma_load_4d_2sm(sa, &tmA2, full_bar(stage), cb * 64, t.ow0, t.oh0, t.q0);
           else tma_load_5d_2sm(sa, &tmA2, full_bar(stage), cb * 64, t.ow0, 0, t.oh0, t.q0);
         }
@@ -118,7 +121,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const long long t_begin = clock64();
       const uint64_t desc_a0 = make_sw128_desc(smem_base);
       for (int pt = pair; pt < a.pair_tiles; pt += n_pairs, ++ti) {
-        const Tile t = decode_tile(a, 2 * pt);
+        const Tile t = pair_tile(pt, 0);
         const int acc = ti & 1;
         mbar_wait_timed(tempty_bar(acc), ((ti >> 1) & 1) ^ 1, w_tempty, a.stats != nullptr);
         tc_fence_after();
@@ -128,7 +131,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait_timed(full_bar(stage), phase, w_full, a.stats != nullptr);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t da = desc_a0 + uint64_t(stage) * (STAGE >> 4);
+            const uint64_t da = desc_a0 + uint64_t(stage) * uint64_t(STAGE >> 4);
             const uint64_t db = da + uint64_t(A_TILE_BYTES >> 4);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) umma_f16_2sm(d_tmem, da + 2u * k, db + 2u * k, a.idesc, k > 0 ? 1u : accumulate);
@@ -158,7 +161,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const long long t_begin = clock64();
     for (int pt = pair; pt < a.pair_tiles; pt += n_pairs, ++ti) {
       const int acc = ti & 1;
-      const Tile t = decode_tile(a, 2 * pt + int(cr));
+      const Tile t = pair_tile(pt, int(cr));
       mbar_wait_timed(tfull_bar(acc), (ti >> 1) & 1, w_tfull, a.stats != nullptr);
       tc_fence_after();
       conv_epilogue_subtile(a, t, tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * a.BN), row, sub_w, PAIR_EPI_WARPS / 4);
@@ -181,28 +184,38 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 static int pair_env() {
-  // opt-in: measured on B200 (profiles/r01k_pair_vs_generic.txt) the 2-SM variant is ~15 % slower than two independent
-  // 128x128 CTAs per SM on ResNet-18 layer2, so the dispatcher only uses it when FAV_PAIR=1 (or when a test forces it)
-  static const int v = [] { const char* e = getenv("FAV_PAIR"); return e ? atoi(e) : 0; }();
+  // -1 (default): N = 256 pair tiles for layers with >= 256 (padded) output channels; the N = 128 form stays opt-in
+  // (FAV_PAIR=1: measured ~15 % slower than two independent 128x128 CTAs per SM on ResNet-18 layer2,
+  // profiles/r01k_pair_vs_generic.txt).  0 disables the 2-SM variant.
+  static const int v = [] { const char* e = getenv("FAV_PAIR"); return e ? atoi(e) : -1; }();
   return v;
 }
 
-// a: fully prepared ConvArgs of the generic TMA path (a_mode 0); returns false if the shape does not fit the pair variant
-bool conv_pair_applicable(const ConvLayer& L, const ConvArgs& a, int force) {
-  if (force == 0 && pair_env() == 0) return false;
-  if (a.a_mode != 0 || L.bn != 128 || L.cout_pad != 128 || !L.tmap64_ok || a.tiles_w != 1 || a.tiles_h != 1) return false;
-  return true;
+// pair-tile width for this layer (0 = not applicable).  a: fully prepared ConvArgs of the generic TMA path (a_mode 0).
+// Both CTAs of a pair must walk the same k-blocks (the leader issues the MMAs for both), so tiles are whole images.
+int conv_pair_bn(const ConvLayer& L, const ConvArgs& a, int force) {
+  if (a.a_mode != 0 || a.stem_tma || L.bn != 128 || a.tiles_w != 1 || a.tiles_h != 1) return 0;
+  const int env = pair_env();
+  if (force == 0 && env == 0) return 0;
+  if ((L.cout_pad % 256) == 0 && (force || env != 0)) return 256;
+  if (L.cout_pad == 128 && L.tmap64_ok && (force || env > 0)) return 128;
+  return 0;
 }
+bool conv_pair_applicable(const ConvLayer& L, const ConvArgs& a, int force) { return conv_pair_bn(L, a, force) != 0; }
 
 int conv_pair_launch(Ctx* ctx, const ConvLayer& L, ConvArgs a, const CUtensorMap& tmA, const CUtensorMap& tmA2, cudaStream_t st) {
+  const int bn = conv_pair_bn(L, a, 1);
+  FAV_REQUIRE(bn != 0, "conv: the 2-SM variant does not fit this layer");
+  a.BN = bn;
+  a.ntiles = L.cout_pad / bn; a.mt_per_tile = 1;
   a.nkb_tot = a.num_kb + a.kb2;
   a.stg_bytes = 0; a.res_prefetch = 0;
-  a.pair_tiles = (a.mtiles + 1) / 2;
-  a.stages = (227 * 1024 - 1024 - 512) / (A_TILE_BYTES + PAIR_BKB_BYTES);          // 9 slots of 24 KB
-  a.tmem_cols = 256;                                                       // two accumulators of 128 columns
-  a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(128 >> 3) << 17) | (uint32_t(256 >> 4) << 24);   // M = 256, N = 128
-  a.ntiles = 1; a.mt_per_tile = 1;
-  const size_t smem = (size_t)a.stages * (A_TILE_BYTES + PAIR_BKB_BYTES) + 1024 + 512;
+  a.pair_tiles = ((a.mtiles + 1) / 2) * a.ntiles;
+  const int stage_bytes = A_TILE_BYTES + (bn / 2) * 128;                   // 24 KB (N = 128) or 32 KB (N = 256) per k-block and CTA
+  a.stages = (227 * 1024 - 1024 - 512) / stage_bytes;
+  a.tmem_cols = 2 * bn;                                                    // two accumulators of N columns
+  a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(bn >> 3) << 17) | (uint32_t(256 >> 4) << 24);   // M = 256, N = bn
+  const size_t smem = (size_t)a.stages * stage_bytes + 1024 + 512;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
@@ -219,7 +232,9 @@ int conv_pair_launch(Ctx* ctx, const ConvLayer& L, ConvArgs a, const CUtensorMap
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 2;
-  FAV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_pair_kernel, tmA, *reinterpret_cast<const CUtensorMap*>(L.tmap_w64), tmA2, a));
+  // N = 256: each CTA loads 128 of the tile's 256 W rows with the layer's standard 128-row box; N = 128: the 64-row box
+  const CUtensorMap& tmW = *reinterpret_cast<const CUtensorMap*>(bn == 256 ? L.tmap_w : L.tmap_w64);
+  FAV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_pair_kernel, tmA, tmW, tmA2, a));
   return FAV_OK;
 }
 
