@@ -147,6 +147,7 @@ class CorruptionSweep:
         self.acc = MetricsAccumulator(self.clf, len(self.cells), self.cfg.n_bins, self.cfg.n_buckets)
         self._x = None
         self._logits = None
+        self._stream_state = None
 
     def reset(self):
         self.acc.reset()
@@ -186,14 +187,90 @@ class CorruptionSweep:
         self.acc.add_logits(ci, logits, labels_dev[lo:hi], cfg.tau)
         return hi - lo
 
+    def run_stream(self, host_images, host_labels, items, first_image=0, on_row=None):
+        """The steps `items` on HOST blocks (uint8 [N,H,W,3] / int32 [N] torch tensors, pinned for async copies):
+        block k+1 is copied host->device on a side stream while block k computes, and after every step the cell's
+        histogram-arena row is read back into pinned memory; `on_row(item, row)` sees it one step later (the only
+        host synchronisation).  Returns the number of evals."""
+        cfg, dev = self.cfg, self.clf.device
+        h, w = cfg.input_hw
+        if self._stream_state is None:
+            B = cfg.block
+            self._stream_state = dict(
+                copy=torch.cuda.Stream(dev),
+                img=[torch.empty((B, h, w, 3), dtype=torch.uint8, device=dev) for _ in range(2)],
+                lab=[torch.empty(B, dtype=torch.int32, device=dev) for _ in range(2)],
+                row=[torch.empty(self.acc.words, dtype=torch.int64).pin_memory() for _ in range(2)],
+                copied=[torch.cuda.Event() for _ in range(2)], done=[torch.cuda.Event() for _ in range(2)])
+        ss = self._stream_state
+        cur = torch.cuda.current_stream(dev)
+        n_img = host_images.shape[0]
+
+        def span(item):
+            lo = item[1] * cfg.block
+            return lo, min(lo + cfg.block, n_img)
+
+        def issue_copy(k):
+            slot = k & 1
+            lo, hi = span(items[k])
+            with torch.cuda.stream(ss["copy"]):
+                if k >= 2:
+                    ss["copy"].wait_event(ss["done"][slot])          # step k-2 has finished with this staging slot
+                else:
+                    ss["copy"].wait_stream(cur)
+                ss["img"][slot][:hi - lo].copy_(host_images[lo:hi], non_blocking=True)
+                ss["lab"][slot][:hi - lo].copy_(host_labels[lo:hi], non_blocking=True)
+                ss["copied"][slot].record(ss["copy"])
+
+        evals = 0
+        if len(items):
+            issue_copy(0)
+        for k, item in enumerate(items):
+            slot = k & 1
+            if k + 1 < len(items):
+                issue_copy(k + 1)
+            lo, hi = span(item)
+            n = hi - lo
+            cur.wait_event(ss["copied"][slot])
+            x, logits = self._buffers(n)
+            self.clf.corrupt_normalize(ss["img"][slot][:n], self.cells[item[0]], cfg.seed, first_image + lo, out=x)
+            self.clf.forward_logits(x, cfg.T, cfg.p_drop, cfg.seed, first_image + lo, out=logits)
+            self.acc.add_logits(item[0], logits, ss["lab"][slot][:n], cfg.tau)
+            ss["row"][slot].copy_(self.acc.arena[item[0]], non_blocking=True)
+            ss["done"][slot].record(cur)
+            if k >= 1:
+                ss["done"][slot ^ 1].synchronize()
+                if on_row is not None:
+                    on_row(items[k - 1], ss["row"][slot ^ 1])
+            evals += n
+        if len(items):
+            last = (len(items) - 1) & 1
+            ss["done"][last].synchronize()
+            if on_row is not None:
+                on_row(items[-1], ss["row"][last])
+        return evals
+
     def run(self, images_u8, labels, rank=0, world_size=1, first_image=0):
         """images uint8 [N,H,W,3] (numpy or torch, host or device), labels int [N].
         Returns {(corruption, severity): metrics} after the cross-rank reduction."""
-        images_dev = self.clf._images(images_u8)
-        labels_dev = self.clf._labels(labels)
-        items = self.work_items(images_dev.shape[0])
-        for i in partition(len(items), rank, world_size):
-            self.run_item(images_dev, labels_dev, items[i], first_image)
+        import numpy as np
+        if isinstance(images_u8, np.ndarray):
+            images_u8 = torch.from_numpy(np.ascontiguousarray(images_u8))
+        if isinstance(labels, np.ndarray):
+            labels = torch.from_numpy(np.ascontiguousarray(labels))
+        items = self.work_items(images_u8.shape[0])
+        mine = [items[i] for i in partition(len(items), rank, world_size)]
+        if not images_u8.is_cuda:
+            # host data: stream the blocks through two pinned-to-device staging slots, copies overlapped with compute
+            self.clf._images(images_u8[:0])                  # shape / dtype validation
+            host_images = images_u8.contiguous().pin_memory()
+            host_labels = torch.as_tensor(labels).to(torch.int32).contiguous().pin_memory()
+            self.run_stream(host_images, host_labels, mine, first_image)
+        else:
+            images_dev = self.clf._images(images_u8)
+            labels_dev = self.clf._labels(labels)
+            for item in mine:
+                self.run_item(images_dev, labels_dev, item, first_image)
         self.acc.allreduce()
         res = self.acc.results()
         return {(c.name or "clean", c.severity): r for c, r in zip(self.cells, res)}

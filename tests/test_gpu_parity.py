@@ -336,6 +336,14 @@ def test_sweep_partition_is_bit_identical(fav):
         total += sw.acc.arena
     assert torch.equal(total, whole)
     assert int(whole[:, 0].sum()) == 100 * 4
+    # the host-streaming API reports every step's arena row (one step late); the last row of a cell is its final state
+    sw.reset()
+    rows = {}
+    hx, hy = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).to(torch.int32).pin_memory()
+    n = sw.run_stream(hx, hy, sw.work_items(100), on_row=lambda item, row: rows.__setitem__(item[0], row.clone()))
+    assert n == 100 * 4 and torch.equal(sw.acc.arena, whole)
+    for ci, row in rows.items():
+        assert torch.equal(row, whole[ci].cpu())
 
 
 # ------------------------------------------------------------------------------------------- f1 + gate
