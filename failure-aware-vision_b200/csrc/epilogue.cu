@@ -25,6 +25,25 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// softmax / entropy transcendentals on the SFU: ex2.approx and lg2.approx have <= 2 ulp relative error, which keeps
+// confidence within 1e-6 and entropy / MI within 1e-5 of the fp32 oracle (tests/test_gpu_parity.py tolerances) at a
+// fraction of the instruction count of expf / logf / IEEE division
+__device__ __forceinline__ float fast_exp(float d) {          // exp(d), d <= 0 (exp(-inf) = 0)
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d * 1.4426950408889634f));
+  return r;
+}
+__device__ __forceinline__ float fast_log(float x) {          // ln(x), x > 0
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r * 0.6931471805599453f;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 struct SampleOut {
   float conf, H, mi;
   int pred;
@@ -52,16 +71,16 @@ __device__ __forceinline__ SampleOut sample_uncertainty(const float* __restrict_
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
       const float d = v[i] - m;                      // -inf for padding lanes
-      v[i] = expf(d);                                // exp(-inf) = 0
+      v[i] = fast_exp(d);                            // exp(-inf) = 0
       s += v[i];
       w += v[i] > 0.f ? v[i] * d : 0.f;
     }
     s = warp_sum(s);
     w = warp_sum(w);
-    const float inv_s = __fdiv_rn(1.0f, s);
+    const float inv_s = fast_rcp(s);
 #pragma unroll
     for (int i = 0; i < NC; ++i) pbar[i] += v[i] * inv_s;
-    hsum += logf(s) - w * inv_s;                     // H(p_t) = ln S - sum_i e_i (z_i - m) / S   (no per-class log)
+    hsum += fast_log(s) - w * inv_s;                     // H(p_t) = ln S - sum_i e_i (z_i - m) / S   (no per-class log)
   }
   const float invT = 1.0f / float(T);
   float best = -1.f;
@@ -73,7 +92,7 @@ __device__ __forceinline__ SampleOut sample_uncertainty(const float* __restrict_
     const float p = pbar[i] * invT;
     if (c < C) {
       if (p > best) { best = p; arg = c; }          // ascending c inside a lane: first max kept
-      if (p > 0.f) H -= p * logf(p);
+      if (p > 0.f) H -= p * fast_log(p);
     }
   }
   H = warp_sum(H);
@@ -106,14 +125,14 @@ __device__ __forceinline__ SampleOut sample_uncertainty_small(const float* __res
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
       const float d = v[c] - m;
-      v[c] = expf(d);
+      v[c] = fast_exp(d);
       s += v[c];
       w += v[c] > 0.f ? v[c] * d : 0.f;
     }
-    const float inv_s = __fdiv_rn(1.0f, s);
+    const float inv_s = fast_rcp(s);
 #pragma unroll
     for (int c = 0; c < 16; ++c) pbar[c] += v[c] * inv_s;
-    hsum += logf(s) - w * inv_s;
+    hsum += fast_log(s) - w * inv_s;
   }
   const float invT = 1.0f / float(T);
   hsum = warp_sum(hsum);
@@ -124,7 +143,7 @@ __device__ __forceinline__ SampleOut sample_uncertainty_small(const float* __res
     const float p = warp_sum(pbar[c]) * invT;       // identical in every lane
     if (c < C) {
       if (p > best) { best = p; arg = c; }          // ascending c: lowest index wins ties
-      if (p > 0.f) H -= p * logf(p);
+      if (p > 0.f) H -= p * fast_log(p);
     }
   }
   SampleOut r;
@@ -144,14 +163,18 @@ __device__ __forceinline__ unsigned long long q32(float x) {
 __device__ __forceinline__ float clip01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
 
 // shared histogram: [3*n_bins (count, correct, pad)] + [6*n_buckets]; Q32 sums go straight to global.
+// s_binsum / s_cm (optional, small-C kernel): per-CTA copies of the per-bin confidence sums (u64) and of the C x C confusion
+// matrix (u32); without them those two go straight to global atomics, which serialise on a handful of hot addresses
 __device__ __forceinline__ void accumulate_sample(const HistGeom& g, unsigned* s_hist, unsigned long long* hist,
-                                                  float conf, float H, float mi, int pred, int label) {
+                                                  float conf, float H, float mi, int pred, int label,
+                                                  unsigned long long* s_binsum = nullptr, unsigned* s_cm = nullptr) {
   const bool correct = pred == label;
   int b = int(ceilf(conf * float(g.n_bins))) - 1;
   b = min(max(b, 0), g.n_bins - 1);
   atomicAdd(&s_hist[2 * b], 1u);
   if (correct) atomicAdd(&s_hist[2 * b + 1], 1u);
-  atomicAdd(&hist[FAV_HIST_HDR + 3 * b + 1], q32(conf));
+  if (s_binsum) atomicAdd(&s_binsum[b], q32(conf));
+  else atomicAdd(&hist[FAV_HIST_HDR + 3 * b + 1], q32(conf));
   const float s0 = clip01(1.0f - conf), s1 = clip01(H * g.inv_lnC), s2 = clip01(mi * g.inv_lnC);
   const float sc[3] = {s0, s1, s2};
 #pragma unroll
@@ -161,7 +184,9 @@ __device__ __forceinline__ void accumulate_sample(const HistGeom& g, unsigned* s
     atomicAdd(&s_hist[2 * g.n_bins + (s * g.n_buckets + k) * 2 + (correct ? 0 : 1)], 1u);
   }
   const size_t cb = FAV_HIST_HDR + 3 * (size_t)g.n_bins + 6 * (size_t)g.n_buckets;
-  if (g.C <= 100) {
+  if (s_cm) {
+    atomicAdd(&s_cm[label * g.C + pred], 1u);
+  } else if (g.C <= 100) {
     atomicAdd(&hist[cb + (size_t)label * g.C + pred], 1ull);
   } else {
     atomicAdd(&hist[cb + 2 * (size_t)label], 1ull);
@@ -239,6 +264,164 @@ __global__ void __launch_bounds__(256) k34_kernel(const float* __restrict__ logi
   }
 }
 
+
+// ---- C <= 16 (CIFAR-shaped sweeps): TPS threads per sample, 512 / TPS samples per tile ----
+// A sample's T*C logits are one contiguous run and so is a whole tile: it is copied global -> shared with 16-byte
+// cp.async (fully coalesced), double-buffered so the next tile streams in while this one is reduced.  Thread q of a
+// sample softmaxes passes q, q + TPS, ... serially in registers (no shuffles, no idle class lanes); the pass-mean is a
+// log2(TPS)-stage butterfly; thread 0 of the sample finishes entropy / argmax / flag and accumulates.
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(uint32_t(__cvta_generic_to_shared(dst_smem))), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_le1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+constexpr int K34S_THREADS = 512;
+
+template <int TPS, int CT>   // CT > 0: C == CT exactly (no predicated class slots); CT == 0: any C <= 16
+__global__ void __launch_bounds__(K34S_THREADS) k34_small_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
+                                                        int n, int T, HistGeom g, unsigned long long* __restrict__ hist,
+                                                        int hist_bytes, float* __restrict__ o_conf, float* __restrict__ o_H,
+                                                        float* __restrict__ o_mi, int32_t* __restrict__ o_pred,
+                                                        uint8_t* __restrict__ o_flag) {
+  constexpr int S = K34S_THREADS / TPS, CM = CT > 0 ? CT : 16;
+  extern __shared__ __align__(16) unsigned char k34_smem[];
+  // [n_slots u32 | pad to 8 | n_bins u64 confidence sums | C*C u32 confusion | pad to 16] = hist_bytes, then the two tiles
+  unsigned* s_hist = reinterpret_cast<unsigned*>(k34_smem);
+  float* tiles = reinterpret_cast<float*>(k34_smem + hist_bytes);
+  __shared__ unsigned long long s_sums[6];
+  const int C = CT > 0 ? CT : g.C;
+  const int n_slots = 2 * g.n_bins + 6 * g.n_buckets;
+  unsigned long long* s_binsum = reinterpret_cast<unsigned long long*>(k34_smem + ((size_t(n_slots) * 4 + 7) & ~size_t(7)));
+  unsigned* s_cm = reinterpret_cast<unsigned*>(s_binsum + g.n_bins);
+  const bool do_hist = hist != nullptr;
+  if (do_hist) {
+    for (int i = threadIdx.x; i < n_slots; i += blockDim.x) s_hist[i] = 0;
+    for (int i = threadIdx.x; i < g.n_bins; i += blockDim.x) s_binsum[i] = 0;
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x) s_cm[i] = 0;
+    if (threadIdx.x < 6) s_sums[threadIdx.x] = 0;
+  }
+  const int row = T * C, tile_floats = S * row;
+  const int ntiles = (n + S - 1) / S;
+  auto issue = [&](int tile, int buf) {
+    const size_t base = (size_t)tile * tile_floats;
+    const int cnt = min(S, n - tile * S) * row;
+    float* dst = tiles + (size_t)buf * tile_floats;
+    for (int v = threadIdx.x; v < (cnt >> 2); v += K34S_THREADS) cp_async16(dst + 4 * v, logits + base + 4 * v);
+    if (threadIdx.x < (cnt & 3)) dst[(cnt & ~3) + threadIdx.x] = logits[base + (cnt & ~3) + threadIdx.x];
+  };
+  int tile = blockIdx.x, buf = 0;
+  if (tile < ntiles) issue(tile, 0);
+  cp_async_commit();
+  const int sidx = threadIdx.x / TPS, q = threadIdx.x % TPS;
+  unsigned long long my[6] = {0, 0, 0, 0, 0, 0};
+  for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait_le1();                 // this tile's group has landed (the prefetch may still be in flight)
+    __syncthreads();
+    const int i = tile * S + sidx;
+    const float* z = tiles + (size_t)buf * tile_floats + (size_t)sidx * row;
+    float pbar[CM];
+#pragma unroll
+    for (int c = 0; c < CM; ++c) pbar[c] = 0.f;
+    float hsum = 0.f;
+    if (i < n) {
+      for (int t = q; t < T; t += TPS) {
+        const float* zt = z + t * C;
+        float v[CM];
+        float m = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < CM; ++c) { v[c] = (CT > 0 || c < C) ? zt[c] : -INFINITY; m = fmaxf(m, v[c]); }
+        float sum = 0.f, w = 0.f;
+#pragma unroll
+        for (int c = 0; c < CM; ++c) {
+          const float d = v[c] - m;
+          v[c] = fast_exp(d);
+          sum += v[c];
+          w += v[c] > 0.f ? v[c] * d : 0.f;
+        }
+        const float inv_s = fast_rcp(sum);
+#pragma unroll
+        for (int c = 0; c < CM; ++c) pbar[c] += v[c] * inv_s;
+        hsum += fast_log(sum) - w * inv_s;
+      }
+    }
+#pragma unroll
+    for (int o = 1; o < TPS; o <<= 1) {          // butterfly over the sample's TPS lanes (aligned lane groups)
+      hsum += __shfl_xor_sync(0xffffffffu, hsum, o);
+#pragma unroll
+      for (int c = 0; c < CM; ++c) pbar[c] += __shfl_xor_sync(0xffffffffu, pbar[c], o);
+    }
+    if (i < n) {
+      // every lane of the sample holds the full pass-sum: all finish redundantly (same warp time as one lane would
+      // take), then lane q does its share of the accumulation: 0 -> outputs + ECE bin + header, 1..3 -> one AUROC score each
+      const float invT = 1.0f / float(T);
+      float best = -1.f, H = 0.f;
+      int arg = 0;
+#pragma unroll
+      for (int c = 0; c < CM; ++c) {
+        const float pc = pbar[c] * invT;
+        if (CT > 0 || c < C) {
+          if (pc > best) { best = pc; arg = c; }          // ascending c: lowest index wins ties
+          if (pc > 0.f) H -= pc * fast_log(pc);
+        }
+      }
+      const float mi = fmaxf(H - hsum * invT, 0.f);
+      const int label = labels ? labels[i] : -1;
+      const bool correct = arg == label;
+      const bool flag = labels && !correct && best >= g.tau;
+      if (q == 0) {
+        if (o_conf) o_conf[i] = best;
+        if (o_H) o_H[i] = H;
+        if (o_mi) o_mi[i] = mi;
+        if (o_pred) o_pred[i] = arg;
+        if (o_flag) o_flag[i] = flag ? 1 : 0;
+      }
+      if (do_hist) {
+        const float sc0 = clip01(1.0f - best), sc1 = clip01(H * g.inv_lnC), sc2 = clip01(mi * g.inv_lnC);
+        if (q == 0) {
+          int b = int(ceilf(best * float(g.n_bins))) - 1;
+          b = min(max(b, 0), g.n_bins - 1);
+          atomicAdd(&s_hist[2 * b], 1u);
+          if (correct) atomicAdd(&s_hist[2 * b + 1], 1u);
+          atomicAdd(&s_binsum[b], q32(best));
+          atomicAdd(&s_cm[label * C + arg], 1u);
+          my[0] += 1; my[1] += correct; my[2] += flag;
+          my[3] += q32(best); my[4] += q32(sc1); my[5] += q32(sc2);
+        }
+        // AUROC buckets: score (q - 1) for q = 1..3; with TPS == 4 that is one score per lane, larger groups idle the rest
+        if (q >= 1 && q <= 3) {
+          const float sc = q == 1 ? sc0 : (q == 2 ? sc1 : sc2);
+          int k = int(floorf(sc * float(g.n_buckets)));
+          k = min(max(k, 0), g.n_buckets - 1);
+          atomicAdd(&s_hist[2 * g.n_bins + ((q - 1) * g.n_buckets + k) * 2 + (correct ? 0 : 1)], 1u);
+        }
+      }
+    }
+    __syncthreads();                       // every reader is done with `buf` before the next iteration refills it
+  }
+  if (!do_hist) return;
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+    if (my[k]) atomicAdd(&s_sums[k], my[k]);
+  __syncthreads();
+  if (threadIdx.x < 6 && s_sums[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_sums[threadIdx.x]);
+  for (int i = threadIdx.x; i < n_slots; i += blockDim.x) {
+    const unsigned v = s_hist[i];
+    if (!v) continue;
+    size_t dst;
+    if (i < 2 * g.n_bins) dst = FAV_HIST_HDR + 3 * (size_t)(i >> 1) + ((i & 1) ? 2 : 0);
+    else dst = FAV_HIST_HDR + 3 * (size_t)g.n_bins + (size_t)(i - 2 * g.n_bins);
+    atomicAdd(&hist[dst], (unsigned long long)v);
+  }
+  for (int i = threadIdx.x; i < g.n_bins; i += blockDim.x)
+    if (s_binsum[i]) atomicAdd(&hist[FAV_HIST_HDR + 3 * (size_t)i + 1], s_binsum[i]);
+  const size_t cb = FAV_HIST_HDR + 3 * (size_t)g.n_bins + 6 * (size_t)g.n_buckets;
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x)
+    if (s_cm[i]) atomicAdd(&hist[cb + i], (unsigned long long)s_cm[i]);
+}
+
 }  // namespace fav
 
 using namespace fav;
@@ -266,6 +449,32 @@ static int launch_k34(fav_handle h, const float* d_logits, const int32_t* d_labe
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   unsigned long long* hist = reinterpret_cast<unsigned long long*>(d_hist);
+  if (d_logits && C <= 16 && (reinterpret_cast<uintptr_t>(d_logits) & 15) == 0) {
+    // thread-group-per-sample path: the largest tile (256 / TPS samples) whose two buffers fit beside the histogram
+    const size_t hist_bytes = d_hist ? ((((smem + 7) & ~size_t(7)) + (size_t)n_bins * 8 + (size_t)C * C * 4 + 15) & ~size_t(15)) : 0;
+    const size_t budget = 220 * 1024;
+    int tps = 0;
+    for (int cand = 8; cand <= 32; cand *= 2)
+      if (hist_bytes + 2 * (size_t)(K34S_THREADS / cand) * T * C * 4 <= budget) { tps = cand; break; }
+    if (tps) {
+      const size_t sm = hist_bytes + 2 * (size_t)(K34S_THREADS / tps) * T * C * 4;
+      const int S = K34S_THREADS / tps;
+      long long nb = (n + S - 1) / S;
+      if (nb > h->num_sms) nb = h->num_sms;
+#define FAV_K34S(TPS, CT)                                                                                               \
+  do {                                                                                                                  \
+    FAV_CUDA_OK(cudaFuncSetAttribute(k34_small_kernel<TPS, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));  \
+    k34_small_kernel<TPS, CT><<<int(nb), K34S_THREADS, sm, st>>>(d_logits, d_labels, n, T, g, hist, int(hist_bytes), d_conf,      \
+                                                        d_entropy, d_mi, d_pred, d_flag);                               \
+  } while (0)
+      if (C == 10) { if (tps == 8) FAV_K34S(8, 10); else if (tps == 16) FAV_K34S(16, 10); else FAV_K34S(32, 10); }
+      else { if (tps == 8) FAV_K34S(8, 0); else if (tps == 16) FAV_K34S(16, 0); else FAV_K34S(32, 0); }
+#undef FAV_K34S
+      h->launches++;
+      FAV_CUDA_OK(cudaGetLastError());
+      return FAV_OK;
+    }
+  }
   const int nc = C <= 16 ? 0 : (C <= 32 ? 1 : (C <= 128 ? 4 : 32));
   const int warps = 8;
   long long blocks = d_logits ? (n + warps - 1) / warps : (n + 255) / 256;
