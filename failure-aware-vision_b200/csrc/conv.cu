@@ -464,7 +464,7 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   // operand-A mode
   const bool tma_s1 = L.stride == 1 && 2 * L.pad == L.r - 1;
   const bool tma_s2 = L.stride == 2 && (c.h % 2) == 0 && (c.w % 2) == 0;
-  const bool tma_ok = !L.cin_store && (L.cin % 64) == 0 && L.r == L.s && a.OW <= 128 && (tma_s1 || tma_s2);
+  const bool tma_ok = !L.cin_store && (L.cin % 64) == 0 && L.r == L.s && (tma_s1 || tma_s2);
   int mode = c.a_mode;
   const bool stem_tma = c.a_mode == 5;
   if (stem_tma) {
@@ -486,8 +486,8 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   a.stem_tma = stem_tma ? 1 : 0;
   if (mode == 0) {
     if (a.OH * a.OW <= BM) { a.bw = a.OW; a.bh = a.OH; a.bn_img = BM / (a.OH * a.OW); }
-    else if (stem_tma) {
-      // any OW: the (bw x bh <= 128) pixel rectangle that covers the output with the fewest tiles
+    else {
+      // the (bw x bh <= 128) pixel rectangle that covers the output with the fewest tiles (ties: the widest one)
       long long best = -1;
       for (int bw = 1; bw <= (a.OW < BM ? a.OW : BM); ++bw) {
         const int bh = (BM / bw) < a.OH ? (BM / bw) : a.OH;
@@ -496,7 +496,6 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
       }
       a.bn_img = 1;
     }
-    else { a.bw = a.OW; a.bh = BM / a.OW; a.bn_img = 1; }
     if (a.bn_img > c.p) a.bn_img = c.p;
     a.tiles_w = (a.OW + a.bw - 1) / a.bw; a.tiles_h = (a.OH + a.bh - 1) / a.bh;
     const int tiles_n = (c.p + a.bn_img - 1) / a.bn_img;

@@ -90,6 +90,48 @@ __global__ void __launch_bounds__(256) k_pool_dropout(const uint4* __restrict__ 
   }
 }
 
+// same for large feature maps (the batch-1 streaming gate: 15x20 pixels, one image): a CTA per (pass-image, 32 channel
+// vectors); its 8 warps sum interleaved pixels, shared-memory reduce, warp 0 applies the mask
+__global__ void __launch_bounds__(256) k_pool_dropout_wide(const uint4* __restrict__ x, uint4* __restrict__ y, int P, int HW,
+                                                           int C8, int T, int drop, uint32_t thr16, float scale, uint32_t k0,
+                                                           uint32_t k1, uint32_t first_image, uint32_t stream) {
+  __shared__ float part[8][32][8];
+  const int groups = (C8 + 31) / 32;
+  const int p = blockIdx.x / groups, c = (blockIdx.x % groups) * 32 + (threadIdx.x & 31), w = threadIdx.x >> 5;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c < C8) {
+    for (int j = w; j < HW; j += 8) {
+      const uint4 v = __ldg(x + ((size_t)p * HW + j) * C8 + c);
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { s[2 * k] += bf16_lo(w4[k]); s[2 * k + 1] += bf16_hi(w4[k]); }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) part[w][threadIdx.x & 31][k] = s[k];
+  __syncthreads();
+  if (w != 0 || c >= C8) return;
+  const float inv = 1.0f / float(HW);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float t = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) t += part[ww][threadIdx.x][k];
+    s[k] = t * inv;
+  }
+  if (drop) {
+    const int n_img = p / T, t = p - n_img * T;
+    const uint4 r = philox4x32_10(uint32_t(c), first_image + uint32_t(n_img), uint32_t(t), stream, k0, k1);
+    const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s[2 * k] = (rw[k] & 0xFFFFu) >= thr16 ? s[2 * k] * scale : 0.f;
+      s[2 * k + 1] = (rw[k] >> 16) >= thr16 ? s[2 * k + 1] * scale : 0.f;
+    }
+  }
+  y[(size_t)p * C8 + c] = make_uint4(pack_bf16x2(s[0], s[1]), pack_bf16x2(s[2], s[3]), pack_bf16x2(s[4], s[5]), pack_bf16x2(s[6], s[7]));
+}
+
 // bf16 NHWC3 -> 2x2 space-to-depth of the zero-padded image, [n][hp][wp][16]: channel (dy*2 + dx)*4 + c of pixel (Y, X) is
 // image pixel (2Y + dy - pad, 2X + dx - pad), zero outside the image and for c = 3 (conv_stem_padded_dims)
 __global__ void __launch_bounds__(256) k_stem_s2d(const unsigned short* __restrict__ x, uint4* __restrict__ y, int n, int h, int w,
@@ -473,9 +515,15 @@ extern "C" int fav_forward_mc(fav_handle h, const void* d_x, float* d_logits, in
   {
     const long long work = (long long)P * (ch / 8);
     const uint32_t thr = mc ? uint32_t(floor(double(p_drop) * 65536.0)) : 0u;
-    k_pool_dropout<<<grid_for(work, 256, h->num_sms), 256, 0, st>>>(
-        reinterpret_cast<const uint4*>(X[cur]), reinterpret_cast<uint4*>(Y1), P, hh * ww, ch / 8, T, mc ? 1 : 0, thr,
-        1.0f / (1.0f - p_drop), k0, k1, uint32_t(first_image), stream_id(KIND_DROPOUT, 255, 0));
+    const int groups = (ch / 8 + 31) / 32;
+    if (hh * ww >= 64 && (long long)P * groups <= (1 << 20))
+      k_pool_dropout_wide<<<P * groups, 256, 0, st>>>(
+          reinterpret_cast<const uint4*>(X[cur]), reinterpret_cast<uint4*>(Y1), P, hh * ww, ch / 8, T, mc ? 1 : 0, thr,
+          1.0f / (1.0f - p_drop), k0, k1, uint32_t(first_image), stream_id(KIND_DROPOUT, 255, 0));
+    else
+      k_pool_dropout<<<grid_for(work, 256, h->num_sms), 256, 0, st>>>(
+          reinterpret_cast<const uint4*>(X[cur]), reinterpret_cast<uint4*>(Y1), P, hh * ww, ch / 8, T, mc ? 1 : 0, thr,
+          1.0f / (1.0f - p_drop), k0, k1, uint32_t(first_image), stream_id(KIND_DROPOUT, 255, 0));
     h->launches++;
   }
   const ConvLayer& fc = pl.convs.back();

@@ -99,7 +99,7 @@ class SignalFinisher:
 class UncertaintyGate:
     def __init__(self, classifier: VisionClassifier = None, frame_hw=(480, 640), T=1, p_drop=0.2, tau=0.9,
                  score_source="uncertainty", model="resnet18", num_classes=1000, device=0, weights_seed=0,
-                 logit_gain=None, use_classifier=True):
+                 logit_gain=None, use_classifier=True, use_graph=None):
         if not torch.cuda.is_available():
             raise RuntimeError("UncertaintyGate needs a CUDA device (sm_100a); there is no CPU fallback")
         self.frame_hw = tuple(frame_hw)
@@ -116,8 +116,40 @@ class UncertaintyGate:
         self._gray = torch.zeros((h, w), dtype=torch.uint8, device=self.device)
         self._stats = torch.zeros(260, dtype=torch.int64, device=self.device)
         self._stats_host = torch.empty(260, dtype=torch.int64).pin_memory()
+        self._packed_host = torch.empty((1, 4), dtype=torch.float32).pin_memory()
         self._fin = SignalFinisher()
+        # CUDA-graph replay of the whole device side of a frame (H2D copy, frame statistics, K1..K3, D2H copies): one
+        # launch instead of ~30.  The dropout masks are keyed by first_image, a kernel argument frozen at capture, so the
+        # default enables it for the deterministic T == 1 gate only (with T > 1 every frame would reuse the same T masks).
+        self.use_graph = (self.T == 1) if use_graph is None else bool(use_graph)
+        self._graph = None
+        self._graph_failed = False
         self.reset()
+
+    def _enqueue_frame(self, first, first_image):
+        """Device side of one frame on the current stream: pinned frame -> device, fused SignalAnalyzer statistics,
+        classifier + uncertainty epilogue, results -> pinned host buffers.  No host synchronisation."""
+        h, w = self.frame_hw
+        self._frame[0].copy_(self._pinned, non_blocking=True)
+        _lib.check(self.lib.fav_frame_stats(self.handle.h, _ptr(self._frame), _ptr(self._gray), h, w,
+                                            1 if first else 0, _ptr(self._stats), _stream()), "fav_frame_stats")
+        if self.clf is not None:
+            u = self.clf.uncertainty(self._frame, None, T=self.T, p=self.p_drop, seed=0, first_image=first_image, bgr=True)
+            packed = torch.stack([u["confidence"], u["entropy"], u["mutual_information"], u["pred"].float()], 1)
+            self._packed_host.copy_(packed, non_blocking=True)
+        self._stats_host.copy_(self._stats, non_blocking=True)
+
+    def _capture(self):
+        try:
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue_frame(False, 0)
+            self._graph = g
+        except Exception:                      # capture is an optimisation: any failure falls back to eager launches
+            self._graph = None
+            self._graph_failed = True
+            torch.cuda.synchronize(self.device)
 
     def reset(self):
         """Clear internal state (signal_analyzer.py:41-45)."""
@@ -132,18 +164,17 @@ class UncertaintyGate:
             raise ValueError(f"frame must be uint8 {(h, w, 3)}, got {frame.dtype} {frame.shape}")
         self._frame_count += 1
         self._pinned.copy_(torch.from_numpy(frame))
-        self._frame[0].copy_(self._pinned, non_blocking=True)
-        _lib.check(self.lib.fav_frame_stats(self.handle.h, _ptr(self._frame), _ptr(self._gray), h, w,
-                                            0 if self._fin.have_prev else 1, _ptr(self._stats), _stream()), "fav_frame_stats")
-        unc = None
-        if self.clf is not None:
-            u = self.clf.uncertainty(self._frame, None, T=self.T, p=self.p_drop, seed=0,
-                                     first_image=self._frame_count, bgr=True)
-            packed = torch.stack([u["confidence"], u["entropy"], u["mutual_information"], u["pred"].float()], 1)
-        self._stats_host.copy_(self._stats, non_blocking=True)
-        if self.clf is not None:
-            packed_host = packed.cpu()
-        torch.cuda.current_stream().synchronize()
+        first = not self._fin.have_prev
+        if self.use_graph and not first and not self._graph_failed and self._frame_count > 2:
+            if self._graph is None:
+                self._capture()
+            if self._graph is not None:
+                self._graph.replay()
+                torch.cuda.current_stream().synchronize()
+        if self._graph is None or first or self._frame_count <= 2:
+            self._enqueue_frame(first, self._frame_count)
+            torch.cuda.current_stream().synchronize()
+        packed_host, unc = self._packed_host, None
         fin = self._fin.finish(self._stats_host.numpy(), h * w)
         signal_score, vision_status = fin["signal_score"], fin["vision_status"]
 

@@ -149,6 +149,9 @@ CONV_CASES = [
     (2, 56, 56, 64, 64, 3, 1, 1, 0, 0, (0, 1)),
     (3, 7, 7, 512, 2048, 1, 1, 0, 0, 1, (0, 1)),
     (1, 9, 13, 16, 24, 3, 1, 1, 1, 0, (1, 2)),
+    (1, 20, 160, 64, 64, 3, 1, 1, 1, 1, (0, 1)),          # wider than one A tile: rectangular pixel tiles
+    (2, 30, 150, 64, 128, 3, 2, 1, 1, 0, (0, 1)),
+    (3, 6, 6, 256, 512, 3, 1, 1, 1, 1, (0, 1)),           # 2-SM N = 256 tiles (auto)
 ]
 
 
@@ -168,7 +171,7 @@ def test_k2_conv_matches_torch_fp32(fav, clf18, case):
     if relu:
         ref = torch.relu(ref)
     modes = tuple(modes) + ((0x200, 0x100) if 0 in modes else ())      # also force 256- and 128-pixel CTA tiles
-    if 0 in modes and cout == 128 and oh * ow <= 128:
+    if 0 in modes and cout in (128, 512) and oh * ow <= 128:
         modes += (0x300,)                                               # 2-SM (cta_group::2) weights-stationary variant
     for mode in modes:
         for out_f32 in (0, 1):
