@@ -52,6 +52,7 @@ extern "C" int fav_destroy(fav_handle h) {
   if (h->plan) plan_destroy(h->plan);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->stats_buf) cudaFree(h->stats_buf);
+  if (h->splitk_buf) cudaFree(h->splitk_buf);
   delete h;
   return FAV_OK;
 }

@@ -94,6 +94,9 @@ struct Ctx {
   size_t ev_used = 0;
   std::vector<float> ev_gflop;
   void* stats_buf = nullptr;      // 512 launches x 8 role counters (cycles)
+  // fp32 accumulation scratch of the split-K convolutions (few output tiles, many k-blocks: the batch-1 streaming gate)
+  void* splitk_buf = nullptr;
+  size_t splitk_bytes = 0;
 };
 
 }  // namespace fav

@@ -101,7 +101,7 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
               for (int hf = 0; hf < a.BN / 64; ++hf) tma_prefetch_l2_4d(&tmR, n_col + hf * 64, t[u].ow0, t[u].oh0, t[u].q0);
         }
         __syncwarp();
-        for_each_kb(a, t[0], [&](int kb, int r, int ss, int cb) {
+        int cd = for_each_kb(a, t[0], [&](int kb, int r, int ss, int cb) {
           mbar_wait_timed(empty_bar(stage), phase ^ 1, w_empty, a.stats != nullptr);
           const uint32_t sa = smem_base + stage * stage_bytes;
           if (elect_one()) {
@@ -131,6 +131,7 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         });
         for (int cb = 0; cb < a.kb2; ++cb) {        // fused downsample branch: 1x1 taps of the block input, same output tile
+          if (!kb_mine(a, cd)) continue;
           mbar_wait_timed(empty_bar(stage), phase ^ 1, w_empty, a.stats != nullptr);
           const uint32_t sa = smem_base + stage * stage_bytes;
           if (elect_one()) {
@@ -188,8 +189,9 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
           accumulate = 1;
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         };
-        for_each_kb(a, t, [&](int, int, int, int) { issue_stage(); });
-        for (int cb = 0; cb < a.kb2; ++cb) issue_stage();
+        int cd = for_each_kb(a, t, [&](int, int, int, int) { issue_stage(); });
+        for (int cb = 0; cb < a.kb2; ++cb)
+          if (kb_mine(a, cd)) issue_stage();
         if (elect_one()) umma_commit(tfull_bar(acc));
         __syncwarp();
       }
@@ -337,6 +339,32 @@ conv_igemm_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                          const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmY,
                   const __grid_constant__ CUtensorMap tmR, const ConvArgs a) {
   conv_igemm_body<true, 1, 8>(tmA, tmB, tmA2, tmY, tmR, a);
+}
+
+// split-K epilogue: acc32 [M][Cout] fp32 partial sums -> + bias (+ residual) (ReLU) -> bf16 NHWC, 8 channels per thread
+__global__ void __launch_bounds__(256) k_splitk_finish(const float* __restrict__ acc, const float* __restrict__ bias,
+                                                       const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y,
+                                                       long long M, int Cout, int relu) {
+  const int c8n = Cout >> 3;
+  const long long total = M * c8n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = int(i % c8n) * 8;
+    const size_t off = (size_t)(i / c8n) * Cout + c0;
+    const float4 a0 = *reinterpret_cast<const float4*>(acc + off), a1 = *reinterpret_cast<const float4*>(acc + off + 4);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
+    float v[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w, a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
+    if (res) {
+      const uint4 r = __ldg(reinterpret_cast<const uint4*>(res + off));
+      const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { v[2 * k] += bf16_lo(rw[k]); v[2 * k + 1] += bf16_hi(rw[k]); }
+    }
+    if (relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+    }
+    *reinterpret_cast<uint4*>(y + off) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -564,12 +592,40 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   const int MT = (mode == 0 && force_mt == 2) ? 2 : 1;
   a.mt_per_tile = MT;
   a.total_tiles = ((mtiles + MT - 1) / MT) * a.ntiles;
+  // split-K (opt-in, FAV_SPLITK=1): a launch that fills less than half the machine but has long K loops (the batch-1 gate's
+  // layer3/4) is cut into ksplit slices per output tile; every slice keeps at least one k-block (the centre tap is never
+  // skipped).  Off by default: (1) fp32 atomics make the sums order-dependent, which would break the sweep's bit-identical
+  // results across block sizes / GPU counts; (2) measured on the 640x480 gate the extra memset + finish launches cost as
+  // much as the shorter K loops save (p50 0.47 vs 0.44 ms).  The round-2 form is an in-kernel fixed-order fix-up by the last
+  // slice to finish (no extra launches, deterministic).
+  static const int env_splitk = [] { const char* e = getenv("FAV_SPLITK"); return e ? atoi(e) : 0; }();
+  a.ksplit = 0;
+  const bool pair_ok = MT == 1 && conv_pair_applicable(L, a, c.force_mt == 3 ? 1 : 0) && c.force_mt != 1;
+  if (env_splitk && mode == 0 && !stem_tma && MT == 1 && !pair_ok && !c.drop && a.rep == 1 && !c.out_f32 && (L.cout % 8) == 0 &&
+      a.cin_blocks >= 2 && a.num_kb + a.kb2 >= 16 && 2 * a.total_tiles <= ctx->num_sms) {
+    int S = (2 * ctx->num_sms) / a.total_tiles;
+    if (S > a.cin_blocks) S = a.cin_blocks;
+    if (S > 8) S = 8;
+    if (S >= 2) {
+      const size_t need = (size_t)M * L.cout * 4;
+      if (need > ctx->splitk_bytes) {
+        if (ctx->splitk_buf) FAV_CUDA_OK(cudaFree(ctx->splitk_buf));
+        ctx->splitk_buf = nullptr; ctx->splitk_bytes = 0;
+        FAV_CUDA_OK(cudaMalloc(&ctx->splitk_buf, need));
+        ctx->splitk_bytes = need;
+      }
+      FAV_CUDA_OK(cudaMemsetAsync(ctx->splitk_buf, 0, need, st));
+      a.ksplit = S;
+      a.acc32 = reinterpret_cast<float*>(ctx->splitk_buf);
+      a.total_tiles *= S;
+    }
+  }
   const int stage_bytes = MT * A_TILE_BYTES + a.BN * 128;
   const int ctas_per_sm = (mode == 0 && MT == 1) ? 2 : 1;
   // staged epilogue (TMA stores from two shared-memory slabs): bf16 NHWC output of the TMA-tiled modes.  The default
   // keeps it for the layers whose epilogue is the bottleneck (few k-blocks per tile, or T masked replicas per tile).
   static const int env_stg = [] { const char* e = getenv("FAV_EPI_TMA"); return e ? atoi(e) : -1; }();   // -1 auto, 0 off, 1 all eligible
-  const bool stg_ok = mode == 0 && !c.out_f32 && (L.cout % 64) == 0;
+  const bool stg_ok = mode == 0 && !c.out_f32 && (L.cout % 64) == 0 && a.ksplit <= 1;
   const bool stg_auto = (a.num_kb + a.kb2) <= 8 || a.rep > 1 || a.BN == 64;
   a.stg_bytes = (stg_ok && env_stg != 0 && (env_stg > 0 || stg_auto)) ? 2 * STG_SLAB_BYTES : 0;
   CUtensorMap tmY;
@@ -586,7 +642,7 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   static const int env_rpf = [] { const char* e = getenv("FAV_RES_PREFETCH"); return e ? atoi(e) : 1; }();
   CUtensorMap tmR;
   memset(&tmR, 0, sizeof(tmR));
-  a.res_prefetch = (env_rpf && mode == 0 && c.res && !c.out_f32 && (L.cout % 64) == 0) ? 1 : 0;
+  a.res_prefetch = (env_rpf && mode == 0 && c.res && !c.out_f32 && (L.cout % 64) == 0 && a.ksplit <= 1) ? 1 : 0;
   if (a.res_prefetch) {
     const cuuint64_t px = (cuuint64_t)L.cout * 2;
     const cuuint64_t dims[4] = {(cuuint64_t)L.cout, (cuuint64_t)a.OW, (cuuint64_t)a.OH, (cuuint64_t)c.p};
@@ -624,7 +680,7 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
     int rc = conv_timing_begin(ctx, st, gf, &e1, &a.stats);
     if (rc) return rc;
   }
-  if (MT == 1 && conv_pair_applicable(L, a, c.force_mt == 3 ? 1 : 0) && c.force_mt != 1) {
+  if (pair_ok) {
     int rc = conv_pair_launch(ctx, L, a, tmA, tmA2, st);
     if (rc) return rc;
   } else {
@@ -638,6 +694,13 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
     if (mode == 0 && MT == 2) FAV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm_m256_kernel, tmA, tmW, tmA2, tmY, tmR, a));
     else if (mode == 0) FAV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm_kernel, tmA, tmW, tmA2, tmY, tmR, a));
     else FAV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm_gather_kernel, tmA, tmW, tmA2, tmY, tmR, a));
+  }
+  if (a.ksplit > 1) {
+    const long long work = M * (L.cout / 8);
+    long long nb = (work + 255) / 256;
+    if (nb > 8LL * ctx->num_sms) nb = 8LL * ctx->num_sms;
+    k_splitk_finish<<<int(nb), 256, 0, st>>>(a.acc32, a.bias, a.res, reinterpret_cast<__nv_bfloat16*>(a.y), M, L.cout, a.relu);
+    ctx->launches++;
   }
   if (e1) FAV_CUDA_OK(cudaEventRecord(e1, st));
   ctx->launches++;

@@ -32,6 +32,8 @@ struct ConvArgs {
   int kb2, stride2, Cin2;      // fused second source (the block's 1x1 downsample branch): extra k-blocks after the main taps
   int stg_bytes;               // > 0: epilogue stages bf16 output in shared memory (two 128 x 64 slabs) and writes it with TMA stores
   int res_prefetch;            // the TMA issuer prefetches each tile's residual rows into L2 (tmR) when it starts the tile
+  int ksplit;                  // > 1: each output tile is computed by ksplit CTA tiles taking interleaved k-blocks; fp32 partial sums
+  float* acc32;                //      are added into acc32 [M][Cout] with global atomics, k_splitk_finish applies bias / residual / ReLU
   int ablate;                  // tuning aid (env FAV_CONV_ABLATE): 1 skip A loads, 2 skip B loads, 4 skip MMAs, 8 skip epilogue math
   unsigned long long* stats;   // optional per-launch role timing (8 counters), see fav_conv_stats_read
 };
@@ -42,10 +44,12 @@ constexpr int THREADS_TMA1 = 32 * (2 + 8);        // MT = 1: 8 epilogue warps, t
 constexpr int THREADS_TMA2 = 32 * (2 + 16);       // MT = 2: 16 epilogue warps, one CTA per SM
 constexpr int THREADS_GATHER = 32 * (2 + 8 + 8);  // gather variant: 8 epilogue + 8 gather warps (two groups on alternate k-blocks)
 
-struct Tile { int mt, nt, q0, oh0, ow0; };   // mt = index of the 128-row M tile
+struct Tile { int mt, nt, q0, oh0, ow0, ks; };   // mt = index of the 128-row M tile, ks = split-K slice
 
 __device__ __forceinline__ Tile decode_tile(const ConvArgs& a, int tile, int u = 0) {
   Tile t;
+  t.ks = 0;
+  if (a.ksplit > 1) { t.ks = tile % a.ksplit; tile /= a.ksplit; }      // slices of one output tile run side by side
   t.nt = tile % a.ntiles; t.mt = (tile / a.ntiles) * a.mt_per_tile + u;
   t.q0 = 0; t.oh0 = 0; t.ow0 = 0;
   if (a.a_mode == 0) {
@@ -56,11 +60,23 @@ __device__ __forceinline__ Tile decode_tile(const ConvArgs& a, int tile, int u =
 }
 // Division-free walk over the k-blocks of a tile: f(kb, r, s, cb).  In a_mode 0 the filter taps whose shifted window
 // only sees padding for the whole tile are skipped (row / column tests hoisted out of the channel-block loop).
+// Split-K interleave: slice ks takes the visited k-blocks number ks, ks + ksplit, ...  `cd` is a countdown (no modulo in the
+// single issuing thread): take the k-block when it reaches 0.
+__device__ __forceinline__ bool kb_mine(const ConvArgs& a, int& cd) {
+  if (a.ksplit <= 1) return true;
+  if (cd == 0) { cd = a.ksplit - 1; return true; }
+  --cd;
+  return false;
+}
+
+// walks the k-blocks of tile t (all-padding filter taps are skipped); returns the split-K countdown after the last one
 template <class F>
-__device__ __forceinline__ void for_each_kb(const ConvArgs& a, const Tile& t, F&& f) {
+__device__ __forceinline__ int for_each_kb(const ConvArgs& a, const Tile& t, F&& f) {
+  int cd = t.ks;
   if (a.a_mode != 0 || a.stem_tma) {
-    for (int kb = 0; kb < a.num_kb; ++kb) f(kb, 0, 0, 0);
-    return;
+    for (int kb = 0; kb < a.num_kb; ++kb)
+      if (kb_mine(a, cd)) f(kb, 0, 0, 0);
+    return cd;
   }
   const int oh_last = min(t.oh0 + a.bh, a.OH) - 1, ow_last = min(t.ow0 + a.bw, a.OW) - 1;
   int kb = 0;
@@ -68,9 +84,11 @@ __device__ __forceinline__ void for_each_kb(const ConvArgs& a, const Tile& t, F&
     const bool row_ok = !(oh_last * a.stride + r - a.pad < 0 || t.oh0 * a.stride + r - a.pad >= a.H);
     for (int ss = 0; ss < a.S; ++ss, kb += a.cin_blocks) {
       if (!row_ok || ow_last * a.stride + ss - a.pad < 0 || t.ow0 * a.stride + ss - a.pad >= a.W) continue;
-      for (int cb = 0; cb < a.cin_blocks; ++cb) f(kb + cb, r, ss, cb);
+      for (int cb = 0; cb < a.cin_blocks; ++cb)
+        if (kb_mine(a, cd)) f(kb + cb, r, ss, cb);
     }
   }
+  return cd;
 }
 
 // output pixel owned by A-tile row `row` of tile t
@@ -138,6 +156,13 @@ __device__ __forceinline__ void conv_epilogue_subtile(const ConvArgs& a, const T
     tmem_ld16(trow + uint32_t(j * 16), acc);       // warp-collective: executed by every lane, valid or not
     tmem_ld_wait();
     if (!valid || c0 >= a.Cout || (a.ablate & 8)) continue;
+    if (a.ksplit > 1) {                      // partial sums of this k slice; bias / residual / ReLU happen in k_splitk_finish
+      float* dst = a.acc32 + res_off + c0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (c0 + i < a.Cout) atomicAdd(dst + i, __uint_as_float(acc[i]));
+      continue;
+    }
     float v[16];
     {
       const float4* bp = reinterpret_cast<const float4*>(a.bias + c0);     // bias is padded to cout_pad

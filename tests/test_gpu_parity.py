@@ -152,6 +152,9 @@ CONV_CASES = [
     (1, 20, 160, 64, 64, 3, 1, 1, 1, 1, (0, 1)),          # wider than one A tile: rectangular pixel tiles
     (2, 30, 150, 64, 128, 3, 2, 1, 1, 0, (0, 1)),
     (3, 6, 6, 256, 512, 3, 1, 1, 1, 1, (0, 1)),           # 2-SM N = 256 tiles (auto)
+    (1, 15, 20, 512, 512, 3, 1, 1, 1, 1, (0, 1)),         # few tiles, long K (split-K when FAV_SPLITK=1)
+    (1, 30, 40, 256, 512, 3, 2, 1, 1, 0, (0,)),
+    (2, 15, 20, 256, 100, 1, 1, 0, 0, 1, (0,)),
 ]
 
 
