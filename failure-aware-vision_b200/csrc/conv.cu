@@ -49,8 +49,11 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
   const int stage_bytes = MT * A_TILE_BYTES + a.BN * 128;
   const uint32_t smem_base = smem_u32(smem);
   uint8_t* stg = smem + a.stages * stage_bytes;                  // staged epilogue: two 16 KB output slabs (a.stg_bytes, may be 0)
-  const uint32_t bars = smem_base + a.stages * stage_bytes + a.stg_bytes;      // full[s], empty[s], tmem_full[2], tmem_empty[2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + a.stages * stage_bytes + a.stg_bytes + (2 * a.stages + 4) * 8);
+  const int ident_bytes = a.res_mma ? IDENT_BYTES : 0;            // resident 64x64 bf16 identity (B operand of the residual MMAs)
+  uint8_t* ident = stg + a.stg_bytes;
+  const int fixed = a.stages * stage_bytes + a.stg_bytes + ident_bytes;
+  const uint32_t bars = smem_base + fixed;                       // full[s], empty[s], tmem_full[2], tmem_empty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + fixed + (2 * a.stages + 4) * 8);
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (a.stages + s); };
   auto tfull_bar = [&](int i) { return bars + 8u * (2 * a.stages + i); };
@@ -63,13 +66,30 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
     if (a.a_mode == 0) tma_prefetch_desc(&tmA);
     if (a.kb2 > 0) tma_prefetch_desc(&tmA2);
     if (a.stg_bytes) tma_prefetch_desc(&tmY);
-    if (a.res_prefetch) tma_prefetch_desc(&tmR);
+    if (a.res_mma) tma_prefetch_desc(&tmR);
     const uint32_t full_count = a.a_mode == 0 ? 1u : 1u + 128u;
     for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), full_count); mbar_init(empty_bar(s), 1u); }
     for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1u); mbar_init(tempty_bar(i), uint32_t(EPI_WARPS)); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), a.tmem_cols);
+  if (a.res_mma && warp >= EPI_WARP0 && warp < EPI_WARP0 + 4) {
+    // identity in the canonical K-major SWIZZLE_128B layout: row n = 128 bytes, 1.0 at k = n, 16-byte chunk index ^= n % 8
+    const int i = threadIdx.x - 32 * EPI_WARP0;                    // 0..127: two threads per row (64 rows), 64 bytes each
+    const int n = i >> 1, half = i & 1;
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      const int chunk = half * 4 + ch;                             // logical chunk: k = 8 * chunk .. 8 * chunk + 7
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if ((n >> 3) == chunk) {
+        const uint32_t one = 0x3F80u << (16 * (n & 1));
+        const int w = (n & 7) >> 1;
+        v.x = w == 0 ? one : 0u; v.y = w == 1 ? one : 0u; v.z = w == 2 ? one : 0u; v.w = w == 3 ? one : 0u;
+      }
+      *reinterpret_cast<uint4*>(ident + n * 128 + ((chunk ^ (n & 7)) << 4)) = v;
+    }
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -93,14 +113,6 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
         for (int u = 0; u < MT; ++u) { t[u] = decode_tile(a, tile, u); if (t[u].mt < a.mtiles) n_sub = u + 1; }
         const uint32_t tx = ((a.ablate & 1) ? 0u : a_bytes * n_sub) + ((a.ablate & 2) ? 0u : uint32_t(a.BN) * 128u);
         const int n_col = t[0].nt * a.BN;
-        if (a.res_prefetch && elect_one()) {
-          // the epilogue reads this tile's residual rows a whole tile later: pull them from HBM into L2 now
-#pragma unroll
-          for (int u = 0; u < MT; ++u)
-            if (u < n_sub)
-              for (int hf = 0; hf < a.BN / 64; ++hf) tma_prefetch_l2_4d(&tmR, n_col + hf * 64, t[u].ow0, t[u].oh0, t[u].q0);
-        }
-        __syncwarp();
         int cd = for_each_kb(a, t[0], [&](int kb, int r, int ss, int cb) {
           mbar_wait_timed(empty_bar(stage), phase ^ 1, w_empty, a.stats != nullptr);
           const uint32_t sa = smem_base + stage * stage_bytes;
@@ -147,6 +159,20 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
           __syncwarp();
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
+        if (a.res_mma) {                             // residual rows of this tile, 64 channels per k-block (no W tile: B is resident)
+          for (int j = 0; j < a.BN / 64; ++j) {
+            mbar_wait_timed(empty_bar(stage), phase ^ 1, w_empty, a.stats != nullptr);
+            const uint32_t sa = smem_base + stage * stage_bytes;
+            if (elect_one()) {
+              mbar_arrive_expect_tx(full_bar(stage), a_bytes * n_sub);
+#pragma unroll
+              for (int u = 0; u < MT; ++u)
+                if (u < n_sub) tma_load_4d(sa + u * A_TILE_BYTES, &tmR, full_bar(stage), n_col + j * 64, t[u].ow0, t[u].oh0, t[u].q0);
+            }
+            __syncwarp();
+            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+          }
+        }
       }
       if (a.stats && lane == 0) {
         atomicAdd(&a.stats[0], (unsigned long long)w_empty);
@@ -192,6 +218,27 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
         int cd = for_each_kb(a, t, [&](int, int, int, int) { issue_stage(); });
         for (int cb = 0; cb < a.kb2; ++cb)
           if (kb_mine(a, cd)) issue_stage();
+        if (a.res_mma) {
+          const uint64_t d_ident = make_sw128_desc(smem_u32(ident));
+          for (int j = 0; j < a.BN / 64; ++j) {      // acc[:, 64j .. 64j+63] += residual[:, 64j ..] x I
+            mbar_wait_timed(full_bar(stage), phase, w_full, a.stats != nullptr);
+            tc_fence_after();
+            const uint64_t da0 = desc0 + uint64_t(stage) * desc_stage;
+            if (elect_one()) {
+#pragma unroll
+              for (int u = 0; u < MT; ++u) {
+                if (u >= n_sub) break;
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                  umma_f16(d_tmem + uint32_t(u * a.BN + j * 64), da0 + uint64_t(u * (A_TILE_BYTES >> 4)) + 2u * k, d_ident + 2u * k,
+                           a.idesc64, 1u);
+              }
+              umma_commit(empty_bar(stage));
+            }
+            __syncwarp();
+            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+          }
+        }
         if (elect_one()) umma_commit(tfull_bar(acc));
         __syncwarp();
       }
@@ -620,6 +667,25 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
       a.total_tiles *= S;
     }
   }
+  // launch-time constants of the tile / row decode as multiply-high divisors
+  a.fd_ntiles = make_fastdiv(uint32_t(a.ntiles));
+  a.fd_ksplit = make_fastdiv(uint32_t(a.ksplit > 1 ? a.ksplit : 1));
+  a.fd_ohw = make_fastdiv(uint32_t(a.OH * a.OW));
+  a.fd_ow = make_fastdiv(uint32_t(a.OW));
+  if (mode == 0) {
+    a.fd_tw = make_fastdiv(uint32_t(a.tiles_w)); a.fd_th = make_fastdiv(uint32_t(a.tiles_h));
+    a.fd_twth = make_fastdiv(uint32_t(a.tiles_w * a.tiles_h));
+    a.fd_perimg = make_fastdiv(uint32_t(a.bw * a.bh)); a.fd_bw = make_fastdiv(uint32_t(a.bw));
+  } else {
+    a.fd_tw = a.fd_th = a.fd_twth = a.fd_perimg = a.fd_bw = make_fastdiv(1u);
+  }
+  {
+    const unsigned long long nmax = (unsigned long long)a.total_tiles + 1, mmax = (unsigned long long)M + BM;
+    unsigned long long dmax = (unsigned long long)a.ntiles;
+    if ((unsigned long long)a.ksplit > dmax) dmax = a.ksplit;
+    if (mode == 0) { if ((unsigned long long)a.tiles_w > dmax) dmax = a.tiles_w; if ((unsigned long long)a.tiles_h > dmax) dmax = a.tiles_h; }
+    a.fastdiv = (nmax * dmax < (1ull << 32) && (mode == 0 || mmax * (unsigned long long)(a.OH * a.OW) < (1ull << 32))) ? 1 : 0;
+  }
   const int stage_bytes = MT * A_TILE_BYTES + a.BN * 128;
   const int ctas_per_sm = (mode == 0 && MT == 1) ? 2 : 1;
   // staged epilogue (TMA stores from two shared-memory slabs): bf16 NHWC output of the TMA-tiled modes.  The default
@@ -638,12 +704,17 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
     int rc = encode_map(&tmY, c.y, 5, dims, strides, box);
     if (rc) return rc;
   }
-  // residual rows of a tile are prefetched into L2 by the TMA issuer (same pixel rectangle as the A tile)
-  static const int env_rpf = [] { const char* e = getenv("FAV_RES_PREFETCH"); return e ? atoi(e) : 1; }();
+  // residual added by the tensor core (identity MMAs): the residual tile arrives by TMA through the operand pipeline,
+  // far ahead of its use, and the epilogue loses its residual loads, bf16 unpacking and adds
+  // Default: only where the epilogue is the bottleneck (same rule as the staged epilogue); on long-K layers the two extra
+  // k-blocks per tile cost more shared-memory bandwidth than the epilogue saves.  FAV_RES_MMA=0 off, 1 everywhere.
+  static const int env_rmma = [] { const char* e = getenv("FAV_RES_MMA"); return e ? atoi(e) : -1; }();
   CUtensorMap tmR;
   memset(&tmR, 0, sizeof(tmR));
-  a.res_prefetch = (env_rpf && mode == 0 && c.res && !c.out_f32 && (L.cout % 64) == 0 && a.ksplit <= 1) ? 1 : 0;
-  if (a.res_prefetch) {
+  a.res_mma = (env_rmma != 0 && (env_rmma > 0 || stg_auto) && mode == 0 && c.res && !c.out_f32 && (L.cout % 64) == 0 && (a.BN % 64) == 0 && a.ksplit <= 1 && !pair_ok) ? 1 : 0;
+  a.idesc64 = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(64 >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+  if (a.res_mma) {
+    a.res = nullptr;
     const cuuint64_t px = (cuuint64_t)L.cout * 2;
     const cuuint64_t dims[4] = {(cuuint64_t)L.cout, (cuuint64_t)a.OW, (cuuint64_t)a.OH, (cuuint64_t)c.p};
     const cuuint64_t strides[3] = {px, px * a.OW, px * a.OW * a.OH};
@@ -652,7 +723,7 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
     if (rc) return rc;
   }
   // two CTAs per SM: (228 KB - 2 x 1 KB reserved) / 2 = 113 KB each, minus 1 KB alignment slack and the barrier block
-  int stages = ((ctas_per_sm == 2 ? 113 * 1024 - 1280 : 200 * 1024) - a.stg_bytes) / stage_bytes;
+  int stages = ((ctas_per_sm == 2 ? 113 * 1024 - 1280 : 200 * 1024) - a.stg_bytes - (a.res_mma ? IDENT_BYTES : 0)) / stage_bytes;
   stages = stages < 2 ? 2 : (stages > 8 ? 8 : stages);
   a.stages = stages;
   uint32_t cols = 32;
@@ -660,7 +731,7 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   a.tmem_cols = cols;
   // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128
   a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(a.BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
-  const size_t smem = (size_t)stages * stage_bytes + a.stg_bytes + 1024 + 256;
+  const size_t smem = (size_t)stages * stage_bytes + a.stg_bytes + (a.res_mma ? IDENT_BYTES : 0) + 1024 + 256;
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {

@@ -9,6 +9,22 @@ namespace fav {
 constexpr int BM = 128, BK = 64;
 constexpr int A_TILE_BYTES = BM * BK * 2;          // 16 KiB
 
+// unsigned division by a launch-time constant: q = umulhi(n, floor(2^32 / d) + 1), exact while n * d < 2^32 (checked on the
+// host: ConvArgs::fastdiv); one IMAD.HI instead of the ~20-instruction division sequence in every role's tile / row decode
+struct FastDiv {
+  uint32_t m, d;
+};
+__host__ __device__ inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  f.m = d > 1 ? uint32_t((1ull << 32) / d) + 1u : 0u;
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f, bool fast) {
+  if (!fast) return n / f.d;
+  return f.d == 1 ? n : __umulhi(n, f.m);
+}
+
 struct ConvArgs {
   const __nv_bfloat16* x;
   void* y;
@@ -31,7 +47,11 @@ struct ConvArgs {
   int pair_tiles, nkb_tot;     // 2-SM variant: CTA-pair tiles (two 128-row M tiles each), resident W k-blocks (main + fused branch)
   int kb2, stride2, Cin2;      // fused second source (the block's 1x1 downsample branch): extra k-blocks after the main taps
   int stg_bytes;               // > 0: epilogue stages bf16 output in shared memory (two 128 x 64 slabs) and writes it with TMA stores
-  int res_prefetch;            // the TMA issuer prefetches each tile's residual rows into L2 (tmR) when it starts the tile
+  int res_mma;                 // the residual is added by the tensor core: extra k-blocks A = residual tile (tmR), B = a 64x64 identity
+                               // resident in shared memory, N = 64 MMAs into the matching accumulator columns (a.res is null then)
+  uint32_t idesc64;            // instruction descriptor of those N = 64 MMAs
+  int fastdiv;                 // 1: every (dividend, divisor) pair of the decode functions satisfies n * d < 2^32
+  FastDiv fd_ntiles, fd_tw, fd_th, fd_twth, fd_perimg, fd_bw, fd_ksplit, fd_ohw, fd_ow;
   int ksplit;                  // > 1: each output tile is computed by ksplit CTA tiles taking interleaved k-blocks; fp32 partial sums
   float* acc32;                //      are added into acc32 [M][Cout] with global atomics, k_splitk_finish applies bias / residual / ReLU
   int ablate;                  // tuning aid (env FAV_CONV_ABLATE): 1 skip A loads, 2 skip B loads, 4 skip MMAs, 8 skip epilogue math
@@ -39,6 +59,7 @@ struct ConvArgs {
 };
 
 constexpr int EPI_WARP0 = 2;
+constexpr int IDENT_BYTES = 64 * 128;              // resident identity tile of the residual MMAs
 constexpr int STG_SLAB_BYTES = 128 * 128;         // staged epilogue: 128 pixels x 64 bf16 channels
 constexpr int THREADS_TMA1 = 32 * (2 + 8);        // MT = 1: 8 epilogue warps, two CTAs per SM
 constexpr int THREADS_TMA2 = 32 * (2 + 16);       // MT = 2: 16 epilogue warps, one CTA per SM
@@ -46,20 +67,29 @@ constexpr int THREADS_GATHER = 32 * (2 + 8 + 8);  // gather variant: 8 epilogue 
 
 struct Tile { int mt, nt, q0, oh0, ow0, ks; };   // mt = index of the 128-row M tile, ks = split-K slice
 
-__device__ __forceinline__ Tile decode_tile(const ConvArgs& a, int tile, int u = 0) {
+__device__ __forceinline__ Tile decode_tile(const ConvArgs& a, int tile_in, int u = 0) {
   Tile t;
+  const bool fast = a.fastdiv != 0;
+  uint32_t tile = uint32_t(tile_in);
   t.ks = 0;
-  if (a.ksplit > 1) { t.ks = tile % a.ksplit; tile /= a.ksplit; }      // slices of one output tile run side by side
-  t.nt = tile % a.ntiles; t.mt = (tile / a.ntiles) * a.mt_per_tile + u;
+  if (a.ksplit > 1) {                                              // slices of one output tile run side by side
+    const uint32_t q = fdiv(tile, a.fd_ksplit, fast);
+    t.ks = int(tile - q * a.fd_ksplit.d);
+    tile = q;
+  }
+  const uint32_t tq = fdiv(tile, a.fd_ntiles, fast);
+  t.nt = int(tile - tq * a.fd_ntiles.d);
+  t.mt = int(tq) * a.mt_per_tile + u;
   t.q0 = 0; t.oh0 = 0; t.ow0 = 0;
   if (a.a_mode == 0) {
-    const int tw = t.mt % a.tiles_w, th = (t.mt / a.tiles_w) % a.tiles_h, tn = t.mt / (a.tiles_w * a.tiles_h);
-    t.q0 = tn * a.bn_img; t.oh0 = th * a.bh; t.ow0 = tw * a.bw;
+    const uint32_t mt = uint32_t(t.mt);
+    const uint32_t r1 = fdiv(mt, a.fd_tw, fast), tw = mt - r1 * a.fd_tw.d;            // mt = (tn * tiles_h + th) * tiles_w + tw
+    const uint32_t tn = fdiv(r1, a.fd_th, fast), th = r1 - tn * a.fd_th.d;
+    t.q0 = int(tn) * a.bn_img; t.oh0 = int(th) * a.bh; t.ow0 = int(tw) * a.bw;
   }
   return t;
 }
-// Division-free walk over the k-blocks of a tile: f(kb, r, s, cb).  In a_mode 0 the filter taps whose shifted window
-// only sees padding for the whole tile are skipped (row / column tests hoisted out of the channel-block loop).
+
 // Split-K interleave: slice ks takes the visited k-blocks number ks, ks + ksplit, ...  `cd` is a countdown (no modulo in the
 // single issuing thread): take the k-block when it reaches 0.
 __device__ __forceinline__ bool kb_mine(const ConvArgs& a, int& cd) {
@@ -93,18 +123,19 @@ __device__ __forceinline__ int for_each_kb(const ConvArgs& a, const Tile& t, F&&
 
 // output pixel owned by A-tile row `row` of tile t
 __device__ __forceinline__ bool decode_row(const ConvArgs& a, const Tile& t, int row, int& q, int& oh, int& ow) {
+  const bool fast = a.fastdiv != 0;
   if (a.a_mode == 0) {
-    const int per_img = a.bw * a.bh;
-    const int nl = row / per_img, rem = row - nl * per_img, hl = rem / a.bw, wl = rem - hl * a.bw;
-    q = t.q0 + nl; oh = t.oh0 + hl; ow = t.ow0 + wl;
-    return nl < a.bn_img && q < a.P && oh < a.OH && ow < a.OW;
+    const uint32_t nl = fdiv(uint32_t(row), a.fd_perimg, fast), rem = uint32_t(row) - nl * a.fd_perimg.d;
+    const uint32_t hl = fdiv(rem, a.fd_bw, fast), wl = rem - hl * a.fd_bw.d;
+    q = t.q0 + int(nl); oh = t.oh0 + int(hl); ow = t.ow0 + int(wl);
+    return int(nl) < a.bn_img && q < a.P && oh < a.OH && ow < a.OW;
   }
   const long long m = (long long)t.mt * BM + row;
   q = 0; oh = 0; ow = 0;
   if (m >= a.M) return false;
-  q = int(m / (a.OH * a.OW));
-  const int rem = int(m - (long long)q * (a.OH * a.OW));
-  oh = rem / a.OW; ow = rem - oh * a.OW;
+  const uint32_t qq = fdiv(uint32_t(m), a.fd_ohw, fast), rem = uint32_t(m) - qq * a.fd_ohw.d;
+  const uint32_t hh = fdiv(rem, a.fd_ow, fast);
+  q = int(qq); oh = int(hh); ow = int(rem - hh * a.fd_ow.d);
   return true;
 }
 
@@ -170,10 +201,14 @@ __device__ __forceinline__ void conv_epilogue_subtile(const ConvArgs& a, const T
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float4 b = __ldg(bp + i);
-        v[4 * i] = __uint_as_float(acc[4 * i]) + b.x + bf16_lo(rw[2 * i]);
-        v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + b.y + bf16_hi(rw[2 * i]);
-        v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b.z + bf16_lo(rw[2 * i + 1]);
-        v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b.w + bf16_hi(rw[2 * i + 1]);
+        v[4 * i] = __uint_as_float(acc[4 * i]) + b.x;
+        v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + b.y;
+        v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b.z;
+        v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b.w;
+      }
+      if (a.res && vec_io) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { v[2 * i] += bf16_lo(rw[i]); v[2 * i + 1] += bf16_hi(rw[i]); }
       }
     }
     if (a.res && !vec_io) {
@@ -274,10 +309,14 @@ __device__ __forceinline__ void conv_epilogue_staged(const ConvArgs& a, const CU
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float4 b = __ldg(bp + i);
-        v[4 * i] = __uint_as_float(acc[4 * i]) + b.x + bf16_lo(rw[2 * i]);
-        v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + b.y + bf16_hi(rw[2 * i]);
-        v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b.z + bf16_lo(rw[2 * i + 1]);
-        v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b.w + bf16_hi(rw[2 * i + 1]);
+        v[4 * i] = __uint_as_float(acc[4 * i]) + b.x;
+        v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + b.y;
+        v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b.z;
+        v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b.w;
+      }
+      if (a.res) {                           // (null when the residual went through the identity MMAs)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { v[2 * i] += bf16_lo(rw[i]); v[2 * i + 1] += bf16_hi(rw[i]); }
       }
       if (a.relu) {
 #pragma unroll
@@ -297,8 +336,12 @@ __device__ __forceinline__ void conv_epilogue_staged(const ConvArgs& a, const CU
         const int jj = sub_w + ch * WPQ;
         uint32_t o[8];                                 // dropped channels -> +0.0 (the dropout product of the direct path)
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          o[i] = pk[ch][i] & (((mask[ch] >> (2 * i)) & 1u) * 0xFFFFu | ((mask[ch] >> (2 * i + 1)) & 1u) * 0xFFFF0000u);
+        for (int i = 0; i < 8; ++i) o[i] = pk[ch][i];
+        if (a.drop) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            o[i] &= ((mask[ch] >> (2 * i)) & 1u) * 0xFFFFu | ((mask[ch] >> (2 * i + 1)) & 1u) * 0xFFFF0000u;
+        }
         *reinterpret_cast<uint4*>(rowp + (((2 * jj) ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
         *reinterpret_cast<uint4*>(rowp + (((2 * jj + 1) ^ (row & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
       }

@@ -208,8 +208,9 @@ int conv_pair_launch(Ctx* ctx, const ConvLayer& L, ConvArgs a, const CUtensorMap
   FAV_REQUIRE(bn != 0, "conv: the 2-SM variant does not fit this layer");
   a.BN = bn;
   a.ntiles = L.cout_pad / bn; a.mt_per_tile = 1;
+  a.fd_ntiles = make_fastdiv(uint32_t(a.ntiles));
   a.nkb_tot = a.num_kb + a.kb2;
-  a.stg_bytes = 0; a.res_prefetch = 0;
+  a.stg_bytes = 0;
   a.pair_tiles = ((a.mtiles + 1) / 2) * a.ntiles;
   const int stage_bytes = A_TILE_BYTES + (bn / 2) * 128;                   // 24 KB (N = 128) or 32 KB (N = 256) per k-block and CTA
   a.stages = (227 * 1024 - 1024 - 512) / stage_bytes;
