@@ -532,6 +532,7 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
     FAV_REQUIRE((L.cout & 15) == 0 && !c.out_f32, "conv: dropout epilogue needs Cout %% 16 == 0 and bf16 output");
     FAV_REQUIRE(c.p_drop >= 0.f && c.p_drop < 1.f, "conv: p_drop must be in [0,1)");
     a.drop_thr16 = uint32_t(floor(double(c.p_drop) * 65536.0));
+    a.drop_thr2 = a.drop_thr16 | (a.drop_thr16 << 16);
     a.drop_scale = 1.0f / (1.0f - c.p_drop);
     a.k0 = uint32_t(c.seed); a.k1 = uint32_t(c.seed >> 32); a.first_image = uint32_t(c.first_image);
     a.drop_stream = stream_id(KIND_DROPOUT, c.layer_id, 0);

@@ -40,7 +40,8 @@ struct ConvArgs {
   int s_store;                 // a_mode 3: filter-row slots (S padded to an even count), Cin stored as 4
   int stem_tma;                // a_mode 0 on the pre-padded NHWC4 stem input: one 5-D TMA box = one filter row x 16 taps x 4 ch per k-block
   int T, rep, drop;
-  uint32_t drop_thr16;
+  uint32_t drop_thr16;         // keep a channel iff its 16-bit Philox lane >= drop_thr16 (= floor(p * 65536))
+  uint32_t drop_thr2;          // the same threshold in both halves of a word (operand of the 2 x 16-bit SIMD compare)
   float drop_scale;
   uint32_t k0, k1, first_image, drop_stream;
   uint32_t tmem_cols, idesc;
@@ -139,6 +140,18 @@ __device__ __forceinline__ bool decode_row(const ConvArgs& a, const Tile& t, int
   return true;
 }
 
+// MC-dropout on 16 packed bf16 channels starting at channel offset e8*8 of the image: two Philox calls give eight words =
+// sixteen 16-bit lanes (channel 2i <- low half of word i, channel 2i+1 <- high half); __vcmpgeu2 turns a word into a
+// 0xFFFF-per-kept-channel mask that is ANDed onto the packed pair (dropped channels become +0.0)
+__device__ __forceinline__ void dropout_and16(const ConvArgs& a, uint32_t e8, uint32_t image, uint32_t tt, const uint32_t (&pk)[8],
+                                              uint32_t (&o)[8]) {
+  const uint4 ra = philox4x32_10(e8, image, tt, a.drop_stream, a.k0, a.k1);
+  const uint4 rb = philox4x32_10(e8 + 1, image, tt, a.drop_stream, a.k0, a.k1);
+  const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = pk[i] & __vcmpgeu2(rw[i], a.drop_thr2);
+}
+
 // Epilogue of one 128-row sub-tile for one warp: TMEM (lanes of this warp's quarter, columns of accumulator `trow`) ->
 // bias + residual + ReLU + MC-dropout mask (+ T masked replicas) -> bf16 NHWC / fp32.  The warp handles the 16-column
 // chunks j = sub_w, sub_w + wpq, ...; residual loads and dropout masks are issued before the TMEM load they combine with.
@@ -151,20 +164,6 @@ __device__ __forceinline__ void conv_epilogue_subtile(const ConvArgs& a, const T
   const bool vec_io = (a.Cout & 7) == 0;
   const int n_img = a.rep > 1 ? q : q / a.T;
   const int tt0 = a.rep > 1 ? 0 : q - n_img * a.T;
-  // dropout keep-mask of the 16 channels starting at c0 (bit i = channel c0 + i kept); independent of the accumulator
-  auto keep_mask = [&](int c0, int tt) -> uint32_t {
-    const uint32_t e8 = uint32_t((size_t)hw * a.Cout + c0) >> 3;
-    const uint4 ra = philox4x32_10(e8, a.first_image + uint32_t(n_img), uint32_t(tt), a.drop_stream, a.k0, a.k1);
-    const uint4 rb = philox4x32_10(e8 + 1, a.first_image + uint32_t(n_img), uint32_t(tt), a.drop_stream, a.k0, a.k1);
-    const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-    uint32_t m = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      m |= ((rw[i] & 0xFFFFu) >= a.drop_thr16 ? 1u : 0u) << (2 * i);
-      m |= ((rw[i] >> 16) >= a.drop_thr16 ? 1u : 0u) << (2 * i + 1);
-    }
-    return m;
-  };
   // residual of chunk j (two 16-byte vectors), prefetched one chunk ahead so its L2 latency overlaps the previous chunk
   auto load_res = [&](int j, uint4& r0, uint4& r1) {
     r0 = make_uint4(0, 0, 0, 0); r1 = r0;
@@ -181,8 +180,6 @@ __device__ __forceinline__ void conv_epilogue_subtile(const ConvArgs& a, const T
     const int c0 = t.nt * a.BN + j * 16;
     const uint4 rv0 = rn0, rv1 = rn1;
     load_res(j + WPQ, rn0, rn1);
-    uint32_t mask = 0xFFFFu;
-    if (a.drop && valid && c0 < a.Cout) mask = keep_mask(c0, tt0);
     uint32_t acc[16];
     tmem_ld16(trow + uint32_t(j * 16), acc);       // warp-collective: executed by every lane, valid or not
     tmem_ld_wait();
@@ -220,33 +217,39 @@ __device__ __forceinline__ void conv_epilogue_subtile(const ConvArgs& a, const T
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
     }
-    if (a.drop) {
+    if (a.drop) {                            // (bf16 output, Cout % 16 == 0: checked at launch)
+      uint32_t pk[8];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] *= a.drop_scale;
+      for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(v[2 * i] * a.drop_scale, v[2 * i + 1] * a.drop_scale);
+      const uint32_t e8 = uint32_t((size_t)hw * a.Cout + c0) >> 3;
+      for (int rp = 0; rp < n_rep; ++rp) {
+        const int p_out = a.rep > 1 ? q * a.rep + rp : q;
+        uint32_t o[8];
+        dropout_and16(a, e8, a.first_image + uint32_t(n_img), uint32_t(a.rep > 1 ? rp : tt0), pk, o);
+        uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + ((size_t)p_out * ohw + hw) * a.Cout + c0);
+        yp[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        yp[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      }
+      continue;
     }
     for (int rp = 0; rp < n_rep; ++rp) {
       const int p_out = a.rep > 1 ? q * a.rep + rp : q;
       const size_t off = ((size_t)p_out * ohw + hw) * a.Cout + c0;
-      const uint32_t next_mask = (a.drop && rp + 1 < n_rep) ? keep_mask(c0, rp + 1) : 0u;   // overlaps this replica's stores
-      float o[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) o[i] = ((mask >> i) & 1u) ? v[i] : 0.f;
-      mask = next_mask;
       if (a.out_f32) {
         float* yp = reinterpret_cast<float*>(a.y) + off;
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (c0 + i < a.Cout) yp[i] = o[i];
+          if (c0 + i < a.Cout) yp[i] = v[i];
       } else if (vec_io) {
         uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + off);
-        yp[0] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+        yp[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         if (c0 + 8 < a.Cout)
-          yp[1] = make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
+          yp[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
       } else {
         __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + off;
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (c0 + i < a.Cout) yp[i] = __float2bfloat16_rn(o[i]);
+          if (c0 + i < a.Cout) yp[i] = __float2bfloat16_rn(v[i]);
       }
     }
   }
@@ -268,23 +271,9 @@ __device__ __forceinline__ void conv_epilogue_staged(const ConvArgs& a, const CU
   const size_t res_off = ((size_t)q * ohw + hw) * a.Cout;
   const int n_img = a.rep > 1 ? q : q / a.T;
   const int tt0 = a.rep > 1 ? 0 : q - n_img * a.T;
-  auto keep_mask = [&](int c0, int tt) -> uint32_t {
-    const uint32_t e8 = uint32_t((size_t)hw * a.Cout + c0) >> 3;
-    const uint4 ra = philox4x32_10(e8, a.first_image + uint32_t(n_img), uint32_t(tt), a.drop_stream, a.k0, a.k1);
-    const uint4 rb = philox4x32_10(e8 + 1, a.first_image + uint32_t(n_img), uint32_t(tt), a.drop_stream, a.k0, a.k1);
-    const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-    uint32_t m = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      m |= ((rw[i] & 0xFFFFu) >= a.drop_thr16 ? 1u : 0u) << (2 * i);
-      m |= ((rw[i] >> 16) >= a.drop_thr16 ? 1u : 0u) << (2 * i + 1);
-    }
-    return m;
-  };
   const uint32_t stg_u32 = smem_u32(stg);
   for (int hf = 0; hf < a.BN / 64; ++hf) {
     uint32_t pk[NCH][8];                               // finished values (bias, residual, ReLU, dropout scale) as bf16 pairs
-    uint32_t mask[NCH];
     uint4 rv[NCH][2];
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {               // residual loads of all chunks first: their latency overlaps the TMEM loads
@@ -298,8 +287,6 @@ __device__ __forceinline__ void conv_epilogue_staged(const ConvArgs& a, const CU
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
       const int jj = sub_w + ch * WPQ, c0 = t.nt * a.BN + hf * 64 + jj * 16;
-      mask[ch] = 0xFFFFu;
-      if (a.drop && valid) mask[ch] = keep_mask(c0, tt0);
       uint32_t acc[16];
       tmem_ld16(trow + uint32_t(hf * 64 + jj * 16), acc);       // warp-collective: executed by every lane, valid or not
       tmem_ld_wait();
@@ -334,13 +321,13 @@ __device__ __forceinline__ void conv_epilogue_staged(const ConvArgs& a, const CU
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
         const int jj = sub_w + ch * WPQ;
-        uint32_t o[8];                                 // dropped channels -> +0.0 (the dropout product of the direct path)
+        uint32_t o[8];
+        if (a.drop && valid) {
+          const uint32_t e8 = uint32_t((size_t)hw * a.Cout + t.nt * a.BN + hf * 64 + jj * 16) >> 3;
+          dropout_and16(a, e8, a.first_image + uint32_t(n_img), uint32_t(a.rep > 1 ? rp : tt0), pk[ch], o);
+        } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = pk[ch][i];
-        if (a.drop) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            o[i] &= ((mask[ch] >> (2 * i)) & 1u) * 0xFFFFu | ((mask[ch] >> (2 * i + 1)) & 1u) * 0xFFFF0000u;
+          for (int i = 0; i < 8; ++i) o[i] = pk[ch][i];
         }
         *reinterpret_cast<uint4*>(rowp + (((2 * jj) ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
         *reinterpret_cast<uint4*>(rowp + (((2 * jj + 1) ^ (row & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
@@ -353,11 +340,6 @@ __device__ __forceinline__ void conv_epilogue_staged(const ConvArgs& a, const CU
         bulk_commit_group();
       }
       ++seq;
-      if (a.drop && rp + 1 < n_rep) {
-#pragma unroll
-        for (int ch = 0; ch < NCH; ++ch)
-          mask[ch] = valid ? keep_mask(t.nt * a.BN + hf * 64 + (sub_w + ch * WPQ) * 16, rp + 1) : 0u;
-      }
     }
   }
 }

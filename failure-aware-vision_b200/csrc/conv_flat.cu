@@ -39,7 +39,7 @@ struct FlatArgs {
   int rows_img, G, slab_rows;  // padded pixels per image, images per slab, G * rows_img (<= 256)
   int n_slabs, n_tiles;        // slabs in the problem, 128-row tiles per slab (1 or 2)
   int relu, T, rep, drop;
-  uint32_t drop_thr16;
+  uint32_t drop_thr16, drop_thr2;      // floor(p * 65536); the same in both halves of a word (2 x 16-bit SIMD compare)
   float drop_scale;
   uint32_t k0, k1, first_image, drop_stream;
   uint32_t idesc;
@@ -210,22 +210,20 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         const int n_img = a.rep > 1 ? q : q / a.T;
         const uint32_t e8 = uint32_t(hw * Cout + cbase) >> 3;
-        auto keep_mask32 = [&](int tt) -> uint32_t {        // bit i set = channel cbase + i kept (four Philox calls)
-          uint32_t m = 0;
+        // MC-dropout on the packed bf16 pairs: four Philox calls give sixteen words = thirty-two 16-bit lanes (channel 2i <-
+        // low half of word i); __vcmpgeu2 makes a 0xFFFF-per-kept-channel mask that is ANDed on (dropped -> +0.0)
+        auto keep_words = [&](int tt, uint32_t (&kw)[16]) {
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
             const uint4 r = philox4x32_10(e8 + c4, a.first_image + uint32_t(n_img), uint32_t(tt), a.drop_stream, a.k0, a.k1);
-            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              m |= ((rw[i] & 0xFFFFu) >= a.drop_thr16 ? 1u : 0u) << (8 * c4 + 2 * i);
-              m |= ((rw[i] >> 16) >= a.drop_thr16 ? 1u : 0u) << (8 * c4 + 2 * i + 1);
-            }
+            kw[4 * c4] = __vcmpgeu2(r.x, a.drop_thr2); kw[4 * c4 + 1] = __vcmpgeu2(r.y, a.drop_thr2);
+            kw[4 * c4 + 2] = __vcmpgeu2(r.z, a.drop_thr2); kw[4 * c4 + 3] = __vcmpgeu2(r.w, a.drop_thr2);
           }
-          return m;
         };
-        uint32_t mask = 0xFFFFFFFFu;
-        if (valid && a.drop) mask = keep_mask32(a.rep > 1 ? 0 : q - n_img * a.T);
+        uint32_t kw[16];                                     // first pass's keep-words: computed BEFORE the accumulator wait
+#pragma unroll
+        for (int i = 0; i < 16; ++i) kw[i] = 0xFFFFFFFFu;
+        if (valid && a.drop) keep_words(a.rep > 1 ? 0 : q - n_img * a.T, kw);
 
         mbar_wait_timed(tfull(ai), aph, w_tfull, a.stats != nullptr);
         tc_fence_after();
@@ -257,18 +255,18 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] *= a.drop_scale;
         }
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
         for (int rp = 0; rp < n_rep; ++rp) {
           const int p_out = a.rep > 1 ? q * a.rep + rp : q;
-          const uint32_t next_mask = (a.drop && rp + 1 < n_rep) ? keep_mask32(rp + 1) : 0u;     // overlaps this replica's stores
+          uint32_t o[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = pk[i] & kw[i];
+          if (a.drop && rp + 1 < n_rep) keep_words(rp + 1, kw);
           uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + ((size_t)p_out * hw_img + hw) * Cout + cbase);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float o[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = ((mask >> (8 * k + i)) & 1u) ? v[8 * k + i] : 0.f;
-            yp[k] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-          }
-          mask = next_mask;
+          for (int k = 0; k < 4; ++k) yp[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
         }
       }
     }
@@ -318,6 +316,7 @@ int conv_flat_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   if (c.drop) {
     FAV_REQUIRE(c.p_drop >= 0.f && c.p_drop < 1.f, "conv: p_drop must be in [0,1)");
     a.drop_thr16 = uint32_t(floor(double(c.p_drop) * 65536.0));
+    a.drop_thr2 = a.drop_thr16 | (a.drop_thr16 << 16);
     a.drop_scale = 1.0f / (1.0f - c.p_drop);
     a.k0 = uint32_t(c.seed); a.k1 = uint32_t(c.seed >> 32); a.first_image = uint32_t(c.first_image);
     a.drop_stream = stream_id(KIND_DROPOUT, c.layer_id, 0);
