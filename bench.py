@@ -151,7 +151,7 @@ def run_reference(args, rank, world):
     import numpy as np
     import torch
     from oracle import model as OM, philox as px, sweep as OS
-    per_step = 16
+    per_step = 64            # bounded sample of a step (the GPU arm's step is BLOCK images): ~0.3 s of CPU work per step
     folded = OM.fold_resnet(OM.build_torchvision("resnet18", 10, 0, logit_gain=8.0))
     torch.set_num_threads(os.cpu_count() or 1)
     x = px.synthetic_images(per_step * 4, 32, 32, 0)
@@ -171,12 +171,13 @@ def run_reference(args, rank, world):
         step(i)
     dt = time.perf_counter() - t0
     v = per_step * args.steps / dt
-    sample = f"{per_step} images per step x T={T_PASSES}, fp32 PyTorch oracle, {torch.get_num_threads()} threads"
+    sample = (f"{per_step} of the {BLOCK} images of a step x T={T_PASSES}, cells {cells} in rotation, fp32 PyTorch oracle, "
+              f"{torch.get_num_threads()} threads")
     print(json.dumps({
         "impl": "reference", "metric": "corrupted-image evals/sec", "value": v, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus, per_step),
+        "config": workload_config(args.gpus, BLOCK), "sample_images_per_step": per_step,
         "cpu_baseline": {"value": v, "unit": "evals/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
