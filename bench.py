@@ -116,6 +116,19 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+_REAL_STDOUT = None
+
+
+def emit_json(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, line)
+    else:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+
+
 def cpu_baseline(sample_images=128, T=T_PASSES, repeats=1):
     """Oracle (kind 'port': the reference has no implementation of this path) on the host cores."""
     import numpy as np
@@ -173,7 +186,7 @@ def run_reference(args, rank, world):
     v = per_step * args.steps / dt
     sample = (f"{per_step} of the {BLOCK} images of a step x T={T_PASSES}, cells {cells} in rotation, fp32 PyTorch oracle, "
               f"{torch.get_num_threads()} threads")
-    print(json.dumps({
+    emit_json({
         "impl": "reference", "metric": "corrupted-image evals/sec", "value": v, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -181,7 +194,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": v, "unit": "evals/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 def workload_config(n_gpus, block):
@@ -205,6 +218,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: library banners (e.g. "NCCL version ...") are sent to stderr instead
+    sys.stdout.flush()
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args, rank, world)
 
@@ -353,7 +371,7 @@ def main():
             "cpu_baseline": base,
             "tflops_whole_step": flops_per_eval(T_PASSES) * evals / (ms * 1e-3) / 1e12 / world,
         }
-        print(json.dumps(out))
+        emit_json(out)
     if world > 1:
         dist.destroy_process_group()
 
