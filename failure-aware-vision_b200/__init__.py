@@ -7,7 +7,7 @@ from .spec import CORRUPTIONS, CORRUPTION_ID, IMPLEMENTED, CorruptionConfig, MEA
 
 __all__ = ["CORRUPTIONS", "CORRUPTION_ID", "IMPLEMENTED", "CorruptionConfig", "MEAN_STD", "SEVERITY",
            "profile_for", "VisionClassifier", "CorruptionSweep", "SweepConfig", "MetricsAccumulator",
-           "UncertaintyGate"]
+           "UncertaintyGate", "TrustReplay"]
 
 
 def __getattr__(name):        # torch-dependent classes load lazily so that `import fav` stays cheap
@@ -20,4 +20,7 @@ def __getattr__(name):        # torch-dependent classes load lazily so that `imp
     if name == "UncertaintyGate":
         from .gate import UncertaintyGate
         return UncertaintyGate
+    if name == "TrustReplay":
+        from .trust import TrustReplay
+        return TrustReplay
     raise AttributeError(name)

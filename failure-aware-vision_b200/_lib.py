@@ -38,6 +38,8 @@ SIGNATURES = {
     "fav_synth_images": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_u64, c_u64, c_void_p]),
     "fav_synth_labels": (c_int, [c_void_p, c_void_p, c_int, c_int, c_u64, c_u64, c_void_p]),
     "fav_frame_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "fav_trust_replay": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_double, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                         c_void_p, c_void_p, c_void_p]),
     "fav_launch_count": (c_u64, [c_void_p]),
     "fav_conv_timing_enable": (c_int, [c_void_p, c_int]),
     "fav_conv_timing_read": (c_int, [c_void_p, C.POINTER(c_float), C.POINTER(c_int)]),

@@ -153,6 +153,20 @@ int fav_synth_labels(fav_handle h, int32_t* d_dst, int n, int C, uint64_t seed,
 int fav_frame_stats(fav_handle h, const uint8_t* d_frame, uint8_t* d_prev_gray, int height,
                     int width, int first_frame, int64_t* d_out, void* stream);
 
+/* ---- f4: batched TrustEngine replay -------------------------------------------------------------
+ * replaces: the per-tick Python loop of the batch replay, platform/backend/main.py:340-352, i.e.
+ * TrustEngine.update (trust_engine.py:139-243) incl. _update_policy (:68-87) and the contradiction
+ * detector (:89-137), for n_seq independent sequences of n_ticks ticks.  Tick-major device arrays:
+ * d_status int8 [n_ticks][n_seq] (0 OK, 1 FROZEN, 2 BLANK, 3 CORRUPTED), d_score f64 (NaN = None),
+ * d_dt f64 [n_ticks] or null (then dt_const).  Outputs (each may be null): d_state f64
+ * [n_ticks][n_seq][5] = {reliability, anomaly_integral, trust_velocity, recovery_debt,
+ * recovery_coeff} unrounded, d_policy u8 (0 ALLOWED, 1 DECLINING, 2 DEGRADED, 3 BLOCKED), d_contra u8,
+ * d_count i32, d_final f64 [n_seq][8] (the five floats, policy, contradiction, count after the last
+ * tick).  float64, bit-identical to the Python engine (tests/golden/trust_replay.json). */
+int fav_trust_replay(fav_handle h, const int8_t* d_status, const double* d_score, const double* d_dt,
+                     double dt_const, int n_seq, int n_ticks, double* d_state, uint8_t* d_policy,
+                     uint8_t* d_contra, int32_t* d_count, double* d_final, void* stream);
+
 /* counters for bench.py's gpu_launches claim */
 uint64_t fav_launch_count(fav_handle h);
 /* in-situ timing of the tensor-core conv launches (bench.py roofline): while enabled, every conv launch is

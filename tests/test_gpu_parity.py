@@ -391,6 +391,36 @@ def test_gate_with_classifier_feeds_trust_engine_contract(fav):
     assert gate.analyze_frame(f[1])["metrics"]["raw"]["frame_diff"] == 10.0
 
 
+# ------------------------------------------------------------------------------------------- f4: trust replay
+def test_trust_replay_kernel_reproduces_the_reference_engine(fav):
+    """The CUDA replay against trajectories of the REAL reference TrustEngine (golden, pinned): float64 state bit for
+    bit, policy / contradiction outputs exactly; plus the oracle on a larger random batch and edge shapes."""
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden_trust_inputs import sequences
+    from oracle import trust as OT
+    tr = fav.TrustReplay()
+    with open(os.path.join(os.path.dirname(__file__), "golden", "trust_replay.json")) as fh:
+        gold = json.load(fh)
+    for c in gold["cases"]:
+        status, score = sequences(c["seed"], c["n_seq"], c["n_ticks"])
+        res = tr.run(status, score, c["dt"])
+        t = np.array(c["trajectories"], dtype=np.float64)
+        assert np.array_equal(res["state"], t[:, :, :5])
+        assert np.array_equal(res["policy"], t[:, :, 5]) and np.array_equal(res["contradiction"], t[:, :, 6])
+        assert np.array_equal(res["contradiction_count"], t[:, :, 7])
+        assert np.array_equal(res["final"][:, :5], t[:, -1, :5]) and np.array_equal(res["final"][:, 5:], t[:, -1, 5:8])
+        d = tr.state_dict(res, 0, c["n_ticks"] - 1, "VISION_OK")
+        assert d["reliability"] == t[0, -1, 8] and d["trust_velocity"] == t[0, -1, 9] and d["tick_count"] == c["n_ticks"]
+    status, score = sequences(7, 300, 257)                       # more sequences than one CTA, ragged against the block size
+    dts = np.random.default_rng(7).uniform(0.005, 0.1, 257)
+    a, b = tr.run(status, score, dts), OT.replay(status, score, dts)
+    for k in ("state", "policy", "contradiction", "contradiction_count"):
+        assert np.array_equal(a[k], b[k]), k
+    only_final = tr.run(status, score, dts, trajectory=False)
+    assert set(only_final) == {"final"} and np.array_equal(only_final["final"], a["final"])
+    assert tr.run(np.zeros((0, 5), np.int8), np.zeros((0, 5)), 0.1)["final"].shape == (0, 8)
+
+
 # ------------------------------------------------------------------------------------------- full BASELINE sizes
 def test_c2_full_size_properties(fav):
     """Config C2 at its full size (N = 10 000 CIFAR-shape images, T = 20) on a few cells: size-independent properties of the

@@ -1,6 +1,8 @@
 """Pins the oracle itself (CPU only): Philox KATs, ResNet restatement vs torchvision, AUROC vs
 sklearn, ECE definition, corruption invariants.  The reference has no tests for this path
 (SURVEY.md section 4), so these are the anchors that exist."""
+import os
+
 import numpy as np
 import pytest
 
@@ -184,3 +186,27 @@ def test_bucketed_auroc_matches_sklearn_and_ece():
     X.accumulate(a1, conf[:2000], H[:2000], mi[:2000], pred[:2000], labels[:2000], 0.9, C_)
     X.accumulate(a2, conf[2000:], H[2000:], mi[2000:], pred[2000:], labels[2000:], 0.9, C_)
     assert np.array_equal(a1 + a2, ar)
+
+
+# ------------------------------------------------------------------------------------------- f4: trust replay (PINNED)
+def test_trust_replay_oracle_reproduces_the_reference_engine():
+    """oracle/trust.py against trajectories of the REAL TrustEngine (tests/golden/make_golden_trust.py): the five float64
+    state variables bit for bit, policy / contradiction outputs exactly."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden_trust_inputs import sequences
+    from oracle import trust as OT
+    with open(os.path.join(os.path.dirname(__file__), "golden", "trust_replay.json")) as fh:
+        gold = json.load(fh)
+    for c in gold["cases"]:
+        status, score = sequences(c["seed"], c["n_seq"], c["n_ticks"])
+        res = OT.replay(status, score, c["dt"])
+        t = np.array(c["trajectories"], dtype=np.float64)
+        assert np.array_equal(res["state"], t[:, :, :5])
+        assert np.array_equal(res["policy"], t[:, :, 5]) and np.array_equal(res["contradiction"], t[:, :, 6])
+        assert np.array_equal(res["contradiction_count"], t[:, :, 7])
+        assert t[:, :, 6].sum() > 0                       # the contradiction branch is exercised
+        for s_, i_ in ((0, 0), (1, c["n_ticks"] // 2), (c["n_seq"] - 1, c["n_ticks"] - 1)):
+            st = OT.reference_state(res, s_, i_)
+            assert st["reliability"] == t[s_, i_, 8] and st["trust_velocity"] == t[s_, i_, 9]
