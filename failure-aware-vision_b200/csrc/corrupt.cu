@@ -280,6 +280,81 @@ __global__ void __launch_bounds__(256) k1_channel_sums(const uint8_t* __restrict
   }
 }
 
+// small images (<= 48 * 32 * 8 bytes, e.g. 32x32): one WARP per image, 8 images per CTA, no atomics and no pre-zeroing
+__global__ void __launch_bounds__(256) k1_channel_sums_small(const uint8_t* __restrict__ src, int per, int n,
+                                                             unsigned long long* __restrict__ sums) {
+  const int img = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (img >= n) return;
+  const uint8_t* p = src + (size_t)img * per;
+  unsigned int s[3] = {0, 0, 0};
+  for (int g = lane; g * 48 < per; g += 32) {
+    const uint4* q = reinterpret_cast<const uint4*>(p + (size_t)g * 48);
+    uint32_t w[12];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { const uint4 v = __ldg(q + i); w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
+#pragma unroll
+    for (int j = 0; j < 48; ++j) s[j % 3] += (w[j >> 2] >> (8 * (j & 3))) & 0xFF;
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    unsigned int v = s[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sums[3 * (size_t)img + c] = (unsigned long long)v;
+  }
+}
+
+// contrast on small images in ONE pass (per <= 48 * 64 bytes, e.g. 32x32x3; RGB in, normalised bf16 out): a warp owns an
+// image, each lane keeps its (up to two) 16-pixel groups in registers, the channel sums are a warp reduction, then the
+// same arithmetic as k1_pointwise<PW_CONTRAST> is applied to the registers -- the image is read once.
+__global__ void __launch_bounds__(256) k1_contrast_small(const PointwiseArgs a) {
+  const int img = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (img >= a.n) return;
+  const uint8_t* p = a.src + (size_t)img * a.per;
+  const int ngroups = a.per / 48;
+  uint32_t w[2][12];
+  unsigned int s[3] = {0, 0, 0};
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int g = lane + 32 * it;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) w[it][i] = 0;
+    if (g < ngroups) {
+      const uint4* q = reinterpret_cast<const uint4*>(p + (size_t)g * 48);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { const uint4 v = __ldg(q + i); w[it][4 * i] = v.x; w[it][4 * i + 1] = v.y; w[it][4 * i + 2] = v.z; w[it][4 * i + 3] = v.w; }
+#pragma unroll
+      for (int j = 0; j < 48; ++j) s[j % 3] += (w[it][j >> 2] >> (8 * (j & 3))) & 0xFF;
+    }
+  }
+  float mu[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    unsigned int v = s[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    mu[c] = __fdiv_rn(__ull2float_rn((unsigned long long)v), 255.0f * float(a.hw));
+  }
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int g = lane + 32 * it;
+    if (g >= ngroups) continue;
+    float x[48];
+#pragma unroll
+    for (int i = 0; i < 48; ++i) {
+      const float b = float((w[it][i >> 2] >> (8 * (i & 3))) & 0xFF);
+      float v = __fadd_rn(__fmul_rn(__fsub_rn(div255(b), mu[i % 3]), a.f0), mu[i % 3]);
+      v = fminf(fmaxf(v, 0.0f), 1.0f);
+      x[i] = __fmul_rn(__fsub_rn(v, a.mean[i % 3]), a.inv_std[i % 3]);
+    }
+    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.dst) + (size_t)img * a.per + (size_t)g * 48);
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      o[i] = make_uint4(pack_bf16x2(x[8 * i], x[8 * i + 1]), pack_bf16x2(x[8 * i + 2], x[8 * i + 3]),
+                        pack_bf16x2(x[8 * i + 4], x[8 * i + 5]), pack_bf16x2(x[8 * i + 6], x[8 * i + 7]));
+  }
+}
+
 // ---------------------------------------------------------------- fog: diamond-square plasma, one CTA per image
 __global__ void __launch_bounds__(1024) k1_plasma(const uint8_t* __restrict__ src, int per, int mapsize,
                                                   float decay, uint32_t k0, uint32_t k1, uint32_t first_image,
@@ -991,9 +1066,19 @@ extern "C" int fav_corrupt_normalize(fav_handle h, const uint8_t* d_src, void* d
       FAV_REQUIRE(d_scratch && scratch_bytes >= fav_corrupt_scratch_bytes(corruption, n, height, width),
                   "contrast needs %zu scratch bytes", fav_corrupt_scratch_bytes(corruption, n, height, width));
       a.f0 = fparams[0];
-      FAV_CUDA_OK(cudaMemsetAsync(d_scratch, 0, (size_t)n * 24, st));
-      const int bx = max(1, min(64, (height * width + 4095) / 4096));
-      k1_channel_sums<<<dim3(n, bx), 256, 0, st>>>(d_src, per, reinterpret_cast<unsigned long long*>(d_scratch));
+      if ((per % 48) == 0 && per <= 48 * 64 && a.flags == 0 && (reinterpret_cast<uintptr_t>(d_src) & 15) == 0 &&
+          (reinterpret_cast<uintptr_t>(a.dst) & 15) == 0) {
+        k1_contrast_small<<<(n + 7) / 8, 256, 0, st>>>(a);          // single pass: sums + apply from registers
+        h->launches += 1;
+        break;
+      }
+      if ((per % 48) == 0 && per <= 48 * 32 * 8 && (reinterpret_cast<uintptr_t>(d_src) & 15) == 0) {
+        k1_channel_sums_small<<<(n + 7) / 8, 256, 0, st>>>(d_src, per, n, reinterpret_cast<unsigned long long*>(d_scratch));
+      } else {
+        FAV_CUDA_OK(cudaMemsetAsync(d_scratch, 0, (size_t)n * 24, st));
+        const int bx = max(1, min(64, (height * width + 4095) / 4096));
+        k1_channel_sums<<<dim3(n, bx), 256, 0, st>>>(d_src, per, reinterpret_cast<unsigned long long*>(d_scratch));
+      }
       k1_pointwise<PW_CONTRAST><<<grid, 256, 0, st>>>(a); h->launches += 2; break;
     }
     case FAV_FOG: {
