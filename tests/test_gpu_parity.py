@@ -391,6 +391,31 @@ def test_gate_with_classifier_feeds_trust_engine_contract(fav):
     assert gate.analyze_frame(f[1])["metrics"]["raw"]["frame_diff"] == 10.0
 
 
+# ------------------------------------------------------------------------------------------- BASELINE shapes C3 / C4 / C5
+@pytest.mark.parametrize("T", [1, 3])
+def test_k2_forward_resnet50_imagenet_shape(fav, T):
+    """ResNet-50 at 224x224, 1000 classes (configs C3 / C4): space-to-depth TMA stem, rectangular pixel tiles, staged
+    epilogue, identity-MMA residuals and the 2-SM tiles at their real shapes, against the bf16-emulating oracle."""
+    clf = _clf_cache(fav, "resnet50", 1000, (224, 224), 4.0)
+    folded = OM.fold_resnet(OM.build_torchvision("resnet50", 1000, 0, logit_gain=4.0))
+    n, p = 3, 0.2
+    xn = OC.to_bf16(np.random.default_rng(1).standard_normal((n, 224, 224, 3)).astype(np.float32))
+    got = clf.forward_logits(torch.from_numpy(xn).to(torch.bfloat16).cuda(), T, p, 9, 40).cpu().numpy()
+    emu = OM.forward(folded, xn, T=T, p=p, seed=9, first_image=40, emulate_bf16=True)
+    assert got.shape == (n, T, 1000)
+    assert np.abs(got - emu).max() <= 3e-2 * np.abs(emu).max(), np.abs(got - emu).max() / np.abs(emu).max()
+
+
+def test_k2_forward_resnet18_camera_shape(fav):
+    """ResNet-18 on a 120x160 frame (the C5 gate's geometry at quarter size: feature maps wider than one 128-pixel tile)."""
+    clf = _clf_cache(fav, "resnet18", 1000, (120, 160), 2.0)
+    folded = OM.fold_resnet(OM.build_torchvision("resnet18", 1000, 0, logit_gain=2.0))
+    xn = OC.to_bf16(np.random.default_rng(2).standard_normal((2, 120, 160, 3)).astype(np.float32))
+    got = clf.forward_logits(torch.from_numpy(xn).to(torch.bfloat16).cuda(), 1, 0.0, 0, 0).cpu().numpy()
+    emu = OM.forward(folded, xn, T=1, emulate_bf16=True)
+    assert np.abs(got - emu).max() <= 3e-2 * np.abs(emu).max(), np.abs(got - emu).max() / np.abs(emu).max()
+
+
 # ------------------------------------------------------------------------------------------- f4: trust replay
 def test_trust_replay_kernel_reproduces_the_reference_engine(fav):
     """The CUDA replay against trajectories of the REAL reference TrustEngine (golden, pinned): float64 state bit for
