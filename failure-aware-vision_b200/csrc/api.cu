@@ -1,6 +1,7 @@
 // api.cu -- handle lifetime, error plumbing.
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 #include "common.cuh"
 
 namespace fav {
@@ -55,6 +56,13 @@ extern "C" int fav_destroy(fav_handle h) {
   if (h->splitk_buf) cudaFree(h->splitk_buf);
   delete h;
   return FAV_OK;
+}
+
+extern "C" int fav_set_option(fav_handle h, const char* name, int value) {
+  FAV_REQUIRE(h && name, "fav_set_option: null argument");
+  if (strcmp(name, "splitk") == 0) { h->allow_splitk = value != 0; return FAV_OK; }
+  set_error("fav_set_option: unknown option '%s'", name);
+  return FAV_E_ARG;
 }
 
 extern "C" uint64_t fav_launch_count(fav_handle h) { return h ? h->launches : 0; }

@@ -95,8 +95,9 @@ struct Ctx {
   std::vector<float> ev_gflop;
   void* stats_buf = nullptr;      // 512 launches x 8 role counters (cycles)
   // fp32 accumulation scratch of the split-K convolutions (few output tiles, many k-blocks: the batch-1 streaming gate)
-  void* splitk_buf = nullptr;
+  void* splitk_buf = nullptr;     // [tickets int per output tile | fp32 partial tiles]
   size_t splitk_bytes = 0;
+  bool allow_splitk = false;      // fav_set_option(h, "splitk", 1)
 };
 
 }  // namespace fav

@@ -348,13 +348,16 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
       const Tile t = decode_tile(a, tile, u);
       if (t.mt >= a.mtiles) break;
       const uint32_t trow = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t((acc_i * MT + u) * a.BN);
-      if (!GATHER && a.stg_bytes) conv_epilogue_staged<WPQ>(a, &tmY, t, trow, row, sub_w, stg, seq, leader);
+      if (!GATHER && MT == 1 && a.ksplit > 1) splitk_store_partials<WPQ>(a, t, trow, row, sub_w);
+      else if (!GATHER && a.stg_bytes) conv_epilogue_staged<WPQ>(a, &tmY, t, trow, row, sub_w, stg, seq, leader);
       else conv_epilogue_subtile(a, t, trow, row, sub_w, WPQ);
       }   // sub-tiles
       // this warp has finished reading the accumulators: hand them back to the MMA issuer
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc_i));
+      if (!GATHER && MT == 1 && a.ksplit > 1)          // accumulator already released: the fix-up only touches global memory
+        splitk_fixup<WPQ>(a, decode_tile(a, tile, 0), row, sub_w, reinterpret_cast<volatile int*>(tmem_slot + 1), leader);
     }
     if (leader && a.stg_bytes) bulk_wait_all();              // shared memory must outlive the last store's reads
     if (a.stats && warp == EPI_WARP0 && lane == 0) {
@@ -386,32 +389,6 @@ conv_igemm_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                          const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmY,
                   const __grid_constant__ CUtensorMap tmR, const ConvArgs a) {
   conv_igemm_body<true, 1, 8>(tmA, tmB, tmA2, tmY, tmR, a);
-}
-
-// split-K epilogue: acc32 [M][Cout] fp32 partial sums -> + bias (+ residual) (ReLU) -> bf16 NHWC, 8 channels per thread
-__global__ void __launch_bounds__(256) k_splitk_finish(const float* __restrict__ acc, const float* __restrict__ bias,
-                                                       const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y,
-                                                       long long M, int Cout, int relu) {
-  const int c8n = Cout >> 3;
-  const long long total = M * c8n;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = int(i % c8n) * 8;
-    const size_t off = (size_t)(i / c8n) * Cout + c0;
-    const float4 a0 = *reinterpret_cast<const float4*>(acc + off), a1 = *reinterpret_cast<const float4*>(acc + off + 4);
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
-    float v[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w, a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
-    if (res) {
-      const uint4 r = __ldg(reinterpret_cast<const uint4*>(res + off));
-      const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { v[2 * k] += bf16_lo(rw[k]); v[2 * k + 1] += bf16_hi(rw[k]); }
-    }
-    if (relu) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
-    }
-    *reinterpret_cast<uint4*>(y + off) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-  }
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -640,31 +617,35 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   const int MT = (mode == 0 && force_mt == 2) ? 2 : 1;
   a.mt_per_tile = MT;
   a.total_tiles = ((mtiles + MT - 1) / MT) * a.ntiles;
-  // split-K (opt-in, FAV_SPLITK=1): a launch that fills less than half the machine but has long K loops (the batch-1 gate's
-  // layer3/4) is cut into ksplit slices per output tile; every slice keeps at least one k-block (the centre tap is never
-  // skipped).  Off by default: (1) fp32 atomics make the sums order-dependent, which would break the sweep's bit-identical
-  // results across block sizes / GPU counts; (2) measured on the 640x480 gate the extra memset + finish launches cost as
-  // much as the shorter K loops save (p50 0.47 vs 0.44 ms).  The round-2 form is an in-kernel fixed-order fix-up by the last
-  // slice to finish (no extra launches, deterministic).
-  static const int env_splitk = [] { const char* e = getenv("FAV_SPLITK"); return e ? atoi(e) : 0; }();
+  // split-K (opt-in: FAV_SPLITK=1 or fav_set_option(h, "splitk", 1)).  MEASURED on the 640x480 batch-1 gate: correct and
+  // deterministic, but each split launch is 1.5-2x SLOWER than the unsplit one (layer4 24-37 us -> 52-63 us, ncu launch
+  // list), so nothing enables it by default; the cause is not yet understood (the fix-up reads are not it).
+  // a launch that fills less than half the machine but has long K loops (batch-1 layer3/4) is cut into ksplit slices per
+  // output tile; every slice keeps at least one k-block (the centre tap is never skipped).  Each slice stores its fp32
+  // partial tile; the last one to finish adds them in slice order, so results are deterministic.  Not used by the sweep:
+  // whether a launch splits depends on its row count, and the sweep's results must not depend on the block size.
+  static const int env_splitk = [] { const char* e = getenv("FAV_SPLITK"); return e ? atoi(e) : -1; }();
+  const bool splitk_on = env_splitk >= 0 ? env_splitk != 0 : ctx->allow_splitk;
   a.ksplit = 0;
   const bool pair_ok = MT == 1 && conv_pair_applicable(L, a, c.force_mt == 3 ? 1 : 0) && c.force_mt != 1;
-  if (env_splitk && mode == 0 && !stem_tma && MT == 1 && !pair_ok && !c.drop && a.rep == 1 && !c.out_f32 && (L.cout % 8) == 0 &&
+  if (splitk_on && mode == 0 && !stem_tma && MT == 1 && !pair_ok && !c.drop && a.rep == 1 && !c.out_f32 &&
       a.cin_blocks >= 2 && a.num_kb + a.kb2 >= 16 && 2 * a.total_tiles <= ctx->num_sms) {
     int S = (2 * ctx->num_sms) / a.total_tiles;
     if (S > a.cin_blocks) S = a.cin_blocks;
     if (S > 8) S = 8;
     if (S >= 2) {
-      const size_t need = (size_t)M * L.cout * 4;
+      const size_t tick_bytes = ((size_t)a.total_tiles * 4 + 255) / 256 * 256;
+      const size_t need = tick_bytes + (size_t)a.total_tiles * S * BM * a.BN * 4;
       if (need > ctx->splitk_bytes) {
         if (ctx->splitk_buf) FAV_CUDA_OK(cudaFree(ctx->splitk_buf));
         ctx->splitk_buf = nullptr; ctx->splitk_bytes = 0;
         FAV_CUDA_OK(cudaMalloc(&ctx->splitk_buf, need));
+        FAV_CUDA_OK(cudaMemset(ctx->splitk_buf, 0, need));          // tickets start at zero; each launch leaves them at zero
         ctx->splitk_bytes = need;
       }
-      FAV_CUDA_OK(cudaMemsetAsync(ctx->splitk_buf, 0, need, st));
       a.ksplit = S;
-      a.acc32 = reinterpret_cast<float*>(ctx->splitk_buf);
+      a.tickets = reinterpret_cast<int*>(ctx->splitk_buf);
+      a.acc32 = reinterpret_cast<float*>(reinterpret_cast<char*>(ctx->splitk_buf) + tick_bytes);
       a.total_tiles *= S;
     }
   }
@@ -766,13 +747,6 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
     if (mode == 0 && MT == 2) FAV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm_m256_kernel, tmA, tmW, tmA2, tmY, tmR, a));
     else if (mode == 0) FAV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm_kernel, tmA, tmW, tmA2, tmY, tmR, a));
     else FAV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm_gather_kernel, tmA, tmW, tmA2, tmY, tmR, a));
-  }
-  if (a.ksplit > 1) {
-    const long long work = M * (L.cout / 8);
-    long long nb = (work + 255) / 256;
-    if (nb > 8LL * ctx->num_sms) nb = 8LL * ctx->num_sms;
-    k_splitk_finish<<<int(nb), 256, 0, st>>>(a.acc32, a.bias, a.res, reinterpret_cast<__nv_bfloat16*>(a.y), M, L.cout, a.relu);
-    ctx->launches++;
   }
   if (e1) FAV_CUDA_OK(cudaEventRecord(e1, st));
   ctx->launches++;

@@ -53,8 +53,9 @@ struct ConvArgs {
   uint32_t idesc64;            // instruction descriptor of those N = 64 MMAs
   int fastdiv;                 // 1: every (dividend, divisor) pair of the decode functions satisfies n * d < 2^32
   FastDiv fd_ntiles, fd_tw, fd_th, fd_twth, fd_perimg, fd_bw, fd_ksplit, fd_ohw, fd_ow;
-  int ksplit;                  // > 1: each output tile is computed by ksplit CTA tiles taking interleaved k-blocks; fp32 partial sums
-  float* acc32;                //      are added into acc32 [M][Cout] with global atomics, k_splitk_finish applies bias / residual / ReLU
+  int ksplit;                  // > 1: each output tile is computed by ksplit CTA tiles taking interleaved k-blocks; every slice stores
+  float* acc32;                //      its fp32 partial tile in acc32 [tile][slice][128][BN]; the LAST slice to finish (tickets[tile]) adds the
+  int* tickets;                //      partials in slice order (deterministic) and applies bias / residual / ReLU
   int ablate;                  // tuning aid (env FAV_CONV_ABLATE): 1 skip A loads, 2 skip B loads, 4 skip MMAs, 8 skip epilogue math
   unsigned long long* stats;   // optional per-launch role timing (8 counters), see fav_conv_stats_read
 };
@@ -66,7 +67,7 @@ constexpr int THREADS_TMA1 = 32 * (2 + 8);        // MT = 1: 8 epilogue warps, t
 constexpr int THREADS_TMA2 = 32 * (2 + 16);       // MT = 2: 16 epilogue warps, one CTA per SM
 constexpr int THREADS_GATHER = 32 * (2 + 8 + 8);  // gather variant: 8 epilogue + 8 gather warps (two groups on alternate k-blocks)
 
-struct Tile { int mt, nt, q0, oh0, ow0, ks; };   // mt = index of the 128-row M tile, ks = split-K slice
+struct Tile { int mt, nt, q0, oh0, ow0, ks, tb; };   // mt = index of the 128-row M tile, ks = split-K slice, tb = output tile index
 
 __device__ __forceinline__ Tile decode_tile(const ConvArgs& a, int tile_in, int u = 0) {
   Tile t;
@@ -78,6 +79,7 @@ __device__ __forceinline__ Tile decode_tile(const ConvArgs& a, int tile_in, int 
     t.ks = int(tile - q * a.fd_ksplit.d);
     tile = q;
   }
+  t.tb = int(tile);
   const uint32_t tq = fdiv(tile, a.fd_ntiles, fast);
   t.nt = int(tile - tq * a.fd_ntiles.d);
   t.mt = int(tq) * a.mt_per_tile + u;
@@ -184,13 +186,6 @@ __device__ __forceinline__ void conv_epilogue_subtile(const ConvArgs& a, const T
     tmem_ld16(trow + uint32_t(j * 16), acc);       // warp-collective: executed by every lane, valid or not
     tmem_ld_wait();
     if (!valid || c0 >= a.Cout || (a.ablate & 8)) continue;
-    if (a.ksplit > 1) {                      // partial sums of this k slice; bias / residual / ReLU happen in k_splitk_finish
-      float* dst = a.acc32 + res_off + c0;
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (c0 + i < a.Cout) atomicAdd(dst + i, __uint_as_float(acc[i]));
-      continue;
-    }
     float v[16];
     {
       const float4* bp = reinterpret_cast<const float4*>(a.bias + c0);     // bias is padded to cout_pad
@@ -253,6 +248,77 @@ __device__ __forceinline__ void conv_epilogue_subtile(const ConvArgs& a, const T
       }
     }
   }
+}
+
+// ---- split-K epilogue (a.ksplit > 1; bf16 output, no dropout / replicas) ----
+// part 1: this slice's fp32 accumulator tile -> acc32[tile][slice][row][col] (plain 16-byte stores)
+template <int WPQ>
+__device__ __forceinline__ void splitk_store_partials(const ConvArgs& a, const Tile& t, uint32_t trow, int row, int sub_w) {
+  float* mine = a.acc32 + (((size_t)t.tb * a.ksplit + t.ks) * BM + row) * a.BN;
+  for (int j = sub_w; j < a.BN / 16; j += WPQ) {
+    uint32_t acc[16];
+    tmem_ld16(trow + uint32_t(j * 16), acc);
+    tmem_ld_wait();
+    float4* d = reinterpret_cast<float4*>(mine + j * 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      d[i] = make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]), __uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3]));
+  }
+}
+// part 2: take a ticket for the output tile; the last slice to arrive sums all partials in slice order and finishes the tile
+template <int WPQ>
+__device__ __forceinline__ void splitk_fixup(const ConvArgs& a, const Tile& t, int row, int sub_w, volatile int* s_flag, bool leader) {
+  __threadfence();                                   // this thread's partial stores are visible device-wide ...
+  named_bar_sync(1, 128 * WPQ);                      // ... before the CTA's ticket is taken
+  if (leader) *s_flag = atomicAdd(&a.tickets[t.tb], 1);
+  named_bar_sync(1, 128 * WPQ);
+  if (*s_flag != a.ksplit - 1) return;
+  __threadfence();
+  int q, oh, ow;
+  const bool valid = decode_row(a, t, row, q, oh, ow);
+  const size_t off = ((size_t)q * (a.OH * a.OW) + oh * a.OW + ow) * a.Cout;
+  const bool vec_io = (a.Cout & 7) == 0;
+  if (valid) {
+    for (int j = sub_w; j < a.BN / 16; j += WPQ) {
+      const int c0 = t.nt * a.BN + j * 16;
+      if (c0 >= a.Cout) continue;
+      float v[16];
+      const float4* p0 = reinterpret_cast<const float4*>(a.acc32 + ((size_t)t.tb * a.ksplit * BM + row) * a.BN + j * 16);
+      const size_t slice = (size_t)BM * a.BN / 4;    // float4 per slice
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {                  // one 16-byte column at a time, all slices' loads in flight together
+        float4 x[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) x[s] = s < a.ksplit ? __ldcg(p0 + s * slice + i) : make_float4(0.f, 0.f, 0.f, 0.f);   // via L2
+        float4 acc = x[0];
+#pragma unroll
+        for (int s = 1; s < 8; ++s) { acc.x += x[s].x; acc.y += x[s].y; acc.z += x[s].z; acc.w += x[s].w; }   // fixed slice order
+        v[4 * i] = acc.x; v[4 * i + 1] = acc.y; v[4 * i + 2] = acc.z; v[4 * i + 3] = acc.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] += __ldg(a.bias + c0 + i);
+      if (a.res) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c0 + i < a.Cout) v[i] += __bfloat162float(a.res[off + c0 + i]);
+      }
+      if (a.relu) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+      __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + off + c0;
+      if (vec_io) {
+        reinterpret_cast<uint4*>(yp)[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        if (c0 + 8 < a.Cout)
+          reinterpret_cast<uint4*>(yp)[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c0 + i < a.Cout) yp[i] = __float2bfloat16_rn(v[i]);
+      }
+    }
+  }
+  if (leader) a.tickets[t.tb] = 0;                   // ready for the next launch
 }
 
 // Staged epilogue (a.stg_bytes > 0): as above, but the bf16 results go to a SWIZZLE_128B shared-memory slab of 128 pixels x

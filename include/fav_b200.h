@@ -167,6 +167,11 @@ int fav_trust_replay(fav_handle h, const int8_t* d_status, const double* d_score
                      double dt_const, int n_seq, int n_ticks, double* d_state, uint8_t* d_policy,
                      uint8_t* d_contra, int32_t* d_count, double* d_final, void* stream);
 
+/* per-handle switches.  "splitk" = 1: convolutions that fill less than half the GPU split their K loop over several CTAs
+ * with a deterministic in-kernel fix-up.  Experimental and off by default: the sweep's results must not depend on how
+ * many rows a launch has, and on the batch-1 gate (main.py:160) the split launches measured slower than the unsplit ones. */
+int fav_set_option(fav_handle h, const char* name, int value);
+
 /* counters for bench.py's gpu_launches claim */
 uint64_t fav_launch_count(fav_handle h);
 /* in-situ timing of the tensor-core conv launches (bench.py roofline): while enabled, every conv launch is

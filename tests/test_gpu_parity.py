@@ -191,6 +191,37 @@ def test_k2_conv_matches_torch_fp32(fav, clf18, case):
             assert err <= tol * max(1.0, ref.abs().max().item()), f"mode {mode} f32={out_f32}: err {err}"
 
 
+def test_k2_conv_splitk_matches_and_is_deterministic(fav):
+    """Split-K (per-handle option, used by the batch-1 gate): same result as the unsplit kernel up to fp32 summation
+    order, bit-identical from run to run (fixed-order fix-up by the last slice), tickets left clean for the next launch."""
+    h2 = fav._lib.Handle(0)
+    fav._lib.check(h2.lib.fav_set_option(h2.h, b"splitk", 1), "fav_set_option")
+    assert h2.lib.fav_set_option(h2.h, b"no-such-option", 1) != 0
+    for (p, h, w, cin, cout, k, stride, pad, relu, use_res) in ((1, 15, 20, 512, 512, 3, 1, 1, 1, 1), (1, 30, 40, 256, 512, 3, 2, 1, 1, 0),
+                                                              (2, 15, 20, 256, 100, 1, 1, 0, 0, 1)):
+        g = torch.Generator(device="cpu").manual_seed(p * 1000 + cin)
+        x = torch.randn((p, h, w, cin), generator=g).to(torch.bfloat16).cuda()
+        wt = (torch.randn((cout, k, k, cin), generator=g) / (k * k * cin) ** 0.5).to(torch.bfloat16).cuda()
+        bias = torch.randn(cout, generator=g).cuda()
+        oh, ow = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+        res = torch.randn((p, oh, ow, cout), generator=g).to(torch.bfloat16).cuda() if use_res else None
+        ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), bias, stride, pad).permute(0, 2, 3, 1)
+        if res is not None:
+            ref = ref + res.float()
+        if relu:
+            ref = torch.relu(ref)
+        outs = []
+        for _ in range(3):
+            y = torch.full((p, oh, ow, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+            fav._lib.check(h2.lib.fav_conv2d(h2.h, _p(x), _p(wt), _p(bias), _p(res), _p(y), p, h, w, cin, cout, k, k, stride, pad,
+                                             relu, 0, 0, _s()), "fav_conv2d")
+            torch.cuda.synchronize()
+            outs.append(y)
+        assert not torch.isnan(outs[0].float()).any()
+        assert (outs[0].float() - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
 # ------------------------------------------------------------------------------------------- K2 forward
 @pytest.mark.parametrize("T", [1, 4])
 def test_k2_forward_logits_vs_oracle(fav, clf18, folded18, T):
