@@ -117,6 +117,7 @@ class UncertaintyGate:
         self._stats = torch.zeros(260, dtype=torch.int64, device=self.device)
         self._stats_host = torch.empty(260, dtype=torch.int64).pin_memory()
         self._packed_host = torch.empty((1, 4), dtype=torch.float32).pin_memory()
+        self._side = torch.cuda.Stream(self.device)
         self._fin = SignalFinisher()
         # CUDA-graph replay of the whole device side of a frame (H2D copy, frame statistics, K1..K3, D2H copies): one
         # launch instead of ~30.  The dropout masks are keyed by first_image, a kernel argument frozen at capture, so the
@@ -130,14 +131,23 @@ class UncertaintyGate:
         """Device side of one frame on the current stream: pinned frame -> device, fused SignalAnalyzer statistics,
         classifier + uncertainty epilogue, results -> pinned host buffers.  No host synchronisation."""
         h, w = self.frame_hw
+        cur = torch.cuda.current_stream(self.device)
         self._frame[0].copy_(self._pinned, non_blocking=True)
-        _lib.check(self.lib.fav_frame_stats(self.handle.h, _ptr(self._frame), _ptr(self._gray), h, w,
-                                            1 if first else 0, _ptr(self._stats), _stream()), "fav_frame_stats")
+        # the SignalAnalyzer statistics (one kernel) run beside the classifier chain on a side stream (fork / join; under
+        # CUDA-graph capture this becomes a parallel branch of the graph)
+        side = self._side if self.clf is not None else cur
+        if side is not cur:
+            side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            _lib.check(self.lib.fav_frame_stats(self.handle.h, _ptr(self._frame), _ptr(self._gray), h, w,
+                                                1 if first else 0, _ptr(self._stats), _stream()), "fav_frame_stats")
+            self._stats_host.copy_(self._stats, non_blocking=True)
         if self.clf is not None:
             u = self.clf.uncertainty(self._frame, None, T=self.T, p=self.p_drop, seed=0, first_image=first_image, bgr=True)
             packed = torch.stack([u["confidence"], u["entropy"], u["mutual_information"], u["pred"].float()], 1)
             self._packed_host.copy_(packed, non_blocking=True)
-        self._stats_host.copy_(self._stats, non_blocking=True)
+        if side is not cur:
+            cur.wait_stream(side)
 
     def _capture(self):
         try:
