@@ -19,6 +19,7 @@ struct PointwiseArgs {
   void* dst;
   int n, per;                 // images, elements per image (h*w*3)
   int groups_per_image;       // ceil(per/48)
+  uint32_t gpi_magic;         // floor(2^32 / groups_per_image) + 1 when total groups * groups_per_image < 2^32, else 0 (-> plain division)
   uint32_t k0, k1;            // Philox key
   uint32_t first_image;
   uint32_t stream;            // Philox c3
@@ -51,7 +52,9 @@ __global__ void __launch_bounds__(256) k1_pointwise(const PointwiseArgs a) {
   const bool no_norm = a.flags & FAV_NO_NORMALIZE;
   for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
        g += (long long)gridDim.x * blockDim.x) {
-    const int img = int(g / a.groups_per_image);
+    // image index = g / groups_per_image: a multiply-high when the host could prove it exact (the 64-bit division it replaces
+    // costs more instructions than the whole clean path of a group)
+    const int img = a.gpi_magic ? (a.groups_per_image == 1 ? int(g) : int(__umulhi(uint32_t(g), a.gpi_magic))) : int(g / a.groups_per_image);
     const int gi = int(g - (long long)img * a.groups_per_image);
     const int e0 = gi * 48;
     const int cnt = min(48, a.per - e0);
@@ -1034,6 +1037,8 @@ extern "C" int fav_corrupt_normalize(fav_handle h, const uint8_t* d_src, void* d
 
   PointwiseArgs a{};
   a.src = d_src; a.dst = d_dst; a.n = n; a.per = per; a.groups_per_image = (per + 47) / 48;
+  a.gpi_magic = ((unsigned long long)n * a.groups_per_image + 1) * (unsigned long long)a.groups_per_image < (1ull << 32)
+                    ? uint32_t((1ull << 32) / (unsigned long long)a.groups_per_image) + 1u : 0u;
   a.k0 = k0; a.k1 = k1; a.first_image = uint32_t(first_image);
   a.stream = stream_id(KIND_CORRUPT, corruption, severity);
   a.table = d_table; a.scratch = d_scratch; a.hw = height * width; a.width = width; a.flags = flags;
