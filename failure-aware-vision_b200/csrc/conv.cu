@@ -619,7 +619,9 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   a.total_tiles = ((mtiles + MT - 1) / MT) * a.ntiles;
   // split-K (opt-in: FAV_SPLITK=1 or fav_set_option(h, "splitk", 1)).  MEASURED on the 640x480 batch-1 gate: correct and
   // deterministic, but each split launch is 1.5-2x SLOWER than the unsplit one (layer4 24-37 us -> 52-63 us, ncu launch
-  // list), so nothing enables it by default; the cause is not yet understood (the fix-up reads are not it).
+  // list), so nothing enables it by default.  Role timers (tools/splitk_dbg.py, 512->512 3x3 on 15x20 pixels): the 96 slice CTAs
+  // only pull ~18 B/clk each from L2 (they hammer the same weight lines), so the MMA span shrinks 23 -> 9 us instead of 3 us,
+  // and store + fence + ticket + fix-up add ~7 us per CTA.
   // a launch that fills less than half the machine but has long K loops (batch-1 layer3/4) is cut into ksplit slices per
   // output tile; every slice keeps at least one k-block (the centre tap is never skipped).  Each slice stores its fp32
   // partial tile; the last one to finish adds them in slice order, so results are deterministic.  Not used by the sweep:
