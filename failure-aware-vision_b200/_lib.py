@@ -40,6 +40,9 @@ SIGNATURES = {
     "fav_frame_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "fav_trust_replay": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_double, c_int, c_int, c_void_p, c_void_p, c_void_p,
                          c_void_p, c_void_p, c_void_p]),
+    "fav_comm_unique_id": (c_int, [c_void_p]),
+    "fav_comm_init": (c_int, [c_void_p, c_void_p, c_int, c_int]),
+    "fav_allreduce": (c_int, [c_void_p, c_void_p, C.c_size_t, c_void_p]),
     "fav_set_option": (c_int, [c_void_p, C.c_char_p, c_int]),
     "fav_launch_count": (c_u64, [c_void_p]),
     "fav_conv_timing_enable": (c_int, [c_void_p, c_int]),

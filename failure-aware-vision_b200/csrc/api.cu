@@ -15,6 +15,7 @@ void set_error(const char* fmt, ...) {
 void plan_destroy(Plan* p);   // forward.cu
 }  // namespace fav
 
+namespace fav { void comm_destroy(Ctx* ctx); }
 using namespace fav;
 
 extern "C" int fav_abi_version(void) { return FAV_ABI_VERSION; }
@@ -54,6 +55,7 @@ extern "C" int fav_destroy(fav_handle h) {
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->stats_buf) cudaFree(h->stats_buf);
   if (h->splitk_buf) cudaFree(h->splitk_buf);
+  comm_destroy(h);
   delete h;
   return FAV_OK;
 }

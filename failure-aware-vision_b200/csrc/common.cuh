@@ -98,6 +98,9 @@ struct Ctx {
   void* splitk_buf = nullptr;     // [tickets int per output tile | fp32 partial tiles]
   size_t splitk_bytes = 0;
   bool allow_splitk = false;      // fav_set_option(h, "splitk", 1)
+  // multi-GPU: one process per GPU, communicator for the histogram all-reduce (comm.cu)
+  void* nccl_comm = nullptr;
+  int world = 1, rank = 0;
 };
 
 }  // namespace fav

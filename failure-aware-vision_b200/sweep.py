@@ -130,8 +130,41 @@ class MetricsAccumulator:
             _stream()), "fav_accumulate")
 
     def allreduce(self):
-        """The path's only exchange: integer sum over ranks (NCCL on GPUs)."""
-        allreduce_arena(self.arena)
+        """The path's only exchange: integer sum of the arena over the ranks.  On GPUs this is the library's own
+        fav_allreduce (ncclAllReduce(sum, int64) on the current stream; the communicator is created on first use, its id
+        broadcast through torch.distributed); FAV_ALLREDUCE=torch or a CPU arena (gloo tests) uses torch.distributed."""
+        import os
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        if not self.arena.is_cuda or os.environ.get("FAV_ALLREDUCE", "nccl") == "torch":
+            allreduce_arena(self.arena)
+            return
+        self.init_comm()
+        handle = self.clf.handle
+        _lib.check(self.clf.lib.fav_allreduce(handle.h, _ptr(self.arena), self.arena.numel(), _stream()), "fav_allreduce")
+
+    def init_comm(self):
+        """Create the library's NCCL communicator (collective; ~0.5 s once per process): rank 0's unique id travels
+        through torch.distributed.  Called by CorruptionSweep.prepare() so that it stays out of timed regions."""
+        import torch.distributed as dist
+        handle = self.clf.handle
+        if getattr(handle, "comm_ready", False) or not self.arena.is_cuda:
+            return
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        uid = torch.zeros(128, dtype=torch.uint8, device=self.arena.device)
+        if dist.get_rank() == 0:
+            buf = C.create_string_buffer(128)
+            _lib.check(self.clf.lib.fav_comm_unique_id(buf), "fav_comm_unique_id")
+            uid.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+        dist.broadcast(uid, src=0)
+        raw = bytes(uid.cpu().numpy().tobytes())
+        _lib.check(self.clf.lib.fav_comm_init(handle.h, C.c_char_p(raw), dist.get_rank(), dist.get_world_size()), "fav_comm_init")
+        handle.comm_ready = True
+        warm = torch.zeros(8, dtype=torch.int64, device=self.arena.device)          # first collective sets up the channels
+        _lib.check(self.clf.lib.fav_allreduce(handle.h, _ptr(warm), warm.numel(), _stream()), "fav_allreduce")
+        torch.cuda.current_stream(self.arena.device).synchronize()
 
     def results(self):
         host = self.arena.cpu().numpy()
@@ -162,6 +195,9 @@ class CorruptionSweep:
             self.clf.corrupt_normalize(x, cell, self.cfg.seed, 0)
         _lib.check(self.clf.lib.fav_reserve(self.clf.handle.h, n, self.cfg.T), "fav_reserve")
         self._buffers(n)
+        import os
+        if os.environ.get("FAV_ALLREDUCE", "nccl") != "torch":
+            self.acc.init_comm()
         torch.cuda.synchronize()
 
     def work_items(self, n_images):

@@ -167,6 +167,16 @@ int fav_trust_replay(fav_handle h, const int8_t* d_status, const double* d_score
                      double dt_const, int n_seq, int n_ticks, double* d_state, uint8_t* d_policy,
                      uint8_t* d_contra, int32_t* d_count, double* d_final, void* stream);
 
+/* ---- multi-GPU: the path's one exchange -------------------------------------------
+ * One process per GPU; work items are sharded with no data-path collective; at sweep end one integer all-reduce makes
+ * the per-cell histogram arenas global (bit-identical metrics on 1/2/4/8 GPUs).  replaces: nothing -- the reference
+ * is single-process (main.py:109-118).  fav_comm_unique_id: rank 0 creates the 128-byte NCCL id and the host language
+ * broadcasts it (torch.distributed / MPI / a file); fav_comm_init: every rank joins; fav_allreduce: in-place
+ * ncclAllReduce(sum, int64) of `count` words on `stream` (a no-op on a single rank). */
+int fav_comm_unique_id(void* out128);
+int fav_comm_init(fav_handle h, const void* id128, int rank, int world_size);
+int fav_allreduce(fav_handle h, int64_t* d_hist, size_t count, void* stream);
+
 /* per-handle switches.  "splitk" = 1: convolutions that fill less than half the GPU split their K loop over several CTAs
  * with a deterministic in-kernel fix-up.  Experimental and off by default: the sweep's results must not depend on how
  * many rows a launch has, and on the batch-1 gate (main.py:160) the split launches measured slower than the unsplit ones. */

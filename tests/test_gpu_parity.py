@@ -383,6 +383,19 @@ def test_sweep_partition_is_bit_identical(fav):
         assert torch.equal(row, whole[ci].cpu())
 
 
+def test_allreduce_entry_points_single_rank(fav, clf18):
+    """fav_allreduce is a no-op on one rank (the N-rank exchange is checked by tools/allreduce_check.py under torchrun and
+    by the multi-GPU bench); the unique-id entry point reaches NCCL."""
+    a = torch.arange(1000, dtype=torch.int64, device="cuda")
+    fav._lib.check(clf18.lib.fav_allreduce(clf18.handle.h, _p(a), a.numel(), _s()), "fav_allreduce")
+    torch.cuda.synchronize()
+    assert torch.equal(a.cpu(), torch.arange(1000, dtype=torch.int64))
+    buf = C.create_string_buffer(128)
+    fav._lib.check(clf18.lib.fav_comm_unique_id(buf), "fav_comm_unique_id")
+    assert any(buf.raw)
+    fav._lib.check(clf18.lib.fav_comm_init(clf18.handle.h, buf, 0, 1), "fav_comm_init")       # world of one: no communicator
+
+
 # ------------------------------------------------------------------------------------------- f1 + gate
 def test_frame_stats_kernel_bit_exact(fav, clf18):
     for seed, (h, w) in ((0, (240, 320)), (1, (480, 640)), (2, (96, 130)), (3, (2, 2)), (4, (33, 1031))):
