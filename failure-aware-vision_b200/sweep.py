@@ -323,3 +323,53 @@ class CorruptionSweep:
             wr.writerow([name, sev] + [round(r[k], 6) if isinstance(r.get(k), float) and not math.isnan(r[k]) else r.get(k, "")
                                       for k in cols[2:]])
         return buf.getvalue()
+
+
+def main(argv=None):
+    """``python -m fav.sweep``: a corruption sweep on synthetic Philox images (there are no datasets offline), results as
+    CSV on stdout.  Under torchrun every rank takes its share of the (cell, block) items; rank 0 prints."""
+    import argparse
+    import ctypes
+    import os
+    import sys
+    import torch.distributed as dist
+    ap = argparse.ArgumentParser(prog="python -m fav.sweep", description=main.__doc__)
+    ap.add_argument("--model", default="resnet18", choices=["resnet18", "resnet50"])
+    ap.add_argument("--hw", type=int, default=32, help="square input size (32: CIFAR profile, 224: ImageNet profile)")
+    ap.add_argument("--classes", type=int, default=10)
+    ap.add_argument("--images", type=int, default=1000)
+    ap.add_argument("--passes", type=int, default=20, help="MC-dropout passes T (1 = deterministic MSP)")
+    ap.add_argument("--p-drop", type=float, default=0.2)
+    ap.add_argument("--tau", type=float, default=0.9)
+    ap.add_argument("--block", type=int, default=2048)
+    ap.add_argument("--corruptions", default="all", help="comma-separated names or 'all'")
+    ap.add_argument("--severities", default="1,2,3,4,5")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--logit-gain", type=float, default=8.0, help="fixture for random-init weights (SURVEY.md section 7)")
+    a = ap.parse_args(argv)
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    names = tuple(spec.IMPLEMENTED) if a.corruptions == "all" else tuple(x for x in a.corruptions.split(",") if x)
+    cfg = SweepConfig(model=a.model, num_classes=a.classes, input_hw=(a.hw, a.hw), T=a.passes, p_drop=a.p_drop, tau=a.tau,
+                      block=min(a.block, a.images), seed=a.seed, logit_gain=a.logit_gain, corruptions=names,
+                      severities=tuple(int(x) for x in a.severities.split(",")))
+    sw = CorruptionSweep(cfg, device=local)
+    sw.prepare(a.images)
+    dev = sw.clf.device
+    x = torch.empty((a.images, a.hw, a.hw, 3), dtype=torch.uint8, device=dev)
+    y = torch.empty(a.images, dtype=torch.int32, device=dev)
+    st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(sw.clf.lib.fav_synth_images(sw.clf.handle.h, _ptr(x), a.images, a.hw, a.hw, a.seed, 0, st), "fav_synth_images")
+    _lib.check(sw.clf.lib.fav_synth_labels(sw.clf.handle.h, _ptr(y), a.images, a.classes, a.seed, 0, st), "fav_synth_labels")
+    res = sw.run(x, y, rank=rank, world_size=world)
+    if rank == 0:
+        sys.stdout.write(CorruptionSweep.to_csv(res))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())
