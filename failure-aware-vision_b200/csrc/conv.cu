@@ -475,11 +475,14 @@ int conv_layer_finalize(ConvLayer& L) {
     int rc = encode_map(reinterpret_cast<CUtensorMap*>(L.tmap_w), L.w, 2, dims, strides, box);
     if (rc) return rc;
     L.tmap_ok = true;
-    if (L.bn == 128 && L.cout_pad == 128) {
-      const cuuint32_t box64[2] = {BK, 64};
+    if (L.bn == 128) {
+      const cuuint32_t box64[2] = {BK, 64}, box32[2] = {BK, 32};
       rc = encode_map(reinterpret_cast<CUtensorMap*>(L.tmap_w64), L.w, 2, dims, strides, box64);
       if (rc) return rc;
       L.tmap64_ok = true;
+      rc = encode_map(reinterpret_cast<CUtensorMap*>(L.tmap_w32), L.w, 2, dims, strides, box32);
+      if (rc) return rc;
+      L.tmap32_ok = true;
     }
   }
   return FAV_OK;
@@ -607,6 +610,22 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   }
   static const int env_ablate = [] { const char* e = getenv("FAV_CONV_ABLATE"); return e ? atoi(e) : 0; }();
   a.ablate = env_ablate;
+  // Small launches (fewer tiles than SMs): one CTA per SM is limited by the 64 B/clk L2->SM ingress of its own SM, so narrower
+  // N tiles -- more CTAs, fewer bytes per CTA and k-block (A 16 KB + W 4 / 8 KB instead of 16 KB) -- shorten the K loop.  The
+  // per-element accumulation order does not depend on the N tiling, and whether the residual goes through the identity
+  // MMAs (which changes the order of the bias and residual adds) is decided from layer properties only (layer_epi_bound),
+  // so results are bit-identical whatever tile width a launch gets.
+  static const int env_narrow = [] { const char* e = getenv("FAV_NARROW_N"); return e ? atoi(e) : 1; }();
+  static const int env_rmma = [] { const char* e = getenv("FAV_RES_MMA"); return e ? atoi(e) : -1; }();   // -1 auto, 0 off, 1 all eligible
+  const bool layer_epi_bound = (a.num_kb + a.kb2) <= 8 || a.rep > 1 || L.bn == 64;       // independent of the launch's row count
+  const bool want_res_mma = env_rmma != 0 && (env_rmma > 0 || layer_epi_bound) && mode == 0 && c.res && !c.out_f32 &&
+                            (L.cout % 64) == 0 && (L.bn % 64) == 0;
+  const CUtensorMap* tmW_sel = reinterpret_cast<const CUtensorMap*>(L.tmap_w);
+  if (env_narrow && mode == 0 && L.bn == 128 && c.force_mt == 0 && !conv_pair_applicable(L, a, 0)) {
+    const long long tiles128 = (long long)mtiles * (L.cout_pad / 128);
+    if (L.tmap32_ok && !want_res_mma && 4 * tiles128 <= ctx->num_sms) { a.BN = 32; tmW_sel = reinterpret_cast<const CUtensorMap*>(L.tmap_w32); }
+    else if (L.tmap64_ok && 2 * tiles128 <= ctx->num_sms) { a.BN = 64; tmW_sel = reinterpret_cast<const CUtensorMap*>(L.tmap_w64); }
+  }
   a.ntiles = L.cout_pad / a.BN;
   a.mtiles = mtiles;
   // M = 256 per CTA when there is enough work to fill the machine twice over with one CTA per SM
@@ -675,8 +694,8 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   // staged epilogue (TMA stores from two shared-memory slabs): bf16 NHWC output of the TMA-tiled modes.  The default
   // keeps it for the layers whose epilogue is the bottleneck (few k-blocks per tile, or T masked replicas per tile).
   static const int env_stg = [] { const char* e = getenv("FAV_EPI_TMA"); return e ? atoi(e) : -1; }();   // -1 auto, 0 off, 1 all eligible
-  const bool stg_ok = mode == 0 && !c.out_f32 && (L.cout % 64) == 0 && a.ksplit <= 1;
-  const bool stg_auto = (a.num_kb + a.kb2) <= 8 || a.rep > 1 || a.BN == 64;
+  const bool stg_ok = mode == 0 && !c.out_f32 && (L.cout % 64) == 0 && (a.BN % 64) == 0 && a.ksplit <= 1;
+  const bool stg_auto = layer_epi_bound || a.BN == 64;       // (staged and direct epilogues compute identical values)
   a.stg_bytes = (stg_ok && env_stg != 0 && (env_stg > 0 || stg_auto)) ? 2 * STG_SLAB_BYTES : 0;
   CUtensorMap tmY;
   memset(&tmY, 0, sizeof(tmY));
@@ -690,12 +709,11 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   }
   // residual added by the tensor core (identity MMAs): the residual tile arrives by TMA through the operand pipeline,
   // far ahead of its use, and the epilogue loses its residual loads, bf16 unpacking and adds
-  // Default: only where the epilogue is the bottleneck (same rule as the staged epilogue); on long-K layers the two extra
-  // k-blocks per tile cost more shared-memory bandwidth than the epilogue saves.  FAV_RES_MMA=0 off, 1 everywhere.
-  static const int env_rmma = [] { const char* e = getenv("FAV_RES_MMA"); return e ? atoi(e) : -1; }();
+  // Default: only where the epilogue is the bottleneck (layer_epi_bound); on long-K layers the two extra k-blocks per tile
+  // cost more shared-memory bandwidth than the epilogue saves.  FAV_RES_MMA=0 off, 1 everywhere.
   CUtensorMap tmR;
   memset(&tmR, 0, sizeof(tmR));
-  a.res_mma = (env_rmma != 0 && (env_rmma > 0 || stg_auto) && mode == 0 && c.res && !c.out_f32 && (L.cout % 64) == 0 && (a.BN % 64) == 0 && a.ksplit <= 1 && !pair_ok) ? 1 : 0;
+  a.res_mma = (want_res_mma && (a.BN % 64) == 0 && a.ksplit <= 1 && !pair_ok) ? 1 : 0;
   a.idesc64 = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(64 >> 3) << 17) | (uint32_t(BM >> 4) << 24);
   if (a.res_mma) {
     a.res = nullptr;
@@ -745,7 +763,7 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    const CUtensorMap& tmW = *reinterpret_cast<const CUtensorMap*>(L.tmap_w);
+    const CUtensorMap& tmW = *tmW_sel;
     if (mode == 0 && MT == 2) FAV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm_m256_kernel, tmA, tmW, tmA2, tmY, tmR, a));
     else if (mode == 0) FAV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm_kernel, tmA, tmW, tmA2, tmY, tmR, a));
     else FAV_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_igemm_gather_kernel, tmA, tmW, tmA2, tmY, tmR, a));

@@ -15,8 +15,10 @@ struct ConvLayer {          // device-resident, BN folded
   int k2pad = 0, cin2 = 0, stride2 = 1;   // fused 1x1 downsample branch: extra K columns [kpad, kpad + k2pad) of w, its Cin and stride
   alignas(64) unsigned char tmap_w[128];   // CUtensorMap for the weights (box 64 x bn, SWIZZLE_128B)
   bool tmap_ok = false;
-  alignas(64) unsigned char tmap_w64[128];  // same weights with a 64-row box (one CTA's half in the 2-SM variant)
+  alignas(64) unsigned char tmap_w64[128];  // same weights with a 64-row box (one CTA's half in the 2-SM variant; narrow N tiles)
   bool tmap64_ok = false;
+  alignas(64) unsigned char tmap_w32[128];  // same weights with a 32-row box (narrow N tiles of small launches)
+  bool tmap32_ok = false;
 };
 
 struct ConvCall {
