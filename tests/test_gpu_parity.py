@@ -250,6 +250,18 @@ def test_k2_forward_logits_vs_oracle(fav, clf18, folded18, T):
     assert (gap[dis] < 0.05).all(), f"argmax differs on non-tied samples: gaps {gap[dis]}"
 
 
+@pytest.mark.parametrize("n,T", [(5, 3), (1, 2), (131, 1)])
+def test_k2_forward_ragged_counts(fav, clf18, folded18, n, T):
+    """Image counts that leave partial tiles everywhere (odd pass-image counts in the flat slabs, a lone image, a count
+    that is not a multiple of any tile), against the bf16-emulating oracle."""
+    seed, first, p = 3, 17, 0.2
+    xn = OC.to_bf16(OC.normalize(px.synthetic_images(n, 32, 32, seed, first).astype(np.float32) / np.float32(255), *OC.MEAN_STD["cifar"]))
+    got = clf18.forward_logits(torch.from_numpy(xn).to(torch.bfloat16).cuda(), T, p, seed, first).cpu().numpy()
+    emu = OM.forward(folded18, xn, T=T, p=p, seed=seed, first_image=first, emulate_bf16=True)
+    assert got.shape == (n, T, 10)
+    assert np.abs(got - emu).max() <= 2e-2 * np.abs(emu).max(), np.abs(got - emu).max() / np.abs(emu).max()
+
+
 def test_k2_forward_resnet50_small(fav):
     clf = _clf_cache(fav, "resnet50", 100, (64, 64), 4.0)
     folded = OM.fold_resnet(OM.build_torchvision("resnet50", 100, 0, logit_gain=4.0))
