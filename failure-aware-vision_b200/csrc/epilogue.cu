@@ -86,16 +86,17 @@ __device__ __forceinline__ SampleOut sample_uncertainty(const float* __restrict_
   float best = -1.f;
   int arg = 0x7fffffff;
   float H = 0.f;
+  const bool single = T == 1;                       // one pass: the mean IS that pass, H = H(p_1) is already in hsum, MI = 0
 #pragma unroll
   for (int i = 0; i < NC; ++i) {
     const int c = lane + 32 * i;
     const float p = pbar[i] * invT;
     if (c < C) {
       if (p > best) { best = p; arg = c; }          // ascending c inside a lane: first max kept
-      if (p > 0.f) H -= p * fast_log(p);
+      if (!single && p > 0.f) H -= p * fast_log(p);
     }
   }
-  H = warp_sum(H);
+  H = single ? hsum : warp_sum(H);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {                // argmax, lowest index on ties
     const float ob = __shfl_xor_sync(0xffffffffu, best, o);
