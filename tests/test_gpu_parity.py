@@ -534,3 +534,38 @@ def test_c2_full_size_properties(fav):
         conf = row[HDR + 45 + 6 * 4096:].reshape(10, 10)
         assert conf.sum() == N and np.trace(conf) == row[1]
         assert row[2] <= N - row[1]                       # flags are a subset of the misclassified samples
+
+
+@pytest.mark.parametrize("cfgname,N,T,blocks", [("C3", 8192, 1, (256, 192)), ("C4", 1536, 30, (64, 48))])
+def test_c3_c4_smoke_size_properties(fav, cfgname, N, T, blocks):
+    """Configs C3 (ResNet-50 224x224, T = 1) and C4 (T = 30, mutual information + AUROC) at their smoke sizes:
+    histogram families sum to N, per-class totals are consistent, MI is exactly 0 for T = 1, and the aggregates do not depend
+    on the block size (images are generated on the device from the Philox stream; 1000 classes -> per-class confusion)."""
+    from fav.sweep import CorruptionSweep, SweepConfig, HDR
+    arenas = []
+    for block in blocks:
+        cfg = SweepConfig(model="resnet50", num_classes=1000, input_hw=(224, 224), corruptions=("brightness",), severities=(3,),
+                          T=T, logit_gain=4.0, block=block, seed=5)
+        sw = CorruptionSweep(cfg, classifier=_clf_cache(fav, "resnet50", 1000, (224, 224), 4.0))
+        h, st = sw.clf.handle.h, C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        x = torch.empty((N, 224, 224, 3), dtype=torch.uint8, device="cuda")
+        y = torch.empty(N, dtype=torch.int32, device="cuda")
+        fav._lib.check(sw.clf.lib.fav_synth_images(h, _p(x), N, 224, 224, 5, 0, st), "synth")
+        fav._lib.check(sw.clf.lib.fav_synth_labels(h, _p(y), N, 1000, 5, 0, st), "synth")
+        res = sw.run(x, y)
+        arenas.append(sw.acc.arena.cpu().numpy())
+        r = res[("brightness", 3)]
+        assert r["n"] == N and 0 <= r["ece"] <= 1 and 0 <= r["auroc_msp"] <= 1
+        if T == 1:
+            assert r["mean_mutual_information"] == 0.0
+        del x
+    a = arenas[0]
+    assert np.array_equal(a, arenas[1]), f"{cfgname}: aggregates depend on the block size"
+    row = a[0]
+    assert row[0] == N
+    bins = row[HDR:HDR + 45].reshape(15, 3)
+    assert bins[:, 0].sum() == N and bins[:, 2].sum() == row[1]
+    buckets = row[HDR + 45:HDR + 45 + 6 * 4096].reshape(3, 4096, 2)
+    assert (buckets.sum(axis=(1, 2)) == N).all() and (buckets[:, :, 0].sum(1) == row[1]).all()
+    per_class = row[HDR + 45 + 6 * 4096:].reshape(1000, 2)
+    assert per_class[:, 0].sum() == N and per_class[:, 1].sum() == row[1] and (per_class[:, 1] <= per_class[:, 0]).all()

@@ -14,7 +14,7 @@ for g in $groups; do
     k1)   run k1 600 "philox or k1" ;;
     k34)  run k34 300 "k3 or k4 or k34 or frame_stats or gate_reproduces or allreduce" ;;
     conv) run conv 300 "conv" ;;
-    fwd)  run fwd 600 "forward or cell or sweep_partition or gate_with or full_size or trust_replay or camera_shape or imagenet_shape" ;;
+    fwd)  run fwd 600 "forward or cell or sweep_partition or gate_with or full_size or trust_replay or camera_shape or imagenet_shape or smoke_size" ;;
     smoke) timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "== smoke: exit $? : $(tail -n 1 gpurun_out/smoke.log)" ;;
     bench) timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "== bench: exit $? : $(tail -c 1500 gpurun_out/bench.log)" ;;
   esac
