@@ -100,6 +100,8 @@ struct Ctx {
   bool allow_splitk = false;      // fav_set_option(h, "splitk", 1)
   // multi-GPU: one process per GPU, communicator for the histogram all-reduce (comm.cu)
   void* nccl_comm = nullptr;
+  // kernel attributes (max dynamic shared memory) are per device: set once per handle, not once per process
+  bool attr_conv = false, attr_flat = false, attr_pair = false;
   int world = 1, rank = 0;
 };
 

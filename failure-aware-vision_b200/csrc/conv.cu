@@ -734,16 +734,12 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128
   a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(a.BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
   const size_t smem = (size_t)stages * stage_bytes + a.stg_bytes + (a.res_mma ? IDENT_BYTES : 0) + 1024 + 256;
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(conv_igemm_m256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(conv_igemm_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
-  FAV_CUDA_OK(attr_err);
+  if (!ctx->attr_conv) {
+    FAV_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FAV_CUDA_OK(cudaFuncSetAttribute(conv_igemm_m256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FAV_CUDA_OK(cudaFuncSetAttribute(conv_igemm_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    ctx->attr_conv = true;
+  }
   const int threads = mode != 0 ? THREADS_GATHER : (MT == 2 ? THREADS_TMA2 : THREADS_TMA1);
   const int grid = a.total_tiles < ctas_per_sm * ctx->num_sms ? a.total_tiles : ctas_per_sm * ctx->num_sms;
   cudaEvent_t e1 = nullptr;

@@ -335,12 +335,10 @@ int conv_flat_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
     if (rc) return rc;
   }
   const size_t smem = 1024 + 2 * FL_MARGIN + FL_NSLAB * FL_SLAB_BYTES + FL_W_BYTES + 256;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv3x3_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);   // + 256 B static
-  });
-  FAV_CUDA_OK(attr_err);
+  if (!ctx->attr_flat) {
+    FAV_CUDA_OK(cudaFuncSetAttribute(conv3x3_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));   // + 256 B static
+    ctx->attr_flat = true;
+  }
   const int grid = a.n_slabs < ctx->num_sms ? a.n_slabs : ctx->num_sms;
   cudaEvent_t e1 = nullptr;
   {

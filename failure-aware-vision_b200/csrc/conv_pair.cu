@@ -217,12 +217,10 @@ int conv_pair_launch(Ctx* ctx, const ConvLayer& L, ConvArgs a, const CUtensorMap
   a.tmem_cols = 2 * bn;                                                    // two accumulators of N columns
   a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(bn >> 3) << 17) | (uint32_t(256 >> 4) << 24);   // M = 256, N = bn
   const size_t smem = (size_t)a.stages * stage_bytes + 1024 + 512;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
-  FAV_CUDA_OK(attr_err);
+  if (!ctx->attr_pair) {
+    FAV_CUDA_OK(cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    ctx->attr_pair = true;
+  }
   const int max_pairs = ctx->num_sms / 2;
   const int n_pairs = a.pair_tiles < max_pairs ? a.pair_tiles : max_pairs;
   cudaLaunchConfig_t cfg{};
