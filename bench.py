@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 T_PASSES = 20
 P_DROP = 0.2
 TAU = 0.9
-BLOCK = 2048           # images per step; measured on B200: 512 -> 0.71 M, 1024 -> 0.85 M, 2048 -> 0.92 M, 4096 -> 0.94 M evals/s
+BLOCK = 4096           # images per step; measured on B200 (short runs): 512 -> 0.71 M, 1024 -> 0.85 M, 2048 -> 0.92 M, 4096 -> 0.94 M evals/s
                        # (a step has ~0.2 ms of per-kernel ramp-up/drain that a larger block amortises), profiles/r01m_block_sweep.txt
 N_IMAGES = 16384
 MFLOP_PREFIX, MFLOP_PASS = 2.408448, 34.608128          # MMAC per image (oracle.model.count_macs); x2 for FLOPs
@@ -204,13 +204,13 @@ def workload_config(n_gpus, block):
                         f"({len(fav.IMPLEMENTED) * 5} cells), ECE(15 bins)+entropy+MI+AUROC(4096 buckets)",
             "images_per_step": block, "passes": T_PASSES, "num_classes": 10,
             "corruptions": list(fav.IMPLEMENTED), "parallelism": f"image-block x cell sharding over {n_gpus} GPU(s)",
-            "l2": "working set (5 activation buffers x 336 MB per step) exceeds the 126 MB L2; image blocks rotate"}
+            "l2": "working set (5 activation buffers x 672 MB per step) exceeds the 126 MB L2; image blocks rotate"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -338,7 +338,10 @@ def main():
         tp = os.path.join(ROOT, "profiles", "conv_traffic.json")      # dram bytes per step from the committed ncu --set full capture
         if os.path.exists(tp):
             with open(tp) as fh:
-                traffic = json.load(fh).get("dram_bytes_per_step")
+                tj = json.load(fh)
+                # bytes per image from the committed capture (taken at 2048 images per step; constant in the HBM-streaming
+                # regime) x the images of one step here
+                traffic = tj["dram_bytes_per_image"] * BLOCK if "dram_bytes_per_image" in tj else tj.get("dram_bytes_per_step")
         peak = peaks["bf16_tflops_sustained"]
         roof = {"bound": "tensor", "kernel": "conv_igemm_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
