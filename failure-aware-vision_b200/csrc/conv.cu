@@ -516,6 +516,11 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
     a.drop_scale = 1.0f / (1.0f - c.p_drop);
     a.k0 = uint32_t(c.seed); a.k1 = uint32_t(c.seed >> 32); a.first_image = uint32_t(c.first_image);
     a.drop_stream = stream_id(KIND_DROPOUT, c.layer_id, 0);
+    if (c.drop2_layer >= 0) {
+      FAV_REQUIRE(a.rep == 1 && a.OH * a.OW == 1, "conv: the fused second dropout needs a 1x1 output map and no replicas");
+      a.drop2 = 1;
+      a.drop_stream2 = stream_id(KIND_DROPOUT, c.drop2_layer, 0);
+    }
   }
   // operand-A mode
   const bool tma_s1 = L.stride == 1 && 2 * L.pad == L.r - 1;
@@ -694,7 +699,7 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   // staged epilogue (TMA stores from two shared-memory slabs): bf16 NHWC output of the TMA-tiled modes.  The default
   // keeps it for the layers whose epilogue is the bottleneck (few k-blocks per tile, or T masked replicas per tile).
   static const int env_stg = [] { const char* e = getenv("FAV_EPI_TMA"); return e ? atoi(e) : -1; }();   // -1 auto, 0 off, 1 all eligible
-  const bool stg_ok = mode == 0 && !c.out_f32 && (L.cout % 64) == 0 && (a.BN % 64) == 0 && a.ksplit <= 1;
+  const bool stg_ok = mode == 0 && !c.out_f32 && (L.cout % 64) == 0 && (a.BN % 64) == 0 && a.ksplit <= 1 && !a.drop2;
   const bool stg_auto = layer_epi_bound || a.BN == 64;       // (staged and direct epilogues compute identical values)
   a.stg_bytes = (stg_ok && env_stg != 0 && (env_stg > 0 || stg_auto)) ? 2 * STG_SLAB_BYTES : 0;
   CUtensorMap tmY;

@@ -41,6 +41,8 @@ struct ConvCall {
   float p_drop = 0.f;
   uint64_t seed = 0, first_image = 0;
   int layer_id = 0;
+  int drop2_layer = -1;           // >= 0: a second, independent mask + scale with this layer id on the same elements (the dropout
+                                  // before fc when the feature map is 1x1, so the pooled feature IS this output); needs drop, rep == 1
 };
 
 int conv_out_dim(int in, int k, int stride, int pad);

@@ -44,6 +44,8 @@ struct ConvArgs {
   uint32_t drop_thr2;          // the same threshold in both halves of a word (operand of the 2 x 16-bit SIMD compare)
   float drop_scale;
   uint32_t k0, k1, first_image, drop_stream;
+  uint32_t drop_stream2;       // second mask stream (ConvCall::drop2_layer), used when drop2 != 0
+  int drop2;
   uint32_t tmem_cols, idesc;
   int pair_tiles, nkb_tot;     // 2-SM variant: CTA-pair tiles (two 128-row M tiles each), resident W k-blocks (main + fused branch)
   int kb2, stride2, Cin2;      // fused second source (the block's 1x1 downsample branch): extra k-blocks after the main taps
@@ -146,9 +148,9 @@ __device__ __forceinline__ bool decode_row(const ConvArgs& a, const Tile& t, int
 // sixteen 16-bit lanes (channel 2i <- low half of word i, channel 2i+1 <- high half); __vcmpgeu2 turns a word into a
 // 0xFFFF-per-kept-channel mask that is ANDed onto the packed pair (dropped channels become +0.0)
 __device__ __forceinline__ void dropout_and16(const ConvArgs& a, uint32_t e8, uint32_t image, uint32_t tt, const uint32_t (&pk)[8],
-                                              uint32_t (&o)[8]) {
-  const uint4 ra = philox4x32_10(e8, image, tt, a.drop_stream, a.k0, a.k1);
-  const uint4 rb = philox4x32_10(e8 + 1, image, tt, a.drop_stream, a.k0, a.k1);
+                                              uint32_t (&o)[8], uint32_t stream) {
+  const uint4 ra = philox4x32_10(e8, image, tt, stream, a.k0, a.k1);
+  const uint4 rb = philox4x32_10(e8 + 1, image, tt, stream, a.k0, a.k1);
   const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = pk[i] & __vcmpgeu2(rw[i], a.drop_thr2);
@@ -220,7 +222,13 @@ __device__ __forceinline__ void conv_epilogue_subtile(const ConvArgs& a, const T
       for (int rp = 0; rp < n_rep; ++rp) {
         const int p_out = a.rep > 1 ? q * a.rep + rp : q;
         uint32_t o[8];
-        dropout_and16(a, e8, a.first_image + uint32_t(n_img), uint32_t(a.rep > 1 ? rp : tt0), pk, o);
+        dropout_and16(a, e8, a.first_image + uint32_t(n_img), uint32_t(a.rep > 1 ? rp : tt0), pk, o, a.drop_stream);
+        if (a.drop2) {                       // dropout before fc on a 1x1 feature map: bf16 value x scale -> bf16, second mask
+          uint32_t p2[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) p2[i] = pack_bf16x2(bf16_lo(o[i]) * a.drop_scale, bf16_hi(o[i]) * a.drop_scale);
+          dropout_and16(a, e8, a.first_image + uint32_t(n_img), uint32_t(tt0), p2, o, a.drop_stream2);
+        }
         uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + ((size_t)p_out * ohw + hw) * a.Cout + c0);
         yp[0] = make_uint4(o[0], o[1], o[2], o[3]);
         yp[1] = make_uint4(o[4], o[5], o[6], o[7]);
@@ -390,7 +398,7 @@ __device__ __forceinline__ void conv_epilogue_staged(const ConvArgs& a, const CU
         uint32_t o[8];
         if (a.drop && valid) {
           const uint32_t e8 = uint32_t((size_t)hw * a.Cout + t.nt * a.BN + hf * 64 + jj * 16) >> 3;
-          dropout_and16(a, e8, a.first_image + uint32_t(n_img), uint32_t(a.rep > 1 ? rp : tt0), pk[ch], o);
+          dropout_and16(a, e8, a.first_image + uint32_t(n_img), uint32_t(a.rep > 1 ? rp : tt0), pk[ch], o, a.drop_stream);
         } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] = pk[ch][i];

@@ -435,10 +435,11 @@ extern "C" int fav_forward_mc(fav_handle h, const void* d_x, float* d_logits, in
   const uint32_t k0 = uint32_t(seed), k1 = uint32_t(seed >> 32);
 
   auto run = [&](const ConvLayer& L, const void* x, void* y, const void* res, int P, int hh, int ww, int relu, int drop,
-                 int rep, int layer_id, int out_f32, const void* x2 = nullptr, int h2 = 0, int w2 = 0, int a_mode = -1) -> int {
+                 int rep, int layer_id, int out_f32, const void* x2 = nullptr, int h2 = 0, int w2 = 0, int a_mode = -1,
+                 int drop2_layer = -1) -> int {
     ConvCall c;
     c.L = &L; c.x = x; c.y = y; c.res = res; c.p = P; c.h = hh; c.w = ww; c.relu = relu; c.out_f32 = out_f32;
-    c.x2 = x2; c.h2 = h2; c.w2 = w2; c.a_mode = a_mode;
+    c.x2 = x2; c.h2 = h2; c.w2 = w2; c.a_mode = a_mode; c.drop2_layer = drop2_layer;
     c.T = T; c.rep = rep; c.drop = drop; c.p_drop = p_drop; c.seed = seed; c.first_image = first_image; c.layer_id = layer_id;
     return conv_launch(h, c, st);
   };
@@ -477,6 +478,7 @@ extern "C" int fav_forward_mc(fav_handle h, const void* d_x, float* d_logits, in
     hh = oh; ww = ow;
   }
   int cur = 0, P = n, ch = stem.cout;
+  bool fused_fc_drop = false;
   for (size_t b = 0; b < pl.blocks.size(); ++b) {
     const BlockDesc& bd = pl.blocks[b];
     const void* ident = X[cur];
@@ -500,8 +502,11 @@ extern "C" int fav_forward_mc(fav_handle h, const void* d_x, float* d_logits, in
         in = tmp[k & 1];
       } else {
         const int rep = (mc && b == 0) ? T : 1;
-        if (bd.fused_ds) rc = run(L, in, X[cur ^ 1], nullptr, P, ih, iw, 1, mc ? 1 : 0, rep, int(b), 0, X[cur], hh, ww);
-        else rc = run(L, in, X[cur ^ 1], ident, P, ch_, cw_, 1, mc ? 1 : 0, rep, int(b), 0);
+        // 1x1 final feature map: the pooled feature is this output, so the dropout before fc is a second mask in this epilogue
+        fused_fc_drop = mc && rep == 1 && b + 1 == pl.blocks.size() && oh * ow == 1 && !L.fold;
+        const int d2 = fused_fc_drop ? 255 : -1;
+        if (bd.fused_ds) rc = run(L, in, X[cur ^ 1], nullptr, P, ih, iw, 1, mc ? 1 : 0, rep, int(b), 0, X[cur], hh, ww, -1, d2);
+        else rc = run(L, in, X[cur ^ 1], ident, P, ch_, cw_, 1, mc ? 1 : 0, rep, int(b), 0, nullptr, 0, 0, -1, d2);
         ch = L.cout / (L.fold ? L.fold : 1);
       }
       if (rc) return rc;
@@ -512,7 +517,10 @@ extern "C" int fav_forward_mc(fav_handle h, const void* d_x, float* d_logits, in
   }
   // global average pool + dropout on the pooled feature, then fc as a 1x1 conv with fp32 output [n, T, C]
   FAV_REQUIRE((ch & 7) == 0, "feature width must be a multiple of 8");
-  {
+  const void* fc_in = Y1;
+  if (hh * ww == 1 && (fused_fc_drop || !mc)) {
+    fc_in = X[cur];                               // nothing to pool; the mask (if any) was applied by the last conv's epilogue
+  } else {
     const long long work = (long long)P * (ch / 8);
     const uint32_t thr = mc ? uint32_t(floor(double(p_drop) * 65536.0)) : 0u;
     const int groups = (ch / 8 + 31) / 32;
@@ -528,7 +536,7 @@ extern "C" int fav_forward_mc(fav_handle h, const void* d_x, float* d_logits, in
   }
   const ConvLayer& fc = pl.convs.back();
   FAV_REQUIRE(fc.cin == ch, "fc input width %d does not match the trunk (%d)", fc.cin, ch);
-  rc = run(fc, Y1, d_logits, nullptr, P, 1, 1, 0, 0, 1, 0, 1);
+  rc = run(fc, fc_in, d_logits, nullptr, P, 1, 1, 0, 0, 1, 0, 1);
   if (rc) return rc;
   FAV_CUDA_OK(cudaGetLastError());
   return FAV_OK;
