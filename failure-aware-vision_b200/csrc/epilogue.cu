@@ -109,6 +109,42 @@ __device__ __forceinline__ SampleOut sample_uncertainty(const float* __restrict_
   return r;
 }
 
+// T == 1 (deterministic MSP path, e.g. the ImageNet-shaped config C3): the mean IS the only pass, so nothing has to be kept
+// per class -- conf = 1 / S (the largest exponential is exp(0) = 1), pred = argmax of the logits (lowest index on ties),
+// H = ln S - sum e (z - m) / S, MI = 0.  Half the instructions and half the registers of the general path.
+template <int NC>
+__device__ __forceinline__ SampleOut sample_uncertainty_single(const float* __restrict__ z, int C, int lane) {
+  float v[NC];
+  float m = -INFINITY;
+  int arg = 0x7fffffff;
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = c < C ? z[c] : -INFINITY;
+    if (v[i] > m) { m = v[i]; arg = c; }              // ascending c inside a lane: first max kept
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {                  // max + argmax, lowest index on ties
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (om > m || (om == m && oa < arg)) { m = om; arg = oa; }
+  }
+  float s = 0.f, w = 0.f;
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const float d = v[i] - m;
+    const float e = fast_exp(d);
+    s += e;
+    w += e > 0.f ? e * d : 0.f;
+  }
+  s = warp_sum(s);
+  w = warp_sum(w);
+  const float inv_s = fast_rcp(s);
+  SampleOut r;
+  r.conf = inv_s; r.pred = arg; r.H = fast_log(s) - w * inv_s; r.mi = 0.f;
+  return r;
+}
+
 // C <= 16: lanes run over the MC passes (lane t owns pass t, t + 32, ...), each lane does its softmax serially in
 // registers; only the pass-mean needs cross-lane reductions.  ~3x fewer shuffles than lanes-over-classes at C = 10.
 __device__ __forceinline__ SampleOut sample_uncertainty_small(const float* __restrict__ z, int T, int C, int lane) {
@@ -200,7 +236,7 @@ struct BlockSums {
   unsigned long long v[6];
 };
 
-template <int NC, bool FUSED>
+template <int NC, bool FUSED, bool SINGLE = false>
 __global__ void __launch_bounds__(256) k34_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
                                                   int n, int T, HistGeom g, unsigned long long* __restrict__ hist,
                                                   float* __restrict__ o_conf, float* __restrict__ o_H,
@@ -224,7 +260,8 @@ __global__ void __launch_bounds__(256) k34_kernel(const float* __restrict__ logi
   if (logits) {
     for (int i = blockIdx.x * warps_per_block + (threadIdx.x >> 5); i < n; i += gridDim.x * warps_per_block) {
       const SampleOut r = NC == 0 ? sample_uncertainty_small(logits + (size_t)i * T * g.C, T, g.C, lane)
-                                  : sample_uncertainty<(NC > 0 ? NC : 1)>(logits + (size_t)i * T * g.C, T, g.C, lane);
+                                  : (SINGLE ? sample_uncertainty_single<(NC > 0 ? NC : 1)>(logits + (size_t)i * g.C, g.C, lane)
+                                            : sample_uncertainty<(NC > 0 ? NC : 1)>(logits + (size_t)i * T * g.C, T, g.C, lane));
       if (lane == 0) {
         const int label = labels ? labels[i] : -1;
         const bool flag = labels && r.pred != label && r.conf >= g.tau;
@@ -488,7 +525,17 @@ static int launch_k34(fav_handle h, const float* d_logits, const int32_t* d_labe
     k34_kernel<NC, true><<<int(blocks), 256, smem, st>>>(d_logits, d_labels, n, T, g, hist, d_conf, d_entropy, d_mi,  \
                                                          d_pred, d_flag, i_conf, i_H, i_mi, i_pred);          \
   } while (0)
-  if (nc == 0) FAV_K34(0); else if (nc == 1) FAV_K34(1); else if (nc == 4) FAV_K34(4); else FAV_K34(32);
+#define FAV_K34_1(NC)                                                                                         \
+  do {                                                                                                        \
+    if (smem > 48 * 1024)                                                                                     \
+      FAV_CUDA_OK(cudaFuncSetAttribute(k34_kernel<NC, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); \
+    k34_kernel<NC, true, true><<<int(blocks), 256, smem, st>>>(d_logits, d_labels, n, T, g, hist, d_conf, d_entropy, d_mi,  \
+                                                               d_pred, d_flag, i_conf, i_H, i_mi, i_pred);    \
+  } while (0)
+  if (d_logits && T == 1 && nc == 4) FAV_K34_1(4);
+  else if (d_logits && T == 1 && nc == 32) FAV_K34_1(32);
+  else if (nc == 0) FAV_K34(0); else if (nc == 1) FAV_K34(1); else if (nc == 4) FAV_K34(4); else FAV_K34(32);
+#undef FAV_K34_1
 #undef FAV_K34
   h->launches++;
   FAV_CUDA_OK(cudaGetLastError());
