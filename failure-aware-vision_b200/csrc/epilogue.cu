@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(K34S_THREADS) k34_small_kernel(const float* __
           if (pc > 0.f) H -= pc * fast_log(pc);
         }
       }
-      const float mi = fmaxf(H - hsum * invT, 0.f);
+      const float mi = T == 1 ? 0.f : fmaxf(H - hsum * invT, 0.f);       // one pass: the mean is that pass, MI is exactly 0
       const int label = labels ? labels[i] : -1;
       const bool correct = arg == label;
       const bool flag = labels && !correct && best >= g.tau;
@@ -428,12 +428,14 @@ __global__ void __launch_bounds__(K34S_THREADS) k34_small_kernel(const float* __
           my[0] += 1; my[1] += correct; my[2] += flag;
           my[3] += q32(best); my[4] += q32(sc1); my[5] += q32(sc2);
         }
-        // AUROC buckets: score (q - 1) for q = 1..3; with TPS == 4 that is one score per lane, larger groups idle the rest
-        if (q >= 1 && q <= 3) {
-          const float sc = q == 1 ? sc0 : (q == 2 ? sc1 : sc2);
+        // AUROC buckets: with >= 4 lanes per sample lanes 1..3 take one score each, otherwise lane 0 does all three
+#pragma unroll
+        for (int si = 0; si < 3; ++si) {
+          if (q != (TPS >= 4 ? si + 1 : 0)) continue;
+          const float sc = si == 0 ? sc0 : (si == 1 ? sc1 : sc2);
           int k = int(floorf(sc * float(g.n_buckets)));
           k = min(max(k, 0), g.n_buckets - 1);
-          atomicAdd(&s_hist[2 * g.n_bins + ((q - 1) * g.n_buckets + k) * 2 + (correct ? 0 : 1)], 1u);
+          atomicAdd(&s_hist[2 * g.n_bins + (si * g.n_buckets + k) * 2 + (correct ? 0 : 1)], 1u);
         }
       }
     }
@@ -492,7 +494,9 @@ static int launch_k34(fav_handle h, const float* d_logits, const int32_t* d_labe
     const size_t hist_bytes = d_hist ? ((((smem + 7) & ~size_t(7)) + (size_t)n_bins * 8 + (size_t)C * C * 4 + 15) & ~size_t(15)) : 0;
     const size_t budget = 220 * 1024;
     int tps = 0;
-    for (int cand = 8; cand <= 32; cand *= 2)
+    int first = 1;                                     // no more lanes per sample than passes (T = 1: thread per sample), at most 8 by choice
+    while (first < T && first < 8) first *= 2;
+    for (int cand = first; cand <= 32; cand *= 2)
       if (hist_bytes + 2 * (size_t)(K34S_THREADS / cand) * T * C * 4 <= budget) { tps = cand; break; }
     if (tps) {
       const size_t sm = hist_bytes + 2 * (size_t)(K34S_THREADS / tps) * T * C * 4;
@@ -505,8 +509,17 @@ static int launch_k34(fav_handle h, const float* d_logits, const int32_t* d_labe
     k34_small_kernel<TPS, CT><<<int(nb), K34S_THREADS, sm, st>>>(d_logits, d_labels, n, T, g, hist, int(hist_bytes), d_conf,      \
                                                         d_entropy, d_mi, d_pred, d_flag);                               \
   } while (0)
-      if (C == 10) { if (tps == 8) FAV_K34S(8, 10); else if (tps == 16) FAV_K34S(16, 10); else FAV_K34S(32, 10); }
-      else { if (tps == 8) FAV_K34S(8, 0); else if (tps == 16) FAV_K34S(16, 0); else FAV_K34S(32, 0); }
+      if (C == 10) {
+        switch (tps) {
+          case 1: FAV_K34S(1, 10); break;  case 2: FAV_K34S(2, 10); break;  case 4: FAV_K34S(4, 10); break;
+          case 8: FAV_K34S(8, 10); break;  case 16: FAV_K34S(16, 10); break; default: FAV_K34S(32, 10); break;
+        }
+      } else {
+        switch (tps) {
+          case 1: FAV_K34S(1, 0); break;  case 2: FAV_K34S(2, 0); break;  case 4: FAV_K34S(4, 0); break;
+          case 8: FAV_K34S(8, 0); break;  case 16: FAV_K34S(16, 0); break; default: FAV_K34S(32, 0); break;
+        }
+      }
 #undef FAV_K34S
       h->launches++;
       FAV_CUDA_OK(cudaGetLastError());
