@@ -204,3 +204,14 @@ def test_div255_fma_correction_is_exact():
     for b in range(256):
         q = f32(b) * r
         assert fma(fma(-q, f32(255.0), f32(b)), r, q) == f32(b) / f32(255.0)
+
+
+def test_cli_and_trust_helpers_without_gpu():
+    """`python -m fav.sweep --help` parses without touching the GPU; the trust-replay host helpers map names to codes."""
+    import subprocess
+    out = subprocess.run([sys.executable, "-m", "fav.sweep", "--help"], capture_output=True, text=True, cwd=ROOT, timeout=120)
+    assert out.returncode == 0 and "--passes" in out.stdout and "--corruptions" in out.stdout
+    from fav import trust
+    codes = trust.status_codes([["VISION_OK", "VISION_BLANK"], ["VISION_CORRUPTED", "VISION_FROZEN"]])
+    assert codes.dtype == np.int8 and codes.tolist() == [[0, 2], [3, 1]]
+    assert trust.POLICY[3] == "VISION_BLOCKED" and trust.DECAY_RATES["VISION_BLANK"] == 0.60
