@@ -49,6 +49,7 @@ SIGNATURES = {
     "fav_conv_timing_read": (c_int, [c_void_p, C.POINTER(c_float), C.POINTER(c_int)]),
     "fav_conv_stats_read": (c_int, [c_void_p, C.POINTER(c_u64), c_int, C.POINTER(c_int)]),
     "fav_conv_timing_read_all": (c_int, [c_void_p, C.POINTER(c_float), C.POINTER(c_float), c_int, C.POINTER(c_int)]),
+    "fav_conv_timing_read_bytes": (c_int, [c_void_p, C.POINTER(c_float), c_int, C.POINTER(c_int)]),
 }
 
 

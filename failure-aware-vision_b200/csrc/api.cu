@@ -74,6 +74,7 @@ extern "C" int fav_conv_timing_enable(fav_handle h, int on) {
   h->timing = on != 0;
   h->ev_used = 0;
   h->ev_gflop.clear();
+  h->ev_gbyte.clear();
   return FAV_OK;
 }
 
@@ -90,6 +91,7 @@ extern "C" int fav_conv_timing_read(fav_handle h, float* total_ms, int* n_launch
   *n_launches = int(h->ev_used / 2);
   h->ev_used = 0;
   h->ev_gflop.clear();
+  h->ev_gbyte.clear();
   return FAV_OK;
 }
 
@@ -104,6 +106,17 @@ extern "C" int fav_conv_timing_read_all(fav_handle h, float* ms, float* gflop, i
   *n_launches = n;
   h->ev_used = 0;
   h->ev_gflop.clear();
+  h->ev_gbyte.clear();
+  return FAV_OK;
+}
+
+// algorithmic GB of each recorded launch; like fav_conv_stats_read it must be called BEFORE fav_conv_timing_read*
+extern "C" int fav_conv_timing_read_bytes(fav_handle h, float* gbyte, int cap, int* n_launches) {
+  FAV_REQUIRE(h && gbyte && n_launches, "fav_conv_timing_read_bytes: null pointer");
+  int n = int(h->ev_used / 2);
+  if (n > cap) n = cap;
+  for (int i = 0; i < n; ++i) gbyte[i] = i < int(h->ev_gbyte.size()) ? h->ev_gbyte[i] : 0.f;
+  *n_launches = n;
   return FAV_OK;
 }
 

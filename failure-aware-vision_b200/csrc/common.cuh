@@ -68,6 +68,18 @@ __device__ __forceinline__ float2 box_muller(uint32_t xa, uint32_t xb) {
   return make_float2(r * __cosf(t), r * __sinf(t));
 }
 
+// MC-dropout contract (oracle twin: oracle/model.py dropout_mask): one Philox call covers 16 consecutive NHWC channels, one
+// BYTE per channel; a channel is dropped iff its byte < thr8 = round(p * 256) (p is quantised to 1/256), kept values are scaled
+// by the exact inverse of the realised keep probability, fl32(256 / (256 - thr8)).  Byte of channel c (0..15) of the chunk:
+// word (c >> 1) & 3, byte (c & 1) * 2 + (c < 8 ? 1 : 0) -- chosen so that the kernels compare two channels at a time with the
+// 16-bit SIMD compare: pairs 0..3 use the words as they are (the HIGH byte of each half decides against thr8 << 8), pairs
+// 4..7 use the words shifted left by 8.
+inline uint32_t dropout_thr8(float p) {
+  const double t = double(p) * 256.0 + 0.5;
+  return t < 0.0 ? 0u : t >= 256.0 ? 255u : uint32_t(t);
+}
+inline float dropout_scale8(uint32_t thr8) { return 256.0f / float(256u - thr8); }
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -93,6 +105,7 @@ struct Ctx {
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
   std::vector<float> ev_gflop;
+  std::vector<float> ev_gbyte;    // algorithmic bytes per launch (operands read once, result written once), in GB
   void* stats_buf = nullptr;      // 512 launches x 8 role counters (cycles)
   // fp32 accumulation scratch of the split-K convolutions (few output tiles, many k-blocks: the batch-1 streaming gate)
   void* splitk_buf = nullptr;     // [tickets int per output tile | fp32 partial tiles]

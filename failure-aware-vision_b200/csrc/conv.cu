@@ -422,7 +422,7 @@ int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* di
 
 // optional per-launch timing (bench roofline / tuning): records the start event, returns the stop event to record after
 // the launch and a zeroed 8-counter stats slot for the kernel's role timers
-int conv_timing_begin(Ctx* ctx, cudaStream_t st, float gflop, cudaEvent_t* stop, unsigned long long** stats) {
+int conv_timing_begin(Ctx* ctx, cudaStream_t st, float gflop, float gbyte, cudaEvent_t* stop, unsigned long long** stats) {
   *stop = nullptr;
   *stats = nullptr;
   if (!ctx->timing) return FAV_OK;
@@ -435,6 +435,7 @@ int conv_timing_begin(Ctx* ctx, cudaStream_t st, float gflop, cudaEvent_t* stop,
   *stop = ctx->ev_pool[ctx->ev_used + 1];
   ctx->ev_used += 2;
   ctx->ev_gflop.push_back(gflop);
+  ctx->ev_gbyte.push_back(gbyte);
   if (!ctx->stats_buf) FAV_CUDA_OK(cudaMalloc(&ctx->stats_buf, 512 * 8 * sizeof(unsigned long long)));
   const size_t li = ctx->ev_used / 2 - 1;
   if (li < 512) {
@@ -511,9 +512,9 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   if (c.drop) {
     FAV_REQUIRE((L.cout & 15) == 0 && !c.out_f32, "conv: dropout epilogue needs Cout %% 16 == 0 and bf16 output");
     FAV_REQUIRE(c.p_drop >= 0.f && c.p_drop < 1.f, "conv: p_drop must be in [0,1)");
-    a.drop_thr16 = uint32_t(floor(double(c.p_drop) * 65536.0));
-    a.drop_thr2 = a.drop_thr16 | (a.drop_thr16 << 16);
-    a.drop_scale = 1.0f / (1.0f - c.p_drop);
+    a.drop_thr8 = dropout_thr8(c.p_drop);
+    a.drop_thr2 = (a.drop_thr8 << 8) | (a.drop_thr8 << 24);
+    a.drop_scale = dropout_scale8(a.drop_thr8);
     a.k0 = uint32_t(c.seed); a.k1 = uint32_t(c.seed >> 32); a.first_image = uint32_t(c.first_image);
     a.drop_stream = stream_id(KIND_DROPOUT, c.layer_id, 0);
     if (c.drop2_layer >= 0) {
@@ -751,7 +752,13 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   {
     const float gf = L.fold ? float(2.0 * double(M) * 36.0 * (L.cin / 4) * (L.cout / 4) * 1e-9)   // nominal (stock PyTorch) FLOPs
                             : float(2.0 * double(M) * (L.r * L.s * L.cin + L.cin2) * L.cout * 1e-9);
-    int rc = conv_timing_begin(ctx, st, gf, &e1, &a.stats);
+    // algorithmic bytes: every operand read once (a strided 1x1 conv touches only the pixels it samples), result written once
+    const double in1 = (L.r == 1 && L.s == 1 && L.stride > 1) ? double(M) * L.cin * 2 : double(c.p) * c.h * c.w * (L.cin_store ? L.cin_store : L.cin) * 2;
+    const double in2 = L.k2pad > 0 ? double(M) * L.cin2 * 2 : 0.0;
+    const double outb = double(M) * L.cout * (c.out_f32 ? 4 : 2) * (c.rep > 1 ? c.rep : 1);
+    const double resb = c.res ? double(M) * L.cout * 2 : 0.0;
+    const double wb = double(L.kpad + L.k2pad) * L.cout_pad * 2;
+    int rc = conv_timing_begin(ctx, st, gf, float((in1 + in2 + outb + resb + wb) * 1e-9), &e1, &a.stats);
     if (rc) return rc;
   }
   if (pair_ok) {

@@ -51,7 +51,7 @@ int conv_pick_bn(int cout);
 int conv_layer_finalize(ConvLayer& L);
 int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st);
 bool conv_stem_padded_dims(const ConvLayer& L, int h, int w, int* hp, int* wp);
-int conv_timing_begin(Ctx* ctx, cudaStream_t st, float gflop, cudaEvent_t* stop, unsigned long long** stats);
+int conv_timing_begin(Ctx* ctx, cudaStream_t st, float gflop, float gbyte, cudaEvent_t* stop, unsigned long long** stats);
 // conv_flat.cu: 3x3 / stride 1 / pad 1, Cin = Cout = 64 on small images: activations resident in shared memory as a
 // flat zero-padded pixel list, weights resident, filter taps = shifted UMMA descriptors
 bool conv_flat_applicable(const ConvCall& c);

@@ -40,8 +40,8 @@ struct ConvArgs {
   int s_store;                 // a_mode 3: filter-row slots (S padded to an even count), Cin stored as 4
   int stem_tma;                // a_mode 0 on the pre-padded NHWC4 stem input: one 5-D TMA box = one filter row x 16 taps x 4 ch per k-block
   int T, rep, drop;
-  uint32_t drop_thr16;         // keep a channel iff its 16-bit Philox lane >= drop_thr16 (= floor(p * 65536))
-  uint32_t drop_thr2;          // the same threshold in both halves of a word (operand of the 2 x 16-bit SIMD compare)
+  uint32_t drop_thr8;          // keep a channel iff its Philox byte >= drop_thr8 (= round(p * 256), common.cuh)
+  uint32_t drop_thr2;          // thr8 << 8 in both halves of a word (operand of the 2 x 16-bit SIMD compare)
   float drop_scale;
   uint32_t k0, k1, first_image, drop_stream;
   uint32_t drop_stream2;       // second mask stream (ConvCall::drop2_layer), used when drop2 != 0
@@ -144,16 +144,19 @@ __device__ __forceinline__ bool decode_row(const ConvArgs& a, const Tile& t, int
   return true;
 }
 
-// MC-dropout on 16 packed bf16 channels starting at channel offset e8*8 of the image: two Philox calls give eight words =
-// sixteen 16-bit lanes (channel 2i <- low half of word i, channel 2i+1 <- high half); __vcmpgeu2 turns a word into a
-// 0xFFFF-per-kept-channel mask that is ANDed onto the packed pair (dropped channels become +0.0)
-__device__ __forceinline__ void dropout_and16(const ConvArgs& a, uint32_t e8, uint32_t image, uint32_t tt, const uint32_t (&pk)[8],
+// MC-dropout on 16 packed bf16 channels starting at channel offset e16*16 of the image: ONE Philox call gives four words =
+// sixteen byte lanes (layout: common.cuh).  __vcmpgeu2 against thr8 << 8 compares the high byte of each 16-bit half, so pairs
+// 0..3 take the words as they are and pairs 4..7 the words shifted left by 8; the result is a 0xFFFF-per-kept-channel mask
+// that is ANDed onto the packed pair (dropped channels become +0.0)
+__device__ __forceinline__ void dropout_and16(const ConvArgs& a, uint32_t e16, uint32_t image, uint32_t tt, const uint32_t (&pk)[8],
                                               uint32_t (&o)[8], uint32_t stream) {
-  const uint4 ra = philox4x32_10(e8, image, tt, stream, a.k0, a.k1);
-  const uint4 rb = philox4x32_10(e8 + 1, image, tt, stream, a.k0, a.k1);
-  const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+  const uint4 r = philox4x32_10(e16, image, tt, stream, a.k0, a.k1);
+  const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = pk[i] & __vcmpgeu2(rw[i], a.drop_thr2);
+  for (int i = 0; i < 4; ++i) {
+    o[i] = pk[i] & __vcmpgeu2(rw[i], a.drop_thr2);
+    o[i + 4] = pk[i + 4] & __vcmpgeu2(rw[i] << 8, a.drop_thr2);
+  }
 }
 
 // Epilogue of one 128-row sub-tile for one warp: TMEM (lanes of this warp's quarter, columns of accumulator `trow`) ->
@@ -218,7 +221,7 @@ __device__ __forceinline__ void conv_epilogue_subtile(const ConvArgs& a, const T
       uint32_t pk[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(v[2 * i] * a.drop_scale, v[2 * i + 1] * a.drop_scale);
-      const uint32_t e8 = uint32_t((size_t)hw * a.Cout + c0) >> 3;
+      const uint32_t e8 = uint32_t((size_t)hw * a.Cout + c0) >> 4;
       for (int rp = 0; rp < n_rep; ++rp) {
         const int p_out = a.rep > 1 ? q * a.rep + rp : q;
         uint32_t o[8];
@@ -397,7 +400,7 @@ __device__ __forceinline__ void conv_epilogue_staged(const ConvArgs& a, const CU
         const int jj = sub_w + ch * WPQ;
         uint32_t o[8];
         if (a.drop && valid) {
-          const uint32_t e8 = uint32_t((size_t)hw * a.Cout + t.nt * a.BN + hf * 64 + jj * 16) >> 3;
+          const uint32_t e8 = uint32_t((size_t)hw * a.Cout + t.nt * a.BN + hf * 64 + jj * 16) >> 4;
           dropout_and16(a, e8, a.first_image + uint32_t(n_img), uint32_t(a.rep > 1 ? rp : tt0), pk[ch], o, a.drop_stream);
         } else {
 #pragma unroll

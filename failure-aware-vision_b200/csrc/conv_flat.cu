@@ -39,7 +39,7 @@ struct FlatArgs {
   int rows_img, G, slab_rows;  // padded pixels per image, images per slab, G * rows_img (<= 256)
   int n_slabs, n_tiles;        // slabs in the problem, 128-row tiles per slab (1 or 2)
   int relu, T, rep, drop;
-  uint32_t drop_thr16, drop_thr2;      // floor(p * 65536); the same in both halves of a word (2 x 16-bit SIMD compare)
+  uint32_t drop_thr8, drop_thr2;       // round(p * 256); thr8 << 8 in both halves of a word (2 x 16-bit SIMD compare)
   float drop_scale;
   uint32_t k0, k1, first_image, drop_stream;
   uint32_t idesc;
@@ -209,15 +209,20 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int i = 0; i < 4; ++i) rv[i] = __ldg(rp + i);
         }
         const int n_img = a.rep > 1 ? q : q / a.T;
-        const uint32_t e8 = uint32_t(hw * Cout + cbase) >> 3;
-        // MC-dropout on the packed bf16 pairs: four Philox calls give sixteen words = thirty-two 16-bit lanes (channel 2i <-
-        // low half of word i); __vcmpgeu2 makes a 0xFFFF-per-kept-channel mask that is ANDed on (dropped -> +0.0)
+        const uint32_t e16 = uint32_t(hw * Cout + cbase) >> 4;
+        // MC-dropout on the packed bf16 pairs: two Philox calls give eight words = thirty-two byte lanes (layout: common.cuh);
+        // __vcmpgeu2 against thr8 << 8 decides on the high byte of each half (pairs 4..7 of a chunk: the word shifted left by
+        // 8) and makes a 0xFFFF-per-kept-channel mask that is ANDed on (dropped -> +0.0)
         auto keep_words = [&](int tt, uint32_t (&kw)[16]) {
 #pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const uint4 r = philox4x32_10(e8 + c4, a.first_image + uint32_t(n_img), uint32_t(tt), a.drop_stream, a.k0, a.k1);
-            kw[4 * c4] = __vcmpgeu2(r.x, a.drop_thr2); kw[4 * c4 + 1] = __vcmpgeu2(r.y, a.drop_thr2);
-            kw[4 * c4 + 2] = __vcmpgeu2(r.z, a.drop_thr2); kw[4 * c4 + 3] = __vcmpgeu2(r.w, a.drop_thr2);
+          for (int c2 = 0; c2 < 2; ++c2) {
+            const uint4 r = philox4x32_10(e16 + c2, a.first_image + uint32_t(n_img), uint32_t(tt), a.drop_stream, a.k0, a.k1);
+            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              kw[8 * c2 + i] = __vcmpgeu2(rw[i], a.drop_thr2);
+              kw[8 * c2 + 4 + i] = __vcmpgeu2(rw[i] << 8, a.drop_thr2);
+            }
           }
         };
         uint32_t kw[16];                                     // first pass's keep-words: computed BEFORE the accumulator wait
@@ -315,9 +320,9 @@ int conv_flat_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   a.relu = c.relu; a.T = c.T > 0 ? c.T : 1; a.rep = c.rep > 1 ? c.rep : 1; a.drop = c.drop;
   if (c.drop) {
     FAV_REQUIRE(c.p_drop >= 0.f && c.p_drop < 1.f, "conv: p_drop must be in [0,1)");
-    a.drop_thr16 = uint32_t(floor(double(c.p_drop) * 65536.0));
-    a.drop_thr2 = a.drop_thr16 | (a.drop_thr16 << 16);
-    a.drop_scale = 1.0f / (1.0f - c.p_drop);
+    a.drop_thr8 = dropout_thr8(c.p_drop);
+    a.drop_thr2 = (a.drop_thr8 << 8) | (a.drop_thr8 << 24);
+    a.drop_scale = dropout_scale8(a.drop_thr8);
     a.k0 = uint32_t(c.seed); a.k1 = uint32_t(c.seed >> 32); a.first_image = uint32_t(c.first_image);
     a.drop_stream = stream_id(KIND_DROPOUT, c.layer_id, 0);
   }
@@ -343,7 +348,8 @@ int conv_flat_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   cudaEvent_t e1 = nullptr;
   {
     const long long M = (long long)c.p * c.h * c.w;
-    int rc = conv_timing_begin(ctx, st, float(2.0 * double(M) * 576.0 * 64.0 * 1e-9), &e1, &a.stats);
+    int rc = conv_timing_begin(ctx, st, float(2.0 * double(M) * 576.0 * 64.0 * 1e-9),
+                               float((double(M) * 64 * 2 * (2 + (c.res ? 1 : 0)) + 576.0 * 64 * 2) * 1e-9), &e1, &a.stats);
     if (rc) return rc;
   }
   {

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256) k_maxpool3x3s2(const uint4* __restrict__ 
 
 // global average pool + MC-dropout on the pooled feature: [P, HW, C] bf16 -> [P, C] bf16
 __global__ void __launch_bounds__(256) k_pool_dropout(const uint4* __restrict__ x, uint4* __restrict__ y, int P, int HW,
-                                                      int C8, int T, int drop, uint32_t thr16, float scale, uint32_t k0,
+                                                      int C8, int T, int drop, uint32_t thr8, float scale, uint32_t k0,
                                                       uint32_t k1, uint32_t first_image, uint32_t stream) {
   const long long total = (long long)P * C8;
   const float inv = 1.0f / float(HW);
@@ -78,12 +78,14 @@ __global__ void __launch_bounds__(256) k_pool_dropout(const uint4* __restrict__ 
     for (int k = 0; k < 8; ++k) s[k] = HW == 1 ? s[k] : s[k] * inv;
     if (drop) {
       const int n_img = p / T, t = p - n_img * T;
-      const uint4 r = philox4x32_10(uint32_t(c), first_image + uint32_t(n_img), uint32_t(t), stream, k0, k1);
+      // this thread's 8 channels are half (c & 1) of a 16-channel Philox chunk (byte layout: common.cuh)
+      const uint4 r = philox4x32_10(uint32_t(c) >> 1, first_image + uint32_t(n_img), uint32_t(t), stream, k0, k1);
       const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+      const int sh = (c & 1) ? 0 : 8;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        s[2 * k] = (rw[k] & 0xFFFFu) >= thr16 ? s[2 * k] * scale : 0.f;
-        s[2 * k + 1] = (rw[k] >> 16) >= thr16 ? s[2 * k + 1] * scale : 0.f;
+        s[2 * k] = ((rw[k] >> sh) & 0xFFu) >= thr8 ? s[2 * k] * scale : 0.f;
+        s[2 * k + 1] = ((rw[k] >> (sh + 16)) & 0xFFu) >= thr8 ? s[2 * k + 1] * scale : 0.f;
       }
     }
     y[i] = make_uint4(pack_bf16x2(s[0], s[1]), pack_bf16x2(s[2], s[3]), pack_bf16x2(s[4], s[5]), pack_bf16x2(s[6], s[7]));
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(256) k_pool_dropout(const uint4* __restrict__ 
 // same for large feature maps (the batch-1 streaming gate: 15x20 pixels, one image): a CTA per (pass-image, 32 channel
 // vectors); its 8 warps sum interleaved pixels, shared-memory reduce, warp 0 applies the mask
 __global__ void __launch_bounds__(256) k_pool_dropout_wide(const uint4* __restrict__ x, uint4* __restrict__ y, int P, int HW,
-                                                           int C8, int T, int drop, uint32_t thr16, float scale, uint32_t k0,
+                                                           int C8, int T, int drop, uint32_t thr8, float scale, uint32_t k0,
                                                            uint32_t k1, uint32_t first_image, uint32_t stream) {
   __shared__ float part[8][32][8];
   const int groups = (C8 + 31) / 32;
@@ -121,12 +123,13 @@ __global__ void __launch_bounds__(256) k_pool_dropout_wide(const uint4* __restri
   }
   if (drop) {
     const int n_img = p / T, t = p - n_img * T;
-    const uint4 r = philox4x32_10(uint32_t(c), first_image + uint32_t(n_img), uint32_t(t), stream, k0, k1);
+    const uint4 r = philox4x32_10(uint32_t(c) >> 1, first_image + uint32_t(n_img), uint32_t(t), stream, k0, k1);
     const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+    const int sh = (c & 1) ? 0 : 8;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      s[2 * k] = (rw[k] & 0xFFFFu) >= thr16 ? s[2 * k] * scale : 0.f;
-      s[2 * k + 1] = (rw[k] >> 16) >= thr16 ? s[2 * k + 1] * scale : 0.f;
+      s[2 * k] = ((rw[k] >> sh) & 0xFFu) >= thr8 ? s[2 * k] * scale : 0.f;
+      s[2 * k + 1] = ((rw[k] >> (sh + 16)) & 0xFFu) >= thr8 ? s[2 * k + 1] * scale : 0.f;
     }
   }
   y[(size_t)p * C8 + c] = make_uint4(pack_bf16x2(s[0], s[1]), pack_bf16x2(s[2], s[3]), pack_bf16x2(s[4], s[5]), pack_bf16x2(s[6], s[7]));
@@ -522,16 +525,17 @@ extern "C" int fav_forward_mc(fav_handle h, const void* d_x, float* d_logits, in
     fc_in = X[cur];                               // nothing to pool; the mask (if any) was applied by the last conv's epilogue
   } else {
     const long long work = (long long)P * (ch / 8);
-    const uint32_t thr = mc ? uint32_t(floor(double(p_drop) * 65536.0)) : 0u;
+    FAV_REQUIRE(!mc || (ch & 15) == 0, "MC-dropout on the pooled feature needs a width that is a multiple of 16");
+    const uint32_t thr = mc ? dropout_thr8(p_drop) : 0u;
     const int groups = (ch / 8 + 31) / 32;
     if (hh * ww >= 64 && (long long)P * groups <= (1 << 20))
       k_pool_dropout_wide<<<P * groups, 256, 0, st>>>(
           reinterpret_cast<const uint4*>(X[cur]), reinterpret_cast<uint4*>(Y1), P, hh * ww, ch / 8, T, mc ? 1 : 0, thr,
-          1.0f / (1.0f - p_drop), k0, k1, uint32_t(first_image), stream_id(KIND_DROPOUT, 255, 0));
+          dropout_scale8(thr), k0, k1, uint32_t(first_image), stream_id(KIND_DROPOUT, 255, 0));
     else
       k_pool_dropout<<<grid_for(work, 256, h->num_sms), 256, 0, st>>>(
           reinterpret_cast<const uint4*>(X[cur]), reinterpret_cast<uint4*>(Y1), P, hh * ww, ch / 8, T, mc ? 1 : 0, thr,
-          1.0f / (1.0f - p_drop), k0, k1, uint32_t(first_image), stream_id(KIND_DROPOUT, 255, 0));
+          dropout_scale8(thr), k0, k1, uint32_t(first_image), stream_id(KIND_DROPOUT, 255, 0));
     h->launches++;
   }
   const ConvLayer& fc = pl.convs.back();

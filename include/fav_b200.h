@@ -191,6 +191,9 @@ int fav_conv_timing_enable(fav_handle h, int on);
 int fav_conv_timing_read(fav_handle h, float* total_ms, int* n_launches);
 /* same, but per launch in launch order: ms[i] and the launch's algorithmic GFLOP (2*M*K*N, padded taps counted). */
 int fav_conv_timing_read_all(fav_handle h, float* ms, float* gflop, int cap, int* n_launches);
+/* per-launch algorithmic GB (each operand read once, result written once) of the launches recorded since the last
+ * read -- the HBM side of the per-layer roofline; call before fav_conv_timing_read* (which clear the record). */
+int fav_conv_timing_read_bytes(fav_handle h, float* gbyte, int cap, int* n_launches);
 /* tuning aid: per-launch role wait counters (cycles summed over CTAs, 8 per launch; layout in api.cu). */
 int fav_conv_stats_read(fav_handle h, uint64_t* out, int cap_launches, int* n_launches);
 

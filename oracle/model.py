@@ -10,9 +10,13 @@ own forward in tests/test_oracle.py.
 
 MC-dropout spec: elementwise dropout with probability p on the output of
 every residual block (after the final ReLU) and on the pooled feature before fc.  Mask lane
-for NHWC offset e of an activation: 16-bit lane (e % 8) of Philox(c0=e//8, c1=global image,
-c2=t, c3=stream(DROPOUT, layer_id)); dropped iff lane < floor(p*65536); kept values are
-scaled by fl32(1/(1-p)).  T == 1 disables dropout (deterministic MSP path).
+for NHWC offset e of an activation: one BYTE of Philox(c0=e//16, c1=global image, c2=t,
+c3=stream(DROPOUT, layer_id)) -- channel c = e % 16 of the chunk reads word (c >> 1) & 3,
+byte (c & 1) * 2 + (1 if c < 8 else 0) (the layout that lets the device compare two channels
+per 16-bit SIMD compare).  p is quantised to thr8 / 256 with thr8 = round(p * 256): a value is
+dropped iff its byte < thr8 and kept values are scaled by the exact inverse of the realised
+keep probability, fl32(256 / (256 - thr8)) -- i.e. torch dropout at p_q = thr8 / 256.
+T == 1 disables dropout (deterministic MSP path).
 """
 import numpy as np
 import torch
@@ -83,19 +87,29 @@ def _bf16(t):
 
 
 def dropout_threshold(p):
-    return int(np.floor(float(p) * 65536.0))
+    """thr8 = round(p * 256), clipped to [0, 255]."""
+    return int(min(max(np.floor(float(p) * 256.0 + 0.5), 0.0), 255.0))
+
+
+def dropout_scale(p):
+    return np.float32(256.0) / np.float32(256 - dropout_threshold(p))
+
+
+# channel c (0..15) of a 16-channel chunk -> (word, byte) of the chunk's Philox call
+_DROP_WORD = np.array([(c >> 1) & 3 for c in range(16)])
+_DROP_BYTE = np.array([(c & 1) * 2 + (1 if c < 8 else 0) for c in range(16)])
 
 
 def dropout_mask(n_images, first_image, t, layer_id, elems_per_image, p, seed):
-    """float32 [n_images, elems_per_image]: 0 where dropped else fl32(1/(1-p))."""
-    assert elems_per_image % 8 == 0
+    """float32 [n_images, elems_per_image]: 0 where dropped else fl32(256 / (256 - thr8))."""
+    assert elems_per_image % 16 == 0
     img = np.arange(first_image, first_image + n_images, dtype=np.uint64)[:, None]
-    ch = np.arange(elems_per_image // 8, dtype=np.uint64)[None, :]
+    ch = np.arange(elems_per_image // 16, dtype=np.uint64)[None, :]
     xs = px.philox4x32_10(ch, img, t, px.stream_id(px.KIND_DROPOUT, layer_id), seed)
-    lanes = px.u16_lanes(*xs).reshape(n_images, elems_per_image)
-    keep = lanes >= np.uint16(dropout_threshold(p)) if dropout_threshold(p) < 65536 else np.zeros_like(lanes, bool)
-    scale = np.float32(1.0) / (np.float32(1.0) - np.float32(p))
-    return np.where(keep, scale, np.float32(0.0)).astype(np.float32)
+    words = np.stack([np.asarray(x, dtype=np.uint32) for x in xs], axis=-1)                  # [n, chunks, 4]
+    lanes = (words[..., _DROP_WORD] >> (8 * _DROP_BYTE).astype(np.uint32)) & np.uint32(0xFF)   # [n, chunks, 16]
+    keep = lanes.reshape(n_images, elems_per_image) >= np.uint32(dropout_threshold(p))
+    return np.where(keep, dropout_scale(p), np.float32(0.0)).astype(np.float32)
 
 
 def _drop(x_nchw, t, layer_id, p, seed, first_image):

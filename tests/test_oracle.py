@@ -126,8 +126,15 @@ def test_param_and_mac_counts():
 
 def test_dropout_mask_rate_and_t1_identity():
     m = M.dropout_mask(4, 0, 3, 2, 4096, 0.2, 0)
-    assert abs((m == 0).mean() - 0.2) < 0.01
-    assert np.allclose(m[m > 0], 1.25)
+    assert M.dropout_threshold(0.2) == 51 and M.dropout_threshold(0.5) == 128 and M.dropout_threshold(0.0) == 0
+    assert abs((m == 0).mean() - 51 / 256) < 0.01
+    assert np.all(m[m > 0] == np.float32(256.0) / np.float32(205.0))       # exact inverse of the realised keep probability
+    assert abs(m.mean() - 1.0) < 0.02                                      # unbiased
+    # the sixteen channels of a chunk read sixteen DIFFERENT bytes of the chunk's Philox call
+    assert sorted(zip(M._DROP_WORD.tolist(), M._DROP_BYTE.tolist())) == [(w, b) for w in range(4) for b in range(4)]
+    # neighbouring channels are uncorrelated
+    k = (m > 0).astype(np.float64)
+    assert abs(np.corrcoef(k[:, :-1].ravel(), k[:, 1:].ravel())[0, 1]) < 0.02
     net = M.build_torchvision("resnet18", 10, 0)
     fd = M.fold_resnet(net)
     x = np.random.default_rng(1).standard_normal((2, 32, 32, 3)).astype(np.float32)
