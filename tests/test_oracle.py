@@ -217,3 +217,49 @@ def test_trust_replay_oracle_reproduces_the_reference_engine():
         for s_, i_ in ((0, 0), (1, c["n_ticks"] // 2), (c["n_seq"] - 1, c["n_ticks"] - 1)):
             st = OT.reference_state(res, s_, i_)
             assert st["reliability"] == t[s_, i_, 8] and st["trust_velocity"] == t[s_, i_, 9]
+
+
+# ---------------------------------------------------------------- third-party anchors of the corruption building blocks
+# (the reference ships no corruption code: these pin the restated pieces to the libraries the canonical ImageNet-C /
+# CIFAR-10-C generators call -- scipy.ndimage and PIL -- at the versions in this image)
+def test_gaussian_taps_match_scipy_gaussian_filter():
+    import scipy.ndimage as ndi
+    for sigma in (0.4, 0.7, 1.0, 1.5, 3.0):
+        r, k = C.gaussian_taps(sigma)
+        imp = np.zeros(2 * r + 9)
+        imp[r + 4] = 1.0
+        g = ndi.gaussian_filter1d(imp, sigma, mode="constant")          # truncate = 4.0, as skimage.filters.gaussian
+        assert np.abs(g[4:4 + 2 * r + 1] - k).max() < 1e-15 and g[:4].max() == 0.0
+
+
+def test_zoom_resampling_matches_scipy_zoom():
+    import scipy.ndimage as ndi
+    rng = np.random.default_rng(3)
+    for size in (32, 224):
+        x = (rng.integers(0, 256, (size, size, 3), dtype=np.uint8).astype(np.float32) / np.float32(255)).astype(np.float32)
+        for z in (1.06, 1.11, 1.33):
+            hc, top, ho, trim = C.zoom_geometry(size, z)
+            ref = ndi.zoom(x[top:top + hc, top:top + hc], (z, z, 1), order=1)      # make_imagenet_c.clipped_zoom
+            assert ref.shape[0] == ho
+            ref = ref[trim:trim + size, trim:trim + size]
+            i0, i1, fr = C._zoom_sample_axis(size, z)
+            fy, fx = fr[:, None, None], fr[None, :, None]
+            t = x[i0][:, i0] * (1 - fx) + x[i0][:, i1] * fx
+            b = x[i1][:, i0] * (1 - fx) + x[i1][:, i1] * fx
+            assert np.abs(t * (1 - fy) + b * fy - ref).max() < 5e-5
+
+
+def test_pixelate_tracks_pil_box_resize():
+    from PIL import Image
+    rng = np.random.default_rng(4)
+    for size in (32, 224):
+        prof = C.profile_for(size, size)
+        x = rng.integers(0, 256, (2, size, size, 3), dtype=np.uint8)
+        for sev in range(1, 6):
+            c = C.CONSTANTS[prof]["pixelate"][sev - 1]
+            small = int(size * c)
+            ref = np.stack([np.asarray(Image.fromarray(x[i]).resize((small, small), Image.BOX).resize((size, size), Image.BOX))
+                            for i in range(2)])
+            d = np.abs(np.rint(C.pixelate(x, sev) * 255.0).astype(np.int64) - ref.astype(np.int64))
+            # PIL weights partially covered source pixels, the restatement takes whole-pixel boxes: never more than one code apart
+            assert d.max() <= 1
