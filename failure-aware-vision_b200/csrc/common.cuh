@@ -69,16 +69,51 @@ __device__ __forceinline__ float2 box_muller(uint32_t xa, uint32_t xb) {
 }
 
 // MC-dropout contract (oracle twin: oracle/model.py dropout_mask): one Philox call covers 16 consecutive NHWC channels, one
-// BYTE per channel; a channel is dropped iff its byte < thr8 = round(p * 256) (p is quantised to 1/256), kept values are scaled
-// by the exact inverse of the realised keep probability, fl32(256 / (256 - thr8)).  Byte of channel c (0..15) of the chunk:
-// word (c >> 1) & 3, byte (c & 1) * 2 + (c < 8 ? 1 : 0) -- chosen so that the kernels compare two channels at a time with the
-// 16-bit SIMD compare: pairs 0..3 use the words as they are (the HIGH byte of each half decides against thr8 << 8), pairs
-// 4..7 use the words shifted left by 8.
+// BYTE per channel in natural order (channel c of the chunk = byte c of the 16 output bytes, x0's low byte first); a channel
+// is dropped iff its byte < thr8 = round(p * 256) (p is quantised to 1/256), kept values are scaled by the exact inverse of
+// the realised keep probability, fl32(256 / (256 - thr8)).
 inline uint32_t dropout_thr8(float p) {
   const double t = double(p) * 256.0 + 0.5;
   return t < 0.0 ? 0u : t >= 256.0 ? 255u : uint32_t(t);
 }
 inline float dropout_scale8(uint32_t thr8) { return 256.0f / float(256u - thr8); }
+// Operands of the four-bytes-at-a-time compare below: byte >= K is  msb | (low7 >= K)  for K <= 128 and
+// msb & (low7 >= K - 128)  for K > 128; "low7 >= k" is the carry of low7 + (0x80 - k) into bit 7 (no carry leaves the byte).
+inline uint32_t dropout_add4(uint32_t thr8) { return (thr8 <= 128u ? 0x80u - thr8 : 0x100u - thr8) * 0x01010101u; }
+inline uint32_t dropout_hi4(uint32_t thr8) { return thr8 > 128u ? 0xFFFFFFFFu : 0u; }
+
+// keep flags of four channels in the sign bits of the four bytes of the result (three instructions: AND, ADD, one LOP3)
+__device__ __forceinline__ uint32_t dropout_keep4(uint32_t r, uint32_t add4, uint32_t hi4) {
+  const uint32_t t = (r & 0x7F7F7F7Fu) + add4;
+  return (t & r) | (~hi4 & (t | r));
+}
+// sign bits of bytes (0, 1) / (2, 3) -> 0xFFFF-per-kept-channel masks for a packed bf16 pair (PRMT sign replication)
+// (inline PTX: __byte_perm only honours the low three bits of each selector nibble, bit 3 = "replicate the sign" needs prmt.b32)
+__device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+__device__ __forceinline__ uint32_t dropout_pair_lo(uint32_t keep4) { return prmt_b32(keep4, 0u, 0x9988u); }
+__device__ __forceinline__ uint32_t dropout_pair_hi(uint32_t keep4) { return prmt_b32(keep4, 0u, 0xBBAAu); }
+
+// Philox4x32-10 with the ten round keys precomputed on the host (kernel parameters: the key schedule costs no instructions)
+struct PhiloxKeys { uint32_t k0[10], k1[10]; };
+inline PhiloxKeys philox_keys(uint32_t k0, uint32_t k1) {
+  PhiloxKeys k;
+  for (int r = 0; r < 10; ++r) { k.k0[r] = k0 + uint32_t(r) * 0x9E3779B9u; k.k1[r] = k1 + uint32_t(r) * 0xBB67AE85u; }
+  return k;
+}
+__device__ __forceinline__ uint4 philox4x32_10_keys(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(PHILOX_M0, c0), lo0 = PHILOX_M0 * c0;
+    const uint32_t hi1 = __umulhi(PHILOX_M1, c2), lo1 = PHILOX_M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k.k0[r], n2 = hi0 ^ c3 ^ k.k1[r];
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -513,9 +513,10 @@ int conv_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
     FAV_REQUIRE((L.cout & 15) == 0 && !c.out_f32, "conv: dropout epilogue needs Cout %% 16 == 0 and bf16 output");
     FAV_REQUIRE(c.p_drop >= 0.f && c.p_drop < 1.f, "conv: p_drop must be in [0,1)");
     a.drop_thr8 = dropout_thr8(c.p_drop);
-    a.drop_thr2 = (a.drop_thr8 << 8) | (a.drop_thr8 << 24);
+    a.drop_add4 = dropout_add4(a.drop_thr8); a.drop_hi4 = dropout_hi4(a.drop_thr8);
     a.drop_scale = dropout_scale8(a.drop_thr8);
     a.k0 = uint32_t(c.seed); a.k1 = uint32_t(c.seed >> 32); a.first_image = uint32_t(c.first_image);
+    a.drop_keys = philox_keys(a.k0, a.k1);
     a.drop_stream = stream_id(KIND_DROPOUT, c.layer_id, 0);
     if (c.drop2_layer >= 0) {
       FAV_REQUIRE(a.rep == 1 && a.OH * a.OW == 1, "conv: the fused second dropout needs a 1x1 output map and no replicas");

@@ -41,7 +41,8 @@ struct ConvArgs {
   int stem_tma;                // a_mode 0 on the pre-padded NHWC4 stem input: one 5-D TMA box = one filter row x 16 taps x 4 ch per k-block
   int T, rep, drop;
   uint32_t drop_thr8;          // keep a channel iff its Philox byte >= drop_thr8 (= round(p * 256), common.cuh)
-  uint32_t drop_thr2;          // thr8 << 8 in both halves of a word (operand of the 2 x 16-bit SIMD compare)
+  uint32_t drop_add4, drop_hi4;   // operands of dropout_keep4 (common.cuh)
+  PhiloxKeys drop_keys;        // round keys of (k0, k1)
   float drop_scale;
   uint32_t k0, k1, first_image, drop_stream;
   uint32_t drop_stream2;       // second mask stream (ConvCall::drop2_layer), used when drop2 != 0
@@ -144,18 +145,18 @@ __device__ __forceinline__ bool decode_row(const ConvArgs& a, const Tile& t, int
   return true;
 }
 
-// MC-dropout on 16 packed bf16 channels starting at channel offset e16*16 of the image: ONE Philox call gives four words =
-// sixteen byte lanes (layout: common.cuh).  __vcmpgeu2 against thr8 << 8 compares the high byte of each 16-bit half, so pairs
-// 0..3 take the words as they are and pairs 4..7 the words shifted left by 8; the result is a 0xFFFF-per-kept-channel mask
-// that is ANDed onto the packed pair (dropped channels become +0.0)
+// MC-dropout on 16 packed bf16 channels starting at channel offset e16*16 of the image: ONE Philox call gives sixteen byte
+// lanes (contract: common.cuh); dropout_keep4 compares four bytes at a time, PRMT sign replication turns the flags into
+// 0xFFFF-per-kept-channel masks that are ANDed onto the packed pairs (dropped channels become +0.0)
 __device__ __forceinline__ void dropout_and16(const ConvArgs& a, uint32_t e16, uint32_t image, uint32_t tt, const uint32_t (&pk)[8],
                                               uint32_t (&o)[8], uint32_t stream) {
-  const uint4 r = philox4x32_10(e16, image, tt, stream, a.k0, a.k1);
+  const uint4 r = philox4x32_10_keys(e16, image, tt, stream, a.drop_keys);
   const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    o[i] = pk[i] & __vcmpgeu2(rw[i], a.drop_thr2);
-    o[i + 4] = pk[i + 4] & __vcmpgeu2(rw[i] << 8, a.drop_thr2);
+    const uint32_t k4 = dropout_keep4(rw[i], a.drop_add4, a.drop_hi4);
+    o[2 * i] = pk[2 * i] & dropout_pair_lo(k4);
+    o[2 * i + 1] = pk[2 * i + 1] & dropout_pair_hi(k4);
   }
 }
 

@@ -39,7 +39,8 @@ struct FlatArgs {
   int rows_img, G, slab_rows;  // padded pixels per image, images per slab, G * rows_img (<= 256)
   int n_slabs, n_tiles;        // slabs in the problem, 128-row tiles per slab (1 or 2)
   int relu, T, rep, drop;
-  uint32_t drop_thr8, drop_thr2;       // round(p * 256); thr8 << 8 in both halves of a word (2 x 16-bit SIMD compare)
+  uint32_t drop_thr8, drop_add4, drop_hi4;   // round(p * 256); operands of dropout_keep4 (common.cuh)
+  PhiloxKeys drop_keys;                // round keys of (k0, k1)
   float drop_scale;
   uint32_t k0, k1, first_image, drop_stream;
   uint32_t idesc;
@@ -210,18 +211,18 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         const int n_img = a.rep > 1 ? q : q / a.T;
         const uint32_t e16 = uint32_t(hw * Cout + cbase) >> 4;
-        // MC-dropout on the packed bf16 pairs: two Philox calls give eight words = thirty-two byte lanes (layout: common.cuh);
-        // __vcmpgeu2 against thr8 << 8 decides on the high byte of each half (pairs 4..7 of a chunk: the word shifted left by
-        // 8) and makes a 0xFFFF-per-kept-channel mask that is ANDed on (dropped -> +0.0)
+        // MC-dropout on the packed bf16 pairs: two Philox calls give thirty-two byte lanes (contract: common.cuh);
+        // dropout_keep4 + PRMT sign replication make 0xFFFF-per-kept-channel masks that are ANDed on (dropped -> +0.0)
         auto keep_words = [&](int tt, uint32_t (&kw)[16]) {
 #pragma unroll
           for (int c2 = 0; c2 < 2; ++c2) {
-            const uint4 r = philox4x32_10(e16 + c2, a.first_image + uint32_t(n_img), uint32_t(tt), a.drop_stream, a.k0, a.k1);
+            const uint4 r = philox4x32_10_keys(e16 + c2, a.first_image + uint32_t(n_img), uint32_t(tt), a.drop_stream, a.drop_keys);
             const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              kw[8 * c2 + i] = __vcmpgeu2(rw[i], a.drop_thr2);
-              kw[8 * c2 + 4 + i] = __vcmpgeu2(rw[i] << 8, a.drop_thr2);
+              const uint32_t k4 = dropout_keep4(rw[i], a.drop_add4, a.drop_hi4);
+              kw[8 * c2 + 2 * i] = dropout_pair_lo(k4);
+              kw[8 * c2 + 2 * i + 1] = dropout_pair_hi(k4);
             }
           }
         };
@@ -321,9 +322,10 @@ int conv_flat_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   if (c.drop) {
     FAV_REQUIRE(c.p_drop >= 0.f && c.p_drop < 1.f, "conv: p_drop must be in [0,1)");
     a.drop_thr8 = dropout_thr8(c.p_drop);
-    a.drop_thr2 = (a.drop_thr8 << 8) | (a.drop_thr8 << 24);
+    a.drop_add4 = dropout_add4(a.drop_thr8); a.drop_hi4 = dropout_hi4(a.drop_thr8);
     a.drop_scale = dropout_scale8(a.drop_thr8);
     a.k0 = uint32_t(c.seed); a.k1 = uint32_t(c.seed >> 32); a.first_image = uint32_t(c.first_image);
+    a.drop_keys = philox_keys(a.k0, a.k1);
     a.drop_stream = stream_id(KIND_DROPOUT, c.layer_id, 0);
   }
   a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(64 >> 3) << 17) | (uint32_t(128 >> 4) << 24);

@@ -78,15 +78,12 @@ __global__ void __launch_bounds__(256) k_pool_dropout(const uint4* __restrict__ 
     for (int k = 0; k < 8; ++k) s[k] = HW == 1 ? s[k] : s[k] * inv;
     if (drop) {
       const int n_img = p / T, t = p - n_img * T;
-      // this thread's 8 channels are half (c & 1) of a 16-channel Philox chunk (byte layout: common.cuh)
+      // this thread's 8 channels are bytes 8 (c & 1) .. + 7 of a 16-channel Philox chunk (contract: common.cuh)
       const uint4 r = philox4x32_10(uint32_t(c) >> 1, first_image + uint32_t(n_img), uint32_t(t), stream, k0, k1);
       const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
-      const int sh = (c & 1) ? 0 : 8;
+      const int w0 = 2 * (c & 1);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        s[2 * k] = ((rw[k] >> sh) & 0xFFu) >= thr8 ? s[2 * k] * scale : 0.f;
-        s[2 * k + 1] = ((rw[k] >> (sh + 16)) & 0xFFu) >= thr8 ? s[2 * k + 1] * scale : 0.f;
-      }
+      for (int k = 0; k < 8; ++k) s[k] = ((rw[w0 + (k >> 2)] >> (8 * (k & 3))) & 0xFFu) >= thr8 ? s[k] * scale : 0.f;
     }
     y[i] = make_uint4(pack_bf16x2(s[0], s[1]), pack_bf16x2(s[2], s[3]), pack_bf16x2(s[4], s[5]), pack_bf16x2(s[6], s[7]));
   }
@@ -125,12 +122,9 @@ __global__ void __launch_bounds__(256) k_pool_dropout_wide(const uint4* __restri
     const int n_img = p / T, t = p - n_img * T;
     const uint4 r = philox4x32_10(uint32_t(c) >> 1, first_image + uint32_t(n_img), uint32_t(t), stream, k0, k1);
     const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
-    const int sh = (c & 1) ? 0 : 8;
+    const int w0 = 2 * (c & 1);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      s[2 * k] = ((rw[k] >> sh) & 0xFFu) >= thr8 ? s[2 * k] * scale : 0.f;
-      s[2 * k + 1] = ((rw[k] >> (sh + 16)) & 0xFFu) >= thr8 ? s[2 * k + 1] * scale : 0.f;
-    }
+    for (int k = 0; k < 8; ++k) s[k] = ((rw[w0 + (k >> 2)] >> (8 * (k & 3))) & 0xFFu) >= thr8 ? s[k] * scale : 0.f;
   }
   y[(size_t)p * C8 + c] = make_uint4(pack_bf16x2(s[0], s[1]), pack_bf16x2(s[2], s[3]), pack_bf16x2(s[4], s[5]), pack_bf16x2(s[6], s[7]));
 }

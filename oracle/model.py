@@ -11,9 +11,8 @@ own forward in tests/test_oracle.py.
 MC-dropout spec: elementwise dropout with probability p on the output of
 every residual block (after the final ReLU) and on the pooled feature before fc.  Mask lane
 for NHWC offset e of an activation: one BYTE of Philox(c0=e//16, c1=global image, c2=t,
-c3=stream(DROPOUT, layer_id)) -- channel c = e % 16 of the chunk reads word (c >> 1) & 3,
-byte (c & 1) * 2 + (1 if c < 8 else 0) (the layout that lets the device compare two channels
-per 16-bit SIMD compare).  p is quantised to thr8 / 256 with thr8 = round(p * 256): a value is
+c3=stream(DROPOUT, layer_id)) -- channel c = e % 16 of the chunk reads byte c of the call's
+16 output bytes (x0's low byte first).  p is quantised to thr8 / 256 with thr8 = round(p * 256): a value is
 dropped iff its byte < thr8 and kept values are scaled by the exact inverse of the realised
 keep probability, fl32(256 / (256 - thr8)) -- i.e. torch dropout at p_q = thr8 / 256.
 T == 1 disables dropout (deterministic MSP path).
@@ -96,8 +95,8 @@ def dropout_scale(p):
 
 
 # channel c (0..15) of a 16-channel chunk -> (word, byte) of the chunk's Philox call
-_DROP_WORD = np.array([(c >> 1) & 3 for c in range(16)])
-_DROP_BYTE = np.array([(c & 1) * 2 + (1 if c < 8 else 0) for c in range(16)])
+_DROP_WORD = np.array([c >> 2 for c in range(16)])
+_DROP_BYTE = np.array([c & 3 for c in range(16)])
 
 
 def dropout_mask(n_images, first_image, t, layer_id, elems_per_image, p, seed):
