@@ -119,6 +119,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// ReLU on a packed bf16 pair (one HMNMX2 instead of two FMNMX before the pack; rounding to bf16 is monotone and keeps 0, so
+// max(round(x), 0) == round(max(x, 0)), also after a multiplication by a positive dropout scale)
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v) {
+  uint32_t d;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(v), "r"(0u));
+  return d;
+}
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 

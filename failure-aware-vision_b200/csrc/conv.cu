@@ -349,7 +349,10 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
       if (t.mt >= a.mtiles) break;
       const uint32_t trow = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t((acc_i * MT + u) * a.BN);
       if (!GATHER && MT == 1 && a.ksplit > 1) splitk_store_partials<WPQ>(a, t, trow, row, sub_w);
-      else if (!GATHER && a.stg_bytes) conv_epilogue_staged<WPQ>(a, &tmY, t, trow, row, sub_w, stg, seq, leader);
+      else if (!GATHER && a.stg_bytes) {
+        if (a.rep > 1) conv_epilogue_staged<WPQ, true>(a, &tmY, t, trow, row, sub_w, stg, seq, leader);
+        else conv_epilogue_staged<WPQ, false>(a, &tmY, t, trow, row, sub_w, stg, seq, leader);
+      }
       else conv_epilogue_subtile(a, t, trow, row, sub_w, WPQ);
       }   // sub-tiles
       // this warp has finished reading the accumulators: hand them back to the MMA issuer

@@ -214,7 +214,8 @@ __device__ __forceinline__ void conv_epilogue_subtile(const ConvArgs& a, const T
       for (int i = 0; i < 16; ++i)
         if (c0 + i < a.Cout) v[i] += __bfloat162float(a.res[res_off + c0 + i]);
     }
-    if (a.relu) {
+    const bool packed_relu = a.relu && !a.out_f32 && vec_io;     // ReLU after the pack (relu_bf16x2), same result
+    if (a.relu && !packed_relu) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
     }
@@ -222,6 +223,10 @@ __device__ __forceinline__ void conv_epilogue_subtile(const ConvArgs& a, const T
       uint32_t pk[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(v[2 * i] * a.drop_scale, v[2 * i + 1] * a.drop_scale);
+      if (a.relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = relu_bf16x2(pk[i]);
+      }
       const uint32_t e8 = uint32_t((size_t)hw * a.Cout + c0) >> 4;
       for (int rp = 0; rp < n_rep; ++rp) {
         const int p_out = a.rep > 1 ? q * a.rep + rp : q;
@@ -248,10 +253,16 @@ __device__ __forceinline__ void conv_epilogue_subtile(const ConvArgs& a, const T
         for (int i = 0; i < 16; ++i)
           if (c0 + i < a.Cout) yp[i] = v[i];
       } else if (vec_io) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        if (a.relu) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pk[i] = relu_bf16x2(pk[i]);
+        }
         uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + off);
-        yp[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-        if (c0 + 8 < a.Cout)
-          yp[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+        yp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        if (c0 + 8 < a.Cout) yp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       } else {
         __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + off;
 #pragma unroll
@@ -338,20 +349,29 @@ __device__ __forceinline__ void splitk_fixup(const ConvArgs& a, const Tile& t, i
 // per pixel instead of 16 bytes per lane at a Cout*2-byte stride (32 L1 wavefronts per store instruction).  The box is the
 // A-tile's pixel rectangle, so rows outside the image or beyond P are clipped by the tensor bounds.  Two slabs alternate:
 // the leader waits for the previous store to finish reading before the barrier that releases the next slab's writers.
-template <int WPQ>
+template <int WPQ, bool REP>   // REP: block 0 of an MC sweep writes a.rep masked replicas of every output row
 __device__ __forceinline__ void conv_epilogue_staged(const ConvArgs& a, const CUtensorMap* tmY, const Tile& t, uint32_t trow, int row,
                                                      int sub_w, uint8_t* stg, int& seq, bool leader) {
   constexpr int NCH = 4 / WPQ;                         // 16-column chunks of a 64-channel slab per warp
-  const int ohw = a.OH * a.OW, n_rep = a.rep > 1 ? a.rep : 1;
+  const int ohw = a.OH * a.OW, n_rep = REP ? a.rep : 1;
   int q, oh, ow;
   const bool valid = decode_row(a, t, row, q, oh, ow);
   const int hw = oh * a.OW + ow;
   const size_t res_off = ((size_t)q * ohw + hw) * a.Cout;
-  const int n_img = a.rep > 1 ? q : q / a.T;
-  const int tt0 = a.rep > 1 ? 0 : q - n_img * a.T;
+  const int n_img = REP ? q : q / a.T;
+  const int tt0 = REP ? 0 : q - n_img * a.T;
   const uint32_t stg_u32 = smem_u32(stg);
+  const bool masked = a.drop && valid;
+  // this row's two 16-byte slots of every chunk inside a slab (SWIZZLE_128B: slot index ^ (row & 7))
+  uint32_t slot[NCH][2];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int jj = sub_w + ch * WPQ;
+    slot[ch][0] = uint32_t(row * 128 + (((2 * jj) ^ (row & 7)) << 4));
+    slot[ch][1] = uint32_t(row * 128 + (((2 * jj + 1) ^ (row & 7)) << 4));
+  }
   for (int hf = 0; hf < a.BN / 64; ++hf) {
-    uint32_t pk[NCH][8];                               // finished values (bias, residual, ReLU, dropout scale) as bf16 pairs
+    uint32_t pk[NCH][8];                               // finished values (bias, residual, dropout scale, ReLU) as bf16 pairs
     uint4 rv[NCH][2];
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {               // residual loads of all chunks first: their latency overlaps the TMEM loads
@@ -383,32 +403,36 @@ __device__ __forceinline__ void conv_epilogue_staged(const ConvArgs& a, const CU
 #pragma unroll
         for (int i = 0; i < 8; ++i) { v[2 * i] += bf16_lo(rw[i]); v[2 * i + 1] += bf16_hi(rw[i]); }
       }
-      if (a.relu) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-      }
       if (a.drop) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] *= a.drop_scale;
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) pk[ch][i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+      if (a.relu) {                          // after the pack: one instruction per pair (relu_bf16x2)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[ch][i] = relu_bf16x2(pk[ch][i]);
+      }
+    }
+    const uint32_t e16 = uint32_t((size_t)hw * a.Cout + t.nt * a.BN + hf * 64 + sub_w * 16) >> 4;   // chunk ch: + ch * WPQ
+    if (!REP && masked) {                              // single pass: the masks go onto the values in place
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch)
+        dropout_and16(a, e16 + uint32_t(ch * WPQ), a.first_image + uint32_t(n_img), uint32_t(tt0), pk[ch], pk[ch], a.drop_stream);
     }
     for (int rp = 0; rp < n_rep; ++rp) {             // one slab (and one TMA store) per masked replica
-      uint8_t* rowp = stg + (seq & 1) * STG_SLAB_BYTES + row * 128;
+      uint8_t* slab = stg + (seq & 1) * STG_SLAB_BYTES;
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
-        const int jj = sub_w + ch * WPQ;
-        uint32_t o[8];
-        if (a.drop && valid) {
-          const uint32_t e8 = uint32_t((size_t)hw * a.Cout + t.nt * a.BN + hf * 64 + jj * 16) >> 4;
-          dropout_and16(a, e8, a.first_image + uint32_t(n_img), uint32_t(a.rep > 1 ? rp : tt0), pk[ch], o, a.drop_stream);
+        if (REP && masked) {
+          uint32_t o[8];
+          dropout_and16(a, e16 + uint32_t(ch * WPQ), a.first_image + uint32_t(n_img), uint32_t(rp), pk[ch], o, a.drop_stream);
+          *reinterpret_cast<uint4*>(slab + slot[ch][0]) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(slab + slot[ch][1]) = make_uint4(o[4], o[5], o[6], o[7]);
         } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = pk[ch][i];
+          *reinterpret_cast<uint4*>(slab + slot[ch][0]) = make_uint4(pk[ch][0], pk[ch][1], pk[ch][2], pk[ch][3]);
+          *reinterpret_cast<uint4*>(slab + slot[ch][1]) = make_uint4(pk[ch][4], pk[ch][5], pk[ch][6], pk[ch][7]);
         }
-        *reinterpret_cast<uint4*>(rowp + (((2 * jj) ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<uint4*>(rowp + (((2 * jj + 1) ^ (row & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
       }
       fence_proxy_async();                             // generic-proxy smem writes -> visible to the TMA store
       if (leader) bulk_wait_read_all();                // the store that last used the OTHER slab has drained it

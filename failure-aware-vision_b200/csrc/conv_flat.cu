@@ -253,10 +253,6 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           v[2 * i] = __uint_as_float(acc[2 * i]) + s_bias[cbase + 2 * i] + bf16_lo(rw);
           v[2 * i + 1] = __uint_as_float(acc[2 * i + 1]) + s_bias[cbase + 2 * i + 1] + bf16_hi(rw);
         }
-        if (a.relu) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-        }
         if (a.drop) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] *= a.drop_scale;
@@ -264,6 +260,10 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        if (a.relu) {                                        // after the pack: one instruction per pair (relu_bf16x2)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = relu_bf16x2(pk[i]);
+        }
         for (int rp = 0; rp < n_rep; ++rp) {
           const int p_out = a.rep > 1 ? q * a.rep + rp : q;
           uint32_t o[16];
