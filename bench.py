@@ -339,7 +339,7 @@ def main():
         if os.path.exists(tp):
             with open(tp) as fh:
                 tj = json.load(fh)
-                # bytes per image from the committed capture (taken at 2048 images per step; constant in the HBM-streaming
+                # bytes per image from the committed capture (taken at the step size named in the file; constant in the HBM-streaming
                 # regime) x the images of one step here
                 traffic = tj["dram_bytes_per_image"] * BLOCK if "dram_bytes_per_image" in tj else tj.get("dram_bytes_per_step")
         peak = peaks["bf16_tflops_sustained"]
