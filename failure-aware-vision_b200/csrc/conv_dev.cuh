@@ -43,6 +43,10 @@ struct ConvArgs {
   uint32_t drop_thr8;          // keep a channel iff its Philox byte >= drop_thr8 (= round(p * 256), common.cuh)
   uint32_t drop_add4, drop_hi4;   // operands of dropout_keep4 (common.cuh)
   PhiloxKeys drop_keys;        // round keys of (k0, k1)
+  // flattened 1x1 convolution (conv_launch): the launch sees ONE image of 1 x (P*OH*OW) pixels, so tiles are 128 consecutive
+  // pixels whatever the image size; the dropout counters still need (image, pixel in image) = divmod(pixel, flat_ohw)
+  int flat_ohw;                // 0 = not flattened
+  unsigned long long flat_m64; // ceil(2^64 / flat_ohw): q = umul64hi(n, m) is exact for every 32-bit n
   float drop_scale;
   uint32_t k0, k1, first_image, drop_stream;
   uint32_t drop_stream2;       // second mask stream (ConvCall::drop2_layer), used when drop2 != 0
@@ -160,6 +164,15 @@ __device__ __forceinline__ void dropout_and16(const ConvArgs& a, uint32_t e16, u
   }
 }
 
+// (image, pixel in image) of output row (q, hw) for the dropout counters: identity unless the launch is a flattened 1x1 conv
+__device__ __forceinline__ void dropout_pixel(const ConvArgs& a, int q, int hw, int& q_img, int& hw_img) {
+  q_img = q; hw_img = hw;
+  if (a.flat_ohw) {
+    q_img = int(__umul64hi((unsigned long long)uint32_t(hw), a.flat_m64));
+    hw_img = hw - q_img * a.flat_ohw;
+  }
+}
+
 // Epilogue of one 128-row sub-tile for one warp: TMEM (lanes of this warp's quarter, columns of accumulator `trow`) ->
 // bias + residual + ReLU + MC-dropout mask (+ T masked replicas) -> bf16 NHWC / fp32.  The warp handles the 16-column
 // chunks j = sub_w, sub_w + wpq, ...; residual loads and dropout masks are issued before the TMEM load they combine with.
@@ -170,8 +183,10 @@ __device__ __forceinline__ void conv_epilogue_subtile(const ConvArgs& a, const T
   const int hw = oh * a.OW + ow;
   const size_t res_off = ((size_t)q * ohw + hw) * a.Cout;
   const bool vec_io = (a.Cout & 7) == 0;
-  const int n_img = a.rep > 1 ? q : q / a.T;
-  const int tt0 = a.rep > 1 ? 0 : q - n_img * a.T;
+  int qd, hwd;                                  // row of the pass-image tensor and pixel inside it, as the mask counters see them
+  dropout_pixel(a, q, hw, qd, hwd);
+  const int n_img = a.rep > 1 ? qd : qd / a.T;
+  const int tt0 = a.rep > 1 ? 0 : qd - n_img * a.T;
   // residual of chunk j (two 16-byte vectors), prefetched one chunk ahead so its L2 latency overlaps the previous chunk
   auto load_res = [&](int j, uint4& r0, uint4& r1) {
     r0 = make_uint4(0, 0, 0, 0); r1 = r0;
@@ -227,7 +242,7 @@ __device__ __forceinline__ void conv_epilogue_subtile(const ConvArgs& a, const T
 #pragma unroll
         for (int i = 0; i < 8; ++i) pk[i] = relu_bf16x2(pk[i]);
       }
-      const uint32_t e8 = uint32_t((size_t)hw * a.Cout + c0) >> 4;
+      const uint32_t e8 = uint32_t((size_t)hwd * a.Cout + c0) >> 4;
       for (int rp = 0; rp < n_rep; ++rp) {
         const int p_out = a.rep > 1 ? q * a.rep + rp : q;
         uint32_t o[8];
@@ -358,8 +373,10 @@ __device__ __forceinline__ void conv_epilogue_staged(const ConvArgs& a, const CU
   const bool valid = decode_row(a, t, row, q, oh, ow);
   const int hw = oh * a.OW + ow;
   const size_t res_off = ((size_t)q * ohw + hw) * a.Cout;
-  const int n_img = REP ? q : q / a.T;
-  const int tt0 = REP ? 0 : q - n_img * a.T;
+  int qd, hwd;                                  // row of the pass-image tensor and pixel inside it, as the mask counters see them
+  dropout_pixel(a, q, hw, qd, hwd);
+  const int n_img = REP ? qd : qd / a.T;
+  const int tt0 = REP ? 0 : qd - n_img * a.T;
   const uint32_t stg_u32 = smem_u32(stg);
   const bool masked = a.drop && valid;
   // this row's two 16-byte slots of every chunk inside a slab (SWIZZLE_128B: slot index ^ (row & 7))
@@ -414,7 +431,7 @@ __device__ __forceinline__ void conv_epilogue_staged(const ConvArgs& a, const CU
         for (int i = 0; i < 8; ++i) pk[ch][i] = relu_bf16x2(pk[ch][i]);
       }
     }
-    const uint32_t e16 = uint32_t((size_t)hw * a.Cout + t.nt * a.BN + hf * 64 + sub_w * 16) >> 4;   // chunk ch: + ch * WPQ
+    const uint32_t e16 = uint32_t((size_t)hwd * a.Cout + t.nt * a.BN + hf * 64 + sub_w * 16) >> 4;   // chunk ch: + ch * WPQ
     if (!REP && masked) {                              // single pass: the masks go onto the values in place
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch)
