@@ -709,11 +709,15 @@ int conv_launch(Ctx* ctx, const ConvCall& c_in, cudaStream_t st) {
     a.fd_tw = a.fd_th = a.fd_twth = a.fd_perimg = a.fd_bw = make_fastdiv(1u);
   }
   {
+    // exactness of the multiply-high divisions (n * d < 2^32), per division: tile / ksplit and tile / ntiles see n <= total_tiles,
+    // m-tile / tiles_w and / tiles_h see n <= mtiles (a flattened 1x1 conv has tiles_w = mtiles in the tens of thousands)
     const unsigned long long nmax = (unsigned long long)a.total_tiles + 1, mmax = (unsigned long long)M + BM;
-    unsigned long long dmax = (unsigned long long)a.ntiles;
-    if ((unsigned long long)a.ksplit > dmax) dmax = a.ksplit;
-    if (mode == 0) { if ((unsigned long long)a.tiles_w > dmax) dmax = a.tiles_w; if ((unsigned long long)a.tiles_h > dmax) dmax = a.tiles_h; }
-    a.fastdiv = (nmax * dmax < (1ull << 32) && (mode == 0 || mmax * (unsigned long long)(a.OH * a.OW) < (1ull << 32))) ? 1 : 0;
+    const unsigned long long mtmax = (unsigned long long)mtiles + 2;
+    unsigned long long d1 = (unsigned long long)a.ntiles, d2 = 1;
+    if ((unsigned long long)a.ksplit > d1) d1 = a.ksplit;
+    if (mode == 0) d2 = (unsigned long long)(a.tiles_w > a.tiles_h ? a.tiles_w : a.tiles_h);
+    a.fastdiv = (nmax * d1 < (1ull << 32) && mtmax * d2 < (1ull << 32) &&
+                 (mode == 0 || mmax * (unsigned long long)(a.OH * a.OW) < (1ull << 32))) ? 1 : 0;
   }
   const int stage_bytes = MT * A_TILE_BYTES + a.BN * 128;
   const int ctas_per_sm = (mode == 0 && MT == 1) ? 2 : 1;

@@ -215,3 +215,25 @@ def test_cli_and_trust_helpers_without_gpu():
     codes = trust.status_codes([["VISION_OK", "VISION_BLANK"], ["VISION_CORRUPTED", "VISION_FROZEN"]])
     assert codes.dtype == np.int8 and codes.tolist() == [[0, 2], [3, 1]]
     assert trust.POLICY[3] == "VISION_BLOCKED" and trust.DECAY_RATES["VISION_BLANK"] == 0.60
+
+
+def test_dropout_four_byte_compare_is_exact_for_every_threshold():
+    """The device compares four Philox bytes at a time (csrc/common.cuh dropout_keep4: AND, ADD, one LOP3, then prmt.b32 sign
+    replication).  Restated in numpy: the sign bit of every result byte equals (byte >= thr8) for all 256 thresholds, and the
+    PRMT selectors 0x9988 / 0xBBAA turn the flags of bytes (0,1) / (2,3) into 0xFFFF-per-channel masks."""
+    rng = np.random.default_rng(0)
+    r = rng.integers(0, 2 ** 32, 50000, dtype=np.uint64).astype(np.uint32)
+    r[:256] = np.arange(256, dtype=np.uint32) * np.uint32(0x01010101)          # every byte value in every lane
+    for thr in range(256):
+        add4 = np.uint32((((0x80 - thr) if thr <= 128 else (0x100 - thr)) * 0x01010101) & 0xFFFFFFFF)
+        hi4 = np.uint32(0xFFFFFFFF if thr > 128 else 0)
+        t = ((r & np.uint32(0x7F7F7F7F)) + add4).astype(np.uint32)
+        keep4 = (t & r) | (~hi4 & (t | r))
+        flags = [((keep4 >> np.uint32(8 * b + 7)) & 1).astype(bool) for b in range(4)]
+        for b in range(4):
+            assert np.array_equal(flags[b], ((r >> np.uint32(8 * b)) & 0xFF) >= thr), (thr, b)
+        lo = np.where(flags[0], 0xFFFF, 0).astype(np.uint32) | (np.where(flags[1], 0xFFFF, 0).astype(np.uint32) << np.uint32(16))
+        # prmt.b32 with selector nibble 8|k = byte k's sign replicated: 0x9988 -> [s0, s0, s1, s1]
+        sign = [np.where(f, 0xFF, 0).astype(np.uint32) for f in flags]
+        prmt_lo = sign[0] | (sign[0] << np.uint32(8)) | (sign[1] << np.uint32(16)) | (sign[1] << np.uint32(24))
+        assert np.array_equal(prmt_lo, lo)
