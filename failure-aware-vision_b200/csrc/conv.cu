@@ -511,7 +511,7 @@ int conv_launch(Ctx* ctx, const ConvCall& c_in, cudaStream_t st) {
     if (L.k2pad) { c.w2 = c.w; c.h2 = 1; }
   }
   if (conv_flat_applicable(c)) return conv_flat_launch(ctx, c, st);
-  FAV_REQUIRE(c.a_mode != 4, "conv: a_mode 4 (flat-padded 3x3) needs 3x3/s1/p1, Cin = Cout = 64 and (H+1)(W+1) <= 256");
+  FAV_REQUIRE(c.a_mode != 4, "conv: a_mode 4 (flat-padded 3x3) needs 3x3/s1/p1, Cin = Cout = 64 and (H+1)(W+1) <= 256 or 3 (W+1) <= 255 (band mode)");
   ConvArgs a{};
   a.x = reinterpret_cast<const __nv_bfloat16*>(c.x); a.y = c.y; a.bias = L.bias;
   a.res = reinterpret_cast<const __nv_bfloat16*>(c.res);

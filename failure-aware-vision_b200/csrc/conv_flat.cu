@@ -10,6 +10,11 @@
 // UMMA descriptor whose start address is shifted by ((r-1)(W+1) + (s-1)) pixels.  The 9x64x64 weights (72 KB) are
 // loaded once per CTA and stay resident.  L2->SM traffic drops from 216 KB to ~20 KB per 128 output pixels.
 //
+// Band mode (images larger than a slab, e.g. ResNet-50 layer1 at 56x56): a slab is a band of bh output rows of ONE image plus
+// the row above and the row below -- one TMA box (64 ch, W+1, bh+2, 1) with origin (-1, y0-1); out-of-bounds rows / the
+// column at x = -1 arrive as zeros.  The MMA tile starts at the band's second padded row (slab row W+1), taps shift exactly as
+// above.  56x56: 228 padded pixels loaded per 112 outputs (29 KB instead of the generic kernel's 9 x 16 KB).
+//
 // Replaces (reference): nothing executable (see conv.cu header); oracle twin oracle/model.py.
 #include <cstdlib>
 #include <cstring>
@@ -38,6 +43,7 @@ struct FlatArgs {
   int P, H, W, Wp;             // images, image size, padded pitch W + 1
   int rows_img, G, slab_rows;  // padded pixels per image, images per slab, G * rows_img (<= 256)
   int n_slabs, n_tiles;        // slabs in the problem, 128-row tiles per slab (1 or 2)
+  int band, bh, bands, row0;   // band mode: output rows per band, bands per image, first slab row of the MMA tiles (= Wp)
   int relu, T, rep, drop;
   uint32_t drop_thr8, drop_add4, drop_hi4;   // round(p * 256); operands of dropout_keep4 (common.cuh)
   PhiloxKeys drop_keys;                // round keys of (k0, k1)
@@ -124,7 +130,12 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait_timed(slab_empty(s), ph ^ 1, w_empty, a.stats != nullptr);
         if (elect_one()) {
           mbar_arrive_expect_tx(slab_full(s), bytes);
-          tma_load_4d(slab0 + s * FL_SLAB_BYTES, &tmA, slab_full(s), 0, -1, -1, slab * a.G);
+          if (a.band) {
+            const int q = slab / a.bands, b = slab - q * a.bands;
+            tma_load_4d(slab0 + s * FL_SLAB_BYTES, &tmA, slab_full(s), 0, -1, b * a.bh - 1, q);
+          } else {
+            tma_load_4d(slab0 + s * FL_SLAB_BYTES, &tmA, slab_full(s), 0, -1, -1, slab * a.G);
+          }
         }
         __syncwarp();
         if (++s == FL_NSLAB) { s = 0; ph ^= 1; }
@@ -148,7 +159,7 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait_timed(tempty(ai), aph ^ 1, w_tempty, a.stats != nullptr);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + uint32_t(ai * 64);
-          const uint32_t a_tile = slab0 + s * FL_SLAB_BYTES + tile * (128 * 128);
+          const uint32_t a_tile = slab0 + s * FL_SLAB_BYTES + (a.row0 + tile * 128) * 128;
           if (elect_one()) {
             uint32_t accumulate = 0;
 #pragma unroll
@@ -197,10 +208,20 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // everything that does not depend on the accumulator happens BEFORE the wait: row decode, residual loads,
         // the first replica's dropout masks -- so their latency overlaps the MMAs of this tile
         const int pi = tile * 128 + row;
-        const int g = pi / a.rows_img, rem = pi - g * a.rows_img, ph_ = rem / a.Wp, pw_ = rem - ph_ * a.Wp;
-        const int q = slab * a.G + g;
-        const bool valid = pi < a.slab_rows && ph_ != 0 && pw_ != 0 && q < a.P;
-        const int hw = (ph_ - 1) * a.W + (pw_ - 1);
+        int q, hw;
+        bool valid;
+        if (a.band) {                                       // slab = (image, band of bh rows); tile row pi = padded pixel row0 + pi
+          q = slab / a.bands;
+          const int y0 = (slab - q * a.bands) * a.bh;
+          const int pb = a.row0 + pi, ph_ = pb / a.Wp, pw_ = pb - ph_ * a.Wp, y = y0 + ph_ - 1;
+          valid = ph_ >= 1 && ph_ <= a.bh && pw_ != 0 && y < a.H;
+          hw = y * a.W + (pw_ - 1);
+        } else {
+          const int g = pi / a.rows_img, rem = pi - g * a.rows_img, ph_ = rem / a.Wp, pw_ = rem - ph_ * a.Wp;
+          q = slab * a.G + g;
+          valid = pi < a.slab_rows && ph_ != 0 && pw_ != 0 && q < a.P;
+          hw = (ph_ - 1) * a.W + (pw_ - 1);
+        }
         uint4 rv[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) rv[i] = make_uint4(0, 0, 0, 0);
@@ -287,6 +308,14 @@ conv3x3_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, 64 * FL_NACC);
 }
 
+// band mode: output rows per band -- the band plus its two halo rows must leave a zero tail row in the 256-row slab buffer and
+// the band's padded pixels must fit one 128-row MMA tile
+static int flat_band_rows(int w) {
+  const int wp = w + 1;
+  const int by_slab = (FL_SLAB_ROWS - 1) / wp - 2, by_tile = 128 / wp;
+  return by_slab < by_tile ? by_slab : by_tile;
+}
+
 static int flat_mode_env() {
   static const int v = [] { const char* e = getenv("FAV_FLAT"); return e ? atoi(e) : 1; }();   // 0 disables, 3 = set the base-offset field
   return v;
@@ -294,10 +323,12 @@ static int flat_mode_env() {
 
 bool conv_flat_applicable(const ConvCall& c) {
   const ConvLayer& L = *c.L;
-  const bool shape_ok = L.r == 3 && L.s == 3 && L.stride == 1 && L.pad == 1 && L.cin == 64 && L.cout == 64 && L.k2pad == 0 &&
-                        !L.fold && !L.cin_store && !c.out_f32 && L.bn == 64 && (c.h + 1) * (c.w + 1) <= FL_SLAB_ROWS && c.w + 1 <= 256 &&
-                        c.h + 1 <= 256;
-  if (!shape_ok) return false;
+  const bool layer_ok = L.r == 3 && L.s == 3 && L.stride == 1 && L.pad == 1 && L.cin == 64 && L.cout == 64 && L.k2pad == 0 &&
+                        !L.fold && !L.cin_store && !c.out_f32 && L.bn == 64;
+  const bool whole_ok = (c.h + 1) * (c.w + 1) <= FL_SLAB_ROWS && c.w + 1 <= 256 && c.h + 1 <= 256;
+  static const int env_band = [] { const char* e = getenv("FAV_FLAT_BAND"); return e ? atoi(e) : 1; }();
+  const bool band_ok = !whole_ok && env_band && flat_band_rows(c.w) >= 1 && (long long)c.p * c.h < (1ll << 30);
+  if (!layer_ok || !(whole_ok || band_ok)) return false;
   if (c.a_mode == 4) return true;
   if (c.rep > 1) return false;      // the replica-writing epilogue dominates there and padding rows would idle half its lanes
   return c.a_mode < 0 && flat_mode_env() != 0;
@@ -310,14 +341,26 @@ int conv_flat_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   a.y = c.y; a.bias = L.bias; a.res = reinterpret_cast<const __nv_bfloat16*>(c.res);
   a.P = c.p; a.H = c.h; a.W = c.w; a.Wp = c.w + 1;
   a.rows_img = (c.h + 1) * (c.w + 1);
-  a.G = FL_SLAB_ROWS / a.rows_img;
-  // small problems: fewer images per slab so that every SM gets the same number of slabs (the epilogue dominates there)
-  if (a.G > 1 && c.p / a.G < 4 * ctx->num_sms) { int g = c.p / (4 * ctx->num_sms); a.G = g < 1 ? 1 : (g < a.G ? g : a.G); }
-  if (a.G > c.p) a.G = c.p;
-  if (a.G > 256) a.G = 256;
-  a.slab_rows = a.G * a.rows_img;
-  a.n_slabs = (c.p + a.G - 1) / a.G;
-  a.n_tiles = (a.slab_rows + 127) / 128;
+  a.band = a.rows_img > FL_SLAB_ROWS ? 1 : 0;
+  if (a.band) {
+    a.bh = flat_band_rows(c.w);
+    FAV_REQUIRE(a.bh >= 1, "conv: image too wide for the flat-padded 3x3 kernel (W = %d)", c.w);
+    a.bands = (c.h + a.bh - 1) / a.bh;
+    a.G = 1;
+    a.slab_rows = (a.bh + 2) * a.Wp;          // the TMA box; rows [slab_rows, 256) stay zero (halo right of the last halo row)
+    a.n_slabs = c.p * a.bands;
+    a.n_tiles = 1;
+    a.row0 = a.Wp;
+  } else {
+    a.G = FL_SLAB_ROWS / a.rows_img;
+    // small problems: fewer images per slab so that every SM gets the same number of slabs (the epilogue dominates there)
+    if (a.G > 1 && c.p / a.G < 4 * ctx->num_sms) { int g = c.p / (4 * ctx->num_sms); a.G = g < 1 ? 1 : (g < a.G ? g : a.G); }
+    if (a.G > c.p) a.G = c.p;
+    if (a.G > 256) a.G = 256;
+    a.slab_rows = a.G * a.rows_img;
+    a.n_slabs = (c.p + a.G - 1) / a.G;
+    a.n_tiles = (a.slab_rows + 127) / 128;
+  }
   a.relu = c.relu; a.T = c.T > 0 ? c.T : 1; a.rep = c.rep > 1 ? c.rep : 1; a.drop = c.drop;
   if (c.drop) {
     FAV_REQUIRE(c.p_drop >= 0.f && c.p_drop < 1.f, "conv: p_drop must be in [0,1)");
@@ -337,7 +380,7 @@ int conv_flat_launch(Ctx* ctx, const ConvCall& c, cudaStream_t st) {
   {
     const cuuint64_t dims[4] = {64, (cuuint64_t)c.w, (cuuint64_t)c.h, (cuuint64_t)c.p};
     const cuuint64_t strides[3] = {128, (cuuint64_t)c.w * 128, (cuuint64_t)c.h * c.w * 128};
-    const cuuint32_t box[4] = {64, (cuuint32_t)(c.w + 1), (cuuint32_t)(c.h + 1), (cuuint32_t)a.G};
+    const cuuint32_t box[4] = {64, (cuuint32_t)(c.w + 1), (cuuint32_t)(a.band ? a.bh + 2 : c.h + 1), (cuuint32_t)a.G};
     int rc = encode_map(&tmA, c.x, 4, dims, strides, box);
     if (rc) return rc;
   }

@@ -155,6 +155,10 @@ CONV_CASES = [
     (1, 15, 20, 512, 512, 3, 1, 1, 1, 1, (0, 1)),         # few tiles, long K (split-K when FAV_SPLITK=1)
     (1, 30, 40, 256, 512, 3, 2, 1, 1, 0, (0,)),
     (2, 15, 20, 256, 100, 1, 1, 0, 0, 1, (0,)),
+    (2, 56, 56, 64, 64, 3, 1, 1, 1, 1, (4,)),             # flat-padded kernel in band mode (image larger than a slab): bands of 2 rows
+    (3, 57, 56, 64, 64, 3, 1, 1, 1, 0, (4,)),             # ... odd height: the last band is half empty
+    (2, 30, 83, 64, 64, 3, 1, 1, 0, 1, (4,)),             # ... widest image that still fits: bands of 1 row
+    (5, 28, 28, 64, 64, 3, 1, 1, 1, 1, (4,)),             # ... bands of 4 rows
 ]
 
 
