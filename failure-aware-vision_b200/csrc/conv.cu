@@ -499,12 +499,13 @@ int conv_launch(Ctx* ctx, const ConvCall& c_in, cudaStream_t st) {
   FAV_REQUIRE(c.p > 0 && c.h > 0 && c.w > 0, "conv: bad shape p=%d h=%d w=%d", c.p, c.h, c.w);
   // 1x1 / stride 1 convolutions on images larger than one tile are pixel-local: present the whole batch as ONE image of
   // 1 x (P*H*W) pixels, so every tile is 128 consecutive pixels instead of a (bw x bh <= 128) rectangle that has to divide the
-  // image (56x56 -> 56x2 = 112 of 128 rows, 14x14 -> 14x9 + 14x5 = 77 %).  NHWC is contiguous, so x / y / residual addresses are
+  // image (56x56 -> 56x2 = 112 of 128 rows, 14x14 -> 14x9 + 14x5 = 77 %, 7x7 -> two images = 98 rows).  NHWC is contiguous, so x / y / residual addresses are
   // unchanged; only the dropout counters need the (image, pixel) split back (ConvArgs::flat_ohw).  Results are bit-identical.
   static const int env_flat1 = [] { const char* e = getenv("FAV_FLAT1X1"); return e ? atoi(e) : 1; }();
   int flat_ohw = 0;
   if (env_flat1 && L.r == 1 && L.s == 1 && L.stride == 1 && L.pad == 0 && !L.cin_store && !L.s2d && !L.fold && (L.cin % 64) == 0 &&
-      c.a_mode <= 0 && c.rep <= 1 && c.drop2_layer < 0 && c.h * c.w > BM && (long long)c.p * c.h * c.w < (1ll << 31) &&
+      c.a_mode <= 0 && c.rep <= 1 && c.drop2_layer < 0 && (c.h * c.w > BM || BM % (c.h * c.w) != 0) &&
+      (long long)c.p * c.h * c.w < (1ll << 31) &&
       (L.k2pad == 0 || (L.stride2 == 1 && c.h2 == c.h && c.w2 == c.w))) {
     flat_ohw = c.h * c.w;
     c.w = c.p * c.h * c.w; c.h = 1; c.p = 1;

@@ -194,7 +194,10 @@ static int pair_env() {
 // pair-tile width for this layer (0 = not applicable).  a: fully prepared ConvArgs of the generic TMA path (a_mode 0).
 // Both CTAs of a pair must walk the same k-blocks (the leader issues the MMAs for both), so tiles are whole images.
 int conv_pair_bn(const ConvLayer& L, const ConvArgs& a, int force) {
-  if (a.a_mode != 0 || a.stem_tma || L.bn != 128 || a.tiles_w != 1 || a.tiles_h != 1) return 0;
+  // (a flattened 1x1 conv of small images walks every k-block in every tile too: no taps to skip)
+  const bool whole_images = a.tiles_w == 1 && a.tiles_h == 1;
+  const bool flat_small = a.flat_ohw > 0 && a.flat_ohw <= BM && L.r == 1 && L.s == 1;
+  if (a.a_mode != 0 || a.stem_tma || L.bn != 128 || !(whole_images || flat_small)) return 0;
   const int env = pair_env();
   if (force == 0 && env == 0) return 0;
   if ((L.cout_pad % 256) == 0 && (force || env != 0)) return 256;

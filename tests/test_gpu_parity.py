@@ -159,6 +159,8 @@ CONV_CASES = [
     (3, 57, 56, 64, 64, 3, 1, 1, 1, 0, (4,)),             # ... odd height: the last band is half empty
     (2, 30, 83, 64, 64, 3, 1, 1, 0, 1, (4,)),             # ... widest image that still fits: bands of 1 row
     (5, 28, 28, 64, 64, 3, 1, 1, 1, 1, (4,)),             # ... bands of 4 rows
+    (11, 7, 7, 256, 512, 1, 1, 0, 1, 1, (0,)),            # flattened 1x1 on 7x7 images in the 2-SM kernel, odd number of pixel tiles
+    (3, 14, 14, 128, 256, 1, 1, 0, 0, 1, (0,)),           # flattened 1x1, generic kernel
 ]
 
 
