@@ -200,6 +200,11 @@ int conv_pair_bn(const ConvLayer& L, const ConvArgs& a, int force) {
   if (a.a_mode != 0 || a.stem_tma || L.bn != 128 || !(whole_images || flat_small)) return 0;
   const int env = pair_env();
   if (force == 0 && env == 0) return 0;
+  // 1x1 convs (no fused downsample branch, not a folded 3x3) with a residual, a dropout mask or fp32 logits to write are
+  // epilogue-bound: the generic kernel's staged TMA-store epilogue with the residual through the identity MMAs beats this
+  // kernel's direct epilogue (ResNet-50 layer4 at T = 30: 512 -> 2048 + residual + dropout 465 -> 322 us, fc 50 -> 38 us), while
+  // the plain 2048 -> 512 reduce conv is faster here (165 vs 193 us).  Decided from layer / sweep properties only.
+  if (force == 0 && L.r == 1 && L.s == 1 && L.k2pad == 0 && !L.fold && (a.res != nullptr || a.drop || a.out_f32)) return 0;
   if ((L.cout_pad % 256) == 0 && (force || env != 0)) return 256;
   if (L.cout_pad == 128 && L.tmap64_ok && (force || env > 0)) return 128;
   return 0;
