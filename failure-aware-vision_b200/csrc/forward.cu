@@ -30,32 +30,38 @@ void plan_destroy(Plan* p) {
 }
 
 // ------------------------------------------------------------------------------------------ small kernels
-// 3x3 / stride 2 / pad 1 max-pool over bf16 NHWC, 8 channels (16 B) per thread.
+// 3x3 / stride 2 / pad 1 max-pool over bf16 NHWC, 8 channels (16 B) per thread.  The maximum of bf16 values needs no
+// unpacking (max.bf16x2 on the packed pairs is exact); indices are 32-bit (the launcher checks the element count).
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
 __global__ void __launch_bounds__(256) k_maxpool3x3s2(const uint4* __restrict__ x, uint4* __restrict__ y, int P, int H,
                                                       int W, int C8, int OH, int OW) {
-  const long long total = (long long)P * OH * OW * C8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = int(i % C8);
-    long long r = i / C8;
-    const int ow = int(r % OW); r /= OW;
-    const int oh = int(r % OH);
-    const int p = int(r / OH);
-    float m[8];
+  const uint32_t total = uint32_t(P) * uint32_t(OH) * uint32_t(OW) * uint32_t(C8);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t r = i / uint32_t(C8);
+    const int c = int(i - r * uint32_t(C8));
+    const uint32_t r2 = r / uint32_t(OW);
+    const int ow = int(r - r2 * uint32_t(OW));
+    const int p = int(r2 / uint32_t(OH));
+    const int oh = int(r2 - uint32_t(p) * uint32_t(OH));
+    uint4 m = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);      // -inf in every bf16 lane
+    const uint4* img = x + (size_t)p * H * W * C8 + c;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
     for (int dy = 0; dy < 3; ++dy) {
       const int ih = oh * 2 - 1 + dy;
       if (ih < 0 || ih >= H) continue;
+#pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
         const int iw = ow * 2 - 1 + dx;
         if (iw < 0 || iw >= W) continue;
-        const uint4 v = __ldg(x + (((size_t)p * H + ih) * W + iw) * C8 + c);
-        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { m[2 * k] = fmaxf(m[2 * k], bf16_lo(w4[k])); m[2 * k + 1] = fmaxf(m[2 * k + 1], bf16_hi(w4[k])); }
+        const uint4 v = __ldg(img + (size_t)(ih * W + iw) * C8);
+        m.x = max_bf16x2(m.x, v.x); m.y = max_bf16x2(m.y, v.y); m.z = max_bf16x2(m.z, v.z); m.w = max_bf16x2(m.w, v.w);
       }
     }
-    y[i] = make_uint4(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]), pack_bf16x2(m[4], m[5]), pack_bf16x2(m[6], m[7]));
+    y[i] = m;
   }
 }
 
@@ -133,14 +139,14 @@ __global__ void __launch_bounds__(256) k_pool_dropout_wide(const uint4* __restri
 // image pixel (2Y + dy - pad, 2X + dx - pad), zero outside the image and for c = 3 (conv_stem_padded_dims)
 __global__ void __launch_bounds__(256) k_stem_s2d(const unsigned short* __restrict__ x, uint4* __restrict__ y, int n, int h, int w,
                                                   int hp, int wp, int pad) {
-  const long long total = (long long)n * hp * wp * 2;          // one thread per (pixel, dy): 16 bytes
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int dy = int(i & 1);
-    const long long pix = i >> 1;
-    const int X = int(pix % wp);
-    const long long row = pix / wp;
-    const int Y = int(row % hp);
-    const long long img = row / hp;
+  const uint32_t total = uint32_t(n) * uint32_t(hp) * uint32_t(wp) * 2u;      // one thread per (pixel, dy): 16 bytes; < 2^31 (launcher)
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int dy = int(i & 1u);
+    const uint32_t pix = i >> 1;                                // 32-bit divisions: the 64-bit ones cost more than the copy itself
+    const uint32_t row = pix / uint32_t(wp);
+    const int X = int(pix - row * uint32_t(wp));
+    const long long img = row / uint32_t(hp);
+    const int Y = int(row - uint32_t(img) * uint32_t(hp));
     const int yy = 2 * Y + dy - pad, x0 = 2 * X - pad;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (yy >= 0 && yy < h) {
@@ -448,6 +454,7 @@ extern "C" int fav_forward_mc(fav_handle h, const void* d_x, float* d_logits, in
   if (conv_stem_padded_dims(stem, pl.in_h, pl.in_w, &hp, &wp)) {
     const long long npix = (long long)n * hp * wp;
     FAV_REQUIRE((size_t)npix * 32 <= pl.buf_bytes, "workspace too small for the space-to-depth input");
+    FAV_REQUIRE(npix < (1ll << 30), "space-to-depth input: too many pixels in one call (%lld)", npix);
     k_stem_s2d<<<grid_for(npix * 2, 256, h->num_sms), 256, 0, st>>>(reinterpret_cast<const unsigned short*>(d_x),
                                                                     reinterpret_cast<uint4*>(DS), n, pl.in_h, pl.in_w, hp, wp, stem.pad);
     FAV_CUDA_OK(cudaGetLastError());
@@ -469,6 +476,7 @@ extern "C" int fav_forward_mc(fav_handle h, const void* d_x, float* d_logits, in
     const int oh = conv_out_dim(hh, 3, 2, 1), ow = conv_out_dim(ww, 3, 2, 1);
     FAV_REQUIRE((stem.cout & 7) == 0, "stem Cout must be a multiple of 8");
     const long long work = (long long)n * oh * ow * (stem.cout / 8);
+    FAV_REQUIRE(work < (1ll << 31), "max-pool: too many outputs in one call (%lld)", work);
     k_maxpool3x3s2<<<grid_for(work, 256, h->num_sms), 256, 0, st>>>(reinterpret_cast<const uint4*>(Y1), reinterpret_cast<uint4*>(X[0]),
                                                                     n, hh, ww, stem.cout / 8, oh, ow);
     h->launches++;
