@@ -98,8 +98,9 @@ int fav_load_weights(fav_handle h, const void* blob, size_t nbytes, int model_id
 /* max images per fav_forward_mc call for a given T (sizes the workspace; allocates). */
 int fav_reserve(fav_handle h, int max_images, int T);
 /* d_x bf16 [n,h,w,3] -> d_logits fp32 [n,T,C].  T MC-dropout passes in one batched launch
- * sequence; masks are generated in the conv epilogues from Philox(seed, first_image+i, t, layer).
- * T == 1 disables dropout. */
+ * sequence; masks are generated in the conv epilogues from Philox(seed, first_image+i, t, layer), one byte per
+ * activation: p_drop is quantised to round(256 p) / 256 and kept values are scaled by the exact inverse of the realised
+ * keep probability (oracle/model.py states the contract).  T == 1 disables dropout. */
 int fav_forward_mc(fav_handle h, const void* d_x, float* d_logits, int n, int T, float p_drop,
                    uint64_t seed, uint64_t first_image, void* stream);
 /* single convolution (unit-test / tooling entry): y = act(conv(x, w) + bias [+ res]).
