@@ -680,6 +680,7 @@ struct ElasticArgs {
   const uint8_t* src;
   OutArgs out;
   int n, h, w, radius;
+  int folded;                 // 1: taps holds the folded smoothing matrices [w][w] (transposed: [src x][dst x]) then [h][h] ([dst y][src y])
   float alpha, mag, c0, c1, sq;
   const float* taps;
   uint32_t k0, k1, first_image, stream, aux_stream;
@@ -747,10 +748,23 @@ __global__ void __launch_bounds__(256) k1_elastic_xpass(const ElasticArgs a) {
     const float* u0 = a.scratch + 3 * (size_t)total + (i - x);
     const float* u1 = a.scratch + 4 * (size_t)total + (i - x);
     float s0 = 0.f, s1 = 0.f;
-    for (int t = -a.radius; t <= a.radius; ++t) {
-      const int xx = reflect_sym(x + t, a.w);
-      const float k = __ldg(a.taps + t + a.radius);
-      s0 = fmaf(k, u0[xx], s0); s1 = fmaf(k, u1[xx], s1);
+    if (a.folded) {
+      // a Gaussian much longer than the row wraps around the reflected row many times (224-pixel rows, 1025 taps at severity 1):
+      // the host folds it into one weight per (destination, source) pixel, so the pass is a w x w mat-vec without index arithmetic
+      const float* mt = a.taps + x;
+      for (int xx = 0; xx < a.w; ++xx) {
+        const float k = __ldg(mt + (size_t)xx * a.w);
+        s0 = fmaf(k, u0[xx], s0); s1 = fmaf(k, u1[xx], s1);
+      }
+    } else {
+      int pos = (x - a.radius) % (2 * a.w);                       // position in the reflected period, advanced without a modulo per tap
+      if (pos < 0) pos += 2 * a.w;
+      for (int t = 0; t <= 2 * a.radius; ++t) {
+        const int xx = pos < a.w ? pos : 2 * a.w - 1 - pos;
+        const float k = __ldg(a.taps + t);
+        s0 = fmaf(k, u0[xx], s0); s1 = fmaf(k, u1[xx], s1);
+        if (++pos == 2 * a.w) pos = 0;
+      }
     }
     a.scratch[5 * (size_t)total + i] = s0;
     a.scratch[6 * (size_t)total + i] = s1;
@@ -765,10 +779,21 @@ __global__ void __launch_bounds__(256) k1_elastic_final(const ElasticArgs a) {
     const float* p0 = a.scratch + 5 * (size_t)total + (size_t)img * hw + x;
     const float* p1 = a.scratch + 6 * (size_t)total + (size_t)img * hw + x;
     float d0 = 0.f, d1 = 0.f;
-    for (int t = -a.radius; t <= a.radius; ++t) {
-      const int yy = reflect_sym(y + t, a.h);
-      const float k = __ldg(a.taps + t + a.radius);
-      d0 = fmaf(k, p0[(size_t)yy * a.w], d0); d1 = fmaf(k, p1[(size_t)yy * a.w], d1);
+    if (a.folded) {
+      const float* mh = a.taps + (size_t)a.w * a.w + (size_t)y * a.h;
+      for (int yy = 0; yy < a.h; ++yy) {
+        const float k = __ldg(mh + yy);
+        d0 = fmaf(k, p0[(size_t)yy * a.w], d0); d1 = fmaf(k, p1[(size_t)yy * a.w], d1);
+      }
+    } else {
+      int pos = (y - a.radius) % (2 * a.h);
+      if (pos < 0) pos += 2 * a.h;
+      for (int t = 0; t <= 2 * a.radius; ++t) {
+        const int yy = pos < a.h ? pos : 2 * a.h - 1 - pos;
+        const float k = __ldg(a.taps + t);
+        d0 = fmaf(k, p0[(size_t)yy * a.w], d0); d1 = fmaf(k, p1[(size_t)yy * a.w], d1);
+        if (++pos == 2 * a.h) pos = 0;
+      }
     }
     const float sx = float(x) + d0 * a.alpha, sy = float(y) + d1 * a.alpha;
     const float fx0 = floorf(sx), fy0 = floorf(sy), fx = sx - fx0, fy = sy - fy0;
@@ -873,8 +898,11 @@ __global__ void __launch_bounds__(256) k1_jpeg(const JpegArgs a) {
 
 // ---------------------------------------------------------------- glass_blur: blur -> sequential local swaps -> blur
 // One CTA per image, the whole image resident in shared memory as packed RGBX words.  Stage 1: exact fixed-point Gaussian
-// (bit-exact bytes).  Stage 2: the scan-order swap chain is inherently sequential -- thread 0 walks it while the other
-// threads pre-compute the Philox offsets chunk by chunk.  Stage 3: fp32 Gaussian + normalize.
+// (bit-exact bytes).  Stage 2: the scan-order swap chain.  A swap at (hh, ww) touches two pixels within rows hh-d .. hh+d-1
+// and columns ww-d .. ww+d-1, so swaps of different scan rows commute unless their columns are closer than 2d: the chain
+// runs as a WAVEFRONT -- lane r of warp 0 walks scan row r, 2d columns behind lane r-1 (every pair of swaps that shares
+// a pixel keeps its sequential order, so the result is bit-identical to the scalar loop of oracle/corruptions.py), while
+// all threads pre-compute the Philox offsets of a band of rows.  Stage 3: fp32 Gaussian + normalize.
 // table: int32 q16[2r+1], float k[2r+1]
 struct GlassArgs {
   const uint8_t* src;
@@ -884,11 +912,11 @@ struct GlassArgs {
   uint32_t k0, k1, first_image, stream;
   unsigned src_bgr;
 };
-constexpr int GLASS_CHUNK = 2048;
+constexpr int GLASS_CHUNK = 16384;      // swap offsets (one byte each) computed ahead, in whole scan rows
 __global__ void __launch_bounds__(256) k1_glass(const GlassArgs a) {
   extern __shared__ uint32_t g_img[];                       // h*w RGBX words, then GLASS_CHUNK packed offsets, then taps
   const int hw = a.h * a.w, nt = 2 * a.radius + 1;
-  short2* s_off = reinterpret_cast<short2*>(g_img + hw);
+  uint8_t* s_off = reinterpret_cast<uint8_t*>(g_img + hw);
   int* s_q = reinterpret_cast<int*>(s_off + GLASS_CHUNK);
   float* s_k = reinterpret_cast<float*>(s_q + nt);
   const int img = blockIdx.x;
@@ -918,26 +946,43 @@ __global__ void __launch_bounds__(256) k1_glass(const GlassArgs a) {
     g_img[i] = b[0] | (b[1] << 8) | (b[2] << 16);
   }
   __syncthreads();
-  // stage 2: swaps.  step j of iteration it visits (hh, ww) descending; offsets d in [-delta, delta-1]
+  // stage 2: swaps.  step j = R * sw + k visits scan row R (iteration R / sh, hh = h - delta - R % sh) at ww = w - delta - k;
+  // offsets d in [-delta, delta-1] from Philox(j)
   const int sh = a.h - 2 * a.delta, sw = a.w - 2 * a.delta;
-  const int per_iter = sh * sw, steps = a.iters * per_iter;
+  const int rows_total = a.iters * sh;
   const uint32_t gimg = a.first_image + uint32_t(img), m = uint32_t(2 * a.delta);
-  for (int base = 0; base < steps; base += GLASS_CHUNK) {
-    const int cnt = min(GLASS_CHUNK, steps - base);
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-      const uint4 r = philox4x32_10(uint32_t(base + i), gimg, 0u, a.stream, a.k0, a.k1);
-      s_off[i] = make_short2(short(int(r.y % m) - a.delta), short(int(r.x % m) - a.delta));     // (dy, dx)
+  int band = GLASS_CHUNK / sw;                                  // scan rows whose offsets fit the buffer
+  if (band > rows_total) band = rows_total;
+  // lag between consecutive rows: 2 delta columns keep conflicting swaps in order; a lane must also be done with its row
+  // before its next one (32 rows later) starts
+  const int lag = max(2 * a.delta, (sw + 31) / 32);
+  const int lane = threadIdx.x & 31;
+  for (int R0 = 0; R0 < rows_total; R0 += band) {
+    const int nb = min(band, rows_total - R0);
+    for (int i = threadIdx.x; i < nb * sw; i += blockDim.x) {
+      const uint4 r = philox4x32_10(uint32_t(R0 * sw + i), gimg, 0u, a.stream, a.k0, a.k1);
+      s_off[i] = uint8_t((r.y % m) | ((r.x % m) << 4));           // (dy + delta) | (dx + delta) << 4
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int i = 0; i < cnt; ++i) {
-        const int j = (base + i) % per_iter;
-        const int hh = a.h - a.delta - j / sw, ww = a.w - a.delta - j % sw;
-        const short2 d = s_off[i];
-        const int i0 = hh * a.w + ww, i1 = (hh + d.x) * a.w + (ww + d.y);
-        const uint32_t t0 = g_img[i0];
-        g_img[i0] = g_img[i1];
-        g_img[i1] = t0;
+    if (threadIdx.x < 32) {
+      int r_cur = lane, k = -lane * lag;                        // this lane's current band row and its column index at step s
+      int hh = a.h - a.delta - (R0 + r_cur) % sh;
+      const int steps = (nb - 1) * lag + sw;
+      for (int s = 0; s < steps; ++s) {
+        if (k >= sw) {                                          // row finished: on to the row 32 further (32 * lag >= sw: k <= 0 again)
+          r_cur += 32; k -= 32 * lag;
+          hh = a.h - a.delta - (R0 + r_cur) % sh;
+        }
+        if (k >= 0 && k < sw && r_cur < nb) {
+          const int ww = a.w - a.delta - k;
+          const uint32_t o = s_off[r_cur * sw + k];
+          const int i0 = hh * a.w + ww, i1 = (hh + int(o & 15u) - a.delta) * a.w + (ww + int(o >> 4) - a.delta);
+          const uint32_t t0 = g_img[i0];
+          g_img[i0] = g_img[i1];
+          g_img[i1] = t0;
+        }
+        ++k;
+        __syncwarp();
       }
     }
     __syncthreads();
@@ -1119,7 +1164,9 @@ extern "C" int fav_corrupt_normalize(fav_handle h, const uint8_t* d_src, void* d
                   "elastic_transform needs %zu scratch bytes", fav_corrupt_scratch_bytes(corruption, n, height, width));
       ElasticArgs e{};
       e.src = d_src; e.out = out; e.n = n; e.h = height; e.w = width; e.radius = iparams[0];
-      FAV_REQUIRE(e.radius >= 0 && table_bytes >= (size_t)(2 * e.radius + 1) * 4, "elastic_transform tap table too small");
+      e.folded = (n_iparams >= 2 && iparams[1] != 0) ? 1 : 0;
+      FAV_REQUIRE(e.radius >= 0 && table_bytes >= (e.folded ? ((size_t)width * width + (size_t)height * height) * 4 : (size_t)(2 * e.radius + 1) * 4),
+                  "elastic_transform table too small");
       e.alpha = fparams[0]; e.mag = fparams[1]; e.c0 = fparams[2]; e.c1 = fparams[3]; e.sq = fparams[4];
       e.taps = reinterpret_cast<const float*>(d_table);
       e.k0 = k0; e.k1 = k1; e.first_image = uint32_t(first_image);
@@ -1167,11 +1214,12 @@ extern "C" int fav_corrupt_normalize(fav_handle h, const uint8_t* d_src, void* d
       GlassArgs g{};
       g.src = d_src; g.out = out; g.n = n; g.h = height; g.w = width;
       g.delta = iparams[0]; g.iters = iparams[1]; g.radius = iparams[2];
-      FAV_REQUIRE(g.delta >= 1 && g.iters >= 1 && g.radius >= 0 && 2 * g.delta < min(height, width), "glass_blur: bad parameters");
+      FAV_REQUIRE(g.delta >= 1 && g.delta <= 7 && g.iters >= 1 && g.radius >= 0 && 2 * g.delta < min(height, width) &&
+                  width - 2 * g.delta <= GLASS_CHUNK, "glass_blur: bad parameters");
       FAV_REQUIRE(table_bytes >= (size_t)(2 * g.radius + 1) * 8, "glass_blur tap table too small");
       g.table = reinterpret_cast<const int*>(d_table);
       g.k0 = k0; g.k1 = k1; g.first_image = uint32_t(first_image); g.stream = a.stream; g.src_bgr = flags & FAV_SRC_BGR;
-      const size_t smem = (size_t)height * width * 4 + GLASS_CHUNK * 4 + (size_t)(2 * g.radius + 1) * 8;
+      const size_t smem = (size_t)height * width * 4 + GLASS_CHUNK + (size_t)(2 * g.radius + 1) * 8;
       FAV_REQUIRE(smem <= 226 * 1024, "glass_blur keeps the image in shared memory: %dx%d is too large", height, width);
       if (smem > 48 * 1024) FAV_CUDA_OK(cudaFuncSetAttribute(k1_glass, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
       k1_glass<<<n, 256, smem, st>>>(g); h->launches++; break;

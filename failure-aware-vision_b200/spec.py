@@ -282,6 +282,17 @@ FROST_TINT = (0.85, 0.92, 1.0)
 FROST_DECAY = 2.0
 
 
+def elastic_fold(k, r, n):
+    """M[d, s] = sum of the fp32 taps k[t] whose source pixel reflect_sym(d + t - r, n) is s (float64 sums)."""
+    t = np.arange(2 * r + 1)
+    m = np.zeros((n, n), dtype=np.float64)
+    for d in range(n):
+        src = np.mod(d + t - r, 2 * n)
+        src = np.where(src >= n, 2 * n - 1 - src, src)
+        np.add.at(m[d], src, k.astype(np.float64))
+    return m
+
+
 def glass_table(sigma):
     """radius, uint8 table = int32 fixed-point taps (sum 65536) followed by fp32 taps."""
     r = int(4.0 * float(sigma) + 0.5)
@@ -343,7 +354,12 @@ def kernel_params(cfg: CorruptionConfig, h, w, profile=None):
             xs = np.arange(-r, r + 1, dtype=np.float64)
             k = np.exp(-0.5 * (xs / sigma) ** 2)
             k = (k / k.sum()).astype(np.float32)
-        return [alpha, mag, float(h // 2), float(w // 2), float(min(h, w) // 3)], [r], k.view(np.uint8)
+        fp = [alpha, mag, float(h // 2), float(w // 2), float(min(h, w) // 3)]
+        if 2 * r + 1 > min(h, w) // 2:
+            # a kernel longer than half the row wraps around the reflected row (224 pixels, 1025 taps at severity 1): fold it
+            # into one weight per (destination, source) pixel -- [w][w] transposed ([src x][dst x]) then [h][h] ([dst y][src y])
+            return fp, [r, 1], np.concatenate([elastic_fold(k, r, w).T.ravel(), elastic_fold(k, r, h).ravel()]).astype(np.float32).view(np.uint8)
+        return fp, [r, 0], k.view(np.uint8)
     if n == "snow":
         loc, scale, zoom, thresh, mb_r, mb_s, blend = c
         geom, taps = _pack_taps([motion_taps(int(mb_r), float(mb_s), a - 135, h, w) for a in range(SNOW_ANGLES)])
