@@ -913,6 +913,9 @@ struct GlassArgs {
   unsigned src_bgr;
 };
 constexpr int GLASS_CHUNK = 16384;      // swap offsets (one byte each) computed ahead, in whole scan rows
+constexpr int GLASS_BAND = 16;          // output rows per thread in the separable blurs
+template <bool BANDED>   // BANDED: separable band-scheme blurs (large images); else one thread per pixel, direct 2-D sums (few registers:
+                         // small images run many CTAs per SM)
 __global__ void __launch_bounds__(256) k1_glass(const GlassArgs a) {
   extern __shared__ uint32_t g_img[];                       // h*w RGBX words, then GLASS_CHUNK packed offsets, then taps
   const int hw = a.h * a.w, nt = 2 * a.radius + 1;
@@ -923,27 +926,67 @@ __global__ void __launch_bounds__(256) k1_glass(const GlassArgs a) {
   const uint8_t* p = a.src + (size_t)img * hw * 3;
   for (int i = threadIdx.x; i < nt; i += blockDim.x) { s_q[i] = a.table[i]; s_k[i] = reinterpret_cast<const float*>(a.table)[nt + i]; }
   __syncthreads();
-  // stage 1: exact integer blur, (sum_y q[y] * ((sum_x q[x] * u8 + 128) >> 8) + 2^23) >> 24
-  for (int i = threadIdx.x; i < hw; i += blockDim.x) {
-    const int y = i / a.w, x = i - y * a.w;
-    unsigned acc[3] = {0, 0, 0};
-    for (int dy = -a.radius; dy <= a.radius; ++dy) {
-      const uint8_t* row = p + (size_t)min(max(y + dy, 0), a.h - 1) * a.w * 3;
-      unsigned h3[3] = {0, 0, 0};
-      for (int dx = -a.radius; dx <= a.radius; ++dx) {
-        const uint8_t* q = row + min(max(x + dx, 0), a.w - 1) * 3;
-        const unsigned wq = unsigned(s_q[dx + a.radius]);
-        h3[0] += wq * q[0]; h3[1] += wq * q[1]; h3[2] += wq * q[2];
+  // stage 1: exact integer blur, (sum_y q[y] * ((sum_x q[x] * u8 + 128) >> 8) + 2^23) >> 24.  Separable without a full
+  // intermediate image: a thread owns column x of a band of GLASS_BAND output rows, computes the x-pass of each source row the
+  // band needs ONCE and adds it into the (<= 2r+1) output rows it contributes to (accumulators in registers).
+  const int bands = (a.h + GLASS_BAND - 1) / GLASS_BAND;
+  if (BANDED) {
+    for (int item = threadIdx.x; item < bands * a.w; item += blockDim.x) {
+      const int bnd = item / a.w, x = item - bnd * a.w, y0 = bnd * GLASS_BAND;
+      unsigned acc[GLASS_BAND][3];
+#pragma unroll
+      for (int j = 0; j < GLASS_BAND; ++j) { acc[j][0] = 0; acc[j][1] = 0; acc[j][2] = 0; }
+      for (int yy = y0 - a.radius; yy < y0 + GLASS_BAND + a.radius; ++yy) {
+        const uint8_t* row = p + (size_t)min(max(yy, 0), a.h - 1) * a.w * 3;
+        unsigned h3[3] = {0, 0, 0};
+        for (int dx = -a.radius; dx <= a.radius; ++dx) {
+          const uint8_t* q = row + min(max(x + dx, 0), a.w - 1) * 3;
+          const unsigned wq = unsigned(s_q[dx + a.radius]);
+          h3[0] += wq * q[0]; h3[1] += wq * q[1]; h3[2] += wq * q[2];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) h3[c] = (h3[c] + 128u) >> 8;
+#pragma unroll
+        for (int j = 0; j < GLASS_BAND; ++j) {
+          const int t = yy - (y0 + j) + a.radius;
+          if (t >= 0 && t <= 2 * a.radius) {
+            const unsigned wy = unsigned(s_q[t]);
+            acc[j][0] += wy * h3[0]; acc[j][1] += wy * h3[1]; acc[j][2] += wy * h3[2];
+          }
+        }
       }
-      const unsigned wy = unsigned(s_q[dy + a.radius]);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) acc[c] += wy * ((h3[c] + 128u) >> 8);
+      for (int j = 0; j < GLASS_BAND; ++j) {
+        if (y0 + j >= a.h) continue;
+        unsigned bb[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) bb[c] = min((acc[j][c] + (1u << 23)) >> 24, 255u);
+        if (a.src_bgr) { const unsigned q = bb[0]; bb[0] = bb[2]; bb[2] = q; }
+        g_img[(y0 + j) * a.w + x] = bb[0] | (bb[1] << 8) | (bb[2] << 16);
+      }
     }
-    unsigned b[3];
+  } else {
+    for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+      const int y = i / a.w, x = i - y * a.w;
+      unsigned acc[3] = {0, 0, 0};
+      for (int dy = -a.radius; dy <= a.radius; ++dy) {
+        const uint8_t* row = p + (size_t)min(max(y + dy, 0), a.h - 1) * a.w * 3;
+        unsigned h3[3] = {0, 0, 0};
+        for (int dx = -a.radius; dx <= a.radius; ++dx) {
+          const uint8_t* q = row + min(max(x + dx, 0), a.w - 1) * 3;
+          const unsigned wq = unsigned(s_q[dx + a.radius]);
+          h3[0] += wq * q[0]; h3[1] += wq * q[1]; h3[2] += wq * q[2];
+        }
+        const unsigned wy = unsigned(s_q[dy + a.radius]);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) b[c] = min((acc[c] + (1u << 23)) >> 24, 255u);
-    if (a.src_bgr) { const unsigned q = b[0]; b[0] = b[2]; b[2] = q; }
-    g_img[i] = b[0] | (b[1] << 8) | (b[2] << 16);
+        for (int c = 0; c < 3; ++c) acc[c] += wy * ((h3[c] + 128u) >> 8);
+      }
+      unsigned bb[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) bb[c] = min((acc[c] + (1u << 23)) >> 24, 255u);
+      if (a.src_bgr) { const unsigned q = bb[0]; bb[0] = bb[2]; bb[2] = q; }
+      g_img[i] = bb[0] | (bb[1] << 8) | (bb[2] << 16);
+    }
   }
   __syncthreads();
   // stage 2: swaps.  step j = R * sw + k visits scan row R (iteration R / sh, hh = h - delta - R % sh) at ww = w - delta - k;
@@ -987,25 +1030,57 @@ __global__ void __launch_bounds__(256) k1_glass(const GlassArgs a) {
     }
     __syncthreads();
   }
-  // stage 3: fp32 Gaussian (x then y, accumulated in tap order like the oracle) -- done directly in 2-D from shared memory
-  for (int i = threadIdx.x; i < hw; i += blockDim.x) {
-    const int y = i / a.w, x = i - y * a.w;
-    float acc[3] = {0.f, 0.f, 0.f};
-    for (int dy = -a.radius; dy <= a.radius; ++dy) {
-      const uint32_t* row = g_img + min(max(y + dy, 0), a.h - 1) * a.w;
-      float h3[3] = {0.f, 0.f, 0.f};
-      for (int dx = -a.radius; dx <= a.radius; ++dx) {
-        const uint32_t v = row[min(max(x + dx, 0), a.w - 1)];
-        const float wk = s_k[dx + a.radius];
-        h3[0] = fmaf(wk, div255(float(v & 0xFF)), h3[0]);
-        h3[1] = fmaf(wk, div255(float((v >> 8) & 0xFF)), h3[1]);
-        h3[2] = fmaf(wk, div255(float((v >> 16) & 0xFF)), h3[2]);
-      }
-      const float wy = s_k[dy + a.radius];
+  // stage 3: fp32 Gaussian (x then y, accumulated in tap order like the oracle), same band scheme: the contributions to an
+  // output row arrive in ascending source-row order, i.e. exactly the tap order of the direct double loop
+  if (BANDED) {
+    for (int item = threadIdx.x; item < bands * a.w; item += blockDim.x) {
+      const int bnd = item / a.w, x = item - bnd * a.w, y0 = bnd * GLASS_BAND;
+      float acc[GLASS_BAND][3];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) acc[c] = fmaf(wy, h3[c], acc[c]);
+      for (int j = 0; j < GLASS_BAND; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; }
+      for (int yy = y0 - a.radius; yy < y0 + GLASS_BAND + a.radius; ++yy) {
+        const uint32_t* row = g_img + min(max(yy, 0), a.h - 1) * a.w;
+        float h3[3] = {0.f, 0.f, 0.f};
+        for (int dx = -a.radius; dx <= a.radius; ++dx) {
+          const uint32_t v = row[min(max(x + dx, 0), a.w - 1)];
+          const float wk = s_k[dx + a.radius];
+          h3[0] = fmaf(wk, div255(float(v & 0xFF)), h3[0]);
+          h3[1] = fmaf(wk, div255(float((v >> 8) & 0xFF)), h3[1]);
+          h3[2] = fmaf(wk, div255(float((v >> 16) & 0xFF)), h3[2]);
+        }
+#pragma unroll
+        for (int j = 0; j < GLASS_BAND; ++j) {
+          const int t = yy - (y0 + j) + a.radius;
+          if (t >= 0 && t <= 2 * a.radius) {
+            const float wy = s_k[t];
+            acc[j][0] = fmaf(wy, h3[0], acc[j][0]); acc[j][1] = fmaf(wy, h3[1], acc[j][1]); acc[j][2] = fmaf(wy, h3[2], acc[j][2]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < GLASS_BAND; ++j)
+        if (y0 + j < a.h) store_pixel(a.out, (size_t)img * hw + (size_t)(y0 + j) * a.w + x, acc[j][0], acc[j][1], acc[j][2]);
     }
-    store_pixel(a.out, (size_t)img * hw + i, acc[0], acc[1], acc[2]);
+  } else {
+    for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+      const int y = i / a.w, x = i - y * a.w;
+      float acc[3] = {0.f, 0.f, 0.f};
+      for (int dy = -a.radius; dy <= a.radius; ++dy) {
+        const uint32_t* row = g_img + min(max(y + dy, 0), a.h - 1) * a.w;
+        float h3[3] = {0.f, 0.f, 0.f};
+        for (int dx = -a.radius; dx <= a.radius; ++dx) {
+          const uint32_t v = row[min(max(x + dx, 0), a.w - 1)];
+          const float wk = s_k[dx + a.radius];
+          h3[0] = fmaf(wk, div255(float(v & 0xFF)), h3[0]);
+          h3[1] = fmaf(wk, div255(float((v >> 8) & 0xFF)), h3[1]);
+          h3[2] = fmaf(wk, div255(float((v >> 16) & 0xFF)), h3[2]);
+        }
+        const float wy = s_k[dy + a.radius];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[c] = fmaf(wy, h3[c], acc[c]);
+      }
+      store_pixel(a.out, (size_t)img * hw + i, acc[0], acc[1], acc[2]);
+    }
   }
 }
 
@@ -1221,8 +1296,15 @@ extern "C" int fav_corrupt_normalize(fav_handle h, const uint8_t* d_src, void* d
       g.k0 = k0; g.k1 = k1; g.first_image = uint32_t(first_image); g.stream = a.stream; g.src_bgr = flags & FAV_SRC_BGR;
       const size_t smem = (size_t)height * width * 4 + GLASS_CHUNK + (size_t)(2 * g.radius + 1) * 8;
       FAV_REQUIRE(smem <= 226 * 1024, "glass_blur keeps the image in shared memory: %dx%d is too large", height, width);
-      if (smem > 48 * 1024) FAV_CUDA_OK(cudaFuncSetAttribute(k1_glass, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-      k1_glass<<<n, 256, smem, st>>>(g); h->launches++; break;
+      // small images: too few (band, column) items to fill a CTA with the band scheme
+      if (height * width > 64 * 64) {
+        if (smem > 48 * 1024) FAV_CUDA_OK(cudaFuncSetAttribute(k1_glass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        k1_glass<true><<<n, 256, smem, st>>>(g);
+      } else {
+        if (smem > 48 * 1024) FAV_CUDA_OK(cudaFuncSetAttribute(k1_glass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        k1_glass<false><<<n, 256, smem, st>>>(g);
+      }
+      h->launches++; break;
     }
     case FAV_DEFOCUS_BLUR:
     case FAV_MOTION_BLUR: {
