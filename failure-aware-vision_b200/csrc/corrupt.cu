@@ -483,7 +483,9 @@ __device__ __forceinline__ int border_idx(int i, int n, int mode) {
 }
 
 __global__ void __launch_bounds__(256) k1_taps(const TapArgs a) {
-  extern __shared__ uint32_t s_tile[];
+  // the tile + halo is staged as one float4 (r, g, b, -) per pixel: the byte -> float conversion happens once per staged
+  // pixel instead of once per (tap, output pixel), and a tap costs one 16-byte shared load + three FMAs per output pixel
+  extern __shared__ float4 s_tile[];
   const int SW = TAP_TILE + a.dx_max - a.dx_min, SH = TAP_TILE + a.dy_max - a.dy_min;
   uint2* s_taps = reinterpret_cast<uint2*>(s_tile + SW * SH);
   const int img = blockIdx.x;
@@ -509,7 +511,7 @@ __global__ void __launch_bounds__(256) k1_taps(const TapArgs a) {
     const uint8_t* q = p + ((size_t)yy * a.w + xx) * 3;
     uint32_t c0 = q[0], c1 = q[1], c2 = q[2];
     if (a.src_bgr) { const uint32_t t = c0; c0 = c2; c2 = t; }
-    s_tile[i] = c0 | (c1 << 8) | (c2 << 16);
+    s_tile[i] = make_float4(float(c0), float(c1), float(c2), 0.f);
   }
   __syncthreads();
   const int lx = threadIdx.x & 31, ly0 = threadIdx.x >> 5;     // 8 rows of threads, 4 pixels each
@@ -521,14 +523,10 @@ __global__ void __launch_bounds__(256) k1_taps(const TapArgs a) {
     const float wgt = __uint_as_float(tp.y);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint32_t v = s_tile[(ly0 + 8 * j) * SW + lx + tp.x];
-      // byte -> float via the 2^23 mantissa trick (full-rate PRMT + FADD instead of I2F)
-      const float r = __uint_as_float(0x4B000000u | (v & 0xFF)) - 8388608.0f;
-      const float g = __uint_as_float(0x4B000000u | ((v >> 8) & 0xFF)) - 8388608.0f;
-      const float b = __uint_as_float(0x4B000000u | ((v >> 16) & 0xFF)) - 8388608.0f;
-      acc[j][0] = fmaf(wgt, r, acc[j][0]);
-      acc[j][1] = fmaf(wgt, g, acc[j][1]);
-      acc[j][2] = fmaf(wgt, b, acc[j][2]);
+      const float4 v = s_tile[(ly0 + 8 * j) * SW + lx + tp.x];
+      acc[j][0] = fmaf(wgt, v.x, acc[j][0]);
+      acc[j][1] = fmaf(wgt, v.y, acc[j][1]);
+      acc[j][2] = fmaf(wgt, v.z, acc[j][2]);
     }
   }
 #pragma unroll
@@ -1321,7 +1319,7 @@ extern "C" int fav_corrupt_normalize(fav_handle h, const uint8_t* d_src, void* d
       t.stream = stream_id(KIND_AUX, corruption, severity);
       t.tiles_x = (width + TAP_TILE - 1) / TAP_TILE; t.tiles_y = (height + TAP_TILE - 1) / TAP_TILE;
       t.src_bgr = flags & FAV_SRC_BGR;
-      const size_t smem = (size_t)(TAP_TILE + t.dx_max - t.dx_min) * (TAP_TILE + t.dy_max - t.dy_min) * 4 + (size_t)t.max_taps * 8;
+      const size_t smem = (size_t)(TAP_TILE + t.dx_max - t.dx_min) * (TAP_TILE + t.dy_max - t.dy_min) * 16 + (size_t)t.max_taps * 8;
       FAV_REQUIRE(smem <= 200 * 1024, "tap stencil halo too large (%zu B of shared memory)", smem);
       if (smem > 48 * 1024) FAV_CUDA_OK(cudaFuncSetAttribute(k1_taps, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
       k1_taps<<<dim3(n, t.tiles_x * t.tiles_y), 256, smem, st>>>(t); h->launches++; break;
