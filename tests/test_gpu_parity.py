@@ -84,7 +84,10 @@ def test_k1_corruption_cifar_shape(fav, clf18, name, sev):
 
 @pytest.mark.parametrize("name,sev", [("gaussian_noise", 5), ("shot_noise", 1), ("defocus_blur", 4), ("motion_blur", 5),
                                       ("zoom_blur", 2), ("fog", 3), ("contrast", 4), ("pixelate", 3), ("brightness", 2),
-                                      ("impulse_noise", 4), ("jpeg_compression", 2), ("frost", 5), ("glass_blur", 1), ("snow", 4), ("elastic_transform", 1), ("elastic_transform", 4)])
+                                      ("impulse_noise", 4), ("jpeg_compression", 2), ("frost", 5), ("glass_blur", 1), ("snow", 4), ("elastic_transform", 1), ("elastic_transform", 4),
+                                      # wavefront swap chain at delta = 2 x 3 iterations and delta = 4, banded blurs at radius 6;
+                                      # elastic taps that wrap around the reflected row (r = 54); the largest defocus disk
+                                      ("glass_blur", 3), ("glass_blur", 5), ("elastic_transform", 2), ("defocus_blur", 5)])
 def test_k1_corruption_imagenet_shape(fav, name, sev):
     clf = _clf_cache(fav, "resnet18", 1000, (224, 224))
     n, first, seed = 2, 77, 1

@@ -237,3 +237,31 @@ def test_dropout_four_byte_compare_is_exact_for_every_threshold():
         sign = [np.where(f, 0xFF, 0).astype(np.uint32) for f in flags]
         prmt_lo = sign[0] | (sign[0] << np.uint32(8)) | (sign[1] << np.uint32(16)) | (sign[1] << np.uint32(24))
         assert np.array_equal(prmt_lo, lo)
+
+
+def test_elastic_folded_matrices_reproduce_the_tap_order_smoothing():
+    """Host table of elastic_transform for long Gaussians (spec.elastic_fold): one weight per (destination, source) pixel.
+    Against the oracle's tap-by-tap fp32 accumulation the displacement differs by far less than a thousandth of a pixel."""
+    import fav
+    from fav import spec
+    from oracle import corruptions as K
+    for (h, w, sev) in ((224, 224, 1), (32, 32, 2)):
+        fp, ip, tab = spec.kernel_params(fav.CorruptionConfig("elastic_transform", sev), h, w)
+        assert ip[1] == 1
+        t = tab.view(np.float32)
+        mwt, mh = t[:w * w].reshape(w, w), t[w * w:].reshape(h, h)
+        assert np.allclose(mwt.sum(0), 1.0, atol=1e-5) and np.allclose(mh.sum(1), 1.0, atol=1e-5)      # a smoothing kernel
+        alpha, sigma, _ = K.elastic_params(h, w, K.CONSTANTS[K.profile_for(h, w)]["elastic_transform"][sev - 1])
+        r, k = K.elastic_gauss_taps(sigma)
+        assert r == ip[0]
+        u = (np.random.default_rng(0).random((h, w)).astype(np.float32) * 2 - 1)
+        p1 = np.zeros_like(u)
+        for tt in range(2 * r + 1):
+            p1 += k[tt] * u[:, K._reflect_sym(np.arange(w) + tt - r, w)]
+        d = np.zeros_like(u)
+        for tt in range(2 * r + 1):
+            d += k[tt] * p1[K._reflect_sym(np.arange(h) + tt - r, h)]
+        df = mh.astype(np.float64) @ (u.astype(np.float64) @ mwt.astype(np.float64))
+        assert np.abs(d - df).max() * alpha < 1e-4
+    # short kernels keep the tap list
+    assert spec.kernel_params(fav.CorruptionConfig("elastic_transform", 5), 224, 224)[1][1] == 0
