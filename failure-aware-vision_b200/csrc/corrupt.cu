@@ -741,6 +741,28 @@ __global__ void __launch_bounds__(256) k1_elastic_prep(const ElasticArgs a) {
 }
 __global__ void __launch_bounds__(256) k1_elastic_xpass(const ElasticArgs a) {
   const long long hw = (long long)a.h * a.w, total = a.n * hw;
+  if (a.folded && (a.w & 3) == 0) {
+    // folded matrices, four destination pixels per thread: one 16-byte load of weights and two broadcast loads of the source
+    // row feed eight FMAs (same per-output operation order as the scalar loop below)
+    const int w4 = a.w >> 2;
+    for (long long i4 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i4 < (total >> 2); i4 += (long long)gridDim.x * blockDim.x) {
+      const long long rowi = i4 / w4;                                  // image row index (img * h + y)
+      const int x = int(i4 - rowi * w4) << 2;
+      const float* u0 = a.scratch + 3 * (size_t)total + rowi * a.w;
+      const float* u1 = a.scratch + 4 * (size_t)total + rowi * a.w;
+      const float4* mt = reinterpret_cast<const float4*>(a.taps + x);
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int xx = 0; xx < a.w; ++xx) {
+        const float4 k = __ldg(mt + (size_t)xx * w4);
+        const float b0 = u0[xx], b1 = u1[xx];
+        s0[0] = fmaf(k.x, b0, s0[0]); s0[1] = fmaf(k.y, b0, s0[1]); s0[2] = fmaf(k.z, b0, s0[2]); s0[3] = fmaf(k.w, b0, s0[3]);
+        s1[0] = fmaf(k.x, b1, s1[0]); s1[1] = fmaf(k.y, b1, s1[1]); s1[2] = fmaf(k.z, b1, s1[2]); s1[3] = fmaf(k.w, b1, s1[3]);
+      }
+      *reinterpret_cast<float4*>(a.scratch + 5 * (size_t)total + rowi * a.w + x) = make_float4(s0[0], s0[1], s0[2], s0[3]);
+      *reinterpret_cast<float4*>(a.scratch + 6 * (size_t)total + rowi * a.w + x) = make_float4(s1[0], s1[1], s1[2], s1[3]);
+    }
+    return;
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int rem = int(i % hw), x = rem % a.w;
     const float* u0 = a.scratch + 3 * (size_t)total + (i - x);
@@ -770,6 +792,44 @@ __global__ void __launch_bounds__(256) k1_elastic_xpass(const ElasticArgs a) {
 }
 __global__ void __launch_bounds__(256) k1_elastic_final(const ElasticArgs a) {
   const long long hw = (long long)a.h * a.w, total = a.n * hw;
+  // displaced bilinear sample of the warped image at pixel (y, x) of image img with displacement (d0, d1) * alpha
+  auto sample_store = [&](int img, int y, int x, float d0, float d1) {
+    const float sx = float(x) + d0 * a.alpha, sy = float(y) + d1 * a.alpha;
+    const float fx0 = floorf(sx), fy0 = floorf(sy), fx = sx - fx0, fy = sy - fy0;
+    const int xa = reflect_sym(int(fx0), a.w), xb = reflect_sym(int(fx0) + 1, a.w);
+    const int ya = reflect_sym(int(fy0), a.h), yb = reflect_sym(int(fy0) + 1, a.h);
+    float o[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* im = a.scratch + (size_t)c * total + (size_t)img * hw;
+      const float top = im[ya * a.w + xa] * (1.0f - fx) + im[ya * a.w + xb] * fx;
+      const float bot = im[yb * a.w + xa] * (1.0f - fx) + im[yb * a.w + xb] * fx;
+      o[c] = top * (1.0f - fy) + bot * fy;
+    }
+    store_pixel(a.out, (size_t)img * hw + (size_t)y * a.w + x, o[0], o[1], o[2]);
+  };
+  if (a.folded && (a.w & 3) == 0) {
+    // folded y-pass, four neighbouring columns per thread: one broadcast weight and two 16-byte loads feed eight FMAs
+    const int w4 = a.w >> 2;
+    for (long long i4 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i4 < (total >> 2); i4 += (long long)gridDim.x * blockDim.x) {
+      const long long rowi = i4 / w4;
+      const int x = int(i4 - rowi * w4) << 2;
+      const int img = int(rowi / a.h), y = int(rowi - (long long)img * a.h);
+      const float4* p0 = reinterpret_cast<const float4*>(a.scratch + 5 * (size_t)total + (size_t)img * hw + x);
+      const float4* p1 = reinterpret_cast<const float4*>(a.scratch + 6 * (size_t)total + (size_t)img * hw + x);
+      const float* mh = a.taps + (size_t)a.w * a.w + (size_t)y * a.h;
+      float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int yy = 0; yy < a.h; ++yy) {
+        const float k = __ldg(mh + yy);
+        const float4 v0 = p0[(size_t)yy * w4], v1 = p1[(size_t)yy * w4];
+        d0[0] = fmaf(k, v0.x, d0[0]); d0[1] = fmaf(k, v0.y, d0[1]); d0[2] = fmaf(k, v0.z, d0[2]); d0[3] = fmaf(k, v0.w, d0[3]);
+        d1[0] = fmaf(k, v1.x, d1[0]); d1[1] = fmaf(k, v1.y, d1[1]); d1[2] = fmaf(k, v1.z, d1[2]); d1[3] = fmaf(k, v1.w, d1[3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sample_store(img, y, x + j, d0[j], d1[j]);
+    }
+    return;
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int img = int(i / hw);
     const int rem = int(i - img * hw);
@@ -793,19 +853,7 @@ __global__ void __launch_bounds__(256) k1_elastic_final(const ElasticArgs a) {
         if (++pos == 2 * a.h) pos = 0;
       }
     }
-    const float sx = float(x) + d0 * a.alpha, sy = float(y) + d1 * a.alpha;
-    const float fx0 = floorf(sx), fy0 = floorf(sy), fx = sx - fx0, fy = sy - fy0;
-    const int xa = reflect_sym(int(fx0), a.w), xb = reflect_sym(int(fx0) + 1, a.w);
-    const int ya = reflect_sym(int(fy0), a.h), yb = reflect_sym(int(fy0) + 1, a.h);
-    float o[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float* im = a.scratch + (size_t)c * total + (size_t)img * hw;
-      const float top = im[ya * a.w + xa] * (1.0f - fx) + im[ya * a.w + xb] * fx;
-      const float bot = im[yb * a.w + xa] * (1.0f - fx) + im[yb * a.w + xb] * fx;
-      o[c] = top * (1.0f - fy) + bot * fy;
-    }
-    store_pixel(a.out, (size_t)i, o[0], o[1], o[2]);
+    sample_store(img, y, x, d0, d1);
   }
 }
 

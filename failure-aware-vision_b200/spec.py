@@ -355,8 +355,8 @@ def kernel_params(cfg: CorruptionConfig, h, w, profile=None):
             k = np.exp(-0.5 * (xs / sigma) ** 2)
             k = (k / k.sum()).astype(np.float32)
         fp = [alpha, mag, float(h // 2), float(w // 2), float(min(h, w) // 3)]
-        if 2 * r + 1 > min(h, w) // 2:
-            # a kernel longer than half the row wraps around the reflected row (224 pixels, 1025 taps at severity 1): fold it
+        if 2 * r + 1 > min(h, w) // 4:
+            # a long kernel (224-pixel rows: 941 taps at severity 1, wrapping around the reflected row; 109 at severity 2): fold it
             # into one weight per (destination, source) pixel -- [w][w] transposed ([src x][dst x]) then [h][h] ([dst y][src y])
             return fp, [r, 1], np.concatenate([elastic_fold(k, r, w).T.ravel(), elastic_fold(k, r, h).ravel()]).astype(np.float32).view(np.uint8)
         return fp, [r, 0], k.view(np.uint8)
