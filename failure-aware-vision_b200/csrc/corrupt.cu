@@ -962,7 +962,7 @@ constexpr int GLASS_CHUNK = 16384;      // swap offsets (one byte each) computed
 constexpr int GLASS_BAND = 16;          // output rows per thread in the separable blurs
 template <bool BANDED>   // BANDED: separable band-scheme blurs (large images); else one thread per pixel, direct 2-D sums (few registers:
                          // small images run many CTAs per SM)
-__global__ void __launch_bounds__(256) k1_glass(const GlassArgs a) {
+__global__ void __launch_bounds__(BANDED ? 512 : 256) k1_glass(const GlassArgs a) {
   extern __shared__ uint32_t g_img[];                       // h*w RGBX words, then GLASS_CHUNK packed offsets, then taps
   const int hw = a.h * a.w, nt = 2 * a.radius + 1;
   uint8_t* s_off = reinterpret_cast<uint8_t*>(g_img + hw);
@@ -1345,7 +1345,7 @@ extern "C" int fav_corrupt_normalize(fav_handle h, const uint8_t* d_src, void* d
       // small images: too few (band, column) items to fill a CTA with the band scheme
       if (height * width > 64 * 64) {
         if (smem > 48 * 1024) FAV_CUDA_OK(cudaFuncSetAttribute(k1_glass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        k1_glass<true><<<n, 256, smem, st>>>(g);
+        k1_glass<true><<<n, 512, smem, st>>>(g);      // one CTA per SM there (the image fills shared memory): 16 warps for the blurs
       } else {
         if (smem > 48 * 1024) FAV_CUDA_OK(cudaFuncSetAttribute(k1_glass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         k1_glass<false><<<n, 256, smem, st>>>(g);
