@@ -265,3 +265,43 @@ def test_elastic_folded_matrices_reproduce_the_tap_order_smoothing():
         assert np.abs(d - df).max() * alpha < 1e-4
     # short kernels keep the tap list
     assert spec.kernel_params(fav.CorruptionConfig("elastic_transform", 5), 224, 224)[1][1] == 0
+
+
+def test_glass_swap_wavefront_schedule_equals_the_sequential_chain():
+    """k1_glass runs the scan-order swap chain of glass_blur as a row wavefront: lane r walks scan row r, `lag` columns behind
+    lane r-1, lag = max(2 delta, ceil(sw / 32)), bands of rows one after the other.  Simulated here step by step (all swaps of
+    a step applied 'simultaneously': none may share a pixel) against the plain sequential loop of oracle/corruptions.py."""
+    rng = np.random.default_rng(7)
+    for (h, w, delta, iters, band) in ((12, 14, 1, 2, 5), (16, 13, 2, 3, 100), (20, 40, 4, 1, 7), (9, 70, 1, 2, 3)):
+        sh, sw = h - 2 * delta, w - 2 * delta
+        rows_total = iters * sh
+        dy = rng.integers(-delta, delta, size=rows_total * sw)
+        dx = rng.integers(-delta, delta, size=rows_total * sw)
+        img0 = rng.permutation(h * w).reshape(h, w)
+        seq = img0.copy()
+        j = 0
+        for _ in range(iters):
+            for hh in range(h - delta, delta, -1):
+                for ww in range(w - delta, delta, -1):
+                    h2, w2 = hh + dy[j], ww + dx[j]
+                    j += 1
+                    seq[hh, ww], seq[h2, w2] = seq[h2, w2], seq[hh, ww]
+        wav = img0.copy()
+        lag = max(2 * delta, (sw + 31) // 32)
+        for r0 in range(0, rows_total, band):
+            nb = min(band, rows_total - r0)
+            for s in range((nb - 1) * lag + sw):
+                touched, swaps = set(), []
+                for r in range(nb):
+                    k = s - r * lag
+                    if 0 <= k < sw:
+                        R = r0 + r
+                        hh, ww = h - delta - R % sh, w - delta - k
+                        jj = R * sw + k
+                        a, b = (hh, ww), (hh + dy[jj], ww + dx[jj])
+                        assert a not in touched and b not in touched, "two swaps of one step share a pixel"
+                        touched.update((a, b))
+                        swaps.append((a, b))
+                for a, b in swaps:
+                    wav[a], wav[b] = wav[b], wav[a]
+        assert np.array_equal(seq, wav), (h, w, delta, iters, band)
