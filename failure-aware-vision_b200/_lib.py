@@ -21,10 +21,15 @@ SIGNATURES = {
     "fav_init": (c_int, [c_int, C.POINTER(c_void_p)]),
     "fav_reset": (c_int, [c_void_p]),
     "fav_destroy": (c_int, [c_void_p]),
-    "fav_corrupt_normalize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                      C.POINTER(c_float), c_int, C.POINTER(C.c_int32), c_int, c_void_p, c_size_t,
-                                      c_void_p, c_size_t, c_u64, c_u64, C.POINTER(c_float), C.POINTER(c_float),
-                                      c_uint, c_void_p]),
+    "fav_corrupt_normalize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_u64, c_u64,
+                                      C.POINTER(c_float), C.POINTER(c_float), c_uint, c_void_p]),
+    "fav_corrupt_normalize_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                         C.POINTER(c_float), c_int, C.POINTER(C.c_int32), c_int, c_void_p, c_size_t,
+                                         c_void_p, c_size_t, c_u64, c_u64, C.POINTER(c_float), C.POINTER(c_float),
+                                         c_uint, c_void_p]),
+    "fav_corrupt_params": (c_int, [c_int, c_int, c_int, c_int, c_uint, C.POINTER(c_float), C.POINTER(c_int),
+                                   C.POINTER(C.c_int32), C.POINTER(c_int), c_void_p, C.POINTER(c_size_t)]),
+    "fav_corruption_constants": (c_int, [c_int, c_int, c_int, C.POINTER(C.c_double), c_int]),
     "fav_corrupt_scratch_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "fav_load_weights": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int]),
     "fav_reserve": (c_int, [c_void_p, c_int, c_int]),
@@ -77,6 +82,36 @@ def check(rc, what):
 
 def f3(v):
     return _f3(*[float(x) for x in v])
+
+
+PROFILE_FLAGS = {None: 0, "auto": 0, "cifar": 0x10, "imagenet": 0x20}
+
+
+def corrupt_params(corruption_id, severity, height, width, profile=None):
+    """Host-only (no GPU): (fparams list, iparams list, table uint8 ndarray or None) of one cell, as the library builds
+    them (csrc/tables.cu) -- what fav_corrupt_normalize uses internally and fav_corrupt_normalize_ex takes as arguments."""
+    import numpy as np
+    lib = load()
+    nf, ni, nb = c_int(0), c_int(0), c_size_t(0)
+    flags = PROFILE_FLAGS[profile]
+    check(min(0, lib.fav_corrupt_params(corruption_id, severity, height, width, flags, None, C.byref(nf), None, C.byref(ni),
+                                        None, C.byref(nb))), "fav_corrupt_params")
+    fp, ip = (c_float * max(1, nf.value))(), (C.c_int32 * max(1, ni.value))()
+    tab = np.zeros(max(1, nb.value), dtype=np.uint8)
+    rc = lib.fav_corrupt_params(corruption_id, severity, height, width, flags, fp, C.byref(nf), ip, C.byref(ni),
+                                C.c_void_p(tab.ctypes.data), C.byref(nb))
+    if rc != 1:
+        check(rc if rc < 0 else -1, "fav_corrupt_params")
+    return list(fp)[:nf.value], list(ip)[:ni.value], (tab[:nb.value] if nb.value else None)
+
+
+def corruption_constants(profile, corruption_id, severity):
+    """Severity constants of one cell as the library holds them (profile 'cifar' / 'imagenet')."""
+    out = (C.c_double * 8)()
+    n = load().fav_corruption_constants({"cifar": 0, "imagenet": 1}[profile], corruption_id, severity, out, 8)
+    if n < 0:
+        check(n, "fav_corruption_constants")
+    return [out[i] for i in range(n)]
 
 
 class Handle:

@@ -21,8 +21,9 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    """The caller's current stream ON `device` (a handle's kernels must run on the handle's own device)."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 class VisionClassifier:
@@ -36,8 +37,7 @@ class VisionClassifier:
         if not torch.cuda.is_available():
             raise RuntimeError("VisionClassifier needs a CUDA device (sm_100a); there is no CPU fallback")
         self.model, self.num_classes, self.input_hw = model, int(num_classes), tuple(input_hw)
-        self.device = torch.device("cuda", device)
-        torch.cuda.set_device(self.device)
+        self.device = torch.device("cuda", device)          # the process-wide current device is left alone
         self.handle = _lib.Handle(device)
         self.lib = self.handle.lib
         self.profile = profile or spec.profile_for(*self.input_hw)
@@ -47,28 +47,13 @@ class VisionClassifier:
         buf = (C.c_char * len(blob)).from_buffer_copy(blob)
         _lib.check(self.lib.fav_load_weights(self.handle.h, buf, len(blob), weights.MODEL_IDS[model], self.num_classes,
                                              self.input_hw[0], self.input_hw[1]), "fav_load_weights")
-        self._tables = {}
-        self._scratch = None
 
     # ------------------------------------------------------------------ housekeeping
     def reset(self):
         self.handle.reset()
-        self._scratch = None
 
-    def _table(self, cfg):
-        key = (cfg.name, cfg.severity)
-        if key not in self._tables:
-            fp, ip, tab = spec.kernel_params(cfg, *self.input_hw, profile=self.profile)
-            dtab = torch.from_numpy(np.ascontiguousarray(tab)).to(self.device) if tab is not None else None
-            self._tables[key] = (fp, ip, dtab)
-        return self._tables[key]
-
-    def _scratch_for(self, nbytes):
-        if nbytes == 0:
-            return None
-        if self._scratch is None or self._scratch.numel() < nbytes:
-            self._scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-        return self._scratch
+    def _st(self):
+        return _stream(self.device)
 
     def _images(self, images_u8):
         if isinstance(images_u8, np.ndarray):
@@ -90,16 +75,11 @@ class VisionClassifier:
         n, h, w, _ = x.shape
         if out is None:
             out = torch.empty((n, h, w, 3), dtype=torch.float32 if out_f32 else torch.bfloat16, device=self.device)
-        fp, ip, dtab = self._table(cfg)
-        fa = (C.c_float * max(1, len(fp)))(*fp)
-        ia = (C.c_int32 * max(1, len(ip)))(*ip)
-        sb = int(self.lib.fav_corrupt_scratch_bytes(cfg.id, n, h, w))
-        scratch = self._scratch_for(sb)
-        flags = (1 if bgr else 0) | (2 if out_f32 else 0) | (0 if normalize else 4)
+        # every per-cell constant / table is derived inside the library (csrc/tables.cu) and cached in the handle
+        flags = (1 if bgr else 0) | (2 if out_f32 else 0) | (0 if normalize else 4) | _lib.PROFILE_FLAGS[self.profile]
         _lib.check(self.lib.fav_corrupt_normalize(
-            self.handle.h, _ptr(x), _ptr(out), n, h, w, cfg.id, cfg.severity, fa, len(fp), ia, len(ip),
-            _ptr(dtab), dtab.numel() if dtab is not None else 0, _ptr(scratch), sb, int(seed), int(first_image),
-            _lib.f3(self.mean), _lib.f3(self.std), flags, _stream()), "fav_corrupt_normalize")
+            self.handle.h, _ptr(x), _ptr(out), n, h, w, cfg.id, cfg.severity, int(seed), int(first_image),
+            _lib.f3(self.mean), _lib.f3(self.std), flags, self._st()), "fav_corrupt_normalize")
         return out
 
     # ------------------------------------------------------------------ K2
@@ -109,7 +89,7 @@ class VisionClassifier:
         if out is None:
             out = torch.empty((n, T, self.num_classes), dtype=torch.float32, device=self.device)
         _lib.check(self.lib.fav_forward_mc(self.handle.h, _ptr(x_bf16), _ptr(out), n, int(T), float(p), int(seed),
-                                           int(first_image), _stream()), "fav_forward_mc")
+                                           int(first_image), self._st()), "fav_forward_mc")
         return out
 
     # ------------------------------------------------------------------ K3
@@ -122,7 +102,7 @@ class VisionClassifier:
         pred = torch.empty(n, dtype=torch.int32, device=dev)
         flag = torch.empty(n, dtype=torch.uint8, device=dev) if labels is not None else None
         _lib.check(self.lib.fav_epilogue(self.handle.h, _ptr(logits), _ptr(labels), n, T, c, float(tau), _ptr(conf),
-                                         _ptr(ent), _ptr(mi), _ptr(pred), _ptr(flag), _stream()), "fav_epilogue")
+                                         _ptr(ent), _ptr(mi), _ptr(pred), _ptr(flag), self._st()), "fav_epilogue")
         out = {"confidence": conf, "entropy": ent, "mutual_information": mi, "pred": pred}
         if flag is not None:
             out["failure_flag"] = flag

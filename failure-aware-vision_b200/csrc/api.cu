@@ -15,7 +15,7 @@ void set_error(const char* fmt, ...) {
 void plan_destroy(Plan* p);   // forward.cu
 }  // namespace fav
 
-namespace fav { void comm_destroy(Ctx* ctx); }
+namespace fav { void comm_destroy(Ctx* ctx); void k1_cache_destroy(Ctx* ctx); }
 using namespace fav;
 
 extern "C" int fav_abi_version(void) { return FAV_ABI_VERSION; }
@@ -56,6 +56,7 @@ extern "C" int fav_destroy(fav_handle h) {
   if (h->stats_buf) cudaFree(h->stats_buf);
   if (h->splitk_buf) cudaFree(h->splitk_buf);
   comm_destroy(h);
+  k1_cache_destroy(h);
   delete h;
   return FAV_OK;
 }

@@ -29,6 +29,13 @@ void set_error(const char* fmt, ...);
     }                                   \
   } while (0)
 
+// entry points run on the handle's device whatever the caller's current device is
+#define FAV_DEVICE(h)                                                              \
+  do {                                                                             \
+    int _dev = -1;                                                                 \
+    if (cudaGetDevice(&_dev) != cudaSuccess || _dev != (h)->device) FAV_CUDA_OK(cudaSetDevice((h)->device)); \
+  } while (0)
+
 // ---------------------------------------------------------------- Philox4x32-10
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
 constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
@@ -155,6 +162,8 @@ struct Ctx {
   bool allow_splitk = false;      // fav_set_option(h, "splitk", 1)
   // multi-GPU: one process per GPU, communicator for the histogram all-reduce (comm.cu)
   void* nccl_comm = nullptr;
+  // K1 host tables (tables.cu): per-(corruption, severity, h, w, profile) constants + device tables, library-owned scratch
+  void* k1_cache = nullptr;
   // kernel attributes (max dynamic shared memory) are per device: set once per handle, not once per process
   bool attr_conv = false, attr_flat = false, attr_pair = false;
   int world = 1, rank = 0;

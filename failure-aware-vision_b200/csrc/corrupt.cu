@@ -9,6 +9,7 @@
 // (seed, global image index, element chunk) so nothing but the source and the result touches HBM.
 // Blur stencils stage the source tile plus halo in shared memory as packed RGBX words.
 #include "common.cuh"
+#include "tables.h"
 
 namespace fav {
 
@@ -578,34 +579,59 @@ __global__ void __launch_bounds__(256) k1_zoom(const ZoomArgs a) {
   }
 }
 
-// ---------------------------------------------------------------- pixelate (integer box means)
-// table: (h + w) x {int16 lo, int16 hi}
+// ---------------------------------------------------------------- pixelate (Pillow BOX down-sample, nearest up-sample)
+// PIL: x.resize((int(w c), int(h c)), BOX).resize((w, h), BOX).  Pillow resamples in two passes (horizontal first) with
+// 22-bit fixed-point coefficients and a uint8 intermediate (src/libImaging/Resample.c: precompute_coeffs,
+// normalize_coeffs_8bpc, ImagingResampleHorizontal_8bpc / Vertical_8bpc); both passes are restated exactly, so the bytes
+// equal PIL's.  BOX up-sampling has a single tap of weight 1: a gather.
+// table (int32): sw x {xmin, cnt, k[kh]} | sh x {ymin, cnt, k[kv]} | upx[w] | upy[h]
 struct PixArgs {
   const uint8_t* src;
   OutArgs out;
-  int n, h, w;
-  const uint32_t* table;
+  int n, h, w, sw, sh, kh, kv;
+  const int* table;
+  uint8_t* small;                // scratch: [n][sh][sw][3]
   unsigned src_bgr;
 };
-__global__ void __launch_bounds__(256) k1_pixelate(const PixArgs a) {
+__global__ void __launch_bounds__(256) k1_pixelate_down(const PixArgs a) {
+  const long long total = (long long)a.n * a.sh * a.sw;
+  const int* hx = a.table;
+  const int* vy = a.table + (size_t)a.sw * (2 + a.kh);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int img = int(i / (a.sh * a.sw));
+    const int rem = int(i - (long long)img * a.sh * a.sw);
+    const int j = rem / a.sw, ii = rem - j * a.sw;
+    const int* rx = hx + (size_t)ii * (2 + a.kh);
+    const int* ry = vy + (size_t)j * (2 + a.kv);
+    const int xmin = __ldg(rx), xcnt = __ldg(rx + 1), ymin = __ldg(ry), ycnt = __ldg(ry + 1);
+    const uint8_t* p = a.src + (size_t)img * a.h * a.w * 3;
+    int acc[3] = {1 << 21, 1 << 21, 1 << 21};
+    for (int r = 0; r < ycnt; ++r) {
+      const uint8_t* row = p + ((size_t)(ymin + r) * a.w + xmin) * 3;
+      int hs[3] = {1 << 21, 1 << 21, 1 << 21};
+      for (int t = 0; t < xcnt; ++t) {
+        const int k = __ldg(rx + 2 + t);
+        hs[0] += k * int(row[3 * t]); hs[1] += k * int(row[3 * t + 1]); hs[2] += k * int(row[3 * t + 2]);
+      }
+      const int kvv = __ldg(ry + 2 + r);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[c] += kvv * min(max(hs[c] >> 22, 0), 255);          // clip8 of the horizontal pass
+    }
+    uint8_t* o = a.small + (size_t)i * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = uint8_t(min(max(acc[c] >> 22, 0), 255));
+  }
+}
+__global__ void __launch_bounds__(256) k1_pixelate_up(const PixArgs a) {
   const long long total = (long long)a.n * a.h * a.w;
+  const int* upx = a.table + (size_t)a.sw * (2 + a.kh) + (size_t)a.sh * (2 + a.kv);
+  const int* upy = upx + a.w;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int img = int(i / (a.h * a.w));
     const int rem = int(i - (long long)img * a.h * a.w);
     const int y = rem / a.w, x = rem - y * a.w;
-    const uint32_t ry = __ldg(a.table + y), rx = __ldg(a.table + a.h + x);
-    const int y0 = int(ry & 0xFFFF), y1 = int(ry >> 16), x0 = int(rx & 0xFFFF), x1 = int(rx >> 16);
-    const uint8_t* p = a.src + (size_t)img * a.h * a.w * 3;
-    unsigned s[3] = {0, 0, 0};
-    for (int yy = y0; yy < y1; ++yy)
-      for (int xx = x0; xx < x1; ++xx) {
-        const uint8_t* q = p + ((size_t)yy * a.w + xx) * 3;
-        s[0] += q[0]; s[1] += q[1]; s[2] += q[2];
-      }
-    const unsigned cnt = unsigned((y1 - y0) * (x1 - x0));
-    float v[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) v[c] = u8f((2 * s[c] + cnt) / (2 * cnt));
+    const uint8_t* q = a.small + (((size_t)img * a.sh + __ldg(upy + y)) * a.sw + __ldg(upx + x)) * 3;
+    float v[3] = {u8f(q[0]), u8f(q[1]), u8f(q[2])};
     if (a.src_bgr) { const float t = v[0]; v[0] = v[2]; v[2] = t; }
     store_pixel(a.out, (size_t)i, v[0], v[1], v[2]);
   }
@@ -857,88 +883,175 @@ __global__ void __launch_bounds__(256) k1_elastic_final(const ElasticArgs a) {
   }
 }
 
-// ---------------------------------------------------------------- jpeg_compression: integer baseline-JPEG round trip
-// One CTA = one 16x16 MCU (4:2:0): JFIF colour transform in libjpeg's 16-bit fixed point, 2x2 chroma mean, six 8x8 blocks
-// through a 13-bit fixed-point orthonormal DCT, Annex-K quantisation, inverse, chroma replication.  All integer:
-// bit-exact against oracle/jpeg.py.  table: int32 lum[64], chr[64], T[64].
+// ---------------------------------------------------------------- jpeg_compression: libjpeg baseline round trip
+// What PIL's save(quality=c) + reload computes (entropy coding is lossless and omitted), stage by stage after libjpeg:
+// jccolor.c rgb_ycc_convert -> jcsample.c h2v2_downsample (bias 1,2,1,2) -> jfdctint.c jpeg_fdct_islow -> jcdctmgr.c
+// quantize (divisor 8 q) -> jidctint.c jpeg_idct_islow + range limit -> jdsample.c h2v2_fancy_upsample -> jdcolor.c
+// ycc_rgb_convert.  All integer: BYTE-EXACT against Pillow (tests) and against oracle/jpeg.py.
+// Two kernels: (1) one CTA of 64 threads per 16x16 MCU: colour transform, chroma subsampling, six 8x8 blocks through
+// FDCT / quantise / IDCT, reconstructed Y / Cb / Cr planes to scratch; (2) per pixel: fancy chroma upsampling (needs the
+// neighbouring MCUs' chroma), colour transform, normalize.  table: int32 lum[64], chr[64] (natural order).
 struct JpegArgs {
   const uint8_t* src;
   OutArgs out;
   int n, h, w, mcu_x, mcu_y;
   const int* table;
+  uint8_t* planes;               // scratch per image: Y [H16][W16] | Cb [H16/2][W16/2] | Cr [H16/2][W16/2]
   unsigned src_bgr;
 };
-__global__ void __launch_bounds__(256) k1_jpeg(const JpegArgs a) {
-  __shared__ int sQ[128], sT[64];
-  __shared__ int blk[6][64];        // Y00, Y01, Y10, Y11, Cb, Cr   (level-shifted samples, then coefficients, then samples)
-  __shared__ int tmp[6][64];
-  __shared__ int sc[2][256];        // full-resolution Cb, Cr before subsampling
+#define JDESCALE(x, n) (((x) + (1 << ((n) - 1))) >> (n))
+// jfdctint.c, one 1-D pass (CONST_BITS 13, PASS1_BITS 2); first: row pass (results scaled up by 4)
+__device__ __forceinline__ void jpeg_fdct_1d(int* d, bool first) {
+  const int tmp0 = d[0] + d[7], tmp7 = d[0] - d[7], tmp1 = d[1] + d[6], tmp6 = d[1] - d[6];
+  const int tmp2 = d[2] + d[5], tmp5 = d[2] - d[5], tmp3 = d[3] + d[4], tmp4 = d[3] - d[4];
+  const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+  const int sh = first ? 11 : 15;
+  d[0] = first ? (tmp10 + tmp11) << 2 : JDESCALE(tmp10 + tmp11, 2);
+  d[4] = first ? (tmp10 - tmp11) << 2 : JDESCALE(tmp10 - tmp11, 2);
+  int z1 = (tmp12 + tmp13) * 4433;
+  d[2] = (z1 + tmp13 * 6270 + (1 << (sh - 1))) >> sh;
+  d[6] = (z1 - tmp12 * 15137 + (1 << (sh - 1))) >> sh;
+  z1 = tmp4 + tmp7;
+  int z2 = tmp5 + tmp6, z3 = tmp4 + tmp6, z4 = tmp5 + tmp7;
+  const int z5 = (z3 + z4) * 9633;
+  const int t4 = tmp4 * 2446, t5 = tmp5 * 16819, t6 = tmp6 * 25172, t7 = tmp7 * 12299;
+  z1 *= -7373; z2 *= -20995; z3 = z3 * -16069 + z5; z4 = z4 * -3196 + z5;
+  d[7] = (t4 + z1 + z3 + (1 << (sh - 1))) >> sh;
+  d[5] = (t5 + z2 + z4 + (1 << (sh - 1))) >> sh;
+  d[3] = (t6 + z2 + z3 + (1 << (sh - 1))) >> sh;
+  d[1] = (t7 + z1 + z4 + (1 << (sh - 1))) >> sh;
+}
+// jidctint.c, one 1-D pass; first: column pass into the workspace (descale 11), else row pass (descale 18)
+__device__ __forceinline__ void jpeg_idct_1d(int* c, bool first) {
+  int z2 = c[2], z3 = c[6];
+  int z1 = (z2 + z3) * 4433;
+  int tmp2 = z1 - z3 * 15137, tmp3 = z1 + z2 * 6270;
+  int tmp0 = (c[0] + c[4]) << 13, tmp1 = (c[0] - c[4]) << 13;
+  const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+  tmp0 = c[7]; tmp1 = c[5]; tmp2 = c[3]; tmp3 = c[1];
+  z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2;
+  int z4 = tmp1 + tmp3;
+  const int z5 = (z3 + z4) * 9633;
+  tmp0 *= 2446; tmp1 *= 16819; tmp2 *= 25172; tmp3 *= 12299;
+  z1 *= -7373; z2 *= -20995; z3 = z3 * -16069 + z5; z4 = z4 * -3196 + z5;
+  tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
+  const int sh = first ? 11 : 18;
+  c[0] = (tmp10 + tmp3 + (1 << (sh - 1))) >> sh; c[7] = (tmp10 - tmp3 + (1 << (sh - 1))) >> sh;
+  c[1] = (tmp11 + tmp2 + (1 << (sh - 1))) >> sh; c[6] = (tmp11 - tmp2 + (1 << (sh - 1))) >> sh;
+  c[2] = (tmp12 + tmp1 + (1 << (sh - 1))) >> sh; c[5] = (tmp12 - tmp1 + (1 << (sh - 1))) >> sh;
+  c[3] = (tmp13 + tmp0 + (1 << (sh - 1))) >> sh; c[4] = (tmp13 - tmp0 + (1 << (sh - 1))) >> sh;
+}
+// jdmaster.c prepare_range_limit_table as the IDCT indexes it: (v & 1023) into a table centred on 128
+__device__ __forceinline__ uint32_t jpeg_range_limit(int v) {
+  v &= 1023;
+  return uint32_t(v < 128 ? v + 128 : (v < 512 ? 255 : (v < 896 ? 0 : v - 896)));
+}
+__device__ __forceinline__ void jpeg_ycc(const uint8_t* q, bool bgr, int& Y, int& Cb, int& Cr) {
+  int R = q[0], G = q[1], B = q[2];
+  if (bgr) { const int t = R; R = B; B = t; }
+  Y = (19595 * R + 38470 * G + 7471 * B + 32768) >> 16;
+  Cb = (-11059 * R - 21709 * G + 32768 * B + 8388608 + 32767) >> 16;
+  Cr = (32768 * R - 27439 * G - 5329 * B + 8388608 + 32767) >> 16;
+}
+__global__ void __launch_bounds__(64) k1_jpeg_codec(const JpegArgs a) {
+  __shared__ int blk[6][8][9];      // Y00, Y01, Y10, Y11, Cb, Cr; rows padded to 9 words
+  __shared__ int sQ[128];
   const int img = blockIdx.x, my = blockIdx.y / a.mcu_x, mx = blockIdx.y - my * a.mcu_x;
-  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
-  if (t < 128) sQ[t] = a.table[t];
-  if (t < 64) sT[t] = a.table[128 + t];
-  const int y = min(my * 16 + ty, a.h - 1), x = min(mx * 16 + tx, a.w - 1);       // edge replication
-  const uint8_t* p = a.src + (((size_t)img * a.h + y) * a.w + x) * 3;
-  int R = p[0], G = p[1], B = p[2];
-  if (a.src_bgr) { const int q = R; R = B; B = q; }
-  const int Y = (19595 * R + 38470 * G + 7471 * B + 32768) >> 16;
-  sc[0][t] = (-11059 * R - 21709 * G + 32768 * B + 8388608 + 32767) >> 16;
-  sc[1][t] = (32768 * R - 27439 * G - 5329 * B + 8388608 + 32767) >> 16;
-  blk[(ty >> 3) * 2 + (tx >> 3)][(ty & 7) * 8 + (tx & 7)] = Y - 128;
-  __syncthreads();
-  if (t < 128) {
-    const int c = t >> 6, i = t & 63, cy = i >> 3, cx = i & 7;
-    const int* q = sc[c] + (2 * cy) * 16 + 2 * cx;
-    blk[4 + c][i] = ((q[0] + q[1] + q[16] + q[17] + 2) >> 2) - 128;
-  }
-  __syncthreads();
-  // forward rows: t1[y][u] = (sum_x T[u][x] f[y][x] + 512) >> 10
-  for (int i = t; i < 384; i += 256) {
-    const int b = i >> 6, yy = (i >> 3) & 7, u = i & 7;
-    int acc = 0;
+  const int t = threadIdx.x;
+  sQ[t] = a.table[t]; sQ[t + 64] = a.table[t + 64];
+  const uint8_t* p = a.src + (size_t)img * a.h * a.w * 3;
+  const bool bgr = a.src_bgr != 0;
+  // luma: right / bottom edges replicate (jcsample.c expand_right_edge, jcprepct.c expand_bottom_edge)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc += sT[u * 8 + k] * blk[b][yy * 8 + k];
-    tmp[b][yy * 8 + u] = (acc + 512) >> 10;
+  for (int j = 0; j < 4; ++j) {
+    const int i = t + 64 * j, ty = i >> 4, tx = i & 15;
+    const int y = min(my * 16 + ty, a.h - 1), x = min(mx * 16 + tx, a.w - 1);
+    int Y, Cb, Cr;
+    jpeg_ycc(p + ((size_t)y * a.w + x) * 3, bgr, Y, Cb, Cr);
+    blk[(ty >> 3) * 2 + (tx >> 3)][ty & 7][tx & 7] = Y - 128;
+  }
+  // chroma: an odd last row is doubled before the 2x2 mean, then the DOWNSAMPLED rows replicate (jcprepct.c pre_process_data)
+  {
+    const int cy = t >> 3, cx = t & 7, ch = (a.h + 1) >> 1;
+    const int gr = min(my * 8 + cy, ch - 1), gc = mx * 8 + cx;
+    const int y0 = 2 * gr, y1 = min(2 * gr + 1, a.h - 1), x0 = min(2 * gc, a.w - 1), x1 = min(2 * gc + 1, a.w - 1);
+    int sb = 0, sr = 0, Y, Cb, Cr;
+    jpeg_ycc(p + ((size_t)y0 * a.w + x0) * 3, bgr, Y, Cb, Cr); sb += Cb; sr += Cr;
+    jpeg_ycc(p + ((size_t)y0 * a.w + x1) * 3, bgr, Y, Cb, Cr); sb += Cb; sr += Cr;
+    jpeg_ycc(p + ((size_t)y1 * a.w + x0) * 3, bgr, Y, Cb, Cr); sb += Cb; sr += Cr;
+    jpeg_ycc(p + ((size_t)y1 * a.w + x1) * 3, bgr, Y, Cb, Cr); sb += Cb; sr += Cr;
+    const int bias = 1 + (cx & 1);                       // h2v2_downsample: 1, 2, 1, 2, ... along the output row
+    blk[4][cy][cx] = ((sb + bias) >> 2) - 128;
+    blk[5][cy][cx] = ((sr + bias) >> 2) - 128;
   }
   __syncthreads();
-  // forward cols + quantise + dequantise: F[v][u] = (sum_y T[v][y] t1[y][u] + 4096) >> 13 (= 8 F_true)
-  for (int i = t; i < 384; i += 256) {
-    const int b = i >> 6, v = (i >> 3) & 7, u = i & 7;
-    int acc = 0;
+  const int b = t >> 3, r = t & 7;
+  int d[8];
+  if (t < 48) {                                          // FDCT pass 1: rows
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc += sT[v * 8 + k] * tmp[b][k * 8 + u];
-    const int F = (acc + 4096) >> 13;
-    const int Q = sQ[(b < 4 ? 0 : 64) + v * 8 + u], Q8 = Q * 8;
-    const int qa = (abs(F) + Q8 / 2) / Q8;
-    blk[b][v * 8 + u] = (F < 0 ? -qa : qa) * Q;
-  }
-  __syncthreads();
-  // inverse cols: t[y][u] = (sum_v T[v][y] F'[v][u] + 1024) >> 11
-  for (int i = t; i < 384; i += 256) {
-    const int b = i >> 6, yy = (i >> 3) & 7, u = i & 7;
-    int acc = 0;
+    for (int k = 0; k < 8; ++k) d[k] = blk[b][r][k];
+    jpeg_fdct_1d(d, true);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc += sT[k * 8 + yy] * blk[b][k * 8 + u];
-    tmp[b][yy * 8 + u] = (acc + 1024) >> 11;
+    for (int k = 0; k < 8; ++k) blk[b][r][k] = d[k];
   }
   __syncthreads();
-  // inverse rows: f'[y][x] = (sum_u T[u][x] t[y][u] + 16384) >> 15, + 128, clamp
-  for (int i = t; i < 384; i += 256) {
-    const int b = i >> 6, yy = (i >> 3) & 7, xx = i & 7;
-    int acc = 0;
+  if (t < 48) {                                          // FDCT pass 2 (columns) -> quantise / dequantise -> IDCT pass 1 (columns)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc += sT[k * 8 + xx] * tmp[b][yy * 8 + k];
-    blk[b][yy * 8 + xx] = min(max(((acc + 16384) >> 15) + 128, 0), 255);
+    for (int k = 0; k < 8; ++k) d[k] = blk[b][k][r];
+    jpeg_fdct_1d(d, false);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int Q = sQ[(b < 4 ? 0 : 64) + k * 8 + r], dv = Q * 8;
+      const int qa = (abs(d[k]) + (dv >> 1)) / dv;       // jcdctmgr.c quantize: round half away from zero
+      d[k] = (d[k] < 0 ? -qa : qa) * Q;
+    }
+    jpeg_idct_1d(d, true);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) blk[b][k][r] = d[k];
   }
   __syncthreads();
-  const int oy = my * 16 + ty, ox = mx * 16 + tx;
-  if (oy < a.h && ox < a.w) {
-    const int Yr = blk[(ty >> 3) * 2 + (tx >> 3)][(ty & 7) * 8 + (tx & 7)];
-    const int cb = blk[4][(ty >> 1) * 8 + (tx >> 1)] - 128, cr = blk[5][(ty >> 1) * 8 + (tx >> 1)] - 128;
-    const int r = min(max(Yr + ((91881 * cr + 32768) >> 16), 0), 255);
-    const int g = min(max(Yr + ((-22554 * cb - 46802 * cr + 32768) >> 16), 0), 255);
-    const int b = min(max(Yr + ((116130 * cb + 32768) >> 16), 0), 255);
-    store_pixel(a.out, ((size_t)img * a.h + oy) * a.w + ox, div255(float(r)), div255(float(g)), div255(float(b)));
+  if (t < 48) {                                          // IDCT pass 2: rows -> range limit -> 8 bytes to the planes
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[k] = blk[b][r][k];
+    jpeg_idct_1d(d, false);
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { lo |= jpeg_range_limit(d[k]) << (8 * k); hi |= jpeg_range_limit(d[k + 4]) << (8 * k); }
+    const int W16 = a.mcu_x * 16, H16 = a.mcu_y * 16;
+    uint8_t* base = a.planes + (size_t)img * ((size_t)H16 * W16 * 3 / 2);
+    uint8_t* o;
+    if (b < 4) o = base + (size_t)(my * 16 + (b >> 1) * 8 + r) * W16 + mx * 16 + (b & 1) * 8;
+    else o = base + (size_t)H16 * W16 + (size_t)(b - 4) * (H16 / 2) * (W16 / 2) + (size_t)(my * 8 + r) * (W16 / 2) + mx * 8;
+    *reinterpret_cast<uint2*>(o) = make_uint2(lo, hi);
+  }
+}
+__global__ void __launch_bounds__(256) k1_jpeg_finish(const JpegArgs a) {
+  const long long total = (long long)a.n * a.h * a.w;
+  const int W16 = a.mcu_x * 16, H16 = a.mcu_y * 16, CW = W16 / 2;
+  const int ch = (a.h + 1) >> 1, cw = (a.w + 1) >> 1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int img = int(i / (a.h * a.w));
+    const int rem = int(i - (long long)img * a.h * a.w);
+    const int y = rem / a.w, x = rem - y * a.w;
+    const uint8_t* pY = a.planes + (size_t)img * ((size_t)H16 * W16 * 3 / 2);
+    const uint8_t* pC = pY + (size_t)H16 * W16;
+    const int Y = pY[(size_t)y * W16 + x];
+    // h2v2_fancy_upsample: the nearer chroma row / column weighs 3, the farther 1; context beyond the image replicates
+    const int r = y >> 1, far = (y & 1) ? min(r + 1, ch - 1) : max(r - 1, 0);
+    const int c = x >> 1, nb = (x & 1) ? min(c + 1, cw - 1) : max(c - 1, 0);
+    const int bias = (x & 1) ? 7 : 8;
+    int cc[2];
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) {
+      const uint8_t* P = pC + (size_t)pl * (H16 / 2) * CW;
+      const int cs = 3 * int(P[r * CW + c]) + int(P[far * CW + c]);
+      const int cn = 3 * int(P[r * CW + nb]) + int(P[far * CW + nb]);
+      cc[pl] = ((3 * cs + cn + bias) >> 4) - 128;
+    }
+    const int R = min(max(Y + ((91881 * cc[1] + 32768) >> 16), 0), 255);
+    const int G = min(max(Y + ((-22554 * cc[0] - 46802 * cc[1] + 32768) >> 16), 0), 255);
+    const int B = min(max(Y + ((116130 * cc[0] + 32768) >> 16), 0), 255);
+    store_pixel(a.out, (size_t)i, div255(float(R)), div255(float(G)), div255(float(B)));
   }
 }
 
@@ -1169,6 +1282,9 @@ extern "C" size_t fav_corrupt_scratch_bytes(int corruption, int n, int height, i
   if (corruption == FAV_CONTRAST) return (size_t)n * 3 * sizeof(unsigned long long);
   if (corruption == FAV_SNOW) return 2 * (size_t)n * height * width * sizeof(float);
   if (corruption == FAV_ELASTIC) return 7 * (size_t)n * height * width * sizeof(float);
+  if (corruption == FAV_JPEG)      // reconstructed Y + 4:2:0 chroma planes, padded to whole 16x16 MCUs
+    return (size_t)n * ((size_t)((height + 15) / 16 * 16) * ((width + 15) / 16 * 16) * 3 / 2);
+  if (corruption == FAV_PIXELATE) return (size_t)n * height * width * 3;      // the down-sampled image (upper bound)
   if (corruption == FAV_FOG || corruption == FAV_FROST) {
     int m = 1;
     while (m < (height > width ? height : width)) m *= 2;
@@ -1178,13 +1294,15 @@ extern "C" size_t fav_corrupt_scratch_bytes(int corruption, int n, int height, i
   return 0;
 }
 
-extern "C" int fav_corrupt_normalize(fav_handle h, const uint8_t* d_src, void* d_dst, int n, int height,
-                                     int width, int corruption, int severity, const float* fparams,
-                                     int n_fparams, const int32_t* iparams, int n_iparams,
-                                     const void* d_table, size_t table_bytes, void* d_scratch,
-                                     size_t scratch_bytes, uint64_t seed, uint64_t first_image,
-                                     const float mean[3], const float std[3], unsigned flags, void* stream) {
+extern "C" int fav_corrupt_normalize_ex(fav_handle h, const uint8_t* d_src, void* d_dst, int n, int height,
+                                        int width, int corruption, int severity, const float* fparams,
+                                        int n_fparams, const int32_t* iparams, int n_iparams,
+                                        const void* d_table, size_t table_bytes, void* d_scratch,
+                                        size_t scratch_bytes, uint64_t seed, uint64_t first_image,
+                                        const float mean[3], const float std[3], unsigned flags, void* stream) {
   FAV_REQUIRE(h, "fav_corrupt_normalize: null handle");
+  FAV_DEVICE(h);
+  flags &= (FAV_SRC_BGR | FAV_OUT_F32 | FAV_NO_NORMALIZE);            // the profile bits only select host tables
   FAV_REQUIRE(n >= 0 && height > 0 && width > 0, "fav_corrupt_normalize: bad shape n=%d h=%d w=%d", n, height, width);
   FAV_REQUIRE(n == 0 || (d_src && d_dst), "fav_corrupt_normalize: null image pointer");
   FAV_REQUIRE(corruption == FAV_CLEAN || (severity >= 1 && severity <= 5), "severity must be 1..5 (got %d)", severity);
@@ -1322,13 +1440,18 @@ extern "C" int fav_corrupt_normalize(fav_handle h, const uint8_t* d_src, void* d
       k1_pointwise<PW_SNOW><<<grid, 256, 0, st>>>(a); h->launches += 3; break;
     }
     case FAV_JPEG: {
-      FAV_REQUIRE(d_table && table_bytes >= 192 * 4, "jpeg_compression needs the 192-int quantisation / DCT table");
+      FAV_REQUIRE(d_table && table_bytes >= 128 * 4, "jpeg_compression needs the 128-int quantisation table");
+      FAV_REQUIRE(d_scratch && scratch_bytes >= fav_corrupt_scratch_bytes(corruption, n, height, width),
+                  "jpeg_compression needs %zu scratch bytes", fav_corrupt_scratch_bytes(corruption, n, height, width));
       JpegArgs j{};
       j.src = d_src; j.out = out; j.n = n; j.h = height; j.w = width;
       j.mcu_x = (width + 15) / 16; j.mcu_y = (height + 15) / 16;
       FAV_REQUIRE(j.mcu_x * j.mcu_y <= 65535, "jpeg_compression: frame too large");
       j.table = reinterpret_cast<const int*>(d_table); j.src_bgr = flags & FAV_SRC_BGR;
-      k1_jpeg<<<dim3(n, j.mcu_x * j.mcu_y), 256, 0, st>>>(j); h->launches++; break;
+      j.planes = reinterpret_cast<uint8_t*>(d_scratch);
+      k1_jpeg_codec<<<dim3(n, j.mcu_x * j.mcu_y), 64, 0, st>>>(j);
+      k1_jpeg_finish<<<grid_for((long long)n * height * width, 256, h->num_sms, 16), 256, 0, st>>>(j);
+      h->launches += 2; break;
     }
     case FAV_GLASS_BLUR: {
       FAV_REQUIRE(need_i(3) && d_table, "glass_blur needs iparams = delta, iterations, radius and the tap table");
@@ -1381,11 +1504,18 @@ extern "C" int fav_corrupt_normalize(fav_handle h, const uint8_t* d_src, void* d
       k1_zoom<<<grid_for((long long)n * height * width, 256, h->num_sms, 16), 256, 0, st>>>(z); h->launches++; break;
     }
     case FAV_PIXELATE: {
-      FAV_REQUIRE(d_table && table_bytes >= (size_t)(height + width) * 4, "pixelate needs a range table");
+      FAV_REQUIRE(need_i(4) && d_table, "pixelate needs iparams = sw, sh, kh, kv and the coefficient table");
       PixArgs p{};
       p.src = d_src; p.out = out; p.n = n; p.h = height; p.w = width;
-      p.table = reinterpret_cast<const uint32_t*>(d_table); p.src_bgr = flags & FAV_SRC_BGR;
-      k1_pixelate<<<grid_for((long long)n * height * width, 256, h->num_sms, 16), 256, 0, st>>>(p); h->launches++; break;
+      p.sw = iparams[0]; p.sh = iparams[1]; p.kh = iparams[2]; p.kv = iparams[3];
+      FAV_REQUIRE(p.sw >= 1 && p.sw <= width && p.sh >= 1 && p.sh <= height && p.kh >= 1 && p.kv >= 1, "pixelate: bad geometry");
+      FAV_REQUIRE(table_bytes >= ((size_t)p.sw * (2 + p.kh) + (size_t)p.sh * (2 + p.kv) + height + width) * 4, "pixelate table too small");
+      FAV_REQUIRE(d_scratch && scratch_bytes >= (size_t)n * p.sh * p.sw * 3, "pixelate needs %zu scratch bytes", (size_t)n * p.sh * p.sw * 3);
+      p.table = reinterpret_cast<const int*>(d_table); p.src_bgr = flags & FAV_SRC_BGR;
+      p.small = reinterpret_cast<uint8_t*>(d_scratch);
+      k1_pixelate_down<<<grid_for((long long)n * p.sh * p.sw, 256, h->num_sms, 16), 256, 0, st>>>(p);
+      k1_pixelate_up<<<grid_for((long long)n * height * width, 256, h->num_sms, 16), 256, 0, st>>>(p);
+      h->launches += 2; break;
     }
     default:
       set_error("corruption id %d is not implemented on the device yet", corruption);
@@ -1393,6 +1523,30 @@ extern "C" int fav_corrupt_normalize(fav_handle h, const uint8_t* d_src, void* d
   }
   FAV_CUDA_OK(cudaGetLastError());
   return FAV_OK;
+}
+
+// The SURVEY.md 8(b) signature: everything per-cell is derived inside the library (tables.cu) and cached in the handle.
+extern "C" int fav_corrupt_normalize(fav_handle h, const uint8_t* d_src, void* d_dst, int n, int height, int width,
+                                     int corruption, int severity, uint64_t seed, uint64_t first_image,
+                                     const float mean[3], const float std[3], unsigned flags, void* stream) {
+  FAV_REQUIRE(h, "fav_corrupt_normalize: null handle");
+  FAV_REQUIRE(height > 0 && width > 0, "fav_corrupt_normalize: bad shape h=%d w=%d", height, width);
+  FAV_REQUIRE(corruption >= FAV_CLEAN && corruption <= FAV_JPEG, "unknown corruption id %d", corruption);
+  FAV_REQUIRE(corruption == FAV_CLEAN || (severity >= 1 && severity <= 5), "severity must be 1..5 (got %d)", severity);
+  FAV_DEVICE(h);
+  if (corruption == FAV_CLEAN)
+    return fav_corrupt_normalize_ex(h, d_src, d_dst, n, height, width, corruption, severity, nullptr, 0, nullptr, 0, nullptr, 0,
+                                    nullptr, 0, seed, first_image, mean, std, flags, stream);
+  const K1Entry* e = nullptr;
+  int rc = k1_lookup(h, corruption, severity, height, width, profile_of(flags, height, width),
+                     reinterpret_cast<cudaStream_t>(stream), &e);
+  if (rc != FAV_OK) return rc;
+  const size_t sb = fav_corrupt_scratch_bytes(corruption, n, height, width);
+  void* scratch = nullptr;
+  if (sb) { rc = k1_scratch(h, sb, &scratch); if (rc != FAV_OK) return rc; }
+  return fav_corrupt_normalize_ex(h, d_src, d_dst, n, height, width, corruption, severity, e->p.fp.data(), int(e->p.fp.size()),
+                                  e->p.ip.data(), int(e->p.ip.size()), e->d_table, e->p.table.size(), scratch, sb, seed,
+                                  first_image, mean, std, flags, stream);
 }
 
 extern "C" int fav_synth_images(fav_handle h, uint8_t* d_dst, int n, int height, int width, uint64_t seed,

@@ -140,7 +140,7 @@ class UncertaintyGate:
             side.wait_stream(cur)
         with torch.cuda.stream(side):
             _lib.check(self.lib.fav_frame_stats(self.handle.h, _ptr(self._frame), _ptr(self._gray), h, w,
-                                                1 if first else 0, _ptr(self._stats), _stream()), "fav_frame_stats")
+                                                1 if first else 0, _ptr(self._stats), _stream(self.device)), "fav_frame_stats")
             self._stats_host.copy_(self._stats, non_blocking=True)
         if self.clf is not None:
             u = self.clf.uncertainty(self._frame, None, T=self.T, p=self.p_drop, seed=0, first_image=first_image, bgr=True)
@@ -180,10 +180,10 @@ class UncertaintyGate:
                 self._capture()
             if self._graph is not None:
                 self._graph.replay()
-                torch.cuda.current_stream().synchronize()
+                torch.cuda.current_stream(self.device).synchronize()
         if self._graph is None or first or self._frame_count <= 2:
             self._enqueue_frame(first, self._frame_count)
-            torch.cuda.current_stream().synchronize()
+            torch.cuda.current_stream(self.device).synchronize()
         packed_host, unc = self._packed_host, None
         fin = self._fin.finish(self._stats_host.numpy(), h * w)
         signal_score, vision_status = fin["signal_score"], fin["vision_status"]

@@ -120,14 +120,14 @@ class MetricsAccumulator:
         _lib.check(self.clf.lib.fav_epilogue_accumulate(
             self.clf.handle.h, _ptr(logits), _ptr(labels), n, T, c, float(tau), self.n_bins, self.n_buckets,
             C.c_void_p(self.arena[cell].data_ptr()), _ptr(o.get("confidence")), _ptr(o.get("entropy")),
-            _ptr(o.get("mutual_information")), _ptr(o.get("pred")), _ptr(o.get("failure_flag")), _stream()),
+            _ptr(o.get("mutual_information")), _ptr(o.get("pred")), _ptr(o.get("failure_flag")), _stream(self.clf.device)),
             "fav_epilogue_accumulate")
 
     def add_scores(self, cell, conf, ent, mi, pred, labels, tau):
         _lib.check(self.clf.lib.fav_accumulate(
             self.clf.handle.h, _ptr(conf), _ptr(ent), _ptr(mi), _ptr(pred), _ptr(labels), conf.numel(),
             self.clf.num_classes, float(tau), self.n_bins, self.n_buckets, C.c_void_p(self.arena[cell].data_ptr()),
-            _stream()), "fav_accumulate")
+            _stream(self.clf.device)), "fav_accumulate")
 
     def allreduce(self):
         """The path's only exchange: integer sum of the arena over the ranks.  On GPUs this is the library's own
@@ -142,7 +142,7 @@ class MetricsAccumulator:
             return
         self.init_comm()
         handle = self.clf.handle
-        _lib.check(self.clf.lib.fav_allreduce(handle.h, _ptr(self.arena), self.arena.numel(), _stream()), "fav_allreduce")
+        _lib.check(self.clf.lib.fav_allreduce(handle.h, _ptr(self.arena), self.arena.numel(), _stream(self.clf.device)), "fav_allreduce")
 
     def init_comm(self):
         """Create the library's NCCL communicator (collective; ~0.5 s once per process): rank 0's unique id travels
@@ -163,7 +163,7 @@ class MetricsAccumulator:
         _lib.check(self.clf.lib.fav_comm_init(handle.h, C.c_char_p(raw), dist.get_rank(), dist.get_world_size()), "fav_comm_init")
         handle.comm_ready = True
         warm = torch.zeros(8, dtype=torch.int64, device=self.arena.device)          # first collective sets up the channels
-        _lib.check(self.clf.lib.fav_allreduce(handle.h, _ptr(warm), warm.numel(), _stream()), "fav_allreduce")
+        _lib.check(self.clf.lib.fav_allreduce(handle.h, _ptr(warm), warm.numel(), _stream(self.clf.device)), "fav_allreduce")
         torch.cuda.current_stream(self.arena.device).synchronize()
 
     def results(self):

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FAV_ABI_VERSION 1
+#define FAV_ABI_VERSION 2
 
 #define FAV_OK 0
 #define FAV_E_ARG (-1)      /* bad argument */
@@ -68,24 +68,45 @@ int fav_reset(fav_handle h);
 int fav_destroy(fav_handle h);
 
 /* ---- K1: corrupt + normalize ---------------------------------------------------------------
- * replaces: vision_simulator.py:25-36 (noise / brightness knobs) and the display-only JS
- * effects (frontend/js/app.js:789-799); the reference has no server-side generator.
+ * replaces: vision_simulator.py:25-36 (set_mode / set_noise / set_brightness knobs; here the 15 x 5
+ * grid of Hendrycks & Dietterich) and the display-only JS effects (frontend/js/app.js:789-799,
+ * 834-851); the reference has no server-side generator.
  *
  * d_src  uint8 [n,h,w,3]; d_dst bf16 (or fp32 with FAV_OUT_F32) [n,h,w,3], RGB order.
- * fparams / iparams: per-corruption constants chosen by the host from the severity table
- *   (failure-aware-vision_b200/spec.py); d_table: optional device table (Poisson inverse-CDF,
- *   stencil taps, resampling ranges); d_scratch: device scratch for two-pass corruptions
- *   (contrast: 3 uint64 per image; fog: plasma map), may be NULL otherwise.
+ * Self-sufficient (the signature of SURVEY.md 8b): the library derives every per-corruption constant
+ * and table (Poisson inverse-CDF thresholds, stencil taps, resampling ranges, libjpeg quantisation
+ * tables, Pillow BOX coefficients, elastic smoothing matrices) from (corruption, severity, h, w,
+ * profile) on the host, caches it in the handle and owns the device scratch of the multi-pass
+ * corruptions.  The first call for a new (corruption, severity, h, w) builds and uploads its table
+ * (host work + a synchronous copy); every later call only enqueues kernels on `stream`.
+ * Profile: CIFAR-10-C constants for frames up to 64 px, ImageNet-C above, or forced by flags.
  * All randomness is Philox4x32-10 keyed by (seed, first_image + image index, position):
  *   results do not depend on batch size or GPU count. */
+#define FAV_PROFILE_CIFAR 0x10u
+#define FAV_PROFILE_IMAGENET 0x20u
 int fav_corrupt_normalize(fav_handle h, const uint8_t* d_src, void* d_dst, int n, int height,
-                          int width, int corruption, int severity, const float* fparams,
-                          int n_fparams, const int32_t* iparams, int n_iparams,
-                          const void* d_table, size_t table_bytes, void* d_scratch,
-                          size_t scratch_bytes, uint64_t seed, uint64_t first_image,
-                          const float mean[3], const float std[3], unsigned flags, void* stream);
-/* bytes of d_scratch fav_corrupt_normalize needs for (corruption, n, h, w). */
+                          int width, int corruption, int severity, uint64_t seed,
+                          uint64_t first_image, const float mean[3], const float std[3],
+                          unsigned flags, void* stream);
+/* Table-taking form (tests / tooling): the caller supplies the constants (fparams / iparams), the
+ * device table and the device scratch; fav_corrupt_params produces them on the host. */
+int fav_corrupt_normalize_ex(fav_handle h, const uint8_t* d_src, void* d_dst, int n, int height,
+                             int width, int corruption, int severity, const float* fparams,
+                             int n_fparams, const int32_t* iparams, int n_iparams,
+                             const void* d_table, size_t table_bytes, void* d_scratch,
+                             size_t scratch_bytes, uint64_t seed, uint64_t first_image,
+                             const float mean[3], const float std[3], unsigned flags, void* stream);
+/* bytes of d_scratch fav_corrupt_normalize_ex needs for (corruption, n, h, w). */
 size_t fav_corrupt_scratch_bytes(int corruption, int n, int height, int width);
+/* Host only (no device needed): the constants and the table image of one cell.  In: capacities in
+ * *n_fparams, *n_iparams, *table_bytes; out: the sizes.  Returns 1 when the buffers were filled, 0 when
+ * only the sizes were reported (call again with room), negative on error.  flags: FAV_PROFILE_*. */
+int fav_corrupt_params(int corruption, int severity, int height, int width, unsigned flags,
+                       float* fparams, int* n_fparams, int32_t* iparams, int* n_iparams, void* table,
+                       size_t* table_bytes);
+/* Host only: the severity constants of (profile 0 CIFAR-10-C / 1 ImageNet-C, corruption, severity)
+ * -> out[0..count); returns count or a negative error. */
+int fav_corruption_constants(int profile, int corruption, int severity, double* out, int cap);
 
 /* ---- K2: classifier forward ---------------------------------------------------------------
  * replaces: nothing in the reference ("image classification", README.md:19; torchvision named in

@@ -362,44 +362,72 @@ def fog(x_u8, severity, seed=0, first_image=0, profile=None):
     return np.clip(out, 0, 1).astype(np.float32)
 
 
-def pixelate_geometry(size, c):
-    """BOX down-sample to int(size*c) then nearest (BOX) up-sample: per output index the
-    [lo,hi) source range whose integer mean it takes."""
-    small = max(1, int(size * c))
-    scale = size / small
-    lo = np.empty(small, dtype=np.int32)
-    hi = np.empty(small, dtype=np.int32)
-    for j in range(small):
-        centre = (j + 0.5) * scale
-        a = int(centre - 0.5 * scale + 0.5)
-        b = int(centre + 0.5 * scale + 0.5)
-        a, b = max(a, 0), min(b, size)
-        if b <= a:
-            b = a + 1
-        lo[j], hi[j] = a, b
-    up = np.minimum(((np.arange(size) + 0.5) * small / size).astype(np.int32), small - 1)
-    return lo[up], hi[up]
+PIL_PRECISION_BITS = 32 - 8 - 2
+
+
+def pil_box_coeffs(in_size, out_size):
+    """Pillow's precompute_coeffs + normalize_coeffs_8bpc for the BOX filter (src/libImaging/Resample.c): per output
+    index (first source index, tap count) and the 22-bit fixed-point coefficients.  box_filter(x) = 1 for -0.5 < x <= 0.5."""
+    scale = in_size / out_size
+    filterscale = max(scale, 1.0)
+    support = 0.5 * filterscale
+    bounds, kk = [], []
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        ss = 1.0 / filterscale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        k = [1.0 if -0.5 < (x + xmin - center + 0.5) * ss <= 0.5 else 0.0 for x in range(xmax)]
+        ww = sum(k)
+        k = [v / ww if ww != 0.0 else v for v in k]
+        bounds.append((xmin, xmax))
+        kk.append([int(v * (1 << PIL_PRECISION_BITS) + (0.5 if v >= 0 else -0.5)) for v in k])
+    return bounds, kk
+
+
+def pil_box_resample_axis(img_u8, axis, out_size):
+    """ImagingResampleHorizontal_8bpc / Vertical_8bpc: ss = 2^21 + sum(pixel * k); clip8(ss >> 22)."""
+    img = np.moveaxis(img_u8, axis, 0).astype(np.int64)
+    bounds, kk = pil_box_coeffs(img.shape[0], out_size)
+    out = np.empty((out_size,) + img.shape[1:], dtype=np.int64)
+    for i, ((xmin, cnt), k) in enumerate(zip(bounds, kk)):
+        ss = np.full(img.shape[1:], 1 << (PIL_PRECISION_BITS - 1), dtype=np.int64)
+        for t in range(cnt):
+            ss += img[xmin + t] * k[t]
+        out[i] = np.clip(ss >> PIL_PRECISION_BITS, 0, 255)
+    return np.moveaxis(out, 0, axis).astype(np.uint8)
+
+
+def pil_box_resize(img_u8, out_w, out_h):
+    """Image.resize((out_w, out_h), BOX) on [..., H, W, 3] uint8: horizontal pass first, uint8 between the passes."""
+    hax, wax = img_u8.ndim - 3, img_u8.ndim - 2
+    t = pil_box_resample_axis(img_u8, wax, out_w) if out_w != img_u8.shape[wax] else img_u8
+    return pil_box_resample_axis(t, hax, out_h) if out_h != img_u8.shape[hax] else t
 
 
 def pixelate(x_u8, severity, seed=0, first_image=0, profile=None):
+    """make_imagenet_c.pixelate: x.resize((int(w c), int(h c)), BOX).resize((w, h), BOX), restated after Pillow's
+    Resample.c; tests/test_oracle.py pins it byte for byte to PIL itself."""
     n, h, w, _ = x_u8.shape
     c = CONSTANTS[profile or profile_for(h, w)]["pixelate"][severity - 1]
-    ylo, yhi = pixelate_geometry(h, c)
-    xlo, xhi = pixelate_geometry(w, c)
-    # integral image -> exact integer box sums; u8 rounding (2*s+cnt)//(2*cnt) like a u8 resize
-    ii = np.zeros((n, h + 1, w + 1, 3), dtype=np.int64)
-    ii[:, 1:, 1:] = x_u8.astype(np.int64).cumsum(1).cumsum(2)
-    Y0, Y1 = ylo[:, None], yhi[:, None]
-    X0, X1 = xlo[None, :], xhi[None, :]
-    s = ii[:, Y1, X1] - ii[:, Y0, X1] - ii[:, Y1, X0] + ii[:, Y0, X0]
-    cnt = ((Y1 - Y0) * (X1 - X0))[None, :, :, None]
-    v = (2 * s + cnt) // (2 * cnt)
-    return (v.astype(np.float32) / np.float32(255.0)).astype(np.float32)
+    small = pil_box_resize(x_u8, max(1, int(w * c)), max(1, int(h * c)))
+    return _to_float(pil_box_resize(small, w, h))
+
+
+def pixelate_pil(x_u8, c):
+    """The real thing: Pillow, image by image (anchor for the restatement above)."""
+    from PIL import Image
+    out = np.empty_like(x_u8)
+    h, w = x_u8.shape[1:3]
+    for i in range(x_u8.shape[0]):
+        im = Image.fromarray(x_u8[i])
+        out[i] = np.array(im.resize((max(1, int(w * c)), max(1, int(h * c))), Image.BOX).resize((w, h), Image.BOX))
+    return out
 
 
 # ----------------------------------------------------------------------------- f2 corruptions
 def jpeg_compression(x_u8, severity, seed=0, first_image=0, profile=None):
-    """Integer JPEG round trip (oracle/jpeg.py) at quality c."""
+    """PIL save(quality=c) + reload, restated after libjpeg (oracle/jpeg.py; pinned byte for byte to Pillow)."""
     from . import jpeg as J
     n, h, w, _ = x_u8.shape
     q = CONSTANTS[profile or profile_for(h, w)]["jpeg_compression"][severity - 1]
@@ -545,8 +573,10 @@ def elastic_gauss_taps(sigma):
     return r, (k / k.sum()).astype(np.float32)
 
 
-def elastic_params(h, w, c):
-    S = min(h, w)
+def elastic_params(h, w, c, profile=None):
+    """alpha, sigma, affine magnitude.  make_imagenet_c scales its constants by the literal 244 on 224-pixel images
+    (c = [(244 * 2, 244 * 0.7, 244 * 0.1), ...]); make_cifar_c by IMSIZE = 32."""
+    S = 244.0 * min(h, w) / 224.0 if (profile or profile_for(h, w)) == "imagenet" else float(min(h, w))
     return float(c[0]) * S, float(c[1]) * S, float(c[2]) * S          # alpha, sigma, affine magnitude
 
 
@@ -580,7 +610,7 @@ def elastic_transform(x_u8, severity, seed=0, first_image=0, profile=None):
     """Random affine warp (bilinear, reflect-101) followed by a Gaussian-smoothed random displacement field sampled
     bilinearly with symmetric reflection; own float formulation of make_imagenet_c.elastic_transform."""
     n, h, w, _ = x_u8.shape
-    alpha, sigma, mag = elastic_params(h, w, CONSTANTS[profile or profile_for(h, w)]["elastic_transform"][severity - 1])
+    alpha, sigma, mag = elastic_params(h, w, CONSTANTS[profile or profile_for(h, w)]["elastic_transform"][severity - 1], profile)
     x = _to_float(x_u8)
     p0, q0, A = elastic_affine(n, h, w, mag, severity, seed, first_image)
     X, Y = np.meshgrid(np.arange(w, dtype=np.float32), np.arange(h, dtype=np.float32))

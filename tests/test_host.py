@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/fav_b200.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes prototype"
-    assert lib.fav_abi_version() == 1
+    assert lib.fav_abi_version() == 2
     assert lib.fav_hist_words(10, 15, 4096) == OX.arena_words(10)
     assert lib.fav_hist_words(1000, 15, 4096) == OX.arena_words(1000)
 
@@ -48,31 +48,141 @@ def test_no_gpu_fails_loudly_no_fallback():
         fav.UncertaintyGate()
 
 
-def test_spec_matches_oracle_tables():
-    from fav import spec
+def _tap_entries(ip, tab):
+    """Decode the tap-list table format of csrc/tables.cu pack_taps: [(dys, dxs, ws)] per entry."""
+    n_entries, max_taps = ip[0], ip[1]
+    rec = 16 + 8 * max_taps
+    out = []
+    for i in range(n_entries):
+        o = i * rec
+        nt = int(tab[o:o + 4].view(np.int32)[0])
+        t = tab[o + 16:o + 16 + 8 * nt].view(np.uint32).reshape(nt, 2)
+        dys = (t[:, 0] & 0xFFFF).astype(np.uint16).view(np.int16).astype(int).tolist()
+        dxs = (t[:, 0] >> 16).astype(np.uint16).view(np.int16).astype(int).tolist()
+        out.append((dys, dxs, np.ascontiguousarray(t[:, 1]).view(np.float32)))
+    return out
+
+
+def test_library_constants_match_oracle_and_spec():
+    """The 15 x 5 x 2 severity grid exists three times -- C++ product (tables.cu), Python display copy (spec.SEVERITY) and the
+    oracle (CONSTANTS): all equal."""
+    from fav import _lib, spec
     assert spec.CORRUPTIONS == OC.CORRUPTIONS and spec.CORRUPTION_ID == OC.CORRUPTION_ID
     for prof in ("cifar", "imagenet"):
+        assert spec.MEAN_STD[prof] == OC.MEAN_STD[prof]
         for name in spec.IMPLEMENTED:
             assert spec.SEVERITY[prof][name] == OC.CONSTANTS[prof][name]
-        assert spec.MEAN_STD[prof] == OC.MEAN_STD[prof]
-    for c in (500, 75, 60, 3):
-        k1, w1, t1 = spec.poisson_table(c)
+            for sev in range(1, 6):
+                want = OC.CONSTANTS[prof][name][sev - 1]
+                want = [float(v) for v in (want if isinstance(want, tuple) else (want,))]
+                assert _lib.corruption_constants(prof, spec.CORRUPTION_ID[name], sev) == want, (prof, name, sev)
+
+
+def test_library_host_tables_match_oracle_definitions():
+    """fav_corrupt_params (host only, csrc/tables.cu) against the oracle's independent numpy / scipy / cv2 / PIL statements
+    of the same tables: Poisson thresholds (scipy), disk kernel (cv2.GaussianBlur), motion taps, zoom geometry, libjpeg
+    quantisation tables, glass-blur fixed-point taps, impulse thresholds."""
+    from fav import _lib, spec
+    from oracle import jpeg as OJ
+    ID = spec.CORRUPTION_ID
+    # shot noise
+    for prof, sev in (("cifar", 1), ("cifar", 4), ("imagenet", 1), ("imagenet", 5)):
+        fp, ip, tab = _lib.corrupt_params(ID["shot_noise"], sev, 32, 32, prof)
+        c = OC.CONSTANTS[prof]["shot_noise"][sev - 1]
         k2, w2, t2 = OC.poisson_table(c)
-        assert w1 == w2 and np.array_equal(k1, k2)
-        assert np.abs(t1.astype(np.int64) - t2.astype(np.int64)).max() <= 1      # fp64 cdf rounding at most 1 LSB of 2^-32
-    for r, a in ((0.3, 0.4), (1.5, 0.1), (3, 0.1), (8, 0.5), (10, 0.5)):
-        assert np.abs(spec.disk_kernel(r, a) - OC.disk_kernel(r, a)).max() < 1e-7
-    for ang in (-45, -7, 0, 33, 45):
-        a = spec.motion_taps(15, 8, ang, 224, 224)
-        b = OC.motion_taps(15, 8, ang)
-        assert a[0] == b[0] and a[1] == b[1] and np.allclose(a[2], b[2], atol=1e-7)
-    lo, hi = spec._pixelate_axis(224, 0.3)
-    lo2, hi2 = OC.pixelate_geometry(224, 0.3)
-    assert np.array_equal(lo, lo2) and np.array_equal(hi, hi2)
-    i0, i1, fr = spec._zoom_axis(32, 1.21)
-    j0, j1, gr = OC._zoom_sample_axis(32, 1.21)
-    assert np.array_equal(i0, j0) and np.array_equal(i1, j1) and np.array_equal(fr, gr)
-    assert spec.zoom_factors((1.33, 0.03)) == OC.zoom_factors((1.33, 0.03))
+        assert fp == [float(c)] and ip == [w2]
+        assert np.array_equal(tab[:1024].view(np.int32), k2)
+        t1 = tab[1024:1024 + 1024 * w2].view(np.uint32).reshape(256, w2)
+        assert np.abs(t1.astype(np.int64) - t2.astype(np.int64)).max() <= 1      # fp64 cdf rounding: at most 1 LSB of 2^-32
+        jump = tab[1024 + 1024 * w2:].view(np.uint16).reshape(256, 256)
+        edges = (np.arange(256, dtype=np.uint64) << np.uint64(24))
+        assert np.array_equal(jump, (t1[:, None, :].astype(np.uint64) < edges[None, :, None]).sum(-1))
+    # impulse thresholds
+    for prof in ("cifar", "imagenet"):
+        for sev in range(1, 6):
+            _, ip, _ = _lib.corrupt_params(ID["impulse_noise"], sev, 32, 32, prof)
+            tp, ts = OC.impulse_thresholds(OC.CONSTANTS[prof]["impulse_noise"][sev - 1])
+            assert [v & 0xFFFFFFFF for v in ip] == [tp, ts]
+    # defocus: nonzero taps of the cv2 disk kernel in row-major order
+    for prof in ("cifar", "imagenet"):
+        for sev in range(1, 6):
+            _, ip, tab = _lib.corrupt_params(ID["defocus_blur"], sev, 224, 224, prof)
+            (dys, dxs, ws), = _tap_entries(ip, tab)
+            dy2, dx2, w2 = OC.defocus_taps(*OC.CONSTANTS[prof]["defocus_blur"][sev - 1])
+            assert dys == dy2 and dxs == dx2 and np.abs(ws - np.asarray(w2)).max() < 1e-7 and ip[2] == 0
+    # motion: 91 integer angles, taps cut where the shift leaves the frame
+    for (prof, sev, h, w) in (("imagenet", 5, 224, 224), ("cifar", 5, 32, 32), ("imagenet", 4, 12, 40)):
+        _, ip, tab = _lib.corrupt_params(ID["motion_blur"], sev, h, w, prof)
+        ent = _tap_entries(ip, tab)
+        radius, sigma = OC.CONSTANTS[prof]["motion_blur"][sev - 1]
+        assert len(ent) == OC.MOTION_ANGLES and ip[2] == 1
+        for ai in (0, 17, 45, 60, 90):
+            dy2, dx2, w2 = OC.motion_taps(radius, sigma, ai - 45)
+            keep = next((j for j, (a, b) in enumerate(zip(dy2, dx2)) if abs(a) >= h or abs(b) >= w), len(w2))
+            assert ent[ai][0] == dy2[:keep] and ent[ai][1] == dx2[:keep] and np.allclose(ent[ai][2], w2[:keep], atol=1e-7)
+    # zoom: factors (numpy.arange quirks included) and the clipped-zoom sampling geometry
+    for (prof, sev, h, w) in (("cifar", 3, 32, 32), ("imagenet", 5, 224, 224), ("imagenet", 1, 120, 160)):
+        _, ip, tab = _lib.corrupt_params(ID["zoom_blur"], sev, h, w, prof)
+        zs = OC.zoom_factors(OC.CONSTANTS[prof]["zoom_blur"][sev - 1])
+        assert ip == [len(zs)]
+        t = tab.view(np.uint32).reshape(len(zs), h + w, 2)
+        for i, z in enumerate(zs):
+            for off, size in ((0, h), (h, w)):
+                j0, j1, gr = OC._zoom_sample_axis(size, z)
+                assert np.array_equal(t[i, off:off + size, 0] & 0xFFFF, j0) and np.array_equal(t[i, off:off + size, 0] >> 16, j1)
+                assert np.array_equal(np.ascontiguousarray(t[i, off:off + size, 1]).view(np.float32), gr)
+    # jpeg: libjpeg quantisation tables
+    for prof in ("cifar", "imagenet"):
+        for sev in range(1, 6):
+            _, ip, tab = _lib.corrupt_params(ID["jpeg_compression"], sev, 32, 32, prof)
+            ql, qc = OJ.quant_tables(OC.CONSTANTS[prof]["jpeg_compression"][sev - 1])
+            assert np.array_equal(tab.view(np.int32), np.concatenate([ql.ravel(), qc.ravel()]))
+    # glass blur: exact fixed-point taps (the swapped bytes depend on them bit for bit) + fp32 taps
+    for prof in ("cifar", "imagenet"):
+        for sev in range(1, 6):
+            sigma, delta, iters = OC.CONSTANTS[prof]["glass_blur"][sev - 1]
+            _, ip, tab = _lib.corrupt_params(ID["glass_blur"], sev, 32, 32, prof)
+            r, q = OC.gaussian_taps_q16(sigma)
+            assert ip == [delta, iters, r]
+            assert np.array_equal(tab[:4 * (2 * r + 1)].view(np.int32), q)
+            assert np.allclose(tab[4 * (2 * r + 1):].view(np.float32), OC.gaussian_taps(sigma)[1].astype(np.float32), atol=1e-9)
+    # snow: tap lists at -135..-45 degrees + zoom geometry
+    _, ip, tab = _lib.corrupt_params(ID["snow"], 3, 32, 32, "cifar")
+    loc, scale, zoom, thresh, mb_r, mb_s, blend = OC.CONSTANTS["cifar"]["snow"][2]
+    ent = _tap_entries(ip, tab)
+    dy2, dx2, w2 = OC.motion_taps(int(mb_r), float(mb_s), 30 - 135)
+    assert ent[30][0] == dy2 and ent[30][1] == dx2 and np.allclose(ent[30][2], w2, atol=1e-7)
+    z = tab[ip[7]:].view(np.uint32).reshape(64, 2)
+    j0, j1, gr = OC._zoom_sample_axis(32, float(zoom))
+    assert np.array_equal(z[:32, 0] & 0xFFFF, j0) and np.array_equal(np.ascontiguousarray(z[:32, 1]).view(np.float32), gr)
+
+
+def test_library_pixelate_table_reproduces_pil():
+    """The BOX coefficient table the pixelate kernels consume, applied in numpy exactly as k1_pixelate_down / _up do,
+    equals Pillow's own resize(BOX) down + up byte for byte."""
+    from fav import _lib, spec
+    rng = np.random.default_rng(3)
+    for (prof, h, w) in (("cifar", 32, 32), ("imagenet", 224, 224), ("imagenet", 120, 160), ("cifar", 33, 47)):
+        x = rng.integers(0, 256, (1, h, w, 3), dtype=np.uint8)
+        for sev in range(1, 6):
+            c = OC.CONSTANTS[prof]["pixelate"][sev - 1]
+            _, (sw, sh, kh, kv), tab = _lib.corrupt_params(spec.CORRUPTION_ID["pixelate"], sev, h, w, prof)
+            t = tab.view(np.int32)
+            hx = t[:sw * (2 + kh)].reshape(sw, 2 + kh)
+            vy = t[sw * (2 + kh):sw * (2 + kh) + sh * (2 + kv)].reshape(sh, 2 + kv)
+            upx = t[sw * (2 + kh) + sh * (2 + kv):][:w]
+            upy = t[sw * (2 + kh) + sh * (2 + kv) + w:][:h]
+            img = x[0].astype(np.int64)
+            tmp = np.empty((h, sw, 3), np.int64)
+            for i in range(sw):
+                xmin, cnt = hx[i, 0], hx[i, 1]
+                tmp[:, i] = np.clip(((img[:, xmin:xmin + cnt] * hx[i, 2:2 + cnt][None, :, None]).sum(1) + (1 << 21)) >> 22, 0, 255)
+            small = np.empty((sh, sw, 3), np.int64)
+            for j in range(sh):
+                ymin, cnt = vy[j, 0], vy[j, 1]
+                small[j] = np.clip(((tmp[ymin:ymin + cnt] * vy[j, 2:2 + cnt][:, None, None]).sum(0) + (1 << 21)) >> 22, 0, 255)
+            got = small[upy][:, upx].astype(np.uint8)
+            assert np.array_equal(got, OC.pixelate_pil(x, c)[0]), (prof, h, w, sev)
 
 
 def test_config_objects():
@@ -240,14 +350,14 @@ def test_dropout_four_byte_compare_is_exact_for_every_threshold():
 
 
 def test_elastic_folded_matrices_reproduce_the_tap_order_smoothing():
-    """Host table of elastic_transform for long Gaussians (spec.elastic_fold): one weight per (destination, source) pixel.
+    """Host table of elastic_transform for long Gaussians (tables.cu elastic_fold): one weight per (destination, source) pixel.
     Against the oracle's tap-by-tap fp32 accumulation the displacement differs by far less than a thousandth of a pixel."""
-    import fav
-    from fav import spec
+    from fav import _lib
     from oracle import corruptions as K
     for (h, w, sev) in ((224, 224, 1), (32, 32, 2)):
-        fp, ip, tab = spec.kernel_params(fav.CorruptionConfig("elastic_transform", sev), h, w)
+        fp, ip, tab = _lib.corrupt_params(K.CORRUPTION_ID["elastic_transform"], sev, h, w)
         assert ip[1] == 1
+        assert abs(fp[0] - np.float32(K.elastic_params(h, w, K.CONSTANTS[K.profile_for(h, w)]["elastic_transform"][sev - 1])[0])) < 1e-4
         t = tab.view(np.float32)
         mwt, mh = t[:w * w].reshape(w, w), t[w * w:].reshape(h, h)
         assert np.allclose(mwt.sum(0), 1.0, atol=1e-5) and np.allclose(mh.sum(1), 1.0, atol=1e-5)      # a smoothing kernel
@@ -264,7 +374,12 @@ def test_elastic_folded_matrices_reproduce_the_tap_order_smoothing():
         df = mh.astype(np.float64) @ (u.astype(np.float64) @ mwt.astype(np.float64))
         assert np.abs(d - df).max() * alpha < 1e-4
     # short kernels keep the tap list
-    assert spec.kernel_params(fav.CorruptionConfig("elastic_transform", 5), 224, 224)[1][1] == 0
+    fp, ip, tab = _lib.corrupt_params(K.CORRUPTION_ID["elastic_transform"], 5, 224, 224)
+    assert ip[1] == 0
+    r, k = K.elastic_gauss_taps(K.elastic_params(224, 224, K.CONSTANTS["imagenet"]["elastic_transform"][4])[1])
+    assert ip[0] == r and np.allclose(tab.view(np.float32), k, atol=1e-9)
+    # ImageNet-C scales by the literal 244 on 224-pixel frames: sigma = 0.7 * 244 at severity 1
+    assert _lib.corrupt_params(K.CORRUPTION_ID["elastic_transform"], 1, 224, 224)[1][0] == int(3 * 0.7 * 244 + 0.5)
 
 
 def test_glass_swap_wavefront_schedule_equals_the_sequential_chain():

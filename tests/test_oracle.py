@@ -59,22 +59,38 @@ def test_corruption_range_and_determinism(name):
         assert d5 > d1          # severity monotone on i.i.d. images
 
 
-def test_jpeg_oracle_tracks_pil():
-    """The integer codec is its own definition (parity unpinned) but must stay close to a real JPEG at the same quality."""
-    import io
-    from PIL import Image
+def _probe_images(h, w, rng):
+    yy, xx = np.mgrid[0:h, 0:w]
+    smooth = np.stack([(xx * 4) % 256, (yy * 3 + xx) % 256, ((xx - w // 2) ** 2 + (yy - h // 2) ** 2) // 8 % 256], -1)
+    smooth = np.clip(smooth + rng.integers(-8, 9, smooth.shape), 0, 255).astype(np.uint8)
+    noise = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    sat = np.where(rng.random((h, w, 3)) < 0.5, 0, 255).astype(np.uint8)
+    return np.stack([smooth, noise, sat])
+
+
+def test_jpeg_restatement_is_byte_exact_against_pillow():
+    """PINNED: oracle/jpeg.py (libjpeg restated stage by stage) == PIL save(quality) + reload, byte for byte, on smooth,
+    noisy and saturated images, every quality of both severity tables, MCU-aligned and ragged sizes (even and odd)."""
     from oracle import jpeg as J
     rng = np.random.default_rng(0)
-    yy, xx = np.mgrid[0:64, 0:64]
-    img = np.stack([(xx * 4) % 256, (yy * 3 + xx) % 256, ((xx - 32) ** 2 + (yy - 32) ** 2) // 8 % 256], -1)
-    img = np.clip(img + rng.integers(-8, 9, img.shape), 0, 255).astype(np.uint8)
-    for q in (80, 25, 7):
-        mine = J.jpeg_roundtrip_u8(img[None], q)[0].astype(np.float64)
-        buf = io.BytesIO()
-        Image.fromarray(img).save(buf, "JPEG", quality=q)
-        pil = np.array(Image.open(buf)).astype(np.float64)
-        psnr = 10 * np.log10(255 ** 2 / np.mean((mine - pil) ** 2))
-        assert psnr > 35, (q, psnr)
+    qualities = sorted(set(C.CONSTANTS["cifar"]["jpeg_compression"] + C.CONSTANTS["imagenet"]["jpeg_compression"])) + [1, 95, 100]
+    for (h, w) in ((32, 32), (224, 224), (48, 64), (33, 47), (40, 24), (18, 9), (120, 160)):
+        x = _probe_images(h, w, rng)
+        for q in (qualities if h * w <= 64 * 64 else qualities[::3]):
+            assert np.array_equal(J.jpeg_roundtrip_u8(x, q), J.pil_roundtrip_u8(x, q)), (h, w, q)
+    x = px.synthetic_images(2, 32, 32, seed=4)
+    assert np.array_equal(np.rint(C.corrupt(x, "jpeg_compression", 3) * 255).astype(np.uint8), J.pil_roundtrip_u8(x, 58))
+
+
+def test_pixelate_restatement_is_byte_exact_against_pillow():
+    """PINNED: the Pillow BOX resampler restated in oracle/corruptions.py == Image.resize(BOX) down + up, byte for byte."""
+    rng = np.random.default_rng(1)
+    for (h, w) in ((32, 32), (224, 224), (120, 160), (33, 47)):
+        x = rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+        prof = C.profile_for(h, w)
+        for s in range(1, 6):
+            c = C.CONSTANTS[prof]["pixelate"][s - 1]
+            assert np.array_equal(np.rint(C.pixelate(x, s) * 255).astype(np.uint8), C.pixelate_pil(x, c)), (h, w, s)
 
 
 def test_shot_noise_is_poisson():
