@@ -85,6 +85,7 @@ extern "C" int fav_comm_unique_id(void* out128) {
 
 extern "C" int fav_comm_init(fav_handle h, const void* id128, int rank, int world_size) {
   FAV_REQUIRE(h && id128, "fav_comm_init: null pointer");
+  FAV_DEVICE(h);
   FAV_REQUIRE(world_size >= 1 && rank >= 0 && rank < world_size, "fav_comm_init: bad rank %d of %d", rank, world_size);
   comm_destroy(h);
   if (world_size == 1) return FAV_OK;
@@ -103,6 +104,7 @@ extern "C" int fav_comm_init(fav_handle h, const void* id128, int rank, int worl
 
 extern "C" int fav_allreduce(fav_handle h, int64_t* d_hist, size_t count, void* stream) {
   FAV_REQUIRE(h, "null handle");
+  FAV_DEVICE(h);
   if (h->world <= 1 || count == 0) return FAV_OK;                 // single rank: nothing to exchange
   FAV_REQUIRE(d_hist, "fav_allreduce: null pointer");
   FAV_REQUIRE(h->nccl_comm, "fav_allreduce: fav_comm_init has not been called");

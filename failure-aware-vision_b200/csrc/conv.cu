@@ -816,6 +816,7 @@ extern "C" int fav_conv2d(fav_handle h, const void* d_x, const void* d_w, const 
                           void* d_y, int p, int height, int width, int cin, int cout, int r, int s, int stride,
                           int pad, int relu, int out_f32, int a_mode, void* stream) {
   FAV_REQUIRE(h && d_x && d_w && d_y, "fav_conv2d: null pointer");
+  FAV_DEVICE(h);
   FAV_REQUIRE(cin > 0 && cout > 0 && r > 0 && s > 0 && stride > 0 && pad >= 0, "fav_conv2d: bad conv geometry");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   ConvLayer L;

@@ -84,7 +84,7 @@ __device__ __forceinline__ SampleOut sample_uncertainty(const float* __restrict_
   }
   const float invT = 1.0f / float(T);
   float best = -1.f;
-  int arg = 0x7fffffff;
+  int arg = 0;                                      // NaN logits never win a compare: pred stays a valid class
   float H = 0.f;
   const bool single = T == 1;                       // one pass: the mean IS that pass, H = H(p_1) is already in hsum, MI = 0
 #pragma unroll
@@ -116,7 +116,7 @@ template <int NC>
 __device__ __forceinline__ SampleOut sample_uncertainty_single(const float* __restrict__ z, int C, int lane) {
   float v[NC];
   float m = -INFINITY;
-  int arg = 0x7fffffff;
+  int arg = lane < C ? lane : 0;                      // a valid class even when every logit is NaN / -inf
 #pragma unroll
   for (int i = 0; i < NC; ++i) {
     const int c = lane + 32 * i;
@@ -271,9 +271,13 @@ __global__ void __launch_bounds__(256) k34_kernel(const float* __restrict__ logi
         if (o_pred) o_pred[i] = r.pred;
         if (o_flag) o_flag[i] = flag ? 1 : 0;
         if (do_hist) {
-          accumulate_sample(g, s_hist, hist, r.conf, r.H, r.mi, r.pred, label);
-          my[0] += 1; my[1] += (r.pred == label); my[2] += flag;
-          my[3] += q32(r.conf); my[4] += q32(clip01(r.H * g.inv_lnC)); my[5] += q32(clip01(r.mi * g.inv_lnC));
+          if (unsigned(label) >= unsigned(g.C)) {          // label outside [0, C): counted, kept out of every histogram
+            atomicAdd(&hist[FAV_HIST_NINVALID], 1ull);
+          } else {
+            accumulate_sample(g, s_hist, hist, r.conf, r.H, r.mi, r.pred, label);
+            my[0] += 1; my[1] += (r.pred == label); my[2] += flag;
+            my[3] += q32(r.conf); my[4] += q32(clip01(r.H * g.inv_lnC)); my[5] += q32(clip01(r.mi * g.inv_lnC));
+          }
         }
       }
     }
@@ -281,6 +285,7 @@ __global__ void __launch_bounds__(256) k34_kernel(const float* __restrict__ logi
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
       const float conf = i_conf[i], H = i_H[i], mi = i_mi[i];
       const int pred = i_pred[i], label = labels[i];
+      if (unsigned(label) >= unsigned(g.C) || unsigned(pred) >= unsigned(g.C)) { atomicAdd(&hist[FAV_HIST_NINVALID], 1ull); continue; }
       accumulate_sample(g, s_hist, hist, conf, H, mi, pred, label);
       my[0] += 1; my[1] += (pred == label); my[2] += (pred != label && conf >= g.tau);
       my[3] += q32(conf); my[4] += q32(clip01(H * g.inv_lnC)); my[5] += q32(clip01(mi * g.inv_lnC));
@@ -416,7 +421,9 @@ __global__ void __launch_bounds__(K34S_THREADS) k34_small_kernel(const float* __
         if (o_pred) o_pred[i] = arg;
         if (o_flag) o_flag[i] = flag ? 1 : 0;
       }
-      if (do_hist) {
+      if (do_hist && unsigned(label) >= unsigned(C)) {     // label outside [0, C): counted, kept out of every histogram
+        if (q == 0) atomicAdd(&hist[FAV_HIST_NINVALID], 1ull);
+      } else if (do_hist) {
         const float sc0 = clip01(1.0f - best), sc1 = clip01(H * g.inv_lnC), sc2 = clip01(mi * g.inv_lnC);
         if (q == 0) {
           int b = int(ceilf(best * float(g.n_bins))) - 1;
@@ -476,6 +483,7 @@ static int launch_k34(fav_handle h, const float* d_logits, const int32_t* d_labe
                       int32_t* d_pred, uint8_t* d_flag, const float* i_conf, const float* i_H, const float* i_mi,
                       const int32_t* i_pred, void* stream) {
   FAV_REQUIRE(h, "null handle");
+  FAV_DEVICE(h);
   FAV_REQUIRE(n >= 0 && C >= 2 && C <= 1024, "C must be in [2,1024] (got %d), n >= 0 (got %d)", C, n);
   FAV_REQUIRE(!d_logits || T >= 1, "T must be >= 1 (got %d)", T);
   if (n == 0) return FAV_OK;

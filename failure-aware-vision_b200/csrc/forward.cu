@@ -207,6 +207,7 @@ using namespace fav;
 extern "C" int fav_load_weights(fav_handle h, const void* blob, size_t nbytes, int model_id, int num_classes, int in_h,
                                 int in_w) {
   FAV_REQUIRE(h && blob, "fav_load_weights: null pointer");
+  FAV_DEVICE(h);
   FAV_REQUIRE(in_h > 0 && in_w > 0 && num_classes >= 2, "fav_load_weights: bad input size / classes");
   const uint8_t* p = reinterpret_cast<const uint8_t*>(blob);
   const uint8_t* end = p + nbytes;
@@ -398,6 +399,7 @@ extern "C" int fav_load_weights(fav_handle h, const void* blob, size_t nbytes, i
 
 extern "C" int fav_reserve(fav_handle h, int max_images, int T) {
   FAV_REQUIRE(h && h->plan, "fav_reserve: load weights first");
+  FAV_DEVICE(h);
   FAV_REQUIRE(max_images > 0 && T >= 1, "fav_reserve: bad max_images/T");
   Plan& pl = *h->plan;
   size_t mx = 0;
@@ -417,6 +419,7 @@ extern "C" int fav_reserve(fav_handle h, int max_images, int T) {
 extern "C" int fav_forward_mc(fav_handle h, const void* d_x, float* d_logits, int n, int T, float p_drop, uint64_t seed,
                               uint64_t first_image, void* stream) {
   FAV_REQUIRE(h && h->plan, "fav_forward_mc: load weights first");
+  FAV_DEVICE(h);
   if (!h->plan) return FAV_E_STATE;
   FAV_REQUIRE(n >= 0 && T >= 1 && (n == 0 || (d_x && d_logits)), "fav_forward_mc: bad arguments");
   FAV_REQUIRE(T == 1 || (p_drop >= 0.f && p_drop < 1.f), "fav_forward_mc: p_drop must be in [0,1)");

@@ -19,7 +19,9 @@ __device__ __forceinline__ int reflect101(int i, int n) {
   if (n == 1) return 0;
   if (i < 0) i = -i;
   if (i >= n) i = 2 * (n - 1) - i;
-  return i;
+  if (i < 0) i = -i;                         // n == 2: one more fold (rows -1 .. n+FS_ROWS of a 2-row frame)
+  if (i >= n) i = 2 * (n - 1) - i;
+  return min(max(i, 0), n - 1);
 }
 
 __global__ void __launch_bounds__(256) k_frame_stats(const uint8_t* __restrict__ frame, uint8_t* __restrict__ prev_gray,
@@ -74,6 +76,7 @@ extern "C" int fav_frame_stats(fav_handle h, const uint8_t* d_frame, uint8_t* d_
                                int first_frame, int64_t* d_out, void* stream) {
   FAV_REQUIRE(h && d_frame && d_prev_gray && d_out, "fav_frame_stats: null pointer");
   FAV_REQUIRE(height >= 2 && width >= 2 && width <= 8192, "fav_frame_stats: frame must be at least 2x2 and at most 8192 wide");
+  FAV_DEVICE(h);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   FAV_CUDA_OK(cudaMemsetAsync(d_out, 0, (4 + 256) * sizeof(int64_t), st));
   const size_t smem = (size_t)(FS_ROWS + 2) * width;

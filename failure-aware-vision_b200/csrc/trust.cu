@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(128) k_trust_replay(const int8_t* __restrict__
   int head = 0, fill = 0;                       // ring buffer: oldest entry at head
   for (int i = 0; i < L; ++i) {
     const size_t at = (size_t)i * S + s;
-    const int st = status[at];
+    int st = status[at];
+    if (unsigned(st) > 3u) st = 3;               // unknown codes are treated as VISION_CORRUPTED (the host wrapper rejects them)
     const double sc = score[at];
     const bool has_sc = !isnan(sc);
     const double d = dts ? dts[i] : dt_const;
@@ -137,6 +138,7 @@ extern "C" int fav_trust_replay(fav_handle h, const int8_t* d_status, const doub
                                 int n_seq, int n_ticks, double* d_state, uint8_t* d_policy, uint8_t* d_contra, int32_t* d_count,
                                 double* d_final, void* stream) {
   FAV_REQUIRE(h, "null handle");
+  FAV_DEVICE(h);
   FAV_REQUIRE(n_seq >= 0 && n_ticks >= 0, "fav_trust_replay: bad shape %d x %d", n_seq, n_ticks);
   if (n_seq == 0 || n_ticks == 0) return FAV_OK;
   FAV_REQUIRE(d_status && d_score, "fav_trust_replay: null pointer");

@@ -75,7 +75,7 @@ def finalize(arena, num_classes, n_bins, n_buckets):
     """int64 arena of one cell -> metrics dict (fp64 on the host)."""
     a = np.asarray(arena, dtype=np.int64)
     n = int(a[0])
-    out = {"n": n}
+    out = {"n": n, "n_invalid": int(a[6])}          # labels outside [0, C) are counted, never histogrammed
     if n == 0:
         return out
     two32 = 4294967296.0
@@ -288,8 +288,11 @@ class CorruptionSweep:
 
     def run(self, images_u8, labels, rank=0, world_size=1, first_image=0):
         """images uint8 [N,H,W,3] (numpy or torch, host or device), labels int [N].
-        Returns {(corruption, severity): metrics} after the cross-rank reduction."""
+        Returns {(corruption, severity): metrics} after the cross-rank reduction.  Starts from an empty arena (after the
+        all-reduce every rank holds the global sums: a second run must not add to them); run_item / run_stream are the
+        accumulate-only calls."""
         import numpy as np
+        self.acc.reset()
         if isinstance(images_u8, np.ndarray):
             images_u8 = torch.from_numpy(np.ascontiguousarray(images_u8))
         if isinstance(labels, np.ndarray):

@@ -37,7 +37,12 @@ class TrustReplay:
         """status [S, L] integer codes, score [S, L] float (NaN where the reference would pass None), dt a float or [L].
         Returns numpy arrays: 'final' [S, 8] and, with trajectory=True, 'state' [S, L, 5], 'policy', 'contradiction',
         'contradiction_count' [S, L]."""
-        st = torch.as_tensor(np.asarray(status), dtype=torch.int8)
+        status = np.asarray(status)
+        if status.size and (status.min() < 0 or status.max() > 3):
+            # the reference engine only knows its four VISION_* strings (trust_engine.py:21-26); any other code would
+            # decay at an undefined rate inside the kernel
+            raise ValueError("status codes must be 0 (OK), 1 (FROZEN), 2 (BLANK) or 3 (CORRUPTED)")
+        st = torch.as_tensor(status, dtype=torch.int8)
         sc = torch.as_tensor(np.asarray(score, dtype=np.float64))
         if st.dim() != 2 or sc.shape != st.shape:
             raise ValueError("status and score must both be [S, L]")

@@ -150,6 +150,7 @@ int fav_epilogue(fav_handle h, const float* d_logits, const int32_t* d_labels, i
 #define FAV_HIST_SUM_CONF 3
 #define FAV_HIST_SUM_H 4
 #define FAV_HIST_SUM_MI 5
+#define FAV_HIST_NINVALID 6   /* samples whose label (or supplied prediction) is outside [0, C): counted here, excluded elsewhere */
 size_t fav_hist_words(int C, int n_bins, int n_buckets);
 int fav_accumulate(fav_handle h, const float* d_conf, const float* d_entropy, const float* d_mi,
                    const int32_t* d_pred, const int32_t* d_labels, int n, int C, float tau,

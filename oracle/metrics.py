@@ -13,7 +13,8 @@ Arena layout (int64 words; mirrored by include/fav_b200.h FAV_HIST_*):
   [3]                 sum_conf_q32
   [4]                 sum_entropy_q32       (H / ln C, clipped to [0,1])
   [5]                 sum_mi_q32            (MI / ln C, clipped to [0,1])
-  [6..7]              reserved
+  [6]                 n_invalid             (label outside [0, C): counted here, excluded from everything else)
+  [7]                 reserved
   [8 + 3*b + {0,1,2}] ECE bin b: count, sum_conf_q32, n_correct          (B bins)
   [8+3B + (s*K + k)*2 + {0,1}]  AUROC score type s (0: 1-conf, 1: H/lnC, 2: MI/lnC),
                                 bucket k: {neg = correct, pos = wrong}   (K buckets)
@@ -56,6 +57,9 @@ def normalised_scores(conf, H, mi, num_classes):
 
 
 def accumulate(arena, conf, H, mi, pred, labels, tau, num_classes, n_bins=N_BINS, n_buckets=N_BUCKETS):
+    ok = (labels >= 0) & (labels < num_classes) & (pred >= 0) & (pred < num_classes)
+    arena[6] += int((~ok).sum())
+    conf, H, mi, pred, labels = conf[ok], H[ok], mi[ok], pred[ok], labels[ok]
     correct = (pred == labels)
     s0, s1, s2 = normalised_scores(conf, H, mi, num_classes)
     arena[0] += len(conf)
@@ -95,7 +99,7 @@ def auroc_from_buckets(neg, pos):
 def finalize(arena, num_classes, n_bins=N_BINS, n_buckets=N_BUCKETS):
     a = np.asarray(arena, dtype=np.int64)
     n = int(a[0])
-    out = dict(n=n)
+    out = dict(n=n, n_invalid=int(a[6]))
     if n == 0:
         return out
     out["accuracy"] = a[1] / n
