@@ -96,10 +96,46 @@ class SignalFinisher:
                     entropy=entropy, entropy_score=entropy_score, signal_score=signal_score, vision_status=status)
 
 
+def assemble_result(fin, unc, score_source="uncertainty", tau=0.9, num_classes=1000):
+    """The dict SignalAnalyzer.analyze_frame returns (signal_analyzer.py:126-142: same keys, same rounding), with the
+    classifier's uncertainty under metrics['uncertainty'] and, depending on score_source, in anomaly_score.
+    fin: SignalFinisher.finish(...); unc: (confidence, entropy, mutual_information, pred) or None.  Pure host code."""
+    signal_score, vision_status = fin["signal_score"], fin["vision_status"]
+    anomaly_score, u = signal_score, None
+    if unc is not None:
+        conf, H, mi, pred = unc
+        norm_h = max(0.0, min(1.0, H / math.log(num_classes)))
+        u = {"confidence": round(conf, 6), "entropy": round(H, 6), "mutual_information": round(mi, 6),
+             "pred": int(pred), "normalized_entropy": round(norm_h, 6), "high_confidence": bool(conf >= tau)}
+        if score_source == "uncertainty":
+            anomaly_score = norm_h
+        elif score_source == "max":
+            anomaly_score = max(signal_score, norm_h)
+    out = {
+        'anomaly_score': round(anomaly_score, 6),
+        'vision_status': vision_status,
+        'metrics': {
+            'blur': round(fin["blur_score"], 4),
+            'brightness': round(fin["brightness_score"], 4),
+            'freeze': round(fin["freeze_score"], 4),
+            'entropy': round(fin["entropy_score"], 4),
+            'raw': {
+                'laplacian_var': round(fin["laplacian_var"], 2),
+                'mean_brightness': round(fin["mean_brightness"], 1),
+                'frame_diff': round(fin["mean_diff"], 2),
+                'entropy': round(fin["entropy"], 3),
+            }
+        }
+    }
+    if u is not None:
+        out['metrics']['uncertainty'] = u
+    return out
+
+
 class UncertaintyGate:
     def __init__(self, classifier: VisionClassifier = None, frame_hw=(480, 640), T=1, p_drop=0.2, tau=0.9,
                  score_source="uncertainty", model="resnet18", num_classes=1000, device=0, weights_seed=0,
-                 logit_gain=None, use_classifier=True, use_graph=None):
+                 logit_gain=None, use_classifier=True, use_graph=None, mask_schedule="per_frame"):
         if not torch.cuda.is_available():
             raise RuntimeError("UncertaintyGate needs a CUDA device (sm_100a); there is no CPU fallback")
         self.frame_hw = tuple(frame_hw)
@@ -120,12 +156,23 @@ class UncertaintyGate:
         self._side = torch.cuda.Stream(self.device)
         self._fin = SignalFinisher()
         # CUDA-graph replay of the whole device side of a frame (H2D copy, frame statistics, K1..K3, D2H copies): one
-        # launch instead of ~30.  The dropout masks are keyed by first_image, a kernel argument frozen at capture, so the
-        # default enables it for the deterministic T == 1 gate only (with T > 1 every frame would reuse the same T masks).
-        self.use_graph = (self.T == 1) if use_graph is None else bool(use_graph)
+        # launch instead of ~30.  The dropout masks are keyed by first_image, a kernel argument frozen at capture:
+        #   mask_schedule = "per_frame" (default): frame i uses masks keyed by i -> eager launches when T > 1;
+        #   mask_schedule = "frozen": every frame sees the SAME T masks (common random numbers: the score is a
+        #                   deterministic function of the frame, differences between frames carry no mask noise) -> graph.
+        if mask_schedule not in ("per_frame", "frozen"):
+            raise ValueError("mask_schedule must be 'per_frame' or 'frozen'")
+        self.mask_schedule = mask_schedule
+        self.use_graph = (self.T == 1 or mask_schedule == "frozen") if use_graph is None else bool(use_graph)
         self._graph = None
         self._graph_failed = False
+        self.graph_error = None
         self.reset()
+
+    @property
+    def graph_active(self):
+        """True once the per-frame device work replays as one CUDA graph (the latency harness asserts on it)."""
+        return self._graph is not None
 
     def _enqueue_frame(self, first, first_image):
         """Device side of one frame on the current stream: pinned frame -> device, fused SignalAnalyzer statistics,
@@ -156,9 +203,13 @@ class UncertaintyGate:
             with torch.cuda.graph(g):
                 self._enqueue_frame(False, 0)
             self._graph = g
-        except Exception:                      # capture is an optimisation: any failure falls back to eager launches
+        except Exception as e:                 # capture is an optimisation: a failure falls back to eager launches, LOUDLY
+            import warnings
             self._graph = None
             self._graph_failed = True
+            self.graph_error = repr(e)
+            warnings.warn(f"UncertaintyGate: CUDA-graph capture failed, running ~30 eager launches per frame instead: {e!r}",
+                          RuntimeWarning)
             torch.cuda.synchronize(self.device)
 
     def reset(self):
@@ -182,39 +233,8 @@ class UncertaintyGate:
                 self._graph.replay()
                 torch.cuda.current_stream(self.device).synchronize()
         if self._graph is None or first or self._frame_count <= 2:
-            self._enqueue_frame(first, self._frame_count)
+            self._enqueue_frame(first, 0 if self.mask_schedule == "frozen" else self._frame_count)
             torch.cuda.current_stream(self.device).synchronize()
-        packed_host, unc = self._packed_host, None
         fin = self._fin.finish(self._stats_host.numpy(), h * w)
-        signal_score, vision_status = fin["signal_score"], fin["vision_status"]
-
-        anomaly_score = signal_score
-        if self.clf is not None:
-            conf, H, mi, pred = (float(v) for v in packed_host[0])
-            norm_h = max(0.0, min(1.0, H / math.log(self.clf.num_classes)))
-            unc = {"confidence": round(conf, 6), "entropy": round(H, 6), "mutual_information": round(mi, 6),
-                   "pred": int(pred), "normalized_entropy": round(norm_h, 6),
-                   "high_confidence": bool(conf >= self.tau)}
-            if self.score_source == "uncertainty":
-                anomaly_score = norm_h
-            elif self.score_source == "max":
-                anomaly_score = max(signal_score, norm_h)
-        out = {
-            'anomaly_score': round(anomaly_score, 6),
-            'vision_status': vision_status,
-            'metrics': {
-                'blur': round(fin["blur_score"], 4),
-                'brightness': round(fin["brightness_score"], 4),
-                'freeze': round(fin["freeze_score"], 4),
-                'entropy': round(fin["entropy_score"], 4),
-                'raw': {
-                    'laplacian_var': round(fin["laplacian_var"], 2),
-                    'mean_brightness': round(fin["mean_brightness"], 1),
-                    'frame_diff': round(fin["mean_diff"], 2),
-                    'entropy': round(fin["entropy"], 3),
-                }
-            }
-        }
-        if unc is not None:
-            out['metrics']['uncertainty'] = unc
-        return out
+        unc = tuple(float(v) for v in self._packed_host[0]) if self.clf is not None else None
+        return assemble_result(fin, unc, self.score_source, self.tau, self.clf.num_classes if self.clf is not None else 0)

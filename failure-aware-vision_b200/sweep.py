@@ -200,9 +200,20 @@ class CorruptionSweep:
             self.acc.init_comm()
         torch.cuda.synchronize()
 
+    def cell_order(self):
+        """Cells in a strided order: with the grid laid out corruption-major, consecutive steps visit different corruptions
+        AND different severities (stride coprime to the cell count, ~ one fifth of it), so any short run of steps -- a
+        bench window, one rank's round-robin share -- samples the whole grid instead of its first few corruptions."""
+        n = len(self.cells)
+        stride = max(1, n // 5 + 1)
+        while math.gcd(stride, n) != 1:
+            stride += 1
+        return [(k * stride) % n for k in range(n)]
+
     def work_items(self, n_images):
         nblk = (n_images + self.cfg.block - 1) // self.cfg.block
-        return [(ci, b) for b in range(nblk) for ci in range(len(self.cells))]
+        order = self.cell_order()
+        return [(ci, b) for b in range(nblk) for ci in order]
 
     def _buffers(self, n):
         h, w = self.cfg.input_hw
@@ -286,7 +297,7 @@ class CorruptionSweep:
                 on_row(items[-1], ss["row"][last])
         return evals
 
-    def run(self, images_u8, labels, rank=0, world_size=1, first_image=0):
+    def run(self, images_u8, labels, rank=0, world_size=1, first_image=0, timing=False):
         """images uint8 [N,H,W,3] (numpy or torch, host or device), labels int [N].
         Returns {(corruption, severity): metrics} after the cross-rank reduction.  Starts from an empty arena (after the
         all-reduce every rank holds the global sums: a second run must not add to them); run_item / run_stream are the
@@ -308,29 +319,101 @@ class CorruptionSweep:
         else:
             images_dev = self.clf._images(images_u8)
             labels_dev = self.clf._labels(labels)
+            evs = []
             for item in mine:
-                self.run_item(images_dev, labels_dev, item, first_image)
+                if timing:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(torch.cuda.current_stream(self.clf.device))
+                n = self.run_item(images_dev, labels_dev, item, first_image)
+                if timing:
+                    e1.record(torch.cuda.current_stream(self.clf.device))
+                    evs.append((item[0], n, e0, e1))
+            if timing:                                   # device ms and evals per cell on this rank
+                torch.cuda.current_stream(self.clf.device).synchronize()
+                self.cell_ms = [0.0] * len(self.cells)
+                self.cell_evals = [0] * len(self.cells)
+                for ci, n, e0, e1 in evs:
+                    self.cell_ms[ci] += e0.elapsed_time(e1)
+                    self.cell_evals[ci] += n
         self.acc.allreduce()
         res = self.acc.results()
         return {(c.name or "clean", c.severity): r for c, r in zip(self.cells, res)}
 
+    COLUMNS = ["corruption", "severity", "n", "accuracy", "ece", "mean_confidence", "mean_entropy",
+               "mean_mutual_information", "failure_rate", "auroc_msp", "auroc_entropy", "auroc_mi"]
+    PERF_COLUMNS = ["gpu_ms", "evals_per_gpu_s", "tflops", "roofline_frac"]
+
     @staticmethod
-    def to_csv(results):
-        """In-memory CSV in the style of session_logger.py:49-51."""
-        cols = ["corruption", "severity", "n", "accuracy", "ece", "mean_confidence", "mean_entropy",
-                "mean_mutual_information", "failure_rate", "auroc_msp", "auroc_entropy", "auroc_mi"]
+    def records(results, perf=None):
+        """Per-cell records in the reference's style: plain dicts of rounded floats (trust_engine.py:247-263), NaN -> None so
+        that json.dumps emits valid JSON like the websocket payload at main.py:200.  perf: optional {cell: {gpu_ms, ...}}
+        (the sweep's metrics rows also carry throughput and roofline fraction)."""
+        out = []
+        for (name, sev), r in results.items():
+            rec = {"corruption": name, "severity": sev}
+            for k in CorruptionSweep.COLUMNS[2:]:
+                v = r.get(k)
+                rec[k] = None if (isinstance(v, float) and math.isnan(v)) else (round(v, 6) if isinstance(v, float) else v)
+            if perf is not None and (name, sev) in perf:
+                for k in CorruptionSweep.PERF_COLUMNS:
+                    v = perf[(name, sev)].get(k)
+                    rec[k] = round(v, 6) if isinstance(v, float) else v
+            out.append(rec)
+        return out
+
+    @staticmethod
+    def to_csv(results, perf=None):
+        """In-memory CSV in the style of session_logger.py:15-51 (header row, one row per record)."""
+        cols = CorruptionSweep.COLUMNS + (CorruptionSweep.PERF_COLUMNS if perf is not None else [])
         buf = io.StringIO()
         wr = csv.writer(buf)
         wr.writerow(cols)
-        for (name, sev), r in results.items():
-            wr.writerow([name, sev] + [round(r[k], 6) if isinstance(r.get(k), float) and not math.isnan(r[k]) else r.get(k, "")
-                                      for k in cols[2:]])
+        for rec in CorruptionSweep.records(results, perf):
+            wr.writerow(["" if rec.get(k) is None else rec.get(k) for k in cols])
         return buf.getvalue()
+
+    @staticmethod
+    def to_json(results, perf=None, header=None):
+        """One JSON document: {'type': 'sweep_result', 'config': ..., 'cells': [records]} -- the shape of the reference's
+        batch reply {'type': 'sequence_result', 'data': [...]} (main.py:354-357)."""
+        import json
+        doc = {"type": "sweep_result"}
+        doc.update(header or {})
+        doc["cells"] = CorruptionSweep.records(results, perf)
+        return json.dumps(doc)
+
+
+def measured_peaks():
+    """Roofline denominators: the driver-written MEASURED_PEAKS.json at the repo root when present, else the profiling
+    guide's fallback numbers."""
+    import json
+    import os
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def step_gflop(sweep, images_dev, labels_dev):
+    """Nominal conv GFLOP of ONE block through the classifier (each launch's own 2*M*K*N as recorded by the library's
+    per-launch timing: the pass-invariant prefix once per image, the rest T times)."""
+    lib, h = sweep.clf.lib, sweep.clf.handle.h
+    lib.fav_conv_timing_enable(h, 1)
+    sweep.run_item(images_dev, labels_dev, (0, 0))
+    ms, gf, cnt = (C.c_float * 512)(), (C.c_float * 512)(), C.c_int()
+    _lib.check(lib.fav_conv_timing_read_all(h, ms, gf, 512, C.byref(cnt)), "fav_conv_timing_read_all")
+    lib.fav_conv_timing_enable(h, 0)
+    return float(sum(gf[i] for i in range(cnt.value)))
 
 
 def main(argv=None):
-    """``python -m fav.sweep``: a corruption sweep on synthetic Philox images (there are no datasets offline), results as
-    CSV on stdout.  Under torchrun every rank takes its share of the (cell, block) items; rank 0 prints."""
+    """``python -m fav.sweep``: a corruption sweep on synthetic Philox images (there are no datasets offline).  Results per
+    (corruption, severity) cell -- n, accuracy, ECE, mean confidence / entropy / MI, failure rate, AUROC x 3 plus device time,
+    evals/s and roofline fraction -- as CSV (session_logger.py style) or one JSON document on stdout or --out.  Under
+    torchrun every rank takes its share of the (cell, block) items; rank 0 prints."""
     import argparse
     import ctypes
     import os
@@ -349,6 +432,8 @@ def main(argv=None):
     ap.add_argument("--severities", default="1,2,3,4,5")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--logit-gain", type=float, default=8.0, help="fixture for random-init weights (SURVEY.md section 7)")
+    ap.add_argument("--format", default="csv", choices=["csv", "json"])
+    ap.add_argument("--out", default="-", help="output file ('-' = stdout)")
     a = ap.parse_args(argv)
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -366,9 +451,30 @@ def main(argv=None):
     st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(sw.clf.lib.fav_synth_images(sw.clf.handle.h, _ptr(x), a.images, a.hw, a.hw, a.seed, 0, st), "fav_synth_images")
     _lib.check(sw.clf.lib.fav_synth_labels(sw.clf.handle.h, _ptr(y), a.images, a.classes, a.seed, 0, st), "fav_synth_labels")
-    res = sw.run(x, y, rank=rank, world_size=world)
+    gflop_block = step_gflop(sw, x, y)                       # also warms every kernel of the forward
+    res = sw.run(x, y, rank=rank, world_size=world, timing=True)
+    ms = torch.tensor(sw.cell_ms, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.SUM)            # GPU-milliseconds per cell, summed over the ranks
     if rank == 0:
-        sys.stdout.write(CorruptionSweep.to_csv(res))
+        peaks = measured_peaks()
+        gflop_eval = gflop_block / min(cfg.block, a.images)
+        perf = {}
+        for c, r, m in zip(sw.cells, res.values(), ms.tolist()):
+            tf = gflop_eval * r["n"] / m if m > 0 else 0.0                   # GFLOP / ms = TFLOP/s (per GPU)
+            perf[(c.name or "clean", c.severity)] = {"gpu_ms": m, "evals_per_gpu_s": r["n"] / m * 1e3 if m > 0 else 0.0,
+                                                      "tflops": tf, "roofline_frac": tf / peaks["bf16_tflops_sustained"]}
+        if a.format == "csv":
+            text = CorruptionSweep.to_csv(res, perf)
+        else:
+            text = CorruptionSweep.to_json(res, perf, {"config": cfg.to_dict(), "images": a.images, "n_gpus": world,
+                                                      "gflop_per_eval": gflop_eval, "roofline_peak_tflops": peaks["bf16_tflops_sustained"],
+                                                      "roofline_peak_source": peaks["source"] + " (sustained cuBLAS bf16)"}) + "\n"
+        if a.out == "-":
+            sys.stdout.write(text)
+        else:
+            with open(a.out, "w") as fh:
+                fh.write(text)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -420,3 +420,115 @@ def test_glass_swap_wavefront_schedule_equals_the_sequential_chain():
                 for a, b in swaps:
                     wav[a], wav[b] = wav[b], wav[a]
         assert np.array_equal(seq, wav), (h, w, delta, iters, band)
+
+
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def _reference_live_tick():
+    """The live-mode body of the reference's loop (platform/backend/main.py:153-196: analyze -> engine.update -> state keys
+    -> attribution -> logging), lifted as TEXT from the unmodified copy in baseline/_ref/main.py into a plain function
+    (main.py itself is never imported)."""
+    import textwrap
+    lines = open(os.path.join(REF_DIR, "main.py")).read().splitlines()
+    live = "\n".join(lines[152:188])                 # :153-188, body of `else:  # Live mode`
+    tail = "\n".join(lines[189:196])                 # :190-196, `if state:` attribution + log
+    assert "analyzer.analyze_frame(frame)" in live and "logger.log(state" in tail, "reference main.py changed"
+    src = ("def tick(video_src, analyzer, engine, attributor, logger, source_mode, dt, last_processed_frame_id, last_analysis,\n"
+           "         _frame_to_base64_jpeg):\n    state = None\n" + textwrap.indent(textwrap.dedent(live), "    ") + "\n" +
+           textwrap.indent(textwrap.dedent(tail), "    ") + "\n    return state, last_processed_frame_id, last_analysis\n")
+    ns = {}
+    exec(compile(src, "baseline/_ref/main.py:153-196", "exec"), ns)
+    return ns["tick"]
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_DIR, "main.py")), reason="baseline/_ref not installed (run build())")
+def test_gate_dict_flows_through_the_reference_loop():
+    """f3: the dict UncertaintyGate.analyze_frame returns (SignalAnalyzer's keys + metrics['uncertainty']) goes through the
+    reference's own loop body unchanged: engine.update accepts it, the state payload stays JSON-serialisable (ws.send_json,
+    main.py:200), SessionLogger.log and FailureAttributor.update work, and the extra keys reach state['signal_metrics']."""
+    sys.path.insert(0, REF_DIR)
+    try:
+        from trust_engine import TrustEngine
+        from session_logger import SessionLogger
+        from failure_attributor import FailureAttributor
+    finally:
+        sys.path.remove(REF_DIR)
+    from fav.gate import SignalFinisher, assemble_result
+    from oracle import frame_stats as OFS
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden_frames import frame_sequence
+
+    class StubGate:
+        """UncertaintyGate without the GPU: same SignalFinisher + assemble_result, frame statistics from the CPU oracle,
+        classifier outputs faked."""
+        def __init__(self):
+            self.fin, self.prev = SignalFinisher(), None
+
+        def analyze_frame(self, frame):
+            st, self.prev = OFS.frame_stats(frame, self.prev)
+            conf = 0.5 + 0.4 * float(frame[0, 0, 0]) / 255.0
+            return assemble_result(self.fin.finish(st, frame.shape[0] * frame.shape[1]), (conf, 2.5, 0.3, 17), "uncertainty", 0.9, 1000)
+
+    class Src:
+        def __init__(self, frames):
+            self.frames, self.i = frames, 0
+
+        def get_frame(self):
+            self.i += 1
+            return self.frames[(self.i - 1) % len(self.frames)], self.i
+
+    tick = _reference_live_tick()
+    engine, logger, attributor, gate = TrustEngine(), SessionLogger(), FailureAttributor(), StubGate()
+    src = Src(frame_sequence(0, 96, 128))
+    last_id, last_analysis = 0, None
+    for _ in range(12):
+        state, last_id, last_analysis = tick(src, gate, engine, attributor, logger, "video", 1 / 30, last_id, last_analysis,
+                                             lambda f: "jpeg")
+        assert state is not None
+        payload = json.loads(json.dumps(state))                              # what ws.send_json would put on the wire
+        u = payload["signal_metrics"]["uncertainty"]
+        assert set(u) == {"confidence", "entropy", "mutual_information", "pred", "normalized_entropy", "high_confidence"}
+        assert payload["anomaly_score"] == round(2.5 / np.log(1000), 6) and payload["vision_status"].startswith("VISION_")
+        assert 0.0 <= payload["reliability"] <= 1.0 and "failure_events" in payload
+    rows = logger.get_csv().strip().splitlines()
+    assert len(rows) == 13 and rows[0].split(",") == SessionLogger.HEADER
+
+
+def test_sweep_wire_format_records():
+    """f3: per-cell records (CSV in session_logger.py style, JSON like the 'sequence_result' reply of main.py:354-357) carry the
+    metrics plus device time, evals/s and roofline fraction; NaN AUROC (single-class cell) becomes null / empty."""
+    from fav.sweep import CorruptionSweep
+    res = {("fog", 1): {"n": 10, "accuracy": 0.5, "ece": 0.123456789, "mean_confidence": 0.3, "mean_entropy": 1.0,
+                        "mean_mutual_information": 0.0, "failure_rate": 0.1, "auroc_msp": float("nan"), "auroc_entropy": 0.6,
+                        "auroc_mi": 0.5}}
+    perf = {("fog", 1): {"gpu_ms": 1.5, "evals_per_gpu_s": 6666.6, "tflops": 100.0, "roofline_frac": 0.07}}
+    doc = json.loads(CorruptionSweep.to_json(res, perf, {"n_gpus": 2}))
+    assert doc["type"] == "sweep_result" and doc["n_gpus"] == 2
+    (c,) = doc["cells"]
+    assert c["auroc_msp"] is None and c["ece"] == 0.123457 and c["roofline_frac"] == 0.07 and c["evals_per_gpu_s"] == 6666.6
+    hdr, row = CorruptionSweep.to_csv(res, perf).strip().splitlines()
+    assert hdr.split(",") == CorruptionSweep.COLUMNS + CorruptionSweep.PERF_COLUMNS
+    assert row.split(",")[:3] == ["fog", "1", "10"] and row.split(",")[9] == ""
+
+
+def test_work_items_interleave_the_grid():
+    """Any 20 consecutive steps (the driver's bench window) visit all 15 corruptions and all 5 severities, any 15 at least 14
+    corruptions; per-rank round-robin shares sample the whole grid; every (cell, block) item appears exactly once."""
+    from fav.sweep import CorruptionSweep, SweepConfig
+
+    class _NoGpu(CorruptionSweep):
+        def __init__(self, cfg):
+            self.cfg, self.cells = cfg, cfg.cells()
+
+    sw = _NoGpu(SweepConfig(block=100))
+    items = sw.work_items(250)
+    assert sorted(items) == [(ci, b) for ci in range(75) for b in range(3)]
+    for start in (0, 7, 60, 75, 100):
+        win = items[start:start + 15]
+        assert len({sw.cells[ci].name for ci, _ in win}) >= 14
+        assert len({sw.cells[ci].severity for ci, _ in win}) == 5
+        assert len({sw.cells[ci].name for ci, _ in items[start:start + 20]}) == 15
+    for world in (2, 4, 8):                       # a rank's round-robin share of the first 75 items still mixes the grid
+        share = [sw.cells[items[i][0]].name for i in range(0, 75, world)]
+        assert len(set(share)) >= min(15, len(share)) - 2
