@@ -531,4 +531,4 @@ def test_work_items_interleave_the_grid():
         assert len({sw.cells[ci].name for ci, _ in items[start:start + 20]}) == 15
     for world in (2, 4, 8):                       # a rank's round-robin share of the first 75 items still mixes the grid
         share = [sw.cells[items[i][0]].name for i in range(0, 75, world)]
-        assert len(set(share)) >= min(15, len(share)) - 2
+        assert len(set(share)) >= 0.75 * min(15, len(share))
