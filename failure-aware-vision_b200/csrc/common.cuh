@@ -165,7 +165,8 @@ struct Ctx {
   // K1 host tables (tables.cu): per-(corruption, severity, h, w, profile) constants + device tables, library-owned scratch
   void* k1_cache = nullptr;
   // kernel attributes (max dynamic shared memory) are per device: set once per handle, not once per process
-  bool attr_conv = false, attr_flat = false, attr_pair = false;
+  bool attr_conv = false, attr_flat = false, attr_pair = false, attr_shot = false, attr_plasma = false;
+  bool k1_legacy = false;         // fav_set_option(h, "k1_legacy", 1): the round-1 K1 kernels (A/B measurements, fallback)
   int world = 1, rank = 0;
 };
 

@@ -436,6 +436,223 @@ __global__ void __launch_bounds__(1024) k1_plasma(const uint8_t* __restrict__ sr
   }
 }
 
+// ---------------------------------------------------------------- element emitters of the fast pointwise kernels
+// clip to [0,1], normalize (unless FAV_NO_NORMALIZE) and store CNT consecutive elements that start at element `base`
+// (channel of element i = (c0 + i) % 3).  CNT = 16: base is a multiple of 16; CNT = 12: base is a multiple of 12.
+template <int CNT>
+__device__ __forceinline__ void emit_elems(void* dst, size_t base, int c0, float* v, const float* mean, const float* inv_std,
+                                           unsigned flags) {
+#pragma unroll
+  for (int i = 0; i < CNT; ++i) {
+    float t = fminf(fmaxf(v[i], 0.0f), 1.0f);
+    if (!(flags & FAV_NO_NORMALIZE)) t = __fmul_rn(__fsub_rn(t, mean[(c0 + i) % 3]), inv_std[(c0 + i) % 3]);
+    v[i] = t;
+  }
+  if (flags & FAV_OUT_F32) {
+    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + base);     // 16-byte aligned for both CNTs
+#pragma unroll
+    for (int i = 0; i < CNT / 4; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else if (CNT == 16) {
+    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(dst) + base);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      o[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                        pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+  } else {
+    uint2* o = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dst) + base);   // 24-byte chunks: 8-byte aligned
+#pragma unroll
+    for (int i = 0; i < CNT / 4; ++i)
+      o[i] = make_uint2(pack_bf16x2(v[4 * i], v[4 * i + 1]), pack_bf16x2(v[4 * i + 2], v[4 * i + 3]));
+  }
+}
+
+// ---------------------------------------------------------------- shot noise with the guide table in shared memory
+// Same definition as k1_pointwise<PW_SHOT> (k = kmin[v] + #{j : thr[v][j] <= u}, u = one Philox word per element), different
+// search: guide[v][u >> 24] (uint16: k for the draw (b << 24) in the low 10 bits, number of thresholds that fall inside the
+// top-byte cell in the high 6, saturated) answers ~80 % of the draws with ONE shared-memory read; only draws whose cell
+// contains a threshold probe the 32-bit thresholds (global, L2-resident).  k / c is the exact division by the 3-FMA
+// residual correction (verified for every k < 1024 and every c of the severity tables, tests/test_host.py).
+struct ShotArgs {
+  const uint8_t* src;
+  void* dst;
+  int n, per, groups_per_image;
+  uint32_t k0, k1, first_image, stream;
+  float c, rc;
+  int width;
+  const int* kmin;
+  const uint32_t* thr;
+  const uint16_t* guide;
+  float mean[3], inv_std[3];
+  unsigned flags;
+};
+__global__ void __launch_bounds__(1024) k1_shot_smem(const ShotArgs a) {
+  extern __shared__ __align__(16) uint16_t s_guide[];          // [256][256]
+  {
+    const uint4* g4 = reinterpret_cast<const uint4*>(a.guide);
+    uint4* s4 = reinterpret_cast<uint4*>(s_guide);
+    for (int i = threadIdx.x; i < 8192; i += blockDim.x) s4[i] = __ldg(g4 + i);
+  }
+  __syncthreads();
+  const long long total = (long long)a.n * a.groups_per_image;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    const int img = int(g / a.groups_per_image);
+    const int gi = int(g - (long long)img * a.groups_per_image);
+    const int e0 = gi * 48;                                      // per % 48 == 0 (host-checked): whole groups only
+    const size_t base = (size_t)img * a.per + e0;
+    const uint32_t gimg = a.first_image + uint32_t(img);
+    const uint4* p = reinterpret_cast<const uint4*>(a.src + base);
+#pragma unroll
+    for (int q3 = 0; q3 < 3; ++q3) {
+      const uint4 v4 = __ldg(p + q3);
+      const uint32_t w[4] = {v4.x, v4.y, v4.z, v4.w};
+      float x[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 r = philox4x32_10(uint32_t(e0 / 4 + 4 * q3 + j), gimg, 0u, a.stream, a.k0, a.k1);
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t b = (w[j] >> (8 * q)) & 0xFFu, u = rr[q];
+          const uint32_t gg = s_guide[b * 256u + (u >> 24)];
+          int k = int(gg & 1023u);
+          if (gg >> 10) {                                        // thresholds inside this cell: count the ones <= u
+            const int km = __ldg(a.kmin + b);
+            const uint32_t* row = a.thr + (size_t)b * a.width;
+            int lo = k - km;
+            while (lo < a.width && __ldg(row + lo) <= u) ++lo;
+            k = km + lo;
+          }
+          const float kf = float(k), qf = __fmul_rn(kf, a.rc);
+          x[4 * j + q] = __fmaf_rn(__fmaf_rn(-qf, a.c, kf), a.rc, qf);         // == __fdiv_rn(kf, c)
+        }
+      }
+      emit_elems<16>(a.dst, base + 16 * q3, q3 % 3, x, a.mean, a.inv_std, a.flags);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- fog / frost on small frames: plasma in shared memory
+// One WARP per image: the diamond-square map (mapsize <= 64) lives in shared memory, the levels are separated by
+// __syncwarp, min / max / image max are warp reductions, and the same warp then applies the map to its image four pixels
+// at a time -- one kernel, the image is read twice (max, apply) and written once, nothing else touches global memory.
+// Arithmetic and operation order are those of k1_plasma + k1_pointwise<PW_FOG / PW_FROST> (bit-identical results).
+struct PlasmaFusedArgs {
+  const uint8_t* src;
+  void* dst;
+  int n, h, w, mapsize, frost;
+  float f0, f1, decay;
+  float tint[3];
+  uint32_t k0, k1, first_image, stream;
+  float mean[3], inv_std[3];
+  unsigned flags;
+};
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) k1_plasma_fused(const PlasmaFusedArgs a) {
+  extern __shared__ float s_maps[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int img = blockIdx.x * WARPS + warp;
+  if (img >= a.n) return;                                       // whole warps leave: no block-wide barrier below
+  const int ms = a.mapsize, mask = ms - 1, hw = a.h * a.w, per = hw * 3;
+  float* M = s_maps + (size_t)warp * ms * ms;
+  const uint32_t gimg = a.first_image + uint32_t(img);
+  auto noise = [&](int y, int x) {
+    const uint4 r = philox4x32_10(uint32_t(y * ms + x), gimg, 0u, a.stream, a.k0, a.k1);
+    return __fsub_rn(__fmul_rn(2.0f, u32_to_uniform(r.x)), 1.0f);
+  };
+  if (lane == 0) M[0] = 0.0f;
+  __syncwarp();
+  float wib = 100.0f;
+  for (int step = ms; step >= 2; step >>= 1) {
+    const int hf = step >> 1, cells = ms / step;
+    const float w2 = __fmul_rn(wib, wib);
+    for (int i = lane; i < cells * cells; i += 32) {            // squares
+      const int y = (i / cells) * step, x = (i % cells) * step;
+      const float c00 = M[y * ms + x], c10 = M[((y + step) & mask) * ms + x];
+      const float c01 = M[y * ms + ((x + step) & mask)], c11 = M[((y + step) & mask) * ms + ((x + step) & mask)];
+      const float sq = __fadd_rn(__fadd_rn(c00, c10), __fadd_rn(c01, c11));
+      M[(y + hf) * ms + x + hf] = __fadd_rn(__fmul_rn(sq, 0.25f), __fmul_rn(w2, noise(y + hf, x + hf)));
+    }
+    __syncwarp();
+    for (int i = lane; i < cells * cells; i += 32) {            // diamonds
+      const int y = (i / cells) * step, x = (i % cells) * step;
+      const float ul = M[y * ms + x], dr = M[(y + hf) * ms + x + hf];
+      const float dru = M[((y - hf) & mask) * ms + x + hf], ulr = M[y * ms + ((x + step) & mask)];
+      const float lt = __fadd_rn(__fadd_rn(dr, dru), __fadd_rn(ul, ulr));
+      const float drl = M[(y + hf) * ms + ((x - hf) & mask)], uld = M[((y + step) & mask) * ms + x];
+      const float tt = __fadd_rn(__fadd_rn(dr, drl), __fadd_rn(ul, uld));
+      M[y * ms + x + hf] = __fadd_rn(__fmul_rn(lt, 0.25f), __fmul_rn(w2, noise(y, x + hf)));
+      M[(y + hf) * ms + x] = __fadd_rn(__fmul_rn(tt, 0.25f), __fmul_rn(w2, noise(y + hf, x)));
+    }
+    __syncwarp();
+    wib = __fdiv_rn(wib, a.decay);
+  }
+  float mn = 3.4e38f, mx = -3.4e38f;
+  for (int i = lane; i < ms * ms; i += 32) { const float v = M[i]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+  unsigned xm = 0;
+  const uint8_t* p = a.src + (size_t)img * per;
+  if ((per & 3) == 0 && (reinterpret_cast<uintptr_t>(p) & 3) == 0) {
+    const uint32_t* p4 = reinterpret_cast<const uint32_t*>(p);
+    for (int i = lane; i < (per >> 2); i += 32) xm = __vmaxu4(xm, __ldg(p4 + i));
+    xm = max(max(xm & 0xFFu, (xm >> 8) & 0xFFu), max((xm >> 16) & 0xFFu, xm >> 24));
+  } else {
+    for (int i = lane; i < per; i += 32) xm = max(xm, (unsigned)p[i]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    xm = max(xm, __shfl_xor_sync(0xffffffffu, xm, o));
+  }
+  const float pmx = __fsub_rn(mx, mn), xmx = __fdiv_rn(float(xm), 255.0f);
+  const float gain = __fdiv_rn(xmx, __fadd_rn(xmx, a.f0));
+  const bool quad_ok = (reinterpret_cast<uintptr_t>(p) & 3) == 0 && !(a.flags & FAV_SRC_BGR);
+  const int nq = (hw + 3) >> 2;
+  for (int q = lane; q < nq; q += 32) {
+    const int pix0 = 4 * q, npx = min(4, hw - pix0);
+    uint32_t w3[3] = {0, 0, 0};
+    if (quad_ok && npx == 4) {
+      const uint32_t* p4 = reinterpret_cast<const uint32_t*>(p + 3 * (size_t)pix0);
+      w3[0] = __ldg(p4); w3[1] = __ldg(p4 + 1); w3[2] = __ldg(p4 + 2);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 12; ++e) {                             // compile-time indices: w3 / v stay in registers
+        const int se = (a.flags & FAV_SRC_BGR) ? e - (e % 3) + 2 - (e % 3) : e;
+        if (e < 3 * npx) w3[e >> 2] |= uint32_t(p[3 * (size_t)pix0 + se]) << (8 * (e & 3));
+      }
+    }
+    float v[12];
+#pragma unroll
+    for (int pp = 0; pp < 4; ++pp) {
+      const int pix = min(pix0 + pp, hw - 1);
+      const int yy = pix / a.w, xx = pix - yy * a.w;
+      const float pl = __fdiv_rn(__fsub_rn(M[yy * ms + xx], mn), pmx);
+      const float f = fminf(fmaxf(__fsub_rn(__fmul_rn(1.35f, pl), 0.1f), 0.f), 1.f);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int e = 3 * pp + c;
+        const float xb = div255(float((w3[e >> 2] >> (8 * (e & 3))) & 0xFFu));
+        v[e] = a.frost ? __fadd_rn(__fmul_rn(a.f0, xb), __fmul_rn(a.f1, __fmul_rn(f, a.tint[c])))
+                       : __fmul_rn(__fadd_rn(xb, __fmul_rn(a.f0, pl)), gain);
+      }
+    }
+    const size_t base = (size_t)img * per + 3 * (size_t)pix0;
+    const bool aligned = (a.flags & FAV_OUT_F32) ? ((reinterpret_cast<uintptr_t>(a.dst) & 15) == 0 && (per & 3) == 0)
+                                                 : ((reinterpret_cast<uintptr_t>(a.dst) & 7) == 0 && (per & 3) == 0);
+    if (npx == 4 && aligned) {
+      emit_elems<12>(a.dst, base, 0, v, a.mean, a.inv_std, a.flags);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 12; ++e) {
+        if (e >= 3 * npx) continue;
+        float t = fminf(fmaxf(v[e], 0.0f), 1.0f);
+        if (!(a.flags & FAV_NO_NORMALIZE)) t = __fmul_rn(__fsub_rn(t, a.mean[e % 3]), a.inv_std[e % 3]);
+        if (a.flags & FAV_OUT_F32) reinterpret_cast<float*>(a.dst)[base + e] = t;
+        else reinterpret_cast<__nv_bfloat16*>(a.dst)[base + e] = __float2bfloat16_rn(t);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- shared store helper for the gather kernels
 struct OutArgs {
   void* dst;
@@ -471,6 +688,8 @@ struct TapArgs {
   uint32_t k0, k1, first_image, stream;  // entry = Philox(AUX).x % n_entries when n_entries > 1
   int tiles_x, tiles_y;
   unsigned src_bgr;
+  int raw_stage;                         // 1: one tile per image, raw image staged in shared memory with 16-byte loads
+  int out_staged;                        // 1: bf16 rows are 16-byte aligned -> coalesced stores through shared memory
 };
 constexpr int TAP_TILE = 32;
 
@@ -505,6 +724,15 @@ __global__ void __launch_bounds__(256) k1_taps(const TapArgs a) {
     s_taps[i] = make_uint2(uint32_t((dy - a.dy_min) * SW + (dx - a.dx_min)), t.y);
   }
   const uint8_t* p = a.src + (size_t)img * a.h * a.w * 3;
+  if (a.raw_stage) {
+    // small frames (one tile per image): the raw image comes in with coalesced 16-byte loads and the halo is expanded from
+    // shared memory (the byte gathers of the generic path cost more than the stencil itself at 32x32)
+    uint4* s_raw = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(s_taps + a.max_taps) + 15) & ~uintptr_t(15));
+    const int nv = (a.h * a.w * 3) >> 4;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) s_raw[i] = __ldg(reinterpret_cast<const uint4*>(p) + i);
+    __syncthreads();
+    p = reinterpret_cast<const uint8_t*>(s_raw);
+  }
   for (int i = threadIdx.x; i < SW * SH; i += blockDim.x) {
     const int sy = i / SW, sx = i - sy * SW;
     const int yy = border_idx(y0 + sy + a.dy_min, a.h, a.border);
@@ -529,6 +757,30 @@ __global__ void __launch_bounds__(256) k1_taps(const TapArgs a) {
       acc[j][1] = fmaf(wgt, v.y, acc[j][1]);
       acc[j][2] = fmaf(wgt, v.z, acc[j][2]);
     }
+  }
+  // bf16 output of a full-width tile whose rows are 16-byte aligned: stage the 32 x 32 x 3 results in shared memory (over
+  // the halo, which is dead now) and write each 192-byte row with 16-byte stores instead of 2-byte stores at a 6-byte stride
+  const bool staged = a.out_staged && x0 + TAP_TILE <= a.w;
+  if (staged) {
+    __syncthreads();                                           // every thread is done reading the halo
+    __nv_bfloat16* s_out = reinterpret_cast<__nv_bfloat16*>(s_tile);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float t = fminf(fmaxf(__fdiv_rn(acc[j][c], 255.0f), 0.0f), 1.0f);
+        if (!(a.out.flags & FAV_NO_NORMALIZE)) t = __fmul_rn(__fsub_rn(t, a.out.mean[c]), a.out.inv_std[c]);
+        s_out[((ly0 + 8 * j) * TAP_TILE + lx) * 3 + c] = __float2bfloat16_rn(t);
+      }
+    }
+    __syncthreads();
+    const int rows = min(TAP_TILE, a.h - y0);
+    for (int i = threadIdx.x; i < rows * 12; i += blockDim.x) {            // 12 x 16 bytes per tile row
+      const int r = i / 12, k = i - r * 12;
+      uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out.dst) + (((size_t)img * a.h + y0 + r) * a.w + x0) * 3) + k;
+      *o = reinterpret_cast<const uint4*>(s_out + (size_t)r * TAP_TILE * 3)[k];
+    }
+    return;
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -1337,11 +1589,33 @@ extern "C" int fav_corrupt_normalize_ex(fav_handle h, const uint8_t* d_src, void
       FAV_REQUIRE(need_f(1), "gaussian_noise needs fparams[0]=sigma");
       a.f0 = fparams[0];
       k1_pointwise<PW_GAUSS><<<grid, 256, 0, st>>>(a); h->launches++; break;
-    case FAV_SHOT_NOISE:
+    case FAV_SHOT_NOISE: {
       FAV_REQUIRE(need_f(1) && need_i(1) && d_table, "shot_noise needs fparams[0]=c, iparams[0]=width, table");
       FAV_REQUIRE(table_bytes >= 1024 + (size_t)iparams[0] * 1024 + 256 * 256 * 2, "shot_noise table too small");
       a.f0 = fparams[0]; a.u0 = uint32_t(iparams[0]);
+      const size_t guide_off = n_iparams >= 2 ? size_t(iparams[1]) : 0;       // 0: no guide table (k does not fit 10 bits)
+      if (guide_off && !h->k1_legacy && table_bytes >= guide_off + 131072 && (per % 48) == 0 && !(flags & FAV_SRC_BGR) &&
+          (reinterpret_cast<uintptr_t>(d_src) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_dst) & 15) == 0 && (guide_off & 15) == 0 &&
+          (reinterpret_cast<uintptr_t>(d_table) & 15) == 0) {
+        ShotArgs sa{};
+        sa.src = d_src; sa.dst = d_dst; sa.n = n; sa.per = per; sa.groups_per_image = per / 48;
+        sa.k0 = k0; sa.k1 = k1; sa.first_image = uint32_t(first_image); sa.stream = a.stream;
+        sa.c = fparams[0]; sa.rc = 1.0f / fparams[0]; sa.width = iparams[0];
+        sa.kmin = reinterpret_cast<const int*>(d_table);
+        sa.thr = reinterpret_cast<const uint32_t*>(d_table) + 256;
+        sa.guide = reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(d_table) + guide_off);
+        for (int c = 0; c < 3; ++c) { sa.mean[c] = mean[c]; sa.inv_std[c] = 1.0f / std[c]; }
+        sa.flags = flags;
+        if (!h->attr_shot) {
+          FAV_CUDA_OK(cudaFuncSetAttribute(k1_shot_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+          h->attr_shot = true;
+        }
+        const long long ctas = (groups + 1023) / 1024;
+        k1_shot_smem<<<int(ctas < h->num_sms ? ctas : h->num_sms), 1024, 131072, st>>>(sa);
+        h->launches++; break;
+      }
       k1_pointwise<PW_SHOT><<<grid, 256, 0, st>>>(a); h->launches++; break;
+    }
     case FAV_IMPULSE_NOISE:
       FAV_REQUIRE(need_i(2), "impulse_noise needs iparams[0..1]=pepper,salt thresholds");
       a.u0 = uint32_t(iparams[0]); a.u1 = uint32_t(iparams[1]);
@@ -1370,32 +1644,42 @@ extern "C" int fav_corrupt_normalize_ex(fav_handle h, const uint8_t* d_src, void
       }
       k1_pointwise<PW_CONTRAST><<<grid, 256, 0, st>>>(a); h->launches += 2; break;
     }
-    case FAV_FOG: {
-      FAV_REQUIRE(need_f(2), "fog needs fparams[0]=c, fparams[1]=wibble decay");
-      FAV_REQUIRE(d_scratch && scratch_bytes >= fav_corrupt_scratch_bytes(corruption, n, height, width),
-                  "fog needs %zu scratch bytes", fav_corrupt_scratch_bytes(corruption, n, height, width));
-      int m = 1;
-      while (m < max(height, width)) m *= 2;
-      a.f0 = fparams[0]; a.mapsize = m;
-      a.map_offset = (((size_t)n * 16) + 255) / 256 * 256;
-      float* stats = reinterpret_cast<float*>(d_scratch);
-      float* maps = reinterpret_cast<float*>(reinterpret_cast<char*>(d_scratch) + a.map_offset);
-      k1_plasma<<<n, 1024, 0, st>>>(d_src, per, m, fparams[1], k0, k1, uint32_t(first_image), a.stream, stats, maps);
-      k1_pointwise<PW_FOG><<<grid, 256, 0, st>>>(a); h->launches += 2; break;
-    }
+    case FAV_FOG:
     case FAV_FROST: {
-      FAV_REQUIRE(need_f(6), "frost needs fparams = c0, c1, plasma decay, tint r, g, b");
-      FAV_REQUIRE(d_scratch && scratch_bytes >= fav_corrupt_scratch_bytes(corruption, n, height, width),
-                  "frost needs %zu scratch bytes", fav_corrupt_scratch_bytes(corruption, n, height, width));
+      const bool frost = corruption == FAV_FROST;
+      FAV_REQUIRE(frost ? need_f(6) : need_f(2), frost ? "frost needs fparams = c0, c1, plasma decay, tint r, g, b"
+                                                       : "fog needs fparams[0]=c, fparams[1]=wibble decay");
       int m = 1;
       while (m < max(height, width)) m *= 2;
-      a.f0 = fparams[0]; a.f1 = fparams[1]; a.mapsize = m;
-      a.tint[0] = fparams[3]; a.tint[1] = fparams[4]; a.tint[2] = fparams[5];
+      if (m <= 64 && !h->k1_legacy) {
+        // small frames: plasma map in shared memory, one warp per image, map + statistics + application in ONE kernel
+        PlasmaFusedArgs pf{};
+        pf.src = d_src; pf.dst = d_dst; pf.n = n; pf.h = height; pf.w = width; pf.mapsize = m; pf.frost = frost ? 1 : 0;
+        pf.f0 = fparams[0]; pf.f1 = frost ? fparams[1] : 0.f; pf.decay = frost ? fparams[2] : fparams[1];
+        for (int c = 0; c < 3; ++c) { pf.tint[c] = frost ? fparams[3 + c] : 0.f; pf.mean[c] = mean[c]; pf.inv_std[c] = 1.0f / std[c]; }
+        pf.k0 = k0; pf.k1 = k1; pf.first_image = uint32_t(first_image); pf.stream = a.stream; pf.flags = flags;
+        if (m <= 32) {
+          k1_plasma_fused<8><<<(n + 7) / 8, 256, (size_t)8 * m * m * 4, st>>>(pf);
+        } else {
+          if (!h->attr_plasma) {
+            FAV_CUDA_OK(cudaFuncSetAttribute(k1_plasma_fused<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 64 * 64 * 4));
+            h->attr_plasma = true;
+          }
+          k1_plasma_fused<4><<<(n + 3) / 4, 128, (size_t)4 * m * m * 4, st>>>(pf);
+        }
+        h->launches++; break;
+      }
+      FAV_REQUIRE(d_scratch && scratch_bytes >= fav_corrupt_scratch_bytes(corruption, n, height, width),
+                  "fog / frost need %zu scratch bytes", fav_corrupt_scratch_bytes(corruption, n, height, width));
+      a.f0 = fparams[0]; a.mapsize = m;
+      if (frost) { a.f1 = fparams[1]; a.tint[0] = fparams[3]; a.tint[1] = fparams[4]; a.tint[2] = fparams[5]; }
       a.map_offset = (((size_t)n * 16) + 255) / 256 * 256;
       float* stats = reinterpret_cast<float*>(d_scratch);
       float* maps = reinterpret_cast<float*>(reinterpret_cast<char*>(d_scratch) + a.map_offset);
-      k1_plasma<<<n, 1024, 0, st>>>(d_src, per, m, fparams[2], k0, k1, uint32_t(first_image), a.stream, stats, maps);
-      k1_pointwise<PW_FROST><<<grid, 256, 0, st>>>(a); h->launches += 2; break;
+      k1_plasma<<<n, 1024, 0, st>>>(d_src, per, m, frost ? fparams[2] : fparams[1], k0, k1, uint32_t(first_image), a.stream, stats, maps);
+      if (frost) k1_pointwise<PW_FROST><<<grid, 256, 0, st>>>(a);
+      else k1_pointwise<PW_FOG><<<grid, 256, 0, st>>>(a);
+      h->launches += 2; break;
     }
     case FAV_ELASTIC: {
       FAV_REQUIRE(need_f(5) && need_i(1) && d_table, "elastic_transform needs fparams[5], iparams[0]=radius and the Gaussian taps");
@@ -1490,7 +1774,12 @@ extern "C" int fav_corrupt_normalize_ex(fav_handle h, const uint8_t* d_src, void
       t.stream = stream_id(KIND_AUX, corruption, severity);
       t.tiles_x = (width + TAP_TILE - 1) / TAP_TILE; t.tiles_y = (height + TAP_TILE - 1) / TAP_TILE;
       t.src_bgr = flags & FAV_SRC_BGR;
-      const size_t smem = (size_t)(TAP_TILE + t.dx_max - t.dx_min) * (TAP_TILE + t.dy_max - t.dy_min) * 16 + (size_t)t.max_taps * 8;
+      const bool src16 = (reinterpret_cast<uintptr_t>(d_src) & 15) == 0 && (per & 15) == 0;
+      t.raw_stage = (!h->k1_legacy && t.tiles_x * t.tiles_y == 1 && src16) ? 1 : 0;
+      t.out_staged = (!h->k1_legacy && !(flags & FAV_OUT_F32) && ((size_t)width * 6) % 16 == 0 && ((size_t)per * 2) % 16 == 0 &&
+                      (reinterpret_cast<uintptr_t>(d_dst) & 15) == 0) ? 1 : 0;
+      const size_t smem = (size_t)(TAP_TILE + t.dx_max - t.dx_min) * (TAP_TILE + t.dy_max - t.dy_min) * 16 + (size_t)t.max_taps * 8 +
+                          (t.raw_stage ? (size_t)per + 16 : 0);
       FAV_REQUIRE(smem <= 200 * 1024, "tap stencil halo too large (%zu B of shared memory)", smem);
       if (smem > 48 * 1024) FAV_CUDA_OK(cudaFuncSetAttribute(k1_taps, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
       k1_taps<<<dim3(n, t.tiles_x * t.tiles_y), 256, smem, st>>>(t); h->launches++; break;

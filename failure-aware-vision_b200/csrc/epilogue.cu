@@ -320,14 +320,19 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_le1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 constexpr int K34S_THREADS = 512;
+constexpr int K34D_THREADS = 128;      // DIRECT variant: small launches, many small CTAs
 
-template <int TPS, int CT>   // CT > 0: C == CT exactly (no predicated class slots); CT == 0: any C <= 16
-__global__ void __launch_bounds__(K34S_THREADS) k34_small_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
+// DIRECT (small launches, e.g. one 4096-sample sweep step): no per-CTA shared-memory histograms -- zeroing and flushing
+// 98 KB of them per CTA costs more than the few thousand samples themselves; every sample's handful of counters goes
+// straight to global atomics (spread over the 25 k slots of the arena row: no contention to speak of).
+template <int TPS, int CT, bool DIRECT = false>   // CT > 0: C == CT exactly (no predicated class slots); CT == 0: any C <= 16
+__global__ void __launch_bounds__(DIRECT ? K34D_THREADS : K34S_THREADS) k34_small_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
                                                         int n, int T, HistGeom g, unsigned long long* __restrict__ hist,
                                                         int hist_bytes, float* __restrict__ o_conf, float* __restrict__ o_H,
                                                         float* __restrict__ o_mi, int32_t* __restrict__ o_pred,
                                                         uint8_t* __restrict__ o_flag) {
-  constexpr int S = K34S_THREADS / TPS, CM = CT > 0 ? CT : 16;
+  constexpr int NTHR = DIRECT ? K34D_THREADS : K34S_THREADS;
+  constexpr int S = NTHR / TPS, CM = CT > 0 ? CT : 16;
   extern __shared__ __align__(16) unsigned char k34_smem[];
   // [n_slots u32 | pad to 8 | n_bins u64 confidence sums | C*C u32 confusion | pad to 16] = hist_bytes, then the two tiles
   unsigned* s_hist = reinterpret_cast<unsigned*>(k34_smem);
@@ -339,18 +344,21 @@ __global__ void __launch_bounds__(K34S_THREADS) k34_small_kernel(const float* __
   unsigned* s_cm = reinterpret_cast<unsigned*>(s_binsum + g.n_bins);
   const bool do_hist = hist != nullptr;
   if (do_hist) {
-    for (int i = threadIdx.x; i < n_slots; i += blockDim.x) s_hist[i] = 0;
-    for (int i = threadIdx.x; i < g.n_bins; i += blockDim.x) s_binsum[i] = 0;
-    for (int i = threadIdx.x; i < C * C; i += blockDim.x) s_cm[i] = 0;
+    if (!DIRECT) {
+      for (int i = threadIdx.x; i < n_slots; i += blockDim.x) s_hist[i] = 0;
+      for (int i = threadIdx.x; i < g.n_bins; i += blockDim.x) s_binsum[i] = 0;
+      for (int i = threadIdx.x; i < C * C; i += blockDim.x) s_cm[i] = 0;
+    }
     if (threadIdx.x < 6) s_sums[threadIdx.x] = 0;
   }
+  const size_t bin0 = FAV_HIST_HDR, bk0 = FAV_HIST_HDR + 3 * (size_t)g.n_bins, cm0 = bk0 + 6 * (size_t)g.n_buckets;
   const int row = T * C, tile_floats = S * row;
   const int ntiles = (n + S - 1) / S;
   auto issue = [&](int tile, int buf) {
     const size_t base = (size_t)tile * tile_floats;
     const int cnt = min(S, n - tile * S) * row;
     float* dst = tiles + (size_t)buf * tile_floats;
-    for (int v = threadIdx.x; v < (cnt >> 2); v += K34S_THREADS) cp_async16(dst + 4 * v, logits + base + 4 * v);
+    for (int v = threadIdx.x; v < (cnt >> 2); v += NTHR) cp_async16(dst + 4 * v, logits + base + 4 * v);
     if (threadIdx.x < (cnt & 3)) dst[(cnt & ~3) + threadIdx.x] = logits[base + (cnt & ~3) + threadIdx.x];
   };
   int tile = blockIdx.x, buf = 0;
@@ -428,10 +436,17 @@ __global__ void __launch_bounds__(K34S_THREADS) k34_small_kernel(const float* __
         if (q == 0) {
           int b = int(ceilf(best * float(g.n_bins))) - 1;
           b = min(max(b, 0), g.n_bins - 1);
-          atomicAdd(&s_hist[2 * b], 1u);
-          if (correct) atomicAdd(&s_hist[2 * b + 1], 1u);
-          atomicAdd(&s_binsum[b], q32(best));
-          atomicAdd(&s_cm[label * C + arg], 1u);
+          if (DIRECT) {
+            atomicAdd(&hist[bin0 + 3 * b], 1ull);
+            if (correct) atomicAdd(&hist[bin0 + 3 * b + 2], 1ull);
+            atomicAdd(&hist[bin0 + 3 * b + 1], q32(best));
+            atomicAdd(&hist[cm0 + label * C + arg], 1ull);
+          } else {
+            atomicAdd(&s_hist[2 * b], 1u);
+            if (correct) atomicAdd(&s_hist[2 * b + 1], 1u);
+            atomicAdd(&s_binsum[b], q32(best));
+            atomicAdd(&s_cm[label * C + arg], 1u);
+          }
           my[0] += 1; my[1] += correct; my[2] += flag;
           my[3] += q32(best); my[4] += q32(sc1); my[5] += q32(sc2);
         }
@@ -442,7 +457,8 @@ __global__ void __launch_bounds__(K34S_THREADS) k34_small_kernel(const float* __
           const float sc = si == 0 ? sc0 : (si == 1 ? sc1 : sc2);
           int k = int(floorf(sc * float(g.n_buckets)));
           k = min(max(k, 0), g.n_buckets - 1);
-          atomicAdd(&s_hist[2 * g.n_bins + (si * g.n_buckets + k) * 2 + (correct ? 0 : 1)], 1u);
+          if (DIRECT) atomicAdd(&hist[bk0 + (size_t)(si * g.n_buckets + k) * 2 + (correct ? 0 : 1)], 1ull);
+          else atomicAdd(&s_hist[2 * g.n_bins + (si * g.n_buckets + k) * 2 + (correct ? 0 : 1)], 1u);
         }
       }
     }
@@ -454,6 +470,7 @@ __global__ void __launch_bounds__(K34S_THREADS) k34_small_kernel(const float* __
     if (my[k]) atomicAdd(&s_sums[k], my[k]);
   __syncthreads();
   if (threadIdx.x < 6 && s_sums[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_sums[threadIdx.x]);
+  if (DIRECT) return;
   for (int i = threadIdx.x; i < n_slots; i += blockDim.x) {
     const unsigned v = s_hist[i];
     if (!v) continue;
@@ -497,6 +514,20 @@ static int launch_k34(fav_handle h, const float* d_logits, const int32_t* d_labe
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   unsigned long long* hist = reinterpret_cast<unsigned long long*>(d_hist);
+  if (d_logits && d_hist && C == 10 && n <= 32768 && T >= 5 && (reinterpret_cast<uintptr_t>(d_logits) & 15) == 0 &&
+      2 * (size_t)(K34D_THREADS / 8) * T * C * 4 <= 200 * 1024) {
+    // small launch (a sweep step): 16 samples per 128-thread CTA, counters straight to global atomics
+    const int S = K34D_THREADS / 8;
+    const size_t sm = 2 * (size_t)S * T * C * 4;
+    if (sm > 48 * 1024) FAV_CUDA_OK(cudaFuncSetAttribute(k34_small_kernel<8, 10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));
+    long long nb = (n + S - 1) / S;
+    const long long cap = (long long)h->num_sms * 8;
+    if (nb > cap) nb = cap;
+    k34_small_kernel<8, 10, true><<<int(nb), K34D_THREADS, sm, st>>>(d_logits, d_labels, n, T, g, hist, 0, d_conf, d_entropy, d_mi, d_pred, d_flag);
+    h->launches++;
+    FAV_CUDA_OK(cudaGetLastError());
+    return FAV_OK;
+  }
   if (d_logits && C <= 16 && (reinterpret_cast<uintptr_t>(d_logits) & 15) == 0) {
     // thread-group-per-sample path: the largest tile (256 / TPS samples) whose two buffers fit beside the histogram
     const size_t hist_bytes = d_hist ? ((((smem + 7) & ~size_t(7)) + (size_t)n_bins * 8 + (size_t)C * C * 4 + 15) & ~size_t(15)) : 0;

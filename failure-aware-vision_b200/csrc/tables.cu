@@ -75,7 +75,7 @@ static void append(std::vector<uint8_t>& buf, const T* p, size_t count) {
 // shot noise: kmin int32[256] | thr uint32[256][width] | jump uint16[256][256]
 // thr[v][j] = floor(CDF_Poisson(v c / 255)(kmin[v] + j) * 2^32) clipped to 2^32 - 1; a 32-bit draw u maps to
 // k = kmin[v] + #{j : thr[v][j] <= u}; jump[v][b] = #{j : thr[v][j] < b << 24} (where the probe for top byte b starts)
-static void poisson_table(double c, int* width_out, std::vector<uint8_t>& tab) {
+static void poisson_table(double c, int* width_out, size_t* guide_off, std::vector<uint8_t>& tab) {
   double lam[256];
   long long kmin[256];
   int width = 0;
@@ -122,6 +122,24 @@ static void poisson_table(double c, int* width_out, std::vector<uint8_t>& tab) {
   append(tab, thr.data(), thr.size());
   append(tab, jump.data(), jump.size());
   *width_out = width;
+  // guide[v][b] (k1_shot_smem): low 10 bits = k of the draw b << 24 (kmin + jump), high 6 bits = number of thresholds inside
+  // the cell [b << 24, (b + 1) << 24), saturated at 63.  Only when every k fits 10 bits.
+  *guide_off = 0;
+  bool fits = true;
+  std::vector<uint16_t> guide(size_t(256) * 256);
+  for (int v = 0; v < 256 && fits; ++v)
+    for (int b = 0; b < 256; ++b) {
+      const int j0 = jump[size_t(v) * 256 + b];
+      const int j1 = b < 255 ? int(jump[size_t(v) * 256 + b + 1]) : width;
+      const long long k = kmin[v] + j0;
+      if (k > 1023) { fits = false; break; }
+      guide[size_t(v) * 256 + b] = uint16_t(k) | uint16_t(std::min(j1 - j0, 63) << 10);
+    }
+  if (fits) {
+    while (tab.size() % 16) tab.push_back(0);
+    *guide_off = tab.size();
+    append(tab, guide.data(), guide.size());
+  }
 }
 
 static std::vector<double> gaussian_1d(int ksize, double sigma) {
@@ -316,9 +334,10 @@ int corrupt_params(int corruption, int severity, int h, int w, int profile, K1Pa
       break;
     case FAV_SHOT_NOISE: {
       int width = 0;
-      poisson_table(c[0], &width, out.table);
+      size_t guide_off = 0;
+      poisson_table(c[0], &width, &guide_off, out.table);
       out.fp = {float(c[0])};
-      out.ip = {width};
+      out.ip = {width, int32_t(guide_off)};
       break;
     }
     case FAV_IMPULSE_NOISE: {

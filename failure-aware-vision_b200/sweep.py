@@ -190,7 +190,9 @@ class CorruptionSweep:
         setup: Poisson / stencil tables take tens of ms each on the host)."""
         n = min(self.cfg.block, n_images or self.cfg.block)
         h, w = self.cfg.input_hw
-        x = torch.zeros((min(n, 8), h, w, 3), dtype=torch.uint8, device=self.clf.device)
+        # a FULL block: the library grows its K1 scratch (up to 7 fp32 planes per image for elastic_transform) and builds
+        # every cell's table on first use -- both synchronise, so they must happen here and not inside a timed step
+        x = torch.zeros((n, h, w, 3), dtype=torch.uint8, device=self.clf.device)
         for cell in self.cells:
             self.clf.corrupt_normalize(x, cell, self.cfg.seed, 0)
         _lib.check(self.clf.lib.fav_reserve(self.clf.handle.h, n, self.cfg.T), "fav_reserve")

@@ -119,6 +119,56 @@ def test_k1_ragged_frames_byte_exact_codecs(fav, hw):
             _k1_check(fav, clf, name, sev, x, 5, 9, prof)
 
 
+@pytest.mark.parametrize("name,sev", ALL_CELLS)
+def test_k1_corruption_camera_bgr_frames(fav, name, sev):
+    """All 75 cells on 120x160 BGR frames (the layout the reference hands out, signal_analyzer.py:51,62; ImageNet-C constants;
+    jpeg MCU rows that do not divide the frame): the device output in RGB order equals the oracle on the RGB image."""
+    clf = _clf_cache(fav, "resnet18", 1000, (120, 160))
+    n, first, seed = 2, 31, 8
+    x = px.synthetic_images(n, 120, 160, seed, first)
+    want = OC.corrupt(x, name, sev, seed=seed, first_image=first, profile="imagenet")
+    got = clf.corrupt_normalize(np.ascontiguousarray(x[..., ::-1]), fav.CorruptionConfig(name, sev), seed, first, bgr=True,
+                                out_f32=True, normalize=False).cpu().numpy()
+    assert np.abs(got - want).max() <= 1e-3, f"{name} s{sev}: max abs err {np.abs(got - want).max()}"
+
+
+@pytest.mark.parametrize("bgr", [False, True])
+@pytest.mark.parametrize("name", OC.CORRUPTIONS)
+def test_k1_corruption_odd_small_frames(fav, name, bgr):
+    """40x48 frames (CIFAR-10-C constants, 64-cell plasma maps in shared memory, 2x2 stencil tiles, a JPEG MCU row that is
+    half padding), RGB and BGR sources, fp32 and production bf16 outputs."""
+    clf = _clf_cache(fav, "resnet18", 10, (40, 48))
+    n, first, seed, sev = 5, 3, 12, 3
+    x = px.synthetic_images(n, 40, 48, seed, first)
+    want = OC.corrupt(x, name, sev, seed=seed, first_image=first, profile="cifar")
+    src = np.ascontiguousarray(x[..., ::-1]) if bgr else x
+    cfg = fav.CorruptionConfig(name, sev)
+    got = clf.corrupt_normalize(src, cfg, seed, first, bgr=bgr, out_f32=True, normalize=False).cpu().numpy()
+    assert np.abs(got - want).max() <= 1e-3, f"{name}: max abs err {np.abs(got - want).max()}"
+    gotb = clf.corrupt_normalize(src, cfg, seed, first, bgr=bgr).float().cpu().numpy()
+    wantn = OC.normalize(want, *OC.MEAN_STD["cifar"])
+    assert (gotb == OC.to_bf16(wantn)).mean() > 0.99
+
+
+def test_k1_fast_kernels_equal_legacy_kernels(fav, clf18):
+    """The round-2 K1 kernels (guide-table shot noise, fused shared-memory plasma for fog / frost, raw-staged tap stencils
+    with coalesced stores) produce the SAME BITS as the round-1 kernels they replace (fav_set_option 'k1_legacy')."""
+    lib, h = clf18.lib, clf18.handle.h
+    n, seed, first = 300, 7, 90
+    x = torch.from_numpy(px.synthetic_images(n, 32, 32, seed, first)).cuda()
+    for name in ("shot_noise", "fog", "frost", "defocus_blur", "motion_blur"):
+        for sev in (1, 3, 5):
+            cfg = fav.CorruptionConfig(name, sev)
+            fast = {f32: clf18.corrupt_normalize(x, cfg, seed, first, out_f32=f32, normalize=not f32) for f32 in (False, True)}
+            fav._lib.check(lib.fav_set_option(h, b"k1_legacy", 1), "fav_set_option")
+            try:
+                for f32 in (False, True):
+                    legacy = clf18.corrupt_normalize(x, cfg, seed, first, out_f32=f32, normalize=not f32)
+                    assert torch.equal(fast[f32], legacy), (name, sev, f32)
+            finally:
+                fav._lib.check(lib.fav_set_option(h, b"k1_legacy", 0), "fav_set_option")
+
+
 def test_k1_table_taking_entry_equals_self_sufficient_entry(fav, clf18):
     """fav_corrupt_normalize_ex fed with fav_corrupt_params' host tables == fav_corrupt_normalize (which builds and caches the
     same tables inside the library), bit for bit, for every corruption."""

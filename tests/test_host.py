@@ -90,13 +90,19 @@ def test_library_host_tables_match_oracle_definitions():
         fp, ip, tab = _lib.corrupt_params(ID["shot_noise"], sev, 32, 32, prof)
         c = OC.CONSTANTS[prof]["shot_noise"][sev - 1]
         k2, w2, t2 = OC.poisson_table(c)
-        assert fp == [float(c)] and ip == [w2]
+        assert fp == [float(c)] and ip[0] == w2
         assert np.array_equal(tab[:1024].view(np.int32), k2)
         t1 = tab[1024:1024 + 1024 * w2].view(np.uint32).reshape(256, w2)
         assert np.abs(t1.astype(np.int64) - t2.astype(np.int64)).max() <= 1      # fp64 cdf rounding: at most 1 LSB of 2^-32
-        jump = tab[1024 + 1024 * w2:].view(np.uint16).reshape(256, 256)
+        jump = tab[1024 + 1024 * w2:1024 + 1024 * w2 + 131072].view(np.uint16).reshape(256, 256)
         edges = (np.arange(256, dtype=np.uint64) << np.uint64(24))
         assert np.array_equal(jump, (t1[:, None, :].astype(np.uint64) < edges[None, :, None]).sum(-1))
+        # guide table of k1_shot_smem: k of the draw b << 24 + number of thresholds inside the top-byte cell
+        assert ip[1] > 0 and ip[1] % 16 == 0
+        guide = tab[ip[1]:ip[1] + 131072].view(np.uint16).reshape(256, 256)
+        assert np.array_equal(guide & 1023, k2[:, None] + jump)
+        inside = np.diff(np.concatenate([jump.astype(np.int64), np.full((256, 1), w2)], 1), axis=1)
+        assert np.array_equal(guide >> 10, np.minimum(inside, 63))
     # impulse thresholds
     for prof in ("cifar", "imagenet"):
         for sev in range(1, 6):
@@ -314,6 +320,31 @@ def test_div255_fma_correction_is_exact():
     for b in range(256):
         q = f32(b) * r
         assert fma(fma(-q, f32(255.0), f32(b)), r, q) == f32(b) / f32(255.0)
+
+
+def test_shot_noise_exact_division_by_fma_correction():
+    """k1_shot_smem computes k / c as q = k * rc, q' = fma(fma(-q, c, k), rc, q): equal to the correctly rounded fp32 quotient for
+    every k the guide table can hold and every c of both severity tables."""
+    from fractions import Fraction
+    f32 = np.float32
+
+    def rn(x):
+        cand = f32(float(x))
+        best = None
+        for d in (np.nextafter(cand, f32(-np.inf)), cand, np.nextafter(cand, f32(np.inf))):
+            err = abs(Fraction(float(d)) - x)
+            if best is None or err < best[0] or (err == best[0] and (int(f32(d).view(np.uint32)) & 1) == 0):
+                best = (err, d)
+        return f32(best[1])
+
+    for c in sorted(set(OC.CONSTANTS["cifar"]["shot_noise"] + OC.CONSTANTS["imagenet"]["shot_noise"])):
+        cf = f32(c)
+        rc = f32(1.0) / cf
+        for k in range(0, 1024, 1 if c in (3, 500) else 7):
+            kf = f32(k)
+            q = kf * rc
+            e = rn(Fraction(float(-q)) * Fraction(float(cf)) + Fraction(float(kf)))
+            assert rn(Fraction(float(e)) * Fraction(float(rc)) + Fraction(float(q))) == kf / cf, (c, k)
 
 
 def test_cli_and_trust_helpers_without_gpu():
