@@ -486,11 +486,13 @@ struct ShotArgs {
   unsigned flags;
 };
 __global__ void __launch_bounds__(1024) k1_shot_smem(const ShotArgs a) {
-  extern __shared__ __align__(16) uint16_t s_guide[];          // [256][256]
+  extern __shared__ __align__(16) uint16_t s_guide[];          // [256][256], then int kmin[256]
+  int* s_kmin = reinterpret_cast<int*>(s_guide + 65536);
   {
     const uint4* g4 = reinterpret_cast<const uint4*>(a.guide);
     uint4* s4 = reinterpret_cast<uint4*>(s_guide);
     for (int i = threadIdx.x; i < 8192; i += blockDim.x) s4[i] = __ldg(g4 + i);
+    if (threadIdx.x < 256) s_kmin[threadIdx.x] = __ldg(a.kmin + threadIdx.x);
   }
   __syncthreads();
   const long long total = (long long)a.n * a.groups_per_image;
@@ -510,17 +512,43 @@ __global__ void __launch_bounds__(1024) k1_shot_smem(const ShotArgs a) {
       for (int j = 0; j < 4; ++j) {
         const uint4 r = philox4x32_10(uint32_t(e0 / 4 + 4 * q3 + j), gimg, 0u, a.stream, a.k0, a.k1);
         const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+        int k4[4], idx4[4];
+        uint32_t c4[4], t[4][3];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const uint32_t b = (w[j] >> (8 * q)) & 0xFFu, u = rr[q];
-          const uint32_t gg = s_guide[b * 256u + (u >> 24)];
-          int k = int(gg & 1023u);
-          if (gg >> 10) {                                        // thresholds inside this cell: count the ones <= u
-            const int km = __ldg(a.kmin + b);
-            const uint32_t* row = a.thr + (size_t)b * a.width;
-            int lo = k - km;
-            while (lo < a.width && __ldg(row + lo) <= u) ++lo;
-            k = km + lo;
+          const uint32_t b = (w[j] >> (8 * q)) & 0xFFu;
+          const uint32_t gg = s_guide[b * 256u + (rr[q] >> 24)];
+          k4[q] = int(gg & 1023u);
+          c4[q] = gg >> 10;                                      // thresholds inside this draw's top-byte cell (saturated at 63)
+          idx4[q] = int(b) * a.width + k4[q] - s_kmin[b];
+        }
+        // up to three thresholds of the cell as PREDICATED, mutually independent loads (no divergent loop, twelve loads in
+        // flight per thread): ~80 % of the draws need none.  Cells b >= 1 count UP from the cell's start (probe idx + i),
+        // cell 0 counts DOWN from its end (probe idx - 1 - i): see the guide table in tables.cu.
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const bool down = (rr[q] >> 24) == 0u;
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            t[q][i] = c4[q] > uint32_t(i) ? __ldg(a.thr + (down ? idx4[q] - 1 - i : idx4[q] + i)) : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t u = rr[q];
+          const bool down = (u >> 24) == 0u;
+          int step = 0;                                          // sorted thresholds: the passing probes form a prefix
+#pragma unroll
+          for (int i = 0; i < 3; ++i) step += (c4[q] > uint32_t(i) && (down ? t[q][i] > u : t[q][i] <= u)) ? 1 : 0;
+          int k = down ? k4[q] - step : k4[q] + step;
+          if (c4[q] > 3u && step == 3) {                         // rare: more than three thresholds of the cell on the draw's side
+            const int row0 = int((w[j] >> (8 * q)) & 0xFFu) * a.width;
+            if (down) {
+              int pp = idx4[q] - 4;
+              while (pp >= row0 && __ldg(a.thr + pp) > u) { --pp; --k; }
+            } else {
+              int pp = idx4[q] + 3;
+              while (pp < row0 + a.width && __ldg(a.thr + pp) <= u) { ++pp; ++k; }
+            }
           }
           const float kf = float(k), qf = __fmul_rn(kf, a.rc);
           x[4 * j + q] = __fmaf_rn(__fmaf_rn(-qf, a.c, kf), a.rc, qf);         // == __fdiv_rn(kf, c)
@@ -724,23 +752,31 @@ __global__ void __launch_bounds__(256) k1_taps(const TapArgs a) {
     s_taps[i] = make_uint2(uint32_t((dy - a.dy_min) * SW + (dx - a.dx_min)), t.y);
   }
   const uint8_t* p = a.src + (size_t)img * a.h * a.w * 3;
+  // source row / column of every halo row / column (border rule resolved once per row and column, not once per staged pixel)
+  int* s_ymap = reinterpret_cast<int*>(s_taps + a.max_taps);
+  int* s_xmap = s_ymap + SH;
+  for (int i = threadIdx.x; i < SH + SW; i += blockDim.x) {
+    if (i < SH) s_ymap[i] = border_idx(y0 + i + a.dy_min, a.h, a.border);
+    else s_xmap[i - SH] = border_idx(x0 + (i - SH) + a.dx_min, a.w, a.border);
+  }
   if (a.raw_stage) {
     // small frames (one tile per image): the raw image comes in with coalesced 16-byte loads and the halo is expanded from
     // shared memory (the byte gathers of the generic path cost more than the stencil itself at 32x32)
-    uint4* s_raw = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(s_taps + a.max_taps) + 15) & ~uintptr_t(15));
+    uint4* s_raw = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(s_xmap + SW) + 15) & ~uintptr_t(15));
     const int nv = (a.h * a.w * 3) >> 4;
     for (int i = threadIdx.x; i < nv; i += blockDim.x) s_raw[i] = __ldg(reinterpret_cast<const uint4*>(p) + i);
-    __syncthreads();
     p = reinterpret_cast<const uint8_t*>(s_raw);
   }
+  __syncthreads();
+  const float inv_sw = 1.0f / float(SW);
   for (int i = threadIdx.x; i < SW * SH; i += blockDim.x) {
-    const int sy = i / SW, sx = i - sy * SW;
-    const int yy = border_idx(y0 + sy + a.dy_min, a.h, a.border);
-    const int xx = border_idx(x0 + sx + a.dx_min, a.w, a.border);
-    const uint8_t* q = p + ((size_t)yy * a.w + xx) * 3;
+    int sy = __float2int_rd(__fmul_rn(float(i) + 0.5f, inv_sw));          // i / SW without an integer division (exact: i < 2^20)
+    int sx = i - sy * SW;
+    if (sx < 0) { sx += SW; --sy; } else if (sx >= SW) { sx -= SW; ++sy; }
+    const uint8_t* q = p + ((size_t)s_ymap[sy] * a.w + s_xmap[sx]) * 3;
     uint32_t c0 = q[0], c1 = q[1], c2 = q[2];
     if (a.src_bgr) { const uint32_t t = c0; c0 = c2; c2 = t; }
-    s_tile[i] = make_float4(float(c0), float(c1), float(c2), 0.f);
+    s_tile[i] = make_float4(u8f(c0), u8f(c1), u8f(c2), 0.f);              // x / 255 once per staged pixel: no division per output
   }
   __syncthreads();
   const int lx = threadIdx.x & 31, ly0 = threadIdx.x >> 5;     // 8 rows of threads, 4 pixels each
@@ -768,7 +804,7 @@ __global__ void __launch_bounds__(256) k1_taps(const TapArgs a) {
     for (int j = 0; j < 4; ++j) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        float t = fminf(fmaxf(__fdiv_rn(acc[j][c], 255.0f), 0.0f), 1.0f);
+        float t = fminf(fmaxf(acc[j][c], 0.0f), 1.0f);
         if (!(a.out.flags & FAV_NO_NORMALIZE)) t = __fmul_rn(__fsub_rn(t, a.out.mean[c]), a.out.inv_std[c]);
         s_out[((ly0 + 8 * j) * TAP_TILE + lx) * 3 + c] = __float2bfloat16_rn(t);
       }
@@ -786,8 +822,7 @@ __global__ void __launch_bounds__(256) k1_taps(const TapArgs a) {
   for (int j = 0; j < 4; ++j) {
     const int y = y0 + ly0 + 8 * j, x = x0 + lx;
     if (y < a.h && x < a.w)
-      store_pixel(a.out, ((size_t)img * a.h + y) * a.w + x, __fdiv_rn(acc[j][0], 255.0f), __fdiv_rn(acc[j][1], 255.0f),
-                  __fdiv_rn(acc[j][2], 255.0f));
+      store_pixel(a.out, ((size_t)img * a.h + y) * a.w + x, acc[j][0], acc[j][1], acc[j][2]);
   }
 }
 
@@ -1607,11 +1642,11 @@ extern "C" int fav_corrupt_normalize_ex(fav_handle h, const uint8_t* d_src, void
         for (int c = 0; c < 3; ++c) { sa.mean[c] = mean[c]; sa.inv_std[c] = 1.0f / std[c]; }
         sa.flags = flags;
         if (!h->attr_shot) {
-          FAV_CUDA_OK(cudaFuncSetAttribute(k1_shot_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+          FAV_CUDA_OK(cudaFuncSetAttribute(k1_shot_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 1024));
           h->attr_shot = true;
         }
         const long long ctas = (groups + 1023) / 1024;
-        k1_shot_smem<<<int(ctas < h->num_sms ? ctas : h->num_sms), 1024, 131072, st>>>(sa);
+        k1_shot_smem<<<int(ctas < h->num_sms ? ctas : h->num_sms), 1024, 131072 + 1024, st>>>(sa);
         h->launches++; break;
       }
       k1_pointwise<PW_SHOT><<<grid, 256, 0, st>>>(a); h->launches++; break;
@@ -1779,7 +1814,7 @@ extern "C" int fav_corrupt_normalize_ex(fav_handle h, const uint8_t* d_src, void
       t.out_staged = (!h->k1_legacy && !(flags & FAV_OUT_F32) && ((size_t)width * 6) % 16 == 0 && ((size_t)per * 2) % 16 == 0 &&
                       (reinterpret_cast<uintptr_t>(d_dst) & 15) == 0) ? 1 : 0;
       const size_t smem = (size_t)(TAP_TILE + t.dx_max - t.dx_min) * (TAP_TILE + t.dy_max - t.dy_min) * 16 + (size_t)t.max_taps * 8 +
-                          (t.raw_stage ? (size_t)per + 16 : 0);
+                          (size_t)(2 * TAP_TILE + t.dx_max - t.dx_min + t.dy_max - t.dy_min) * 4 + (t.raw_stage ? (size_t)per + 16 : 0);
       FAV_REQUIRE(smem <= 200 * 1024, "tap stencil halo too large (%zu B of shared memory)", smem);
       if (smem > 48 * 1024) FAV_CUDA_OK(cudaFuncSetAttribute(k1_taps, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
       k1_taps<<<dim3(n, t.tiles_x * t.tiles_y), 256, smem, st>>>(t); h->launches++; break;

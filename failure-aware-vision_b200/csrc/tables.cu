@@ -122,8 +122,11 @@ static void poisson_table(double c, int* width_out, size_t* guide_off, std::vect
   append(tab, thr.data(), thr.size());
   append(tab, jump.data(), jump.size());
   *width_out = width;
-  // guide[v][b] (k1_shot_smem): low 10 bits = k of the draw b << 24 (kmin + jump), high 6 bits = number of thresholds inside
-  // the cell [b << 24, (b + 1) << 24), saturated at 63.  Only when every k fits 10 bits.
+  // guide[v][b] (k1_shot_smem), 10 + 6 bits.  b >= 1: k of the draw b << 24 (= kmin + jump[b]) and the number of thresholds
+  // inside the cell [b << 24, (b + 1) << 24), saturated at 63 -- the kernel counts UP from the cell's start.  b == 0 (the
+  // lower tail: dozens of tiny thresholds, almost all of them below any given draw): k of the cell's END (= kmin + jump[1])
+  // and the number of non-zero thresholds inside -- the kernel counts DOWN from the top, a couple of steps on average
+  // instead of walking the whole tail.  Only when every k fits 10 bits.
   *guide_off = 0;
   bool fits = true;
   std::vector<uint16_t> guide(size_t(256) * 256);
@@ -131,9 +134,16 @@ static void poisson_table(double c, int* width_out, size_t* guide_off, std::vect
     for (int b = 0; b < 256; ++b) {
       const int j0 = jump[size_t(v) * 256 + b];
       const int j1 = b < 255 ? int(jump[size_t(v) * 256 + b + 1]) : width;
-      const long long k = kmin[v] + j0;
+      long long k = kmin[v] + j0;
+      int cnt = j1 - j0;
+      if (b == 0) {
+        int nz = 0;
+        while (nz < j1 && thr[size_t(v) * width + nz] == 0u) ++nz;
+        k = kmin[v] + j1;
+        cnt = j1 - nz;
+      }
       if (k > 1023) { fits = false; break; }
-      guide[size_t(v) * 256 + b] = uint16_t(k) | uint16_t(std::min(j1 - j0, 63) << 10);
+      guide[size_t(v) * 256 + b] = uint16_t(k) | uint16_t(std::min(cnt, 63) << 10);
     }
   if (fits) {
     while (tab.size() % 16) tab.push_back(0);

@@ -97,12 +97,50 @@ def test_library_host_tables_match_oracle_definitions():
         jump = tab[1024 + 1024 * w2:1024 + 1024 * w2 + 131072].view(np.uint16).reshape(256, 256)
         edges = (np.arange(256, dtype=np.uint64) << np.uint64(24))
         assert np.array_equal(jump, (t1[:, None, :].astype(np.uint64) < edges[None, :, None]).sum(-1))
-        # guide table of k1_shot_smem: k of the draw b << 24 + number of thresholds inside the top-byte cell
+        # guide table of k1_shot_smem: cells b >= 1 hold the k of the draw b << 24 and the number of thresholds inside the
+        # cell (count up); cell 0 holds the k at the cell's END and the number of non-zero thresholds inside (count down)
         assert ip[1] > 0 and ip[1] % 16 == 0
         guide = tab[ip[1]:ip[1] + 131072].view(np.uint16).reshape(256, 256)
-        assert np.array_equal(guide & 1023, k2[:, None] + jump)
         inside = np.diff(np.concatenate([jump.astype(np.int64), np.full((256, 1), w2)], 1), axis=1)
-        assert np.array_equal(guide >> 10, np.minimum(inside, 63))
+        assert np.array_equal((guide & 1023)[:, 1:], (k2[:, None] + jump)[:, 1:])
+        assert np.array_equal((guide >> 10)[:, 1:], np.minimum(inside, 63)[:, 1:])
+        assert np.array_equal(guide[:, 0] & 1023, k2 + jump[:, 1])
+        nonzero0 = ((t1 > 0) & (t1 < (1 << 24))).sum(1)
+        assert np.array_equal(guide[:, 0] >> 10, np.minimum(nonzero0, 63))
+        # the search k1_shot_smem runs on it (three predicated probes, then the rare loop), emulated in numpy, returns the
+        # plain inverse-CDF count for every (value, draw) -- including draws of 0, 2^32 - 1 and exact cell boundaries
+        rng = np.random.default_rng(sev)
+        n = 100000
+        v = rng.integers(0, 256, n)
+        u = rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32)
+        u[:500], u[500:1000] = 0xFFFFFFFF, 0
+        u[1000:2000] = rng.integers(0, 256, 1000).astype(np.uint32) << 24
+        u[2000:12000] = rng.integers(0, 1 << 24, 10000).astype(np.uint32)                 # the lower-tail cell
+        want = k2[v] + (t1[v] <= u[:, None]).sum(1)
+        gg = guide[v, u >> 24]
+        k = (gg & 1023).astype(np.int64)
+        cnt = (gg >> 10).astype(np.int64)
+        idx = k - k2[v]
+        down = (u >> 24) == 0
+        step = np.zeros(n, np.int64)
+        for i in range(3):
+            ok = cnt > i
+            pos = np.clip(np.where(down, idx - 1 - i, idx + i), 0, w2 - 1)
+            t = t1[v, pos]
+            step += ok & np.where(down, t > u, t <= u)
+        got = np.where(down, k - step, k + step)
+        for j in np.nonzero((cnt > 3) & (step == 3))[0]:
+            if down[j]:
+                pp = idx[j] - 4
+                while pp >= 0 and t1[v[j], pp] > u[j]:
+                    pp -= 1
+                    got[j] -= 1
+            else:
+                pp = idx[j] + 3
+                while pp < w2 and t1[v[j], pp] <= u[j]:
+                    pp += 1
+                    got[j] += 1
+        assert np.array_equal(got, want), (prof, sev, int((got != want).sum()))
     # impulse thresholds
     for prof in ("cifar", "imagenet"):
         for sev in range(1, 6):
