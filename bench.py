@@ -78,6 +78,10 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device_index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")          # nvidia-smi counts physical GPUs, torch the visible ones
+        ids = [v.strip() for v in vis.split(",") if v.strip()]
+        if ids and device_index < len(ids) and ids[device_index].isdigit():
+            device_index = int(ids[device_index])
         self.idx, self.rows, self.proc = device_index, [], None
 
     def start(self):
@@ -386,9 +390,11 @@ def main():
     ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4", "C5"])
     ap.add_argument("--mode", default="steps", choices=["steps", "sweep"])
     ap.add_argument("--images", type=int, default=0, help="mode sweep: total images of the sweep (default: the config's resident set)")
+    ap.add_argument("--block", type=int, default=0, help="override the config's images per step (tuning)")
     ap.add_argument("--soak", type=float, default=5.0, help="seconds of sustained soak after the timed steps (0 = off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-rooflines", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short C3 / C4 / C5 sub-records of the default C2 line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -420,6 +426,9 @@ def main():
     K = args.steps
     name = args.config
     cf = CONFIGS[name]
+    if args.block > 0:
+        cf["n_images"] = cf["n_images"] * args.block // cf["block"]
+        cf["block"] = args.block
     T, BLOCK, H, Wd, NCLS = cf["T"], cf["block"], cf["hw"][0], cf["hw"][1], cf["classes"]
 
     cfg = SweepConfig(model=cf["model"], num_classes=NCLS, input_hw=cf["hw"], T=T, p_drop=P_DROP, tau=TAU, logit_gain=cf["gain"],
@@ -640,9 +649,34 @@ def main():
             "tflops_whole_step_algorithmic": flops_per_eval(cf) * evals / (ms * 1e-3) / 1e12 / world,
         }
         out.update(extra)
+        if name == "C2" and world == 1 and not args.no_extras:
+            out["other_configs"] = other_config_records()
         emit_json(out)
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_config_records():
+    """Short single-GPU records of the other BASELINE.json configs, each measured by this same script in a child process
+    (C3 / C4: step mode without the soak; C5: the frame-latency line with the reference's real per-frame code timed beside
+    it), so that the driver's one default invocation also carries them.  Multi-GPU C3 / C4 lines: profiles/."""
+    recs = {}
+    for key, argv in (("C3", ["--config", "C3", "--steps", "40", "--warmup", "3", "--soak", "0", "--no-cpu-baseline", "--no-kernel-rooflines"]),
+                      ("C4", ["--config", "C4", "--steps", "10", "--warmup", "3", "--soak", "0", "--no-cpu-baseline", "--no-kernel-rooflines"]),
+                      ("C5", ["--config", "C5"])):
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__)] + argv, capture_output=True, text=True, timeout=300, cwd=ROOT)
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+            keep = ("metric", "value", "unit", "ms_per_step", "steps", "clocks", "e2e", "p99_ms", "gpu_launches", "variants", "cpu_baseline")
+            rec = {k: d[k] for k in keep if k in d}
+            rec["workload"] = d["config"]["workload"]
+            if d.get("roofline"):
+                rec["roofline"] = {k: d["roofline"][k] for k in ("achieved", "peak", "frac", "unit", "peak_regime", "algorithmic_tflops",
+                                                                  "conv_share_of_step", "conv_hbm_frac")}
+            recs[key] = rec
+        except Exception as e:                              # a sub-record must never take the main line down
+            recs[key] = {"error": repr(e)[:300]}
+    return recs
 
 
 def kernel_rooflines(sweep, images, labels, cf, peaks):

@@ -167,7 +167,11 @@ class MetricsAccumulator:
         torch.cuda.current_stream(self.arena.device).synchronize()
 
     def results(self):
-        host = self.arena.cpu().numpy()
+        if getattr(self, "_host", None) is None or self._host.shape != self.arena.shape:
+            self._host = torch.empty(self.arena.shape, dtype=torch.int64).pin_memory()
+        self._host.copy_(self.arena, non_blocking=True)
+        torch.cuda.current_stream(self.arena.device).synchronize()
+        host = self._host.numpy()
         return [finalize(host[i], self.clf.num_classes, self.n_bins, self.n_buckets) for i in range(host.shape[0])]
 
 

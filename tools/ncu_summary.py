@@ -40,10 +40,25 @@ def full(path):
     rd = csv.reader(io.StringIO(out))
     hdr, units = next(rd), next(rd)
     idx = [i for i, h in enumerate(hdr) if any((h + " [").startswith(k) or h.startswith(k) for k in KEYS)]
+    it = hdr.index("gpu__time_duration.sum") if "gpu__time_duration.sum" in hdr else None
+    ip = next((i for i, h in enumerate(hdr) if h.startswith("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")), None)
+    idr = next((i for i, h in enumerate(hdr) if h.startswith("dram__bytes_read.sum") and units[i].endswith("byte")), None)
+    idw = next((i for i, h in enumerate(hdr) if h.startswith("dram__bytes_write.sum") and units[i].endswith("byte")), None)
+    tw = tt = dram = 0.0
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for n, row in enumerate(rd):
         print(f"--- launch {n}")
         for i in idx:
             print(f"  {hdr[i]} [{units[i]}] = {row[i]}")
+        try:
+            t = float(row[it].replace(",", ""))
+            tt += t
+            tw += t * float(row[ip].replace(",", ""))
+            dram += float(row[idr].replace(",", "")) * scale.get(units[idr], 1.0) + float(row[idw].replace(",", "")) * scale.get(units[idw], 1.0)
+        except Exception:
+            pass
+    if tt > 0:
+        print(f"=== time-weighted sm__pipe_tensor_cycles_active over these launches: {tw / tt:.1f} %  (total {tt:.4f} {units[it]}, dram read+write {dram / 1e9:.3f} GB)")
 
 
 if __name__ == "__main__":
