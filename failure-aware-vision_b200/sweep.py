@@ -240,68 +240,100 @@ class CorruptionSweep:
         self.acc.add_logits(ci, logits, labels_dev[lo:hi], cfg.tau)
         return hi - lo
 
-    def run_stream(self, host_images, host_labels, items, first_image=0, on_row=None):
-        """The steps `items` on HOST blocks (uint8 [N,H,W,3] / int32 [N] torch tensors, pinned for async copies):
-        block k+1 is copied host->device on a side stream while block k computes, and after every step the cell's
-        histogram-arena row is read back into pinned memory; `on_row(item, row)` sees it one step later (the only
-        host synchronisation).  Returns the number of evals."""
+    def _pipe_state(self):
+        """Two staging slots for the software-pipelined paths: uint8 / label staging (host data only), the bf16 K1 output, a
+        pinned arena row, and the events that order the side stream (copies + K1) against the main stream (forward + K3/K4)."""
         cfg, dev = self.cfg, self.clf.device
         h, w = cfg.input_hw
         if self._stream_state is None:
             B = cfg.block
             self._stream_state = dict(
-                copy=torch.cuda.Stream(dev),
-                img=[torch.empty((B, h, w, 3), dtype=torch.uint8, device=dev) for _ in range(2)],
-                lab=[torch.empty(B, dtype=torch.int32, device=dev) for _ in range(2)],
+                side=torch.cuda.Stream(dev),
+                img=None, lab=None,
+                x=[torch.empty((B, h, w, 3), dtype=torch.bfloat16, device=dev) for _ in range(2)],
                 row=[torch.empty(self.acc.words, dtype=torch.int64).pin_memory() for _ in range(2)],
-                copied=[torch.cuda.Event() for _ in range(2)], done=[torch.cuda.Event() for _ in range(2)])
-        ss = self._stream_state
-        cur = torch.cuda.current_stream(dev)
-        n_img = host_images.shape[0]
+                ready=[torch.cuda.Event() for _ in range(2)], done=[torch.cuda.Event() for _ in range(2)])
+        return self._stream_state
+
+    def _pipeline(self, items, n_img, fetch, first_image, on_row=None):
+        """Software pipeline over `items`: on the SIDE stream step k+1's input is fetched (`fetch(slot, lo, hi)` -> uint8
+        device block + int32 device labels: an H2D copy for host data, a view for resident data) and taken through K1
+        (corrupt + normalize) while the MAIN stream runs step k's forward and K3+K4.  The conv kernels fill every SM, so
+        the K1 CTAs run in the ramp-up / drain gaps between the conv launches instead of adding to the step.  Same kernels,
+        same inputs, same order of the integer accumulation per cell: results are bit-identical to the sequential path."""
+        cfg, dev = self.cfg, self.clf.device
+        ss = self._pipe_state()
+        cur, side = torch.cuda.current_stream(dev), ss["side"]
+        if ss.get("logits") is None:
+            ss["logits"] = torch.empty((cfg.block, cfg.T, cfg.num_classes), dtype=torch.float32, device=dev)
+        labs = [None, None]
 
         def span(item):
             lo = item[1] * cfg.block
             return lo, min(lo + cfg.block, n_img)
 
-        def issue_copy(k):
+        def stage(k):
             slot = k & 1
             lo, hi = span(items[k])
-            with torch.cuda.stream(ss["copy"]):
+            with torch.cuda.stream(side):
                 if k >= 2:
-                    ss["copy"].wait_event(ss["done"][slot])          # step k-2 has finished with this staging slot
+                    side.wait_event(ss["done"][slot])            # step k-2 is done with this slot's buffers
                 else:
-                    ss["copy"].wait_stream(cur)
-                ss["img"][slot][:hi - lo].copy_(host_images[lo:hi], non_blocking=True)
-                ss["lab"][slot][:hi - lo].copy_(host_labels[lo:hi], non_blocking=True)
-                ss["copied"][slot].record(ss["copy"])
+                    side.wait_stream(cur)
+                img, labs[slot] = fetch(slot, lo, hi)
+                self.clf.corrupt_normalize(img, self.cells[items[k][0]], cfg.seed, first_image + lo, out=ss["x"][slot][:hi - lo])
+                ss["ready"][slot].record(side)
 
         evals = 0
         if len(items):
-            issue_copy(0)
+            stage(0)
         for k, item in enumerate(items):
             slot = k & 1
             if k + 1 < len(items):
-                issue_copy(k + 1)
+                stage(k + 1)
             lo, hi = span(item)
             n = hi - lo
-            cur.wait_event(ss["copied"][slot])
-            x, logits = self._buffers(n)
-            self.clf.corrupt_normalize(ss["img"][slot][:n], self.cells[item[0]], cfg.seed, first_image + lo, out=x)
-            self.clf.forward_logits(x, cfg.T, cfg.p_drop, cfg.seed, first_image + lo, out=logits)
-            self.acc.add_logits(item[0], logits, ss["lab"][slot][:n], cfg.tau)
-            ss["row"][slot].copy_(self.acc.arena[item[0]], non_blocking=True)
+            cur.wait_event(ss["ready"][slot])
+            logits = ss["logits"][:n]
+            self.clf.forward_logits(ss["x"][slot][:n], cfg.T, cfg.p_drop, cfg.seed, first_image + lo, out=logits)
+            self.acc.add_logits(item[0], logits, labs[slot], cfg.tau)
+            if on_row is not None:
+                ss["row"][slot].copy_(self.acc.arena[item[0]], non_blocking=True)
             ss["done"][slot].record(cur)
-            if k >= 1:
+            if on_row is not None and k >= 1:
                 ss["done"][slot ^ 1].synchronize()
-                if on_row is not None:
-                    on_row(items[k - 1], ss["row"][slot ^ 1])
+                on_row(items[k - 1], ss["row"][slot ^ 1])
             evals += n
-        if len(items):
+        if len(items) and on_row is not None:
             last = (len(items) - 1) & 1
             ss["done"][last].synchronize()
-            if on_row is not None:
-                on_row(items[-1], ss["row"][last])
+            on_row(items[-1], ss["row"][last])
+        side.wait_stream(cur)                                    # leave both streams ordered for whoever comes next
+        cur.wait_stream(side)
         return evals
+
+    def run_items(self, images_dev, labels_dev, items, first_image=0):
+        """The steps `items` on RESIDENT device data, software-pipelined (K1 of step k+1 beside the forward of step k)."""
+        return self._pipeline(items, images_dev.shape[0], lambda slot, lo, hi: (images_dev[lo:hi], labels_dev[lo:hi]), first_image)
+
+    def run_stream(self, host_images, host_labels, items, first_image=0, on_row=None):
+        """The steps `items` on HOST blocks (uint8 [N,H,W,3] / int32 [N] torch tensors, pinned for async copies): block k+1 is
+        copied host->device and corrupted on a side stream while block k's forward runs, and after every step the cell's
+        histogram-arena row is read back into pinned memory; `on_row(item, row)` sees it one step later (the only host
+        synchronisation).  Returns the number of evals."""
+        cfg, dev = self.cfg, self.clf.device
+        h, w = cfg.input_hw
+        ss = self._pipe_state()
+        if ss["img"] is None:
+            ss["img"] = [torch.empty((cfg.block, h, w, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
+            ss["lab"] = [torch.empty(cfg.block, dtype=torch.int32, device=dev) for _ in range(2)]
+
+        def fetch(slot, lo, hi):
+            ss["img"][slot][:hi - lo].copy_(host_images[lo:hi], non_blocking=True)
+            ss["lab"][slot][:hi - lo].copy_(host_labels[lo:hi], non_blocking=True)
+            return ss["img"][slot][:hi - lo], ss["lab"][slot][:hi - lo]
+
+        return self._pipeline(items, host_images.shape[0], fetch, first_image, on_row if on_row is not None else (lambda item, row: None))
 
     def run(self, images_u8, labels, rank=0, world_size=1, first_image=0, timing=False):
         """images uint8 [N,H,W,3] (numpy or torch, host or device), labels int [N].
@@ -326,7 +358,9 @@ class CorruptionSweep:
             images_dev = self.clf._images(images_u8)
             labels_dev = self.clf._labels(labels)
             evs = []
-            for item in mine:
+            if not timing:
+                self.run_items(images_dev, labels_dev, mine, first_image)
+            for item in (mine if timing else []):
                 if timing:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record(torch.cuda.current_stream(self.clf.device))

@@ -631,6 +631,13 @@ def test_sweep_partition_is_bit_identical(fav):
     assert n == 100 * 4 and torch.equal(sw.acc.arena, whole)
     for ci, row in rows.items():
         assert torch.equal(row, whole[ci].cpu())
+    # the pipelined resident path (K1 of step k+1 on a side stream beside the forward of step k) and the step-by-step path
+    sw.reset()
+    assert sw.run_items(xd, yd, sw.work_items(100)) == 100 * 4 and torch.equal(sw.acc.arena, whole)
+    sw.reset()
+    for it in sw.work_items(100):
+        sw.run_item(xd, yd, it)
+    assert torch.equal(sw.acc.arena, whole)
 
 
 def test_allreduce_entry_points_single_rank(fav, clf18):
