@@ -5,7 +5,8 @@
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Configs (BASELINE.json `configs`; C1 is the CPU-runnable parity case, not a bench line):
-  C2 (default, the driver's line)  ResNet-18 random-init, 32x32 CIFAR-shape, MC-dropout T=20, 15 x 5 sweep, 4096 images/step
+  C2 (default, the driver's line)  ResNet-18 random-init, 32x32 CIFAR-shape, MC-dropout T=20, 15 x 5 sweep, 8192 images/step
+                                   (5 s soak, power-capped: 1024 -> 801 k, 2048 -> 840 k, 4096 -> 868 k, 8192 -> 878 k evals/s)
   C3                               ResNet-50 224x224 ImageNet-C-shape sweep, T=1 (MSP + entropy + ECE), 1024 images/step
                                    (measured: 256 -> 57.0 k, 512 -> 58.4 k, 1024 -> 59.6 k evals/s: ~0.4 ms of per-step kernel ramp-up / drain)
   C4                               ResNet-50 224x224, MC-dropout T=30 (mutual information + AUROC), 64 images/step
@@ -46,7 +47,7 @@ TAU = 0.9
 # conv + fc MMAC per image: (pass-invariant prefix, per MC pass) -- oracle.model.count_macs on stock torchvision models
 # (BASELINE.md section 4); x2 for FLOPs.  C2: 2*(2.408 + 20*34.61) MFLOP = 1.389 GFLOP per eval.
 CONFIGS = {
-    "C2": dict(model="resnet18", classes=10, hw=(32, 32), T=20, block=4096, n_images=16384, gain=8.0,
+    "C2": dict(model="resnet18", classes=10, hw=(32, 32), T=20, block=8192, n_images=32768, gain=8.0,
                mmac=(2.408448, 34.608128), ref_images=64, cpu_images=128,
                what="C2: ResNet-18 random-init (torchvision, logit-gain fixture 8.0), 32x32 CIFAR-shape"),
     "C3": dict(model="resnet50", classes=1000, hw=(224, 224), T=1, block=1024, n_images=4096, gain=4.0,
