@@ -15,7 +15,7 @@ void set_error(const char* fmt, ...) {
 void plan_destroy(Plan* p);   // forward.cu
 }  // namespace fav
 
-namespace fav { void comm_destroy(Ctx* ctx); void k1_cache_destroy(Ctx* ctx); }
+namespace fav { void comm_destroy(Ctx* ctx); void k1_cache_destroy(Ctx* ctx); int k1_scratch_release(Ctx* ctx); }
 using namespace fav;
 
 extern "C" int fav_abi_version(void) { return FAV_ABI_VERSION; }
@@ -45,7 +45,7 @@ extern "C" int fav_init(int device, fav_handle* out) {
 extern "C" int fav_reset(fav_handle h) {
   FAV_REQUIRE(h, "fav_reset: null handle");
   if (h->ws) { FAV_CUDA_OK(cudaFree(h->ws)); h->ws = nullptr; h->ws_bytes = 0; }
-  return FAV_OK;
+  return k1_scratch_release(h);          // the K1 scratch goes too; weights and the per-cell K1 tables stay
 }
 
 extern "C" int fav_destroy(fav_handle h) {

@@ -521,6 +521,16 @@ int k1_scratch(Ctx* ctx, size_t bytes, void** out) {
   return FAV_OK;
 }
 
+int k1_scratch_release(Ctx* ctx) {
+  K1Cache* cache = static_cast<K1Cache*>(ctx->k1_cache);
+  if (cache && cache->scratch) {
+    FAV_CUDA_OK(cudaFree(cache->scratch));
+    cache->scratch = nullptr;
+    cache->scratch_bytes = 0;
+  }
+  return FAV_OK;
+}
+
 void k1_cache_destroy(Ctx* ctx) {
   K1Cache* cache = static_cast<K1Cache*>(ctx->k1_cache);
   if (!cache) return;

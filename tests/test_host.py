@@ -329,6 +329,18 @@ def test_bench_reference_arm_runs_on_cpu():
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "baseline", "_ref", "signal_analyzer.py")), reason="baseline/_ref not installed (run build())")
+def test_bench_reference_arm_c5_times_the_real_reference_code():
+    """bench.py --impl reference --config C5: the reference's own SignalAnalyzer.analyze_frame + TrustEngine.update per frame,
+    imported from the unmodified copy in baseline/_ref (kind 'reference'), p50 latency in ms, lower is better."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "C5", "--steps", "50"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "ms" and line["higher_is_better"] is False and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "reference" and line["p99_ms"] >= line["value"]
+
+
 def test_trust_engine_golden_transcript_is_recorded():
     """The consumer (TrustEngine.update, trust_engine.py:139) is unchanged; the golden transcript of the
     reference's own smoke script (test_trust.py) is kept as the regression vector."""
