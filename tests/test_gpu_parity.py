@@ -571,6 +571,23 @@ def test_c_only_driver_matches_python_host(fav, tmp_path):
         assert int(f["fnv"]) == fnv, (r[1], r[2])
 
 
+def test_sweep_cli_emits_the_wire_format(fav, tmp_path, capsys):
+    """f3: `python -m fav.sweep --format json` (run in-process) writes one 'sweep_result' document whose per-cell records carry
+    the metrics AND device time, evals/s, TFLOP/s and roofline fraction; the CSV form has the same columns."""
+    from fav.sweep import main, CorruptionSweep
+    out = tmp_path / "sweep.json"
+    assert main(["--images", "96", "--passes", "3", "--block", "64", "--corruptions", "fog,jpeg_compression", "--severities", "2,5",
+                 "--format", "json", "--out", str(out)]) == 0
+    doc = json.loads(out.read_text())
+    assert doc["type"] == "sweep_result" and doc["images"] == 96 and doc["n_gpus"] == 1 and doc["gflop_per_eval"] > 0
+    assert [(c["corruption"], c["severity"]) for c in doc["cells"]] == [("fog", 2), ("fog", 5), ("jpeg_compression", 2), ("jpeg_compression", 5)]
+    for c in doc["cells"]:
+        assert c["n"] == 96 and 0 <= c["ece"] <= 1 and c["gpu_ms"] > 0 and c["evals_per_gpu_s"] > 0 and 0 < c["roofline_frac"] < 1
+    assert main(["--images", "64", "--passes", "1", "--block", "64", "--corruptions", "contrast", "--severities", "3", "--format", "csv"]) == 0
+    hdr = capsys.readouterr().out.strip().splitlines()[0].split(",")
+    assert hdr == CorruptionSweep.COLUMNS + CorruptionSweep.PERF_COLUMNS
+
+
 def _two_gpu_worker(rank, world, port, tmp):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     import torch.distributed as dist
