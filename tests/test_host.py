@@ -613,3 +613,14 @@ def test_work_items_interleave_the_grid():
     for world in (2, 4, 8):                       # a rank's round-robin share of the first 75 items still mixes the grid
         share = [sw.cells[items[i][0]].name for i in range(0, 75, world)]
         assert len(set(share)) >= 0.75 * min(15, len(share))
+
+
+def test_graft_entry_build_is_consistent():
+    """The driver's build check: __graft_entry__.build() compiles the library (incremental), installs baseline/_ref and asserts
+    the ABI version the header declares."""
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    g.build()
+    hdr = open(os.path.join(ROOT, "include", "fav_b200.h")).read()
+    from fav import _lib
+    assert int(re.search(r"#define FAV_ABI_VERSION (\d+)", hdr).group(1)) == _lib.load().fav_abi_version()
