@@ -627,7 +627,7 @@ def main():
                 "conv_share_of_step": conv_ms / KR / (ms / K),
                 "conv_hbm_gbs": conv_gbyte / (conv_ms * 1e-3), "conv_hbm_frac": conv_gbyte / (conv_ms * 1e-3) / peaks["hbm_gbs"],
                 "flops_per_step_algorithmic": alg_flops / KR}
-        if not args.no_kernel_rooflines:
+        if not args.no_kernel_rooflines and world == 1:          # single-kernel studies belong to the N = 1 line
             extra = kernel_rooflines(sweep, images, labels, cf, peaks)
         sampler.stop()
     sweep.reset()
@@ -635,7 +635,7 @@ def main():
         dist.barrier()
 
     if rank == 0:
-        base = None if args.no_cpu_baseline else cpu_baseline(name)
+        base = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(name)       # rank 0 at N = 1 only
         out = {
             "metric": "corrupted-image evals/sec", "value": evals / (ms * 1e-3), "unit": "evals/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
