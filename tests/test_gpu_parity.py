@@ -216,6 +216,18 @@ def test_k1_bgr_and_ragged_and_clean(fav, clf18):
         fav.CorruptionConfig("no_such_corruption", 1)
 
 
+def test_reset_releases_scratch_and_the_handle_keeps_working(fav):
+    """fav_reset (signal_analyzer.py:41-45 style reset()): drops the forward workspace and the K1 scratch, keeps the weights and
+    the per-cell K1 tables; the next calls re-grow what they need and give the same bits."""
+    clf = fav.VisionClassifier("resnet18", 10, (32, 32), weights_seed=0, logit_gain=8.0)
+    x = px.synthetic_images(9, 32, 32, 1)
+    cfg = fav.CorruptionConfig("elastic_transform", 2)
+    a = clf.uncertainty(x, cfg, T=3, labels=px.synthetic_labels(9, 10, 1), seed=1)
+    clf.reset()
+    b = clf.uncertainty(x, cfg, T=3, labels=px.synthetic_labels(9, 10, 1), seed=1)
+    assert torch.equal(a["logits"], b["logits"]) and torch.equal(a["failure_flag"], b["failure_flag"])
+
+
 def test_k1_partition_independence(fav, clf18):
     x = px.synthetic_images(10, 32, 32, 0)
     cfg = fav.CorruptionConfig("shot_noise", 2)
