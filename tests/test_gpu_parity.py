@@ -151,13 +151,14 @@ def test_k1_corruption_odd_small_frames(fav, name, bgr):
 
 
 def test_k1_fast_kernels_equal_legacy_kernels(fav, clf18):
-    """The round-2 K1 kernels (guide-table shot noise, fused shared-memory plasma for fog / frost, raw-staged tap stencils
-    with coalesced stores) produce the SAME BITS as the round-1 kernels they replace (fav_set_option 'k1_legacy')."""
+    """The round-2 K1 kernels (chunk-per-thread clean / gaussian / impulse, guide-table shot noise, fused shared-memory plasma
+    for fog / frost, raw-staged tap stencils with coalesced stores) produce the SAME BITS as the round-1 kernels they replace
+    (fav_set_option 'k1_legacy')."""
     lib, h = clf18.lib, clf18.handle.h
     n, seed, first = 300, 7, 90
     x = torch.from_numpy(px.synthetic_images(n, 32, 32, seed, first)).cuda()
-    for name in ("shot_noise", "fog", "frost", "defocus_blur", "motion_blur"):
-        for sev in (1, 3, 5):
+    for name in (None, "gaussian_noise", "impulse_noise", "shot_noise", "fog", "frost", "defocus_blur", "motion_blur"):
+        for sev in ((0,) if name is None else (1, 3, 5)):
             cfg = fav.CorruptionConfig(name, sev)
             fast = {f32: clf18.corrupt_normalize(x, cfg, seed, first, out_f32=f32, normalize=not f32) for f32 in (False, True)}
             fav._lib.check(lib.fav_set_option(h, b"k1_legacy", 1), "fav_set_option")
