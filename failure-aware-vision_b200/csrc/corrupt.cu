@@ -508,6 +508,16 @@ __global__ void __launch_bounds__(256) k1_chunk16(const PointwiseArgs a) {
     }
     // channel of element i = (16 cc + i) % 3 = (cc + i) % 3: rotate the per-channel constants once instead of indexing them
     const int c0 = cc % 3;
+    if (MODE == PW_CONTRAST) {                                   // (x - mu_c) * c + mu_c with the per-image channel means of the pre-pass
+      const unsigned long long* sums = reinterpret_cast<const unsigned long long*>(a.scratch) + 3 * (size_t)img;
+      float mu[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) mu[c] = __fdiv_rn(__ull2float_rn(__ldg(sums + c)), 255.0f * float(a.hw));
+      const float mr[3] = {c0 == 0 ? mu[0] : (c0 == 1 ? mu[1] : mu[2]), c0 == 0 ? mu[1] : (c0 == 1 ? mu[2] : mu[0]),
+                           c0 == 0 ? mu[2] : (c0 == 1 ? mu[0] : mu[1])};
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = __fadd_rn(__fmul_rn(__fsub_rn(x[i], mr[i % 3]), a.f0), mr[i % 3]);
+    }
     const float m[3] = {c0 == 0 ? a.mean[0] : (c0 == 1 ? a.mean[1] : a.mean[2]), c0 == 0 ? a.mean[1] : (c0 == 1 ? a.mean[2] : a.mean[0]),
                         c0 == 0 ? a.mean[2] : (c0 == 1 ? a.mean[0] : a.mean[1])};
     const float is[3] = {c0 == 0 ? a.inv_std[0] : (c0 == 1 ? a.inv_std[1] : a.inv_std[2]),
@@ -1744,7 +1754,9 @@ extern "C" int fav_corrupt_normalize_ex(fav_handle h, const uint8_t* d_src, void
         const int bx = max(1, min(64, (height * width + 4095) / 4096));
         k1_channel_sums<<<dim3(n, bx), 256, 0, st>>>(d_src, per, reinterpret_cast<unsigned long long*>(d_scratch));
       }
-      k1_pointwise<PW_CONTRAST><<<grid, 256, 0, st>>>(a); h->launches += 2; break;
+      if (chunk_ok) k1_chunk16<PW_CONTRAST><<<grid16, 256, 0, st>>>(a);
+      else k1_pointwise<PW_CONTRAST><<<grid, 256, 0, st>>>(a);
+      h->launches += 2; break;
     }
     case FAV_FOG:
     case FAV_FROST: {

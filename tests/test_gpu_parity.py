@@ -157,7 +157,7 @@ def test_k1_fast_kernels_equal_legacy_kernels(fav, clf18):
     lib, h = clf18.lib, clf18.handle.h
     n, seed, first = 300, 7, 90
     x = torch.from_numpy(px.synthetic_images(n, 32, 32, seed, first)).cuda()
-    for name in (None, "gaussian_noise", "impulse_noise", "shot_noise", "fog", "frost", "defocus_blur", "motion_blur"):
+    for name in (None, "gaussian_noise", "impulse_noise", "contrast", "shot_noise", "fog", "frost", "defocus_blur", "motion_blur"):
         for sev in ((0,) if name is None else (1, 3, 5)):
             cfg = fav.CorruptionConfig(name, sev)
             fast = {f32: clf18.corrupt_normalize(x, cfg, seed, first, out_f32=f32, normalize=not f32) for f32 in (False, True)}
