@@ -21,6 +21,7 @@ struct PointwiseArgs {
   int n, per;                 // images, elements per image (h*w*3)
   int groups_per_image;       // ceil(per/48)
   uint32_t gpi_magic;         // floor(2^32 / groups_per_image) + 1 when total groups * groups_per_image < 2^32, else 0 (-> plain division)
+  unsigned long long cpi_m64; // k1_chunk16: ceil(2^64 / chunks per image): umul64hi(c, m) == c / cpi for every c < 2^32 (0 -> plain division)
   uint32_t k0, k1;            // Philox key
   uint32_t first_image;
   uint32_t stream;            // Philox c3
@@ -477,7 +478,9 @@ __global__ void __launch_bounds__(256) k1_chunk16(const PointwiseArgs a) {
   const int cpi = a.per >> 4;                                    // chunks per image (per % 16 == 0, host-checked)
   const long long total = (long long)a.n * cpi;
   for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
-    const int img = int(c / cpi);
+    // image index = c / cpi: a multiply-high when the host could prove it exact (a 64-bit division costs as much as the
+    // whole clean path of a chunk)
+    const int img = a.cpi_m64 ? int(__umul64hi((unsigned long long)c, a.cpi_m64)) : int(c / cpi);
     const int cc = int(c - (long long)img * cpi);
     const size_t base = (size_t)img * a.per + (size_t)cc * 16;
     const uint32_t gimg = a.first_image + uint32_t(img);
@@ -1677,6 +1680,10 @@ extern "C" int fav_corrupt_normalize_ex(fav_handle h, const uint8_t* d_src, void
   a.src = d_src; a.dst = d_dst; a.n = n; a.per = per; a.groups_per_image = (per + 47) / 48;
   a.gpi_magic = ((unsigned long long)n * a.groups_per_image + 1) * (unsigned long long)a.groups_per_image < (1ull << 32)
                     ? uint32_t((1ull << 32) / (unsigned long long)a.groups_per_image) + 1u : 0u;
+  {
+    const unsigned long long cpi = (unsigned long long)(per >> 4);
+    a.cpi_m64 = (cpi > 1 && (unsigned long long)n * cpi < (1ull << 32)) ? ~0ull / cpi + 1ull : 0ull;       // ceil(2^64 / cpi) for cpi > 1
+  }
   a.k0 = k0; a.k1 = k1; a.first_image = uint32_t(first_image);
   a.stream = stream_id(KIND_CORRUPT, corruption, severity);
   a.table = d_table; a.scratch = d_scratch; a.hw = height * width; a.width = width; a.flags = flags;

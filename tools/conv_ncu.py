@@ -1,5 +1,6 @@
-"""One C2 sweep step (4096 images x T=20) for `ncu --set full` of its 18 tensor-core conv launches:
-  ncu --set full --clock-control none --import-source on -k regex:'conv_' -c 18 -o gpurun_out/conv_full python tools/conv_ncu.py"""
+"""One sweep step for `ncu --set full` of its tensor-core conv launches (C2: 18 launches, C3 / C4: 50):
+  ncu --set full --clock-control none -k regex:'conv' -c 18 -o /tmp/conv_full python tools/conv_ncu.py 4096 20
+  ncu --set full --clock-control none -k regex:'conv' -c 50 -o /tmp/conv_full_c3 python tools/conv_ncu.py 256 1 resnet50 224"""
 import os
 import sys
 
@@ -8,8 +9,12 @@ import torch
 from fav.sweep import CorruptionSweep, SweepConfig
 
 block, T = int(sys.argv[1]) if len(sys.argv) > 1 else 4096, int(sys.argv[2]) if len(sys.argv) > 2 else 20
-sw = CorruptionSweep(SweepConfig(T=T, logit_gain=8.0, block=block, corruptions=("gaussian_noise",), severities=(3,)))
-x = torch.randint(0, 256, (block, 32, 32, 3), dtype=torch.uint8, device="cuda")
-y = torch.randint(0, 10, (block,), dtype=torch.int32, device="cuda")
+model = sys.argv[3] if len(sys.argv) > 3 else "resnet18"
+hw = int(sys.argv[4]) if len(sys.argv) > 4 else 32
+ncls = 10 if hw <= 64 else 1000
+sw = CorruptionSweep(SweepConfig(model=model, num_classes=ncls, input_hw=(hw, hw), T=T, logit_gain=8.0, block=block,
+                                 corruptions=("gaussian_noise",), severities=(3,)))
+x = torch.randint(0, 256, (block, hw, hw, 3), dtype=torch.uint8, device="cuda")
+y = torch.randint(0, ncls, (block,), dtype=torch.int32, device="cuda")
 sw.run_item(x, y, (0, 0))
 torch.cuda.synchronize()
