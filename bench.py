@@ -608,10 +608,12 @@ def main():
         peak = peaks["bf16_tflops_sustained"] if capped else peaks["bf16_tflops"]
         traffic, pipe, pipe_src = None, None, None
         tp = os.path.join(ROOT, "profiles", "conv_traffic.json")      # from the committed ncu --set full capture
-        if os.path.exists(tp) and name == "C2":
+        if os.path.exists(tp):
             with open(tp) as fh:
                 tj = json.load(fh)
-            traffic = tj["dram_bytes_per_image"] * BLOCK if "dram_bytes_per_image" in tj else tj.get("dram_bytes_per_step")
+            tj = tj if name == "C2" else tj.get(name, {})             # top level: C2; per-config sections for the others
+            if "dram_bytes_per_image" in tj:
+                traffic = tj["dram_bytes_per_image"] * BLOCK
             pipe, pipe_src = tj.get("tensor_pipe_active_time_weighted"), tj.get("source")
         roof = {"bound": "tensor", "kernel": "conv_igemm_kernel / conv3x3_flat_kernel / conv_pair_kernel (all conv launches of a step)",
                 "achieved": executed, "peak": peak, "unit": "TFLOP/s", "frac": executed / peak, "traffic": traffic,
