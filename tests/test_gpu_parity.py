@@ -766,6 +766,60 @@ def test_k2_forward_resnet18_c5_geometry(fav, T):
         assert np.abs(got[:, 0] - got[:, 1]).max() > 1e-3               # passes differ
 
 
+def test_k2_forward_resnet50_c4_shape_t30(fav):
+    """Config C4 at its real pass count: ResNet-50, 224x224, T = 30 MC-dropout passes of one image, against the bf16-emulating
+    oracle (the T masked replicas of block 0, dropout epilogues in every residual block, 1000-class fc)."""
+    clf = _clf_cache(fav, "resnet50", 1000, (224, 224), 4.0)
+    folded = OM.fold_resnet(OM.build_torchvision("resnet50", 1000, 0, logit_gain=4.0))
+    xn = OC.to_bf16(np.random.default_rng(4).standard_normal((1, 224, 224, 3)).astype(np.float32))
+    got = clf.forward_logits(torch.from_numpy(xn).to(torch.bfloat16).cuda(), 30, 0.2, 6, 123).cpu().numpy()
+    emu = OM.forward(folded, xn, T=30, p=0.2, seed=6, first_image=123, emulate_bf16=True)
+    assert got.shape == (1, 30, 1000)
+    assert np.abs(got - emu).max() <= 3e-2 * np.abs(emu).max(), np.abs(got - emu).max() / np.abs(emu).max()
+    assert np.abs(got[0, 0] - got[0, 29]).max() > 1e-3
+
+
+def test_cell_end_to_end_resnet50_imagenet_shape(fav):
+    """One C3-shaped cell end to end (ResNet-50, 224x224, 1000 classes, T = 1, 48 images, defocus_blur s3 with the ImageNet-C
+    constants) through the sweep API against the oracle: per-class aggregate layout, ECE / confidence / entropy agreement,
+    accuracy and flags equal apart from near-ties."""
+    from fav.sweep import CorruptionSweep, SweepConfig
+    n, tau, seed = 48, 0.5, 9
+    x = px.synthetic_images(n, 224, 224, seed)
+    y = px.synthetic_labels(n, 1000, seed)
+    cfg = SweepConfig(model="resnet50", num_classes=1000, input_hw=(224, 224), corruptions=("defocus_blur",), severities=(3,), T=1,
+                      tau=tau, seed=seed, logit_gain=4.0, block=32)
+    sw = CorruptionSweep(cfg, classifier=_clf_cache(fav, "resnet50", 1000, (224, 224), 4.0))
+    res = sw.run(x, y)[("defocus_blur", 3)]
+    folded = OM.fold_resnet(OM.build_torchvision("resnet50", 1000, 0, logit_gain=4.0))
+    u, ar = OS.eval_cell(folded, x, y, "defocus_blur", 3, T=1, tau=tau, seed=seed, num_classes=1000, emulate_bf16=True)
+    dev = sw.acc.arena[0].cpu().numpy()
+    ref = OX.finalize(ar, 1000)
+    risky = int((OU.top2_gap(u["pbar"]) < 0.03).sum())
+    assert dev[0] == ar[0] == n and abs(int(dev[1]) - int(ar[1])) <= risky
+    assert abs(int(dev[2]) - int(ar[2])) <= risky + int((np.abs(u["confidence"] - tau) < 0.03).sum())
+    assert abs(res["mean_confidence"] - ref["mean_confidence"]) < 5e-3 and abs(res["mean_entropy"] - ref["mean_entropy"]) < 2e-2
+    assert abs(res["ece"] - ref["ece"]) < 0.02 and res["mean_mutual_information"] == 0.0
+    per_class = dev[8 + 45 + 6 * 4096:].reshape(1000, 2)
+    assert per_class[:, 0].sum() == n and np.array_equal(per_class[:, 0], np.bincount(y, minlength=1000))
+
+
+def test_gate_graph_replay_equals_eager_launches(fav):
+    """The CUDA-graph replay of the per-frame device work returns exactly what the eager launches return: T = 1, and T = 4 with
+    frozen masks (the graph freezes first_image, the frozen schedule keeps it at 0 in eager mode too)."""
+    frames = frame_sequence(3, 96, 128)[:8]
+    for T, sched in ((1, "per_frame"), (4, "frozen")):
+        clf = _clf_cache(fav, "resnet18", 10, (96, 128), 8.0)
+        g = fav.UncertaintyGate(classifier=clf, frame_hw=(96, 128), T=T, mask_schedule=sched, use_graph=True)
+        e = fav.UncertaintyGate(classifier=clf, frame_hw=(96, 128), T=T, mask_schedule=sched, use_graph=False)
+        outs_g = [g.analyze_frame(f) for f in frames]
+        assert g.graph_active and g.graph_error is None
+        outs_e = [e.analyze_frame(f) for f in frames]
+        assert not e.graph_active
+        if T == 1 or sched == "frozen":
+            assert outs_g == outs_e
+
+
 # ------------------------------------------------------------------------------------------- f4: trust replay
 def test_trust_replay_kernel_reproduces_the_reference_engine(fav):
     """The CUDA replay against trajectories of the REAL reference TrustEngine (golden, pinned): float64 state bit for
