@@ -1,7 +1,9 @@
 """Small-footprint run of every K1 kernel (both profiles, ragged frames, RGB / BGR, bf16 / fp32), K3+K4 (direct + histogram
 variants) and a tiny forward, for compute-sanitizer:
   compute-sanitizer --tool memcheck  python tools/sanitize_k1.py
-  compute-sanitizer --tool racecheck python tools/sanitize_k1.py k1only"""
+  compute-sanitizer --tool racecheck python tools/sanitize_k1.py k1only
+(compute-sanitizer is closed on the round-2 GPU pool -- runs under it left GPUs needing a reset -- so this was not run there; the
+script doubles as a no-assert smoke run of every K1 / K3+K4 path: `python tools/sanitize_k1.py`.)"""
 import os
 import sys
 
