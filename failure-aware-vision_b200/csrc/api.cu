@@ -65,6 +65,7 @@ extern "C" int fav_set_option(fav_handle h, const char* name, int value) {
   FAV_REQUIRE(h && name, "fav_set_option: null argument");
   if (strcmp(name, "splitk") == 0) { h->allow_splitk = value != 0; return FAV_OK; }
   if (strcmp(name, "k1_legacy") == 0) { h->k1_legacy = value != 0; return FAV_OK; }
+  if (strcmp(name, "k1_list_stencil") == 0) { h->k1_list_stencil = value != 0; return FAV_OK; }
   set_error("fav_set_option: unknown option '%s'", name);
   return FAV_E_ARG;
 }

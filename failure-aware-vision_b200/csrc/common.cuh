@@ -167,6 +167,7 @@ struct Ctx {
   // kernel attributes (max dynamic shared memory) are per device: set once per handle, not once per process
   bool attr_conv = false, attr_flat = false, attr_pair = false, attr_shot = false, attr_plasma = false;
   bool k1_legacy = false;         // fav_set_option(h, "k1_legacy", 1): the round-1 K1 kernels (A/B measurements, fallback)
+  bool k1_list_stencil = false;   // fav_set_option(h, "k1_list_stencil", 1): defocus_blur through the tap-list loop (A/B of the dense loop)
   int world = 1, rank = 0;
 };
 

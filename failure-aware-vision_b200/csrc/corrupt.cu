@@ -782,6 +782,7 @@ struct TapArgs {
   unsigned src_bgr;
   int raw_stage;                         // 1: one tile per image, raw image staged in shared memory with 16-byte loads
   int out_staged;                        // 1: bf16 rows are 16-byte aligned -> coalesced stores through shared memory
+  int dense;                             // 1: one entry whose taps fill most of their box -> register-tiled dense loop
 };
 constexpr int TAP_TILE = 32;
 
@@ -799,7 +800,13 @@ __global__ void __launch_bounds__(256) k1_taps(const TapArgs a) {
   // pixel instead of once per (tap, output pixel), and a tap costs one 16-byte shared load + three FMAs per output pixel
   extern __shared__ float4 s_tile[];
   const int SW = TAP_TILE + a.dx_max - a.dx_min, SH = TAP_TILE + a.dy_max - a.dy_min;
-  uint2* s_taps = reinterpret_cast<uint2*>(s_tile + SW * SH);
+  // dense mode: the weights of the tap box, replicated per output row of a thread: s_w4[dyy * BW + dx] = {w[dyy][dx],
+  // w[dyy-1][dx], w[dyy-2][dx], w[dyy-3][dx]} (zero outside the box), so that one staged pixel feeds four vertically adjacent
+  // outputs with one 16-byte broadcast load of weights
+  const int BW = a.dx_max - a.dx_min + 1, BH = a.dy_max - a.dy_min + 1;
+  float4* s_w4 = s_tile + SW * SH;
+  const int n_w4 = a.dense ? (BH + 3) * BW : 0;
+  uint2* s_taps = reinterpret_cast<uint2*>(s_w4 + n_w4);
   const int img = blockIdx.x;
   const int ty = blockIdx.y / a.tiles_x, tx = blockIdx.y - ty * a.tiles_x;
   const int y0 = ty * TAP_TILE, x0 = tx * TAP_TILE;
@@ -810,10 +817,27 @@ __global__ void __launch_bounds__(256) k1_taps(const TapArgs a) {
   }
   const uint8_t* ent = a.table + (size_t)entry * (16 + 8 * (size_t)a.max_taps);
   const int ntaps = *reinterpret_cast<const int*>(ent);
+  for (int i = threadIdx.x; i < n_w4; i += blockDim.x) s_w4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int disorder = 0;                        // the dense loop reproduces the list order only if the list is row-major
   for (int i = threadIdx.x; i < ntaps; i += blockDim.x) {
     const uint2 t = reinterpret_cast<const uint2*>(ent + 16)[i];
     const int dy = int(short(t.x & 0xFFFF)), dx = int(short(t.x >> 16));
     s_taps[i] = make_uint2(uint32_t((dy - a.dy_min) * SW + (dx - a.dx_min)), t.y);
+    if (a.dense && i > 0) {
+      const uint32_t q = reinterpret_cast<const uint2*>(ent + 16)[i - 1].x;
+      const int py = int(short(q & 0xFFFF)), px = int(short(q >> 16));
+      disorder |= (py > dy) || (py == dy && px >= dx);
+    }
+  }
+  const bool dense = a.dense && !__syncthreads_or(disorder);   // also orders the zero fill before the scatter below
+  if (dense) {
+    float* w4 = reinterpret_cast<float*>(s_w4);
+    for (int i = threadIdx.x; i < ntaps; i += blockDim.x) {
+      const uint2 t = reinterpret_cast<const uint2*>(ent + 16)[i];
+      const int ddy = int(short(t.x & 0xFFFF)) - a.dy_min, ddx = int(short(t.x >> 16)) - a.dx_min;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w4[((ddy + j) * BW + ddx) * 4 + j] = __uint_as_float(t.y);
+    }
   }
   const uint8_t* p = a.src + (size_t)img * a.h * a.w * 3;
   // source row / column of every halo row / column (border rule resolved once per row and column, not once per staged pixel)
@@ -843,19 +867,36 @@ __global__ void __launch_bounds__(256) k1_taps(const TapArgs a) {
     s_tile[i] = make_float4(u8f(c0), u8f(c1), u8f(c2), 0.f);              // x / 255 once per staged pixel: no division per output
   }
   __syncthreads();
-  const int lx = threadIdx.x & 31, ly0 = threadIdx.x >> 5;     // 8 rows of threads, 4 pixels each
+  const int lx = threadIdx.x & 31, ly0 = (threadIdx.x >> 5) * 4;   // a warp owns four adjacent rows: 4 pixels per thread
   float acc[4][3];
 #pragma unroll
   for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = 0.f;
-  for (int t = 0; t < ntaps; ++t) {
-    const uint2 tp = s_taps[t];
-    const float wgt = __uint_as_float(tp.y);
+  if (dense) {
+    // output j of the thread takes tap row ddy from halo row ly0 + j + ddy: walking the halo rows dyy = j + ddy in order
+    // visits every output's taps in list (row-major) order; the zero weights of the padding add exactly nothing
+    for (int dyy = 0; dyy < BH + 3; ++dyy) {
+      const float4* trow = s_tile + (ly0 + dyy) * SW + lx;
+      const float4* wrow = s_w4 + dyy * BW;
+      for (int dx = 0; dx < BW; ++dx) {
+        const float4 v = trow[dx];
+        const float4 wq = wrow[dx];
+        acc[0][0] = fmaf(wq.x, v.x, acc[0][0]); acc[0][1] = fmaf(wq.x, v.y, acc[0][1]); acc[0][2] = fmaf(wq.x, v.z, acc[0][2]);
+        acc[1][0] = fmaf(wq.y, v.x, acc[1][0]); acc[1][1] = fmaf(wq.y, v.y, acc[1][1]); acc[1][2] = fmaf(wq.y, v.z, acc[1][2]);
+        acc[2][0] = fmaf(wq.z, v.x, acc[2][0]); acc[2][1] = fmaf(wq.z, v.y, acc[2][1]); acc[2][2] = fmaf(wq.z, v.z, acc[2][2]);
+        acc[3][0] = fmaf(wq.w, v.x, acc[3][0]); acc[3][1] = fmaf(wq.w, v.y, acc[3][1]); acc[3][2] = fmaf(wq.w, v.z, acc[3][2]);
+      }
+    }
+  } else {
+    for (int t = 0; t < ntaps; ++t) {
+      const uint2 tp = s_taps[t];
+      const float wgt = __uint_as_float(tp.y);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 v = s_tile[(ly0 + 8 * j) * SW + lx + tp.x];
-      acc[j][0] = fmaf(wgt, v.x, acc[j][0]);
-      acc[j][1] = fmaf(wgt, v.y, acc[j][1]);
-      acc[j][2] = fmaf(wgt, v.z, acc[j][2]);
+      for (int j = 0; j < 4; ++j) {
+        const float4 v = s_tile[(ly0 + j) * SW + lx + tp.x];
+        acc[j][0] = fmaf(wgt, v.x, acc[j][0]);
+        acc[j][1] = fmaf(wgt, v.y, acc[j][1]);
+        acc[j][2] = fmaf(wgt, v.z, acc[j][2]);
+      }
     }
   }
   // bf16 output of a full-width tile whose rows are 16-byte aligned: stage the 32 x 32 x 3 results in shared memory (over
@@ -870,7 +911,7 @@ __global__ void __launch_bounds__(256) k1_taps(const TapArgs a) {
       for (int c = 0; c < 3; ++c) {
         float t = fminf(fmaxf(acc[j][c], 0.0f), 1.0f);
         if (!(a.out.flags & FAV_NO_NORMALIZE)) t = __fmul_rn(__fsub_rn(t, a.out.mean[c]), a.out.inv_std[c]);
-        s_out[((ly0 + 8 * j) * TAP_TILE + lx) * 3 + c] = __float2bfloat16_rn(t);
+        s_out[((ly0 + j) * TAP_TILE + lx) * 3 + c] = __float2bfloat16_rn(t);
       }
     }
     __syncthreads();
@@ -884,7 +925,7 @@ __global__ void __launch_bounds__(256) k1_taps(const TapArgs a) {
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const int y = y0 + ly0 + 8 * j, x = x0 + lx;
+    const int y = y0 + ly0 + j, x = x0 + lx;
     if (y < a.h && x < a.w)
       store_pixel(a.out, ((size_t)img * a.h + y) * a.w + x, acc[j][0], acc[j][1], acc[j][2]);
   }
@@ -1899,7 +1940,15 @@ extern "C" int fav_corrupt_normalize_ex(fav_handle h, const uint8_t* d_src, void
       t.raw_stage = (!h->k1_legacy && t.tiles_x * t.tiles_y == 1 && src16) ? 1 : 0;
       t.out_staged = (!h->k1_legacy && !(flags & FAV_OUT_F32) && ((size_t)width * 6) % 16 == 0 && ((size_t)per * 2) % 16 == 0 &&
                       (reinterpret_cast<uintptr_t>(d_dst) & 15) == 0) ? 1 : 0;
+      // register-tiled dense loop: 5 shared-memory wavefronts per (halo row, box column) of a warp against 17 per list tap;
+      // it walks box_h + 3 halo rows, so a 3 x 3 box (twice the FMAs of its nine list taps) stays on the list loop
+      // (measured: 3 x 3 list 0.52 ms vs dense 0.61 ms per 65 536 CIFAR frames; 5 x 5 dense 0.81 vs list 0.84-0.96;
+      // 9 x 9 .. 21 x 21 at 224 x 224 dense x1.4 .. x2.2, tools/k1_stencil_bench.py)
+      const long long box_w = t.dx_max - t.dx_min + 1, box_h = t.dy_max - t.dy_min + 1;
+      t.dense = (!h->k1_legacy && !h->k1_list_stencil && t.n_entries == 1 && box_h >= 5 &&
+                 5 * (box_h + 3) * box_w < 17LL * t.max_taps) ? 1 : 0;
       const size_t smem = (size_t)(TAP_TILE + t.dx_max - t.dx_min) * (TAP_TILE + t.dy_max - t.dy_min) * 16 + (size_t)t.max_taps * 8 +
+                          (t.dense ? (size_t)(box_h + 3) * box_w * 16 : 0) +
                           (size_t)(2 * TAP_TILE + t.dx_max - t.dx_min + t.dy_max - t.dy_min) * 4 + (t.raw_stage ? (size_t)per + 16 : 0);
       FAV_REQUIRE(smem <= 200 * 1024, "tap stencil halo too large (%zu B of shared memory)", smem);
       if (smem > 48 * 1024) FAV_CUDA_OK(cudaFuncSetAttribute(k1_taps, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));

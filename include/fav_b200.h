@@ -202,7 +202,9 @@ int fav_allreduce(fav_handle h, int64_t* d_hist, size_t count, void* stream);
 
 /* per-handle switches.  "splitk" = 1: convolutions that fill less than half the GPU split their K loop over several CTAs
  * with a deterministic in-kernel fix-up.  Experimental and off by default: the sweep's results must not depend on how
- * many rows a launch has, and on the batch-1 gate (main.py:160) the split launches measured slower than the unsplit ones. */
+ * many rows a launch has, and on the batch-1 gate (main.py:160) the split launches measured slower than the unsplit ones.
+ * "k1_legacy" = 1: the round-1 corruption kernels; "k1_list_stencil" = 1: defocus_blur through the tap-list loop instead of
+ * the register-tiled dense loop.  Both are A/B switches for measurements and tests: the results are bit-identical. */
 int fav_set_option(fav_handle h, const char* name, int value);
 
 /* counters for bench.py's gpu_launches claim */

@@ -170,6 +170,25 @@ def test_k1_fast_kernels_equal_legacy_kernels(fav, clf18):
                 fav._lib.check(lib.fav_set_option(h, b"k1_legacy", 0), "fav_set_option")
 
 
+@pytest.mark.parametrize("hw,classes", [((224, 224), 1000), ((40, 48), 10), ((120, 160), 1000)])
+def test_k1_dense_stencil_equals_list_stencil(fav, hw, classes):
+    """defocus_blur's register-tiled dense loop (one staged pixel feeds four vertically adjacent outputs, weights of the tap
+    box replicated per output row) adds the taps of every output in the list's row-major order: the SAME BITS as the
+    tap-list loop ('k1_legacy'), on multi-tile frames, ragged tiles and the largest disk (radius 10, 21 x 21 box)."""
+    clf = _clf_cache(fav, "resnet18", classes, hw)
+    lib, h = clf.lib, clf.handle.h
+    x = torch.from_numpy(px.synthetic_images(3, hw[0], hw[1], 4, 21)).cuda()
+    for sev in (1, 2, 3, 4, 5):
+        cfg = fav.CorruptionConfig("defocus_blur", sev)
+        fast = {f32: clf.corrupt_normalize(x, cfg, 4, 21, out_f32=f32, normalize=not f32) for f32 in (False, True)}
+        fav._lib.check(lib.fav_set_option(h, b"k1_legacy", 1), "fav_set_option")
+        try:
+            for f32 in (False, True):
+                assert torch.equal(fast[f32], clf.corrupt_normalize(x, cfg, 4, 21, out_f32=f32, normalize=not f32)), (hw, sev, f32)
+        finally:
+            fav._lib.check(lib.fav_set_option(h, b"k1_legacy", 0), "fav_set_option")
+
+
 def test_k1_table_taking_entry_equals_self_sufficient_entry(fav, clf18):
     """fav_corrupt_normalize_ex fed with fav_corrupt_params' host tables == fav_corrupt_normalize (which builds and caches the
     same tables inside the library), bit for bit, for every corruption."""
