@@ -470,20 +470,21 @@ __global__ void __launch_bounds__(DIRECT ? K34D_THREADS : K34S_THREADS) k34_smal
     if (my[k]) atomicAdd(&s_sums[k], my[k]);
   __syncthreads();
   if (threadIdx.x < 6 && s_sums[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_sums[threadIdx.x]);
-  if (DIRECT) return;
-  for (int i = threadIdx.x; i < n_slots; i += blockDim.x) {
-    const unsigned v = s_hist[i];
-    if (!v) continue;
-    size_t dst;
-    if (i < 2 * g.n_bins) dst = FAV_HIST_HDR + 3 * (size_t)(i >> 1) + ((i & 1) ? 2 : 0);
-    else dst = FAV_HIST_HDR + 3 * (size_t)g.n_bins + (size_t)(i - 2 * g.n_bins);
-    atomicAdd(&hist[dst], (unsigned long long)v);
+  if constexpr (!DIRECT) {
+    for (int i = threadIdx.x; i < n_slots; i += blockDim.x) {
+      const unsigned v = s_hist[i];
+      if (!v) continue;
+      size_t dst;
+      if (i < 2 * g.n_bins) dst = FAV_HIST_HDR + 3 * (size_t)(i >> 1) + ((i & 1) ? 2 : 0);
+      else dst = FAV_HIST_HDR + 3 * (size_t)g.n_bins + (size_t)(i - 2 * g.n_bins);
+      atomicAdd(&hist[dst], (unsigned long long)v);
+    }
+    for (int i = threadIdx.x; i < g.n_bins; i += blockDim.x)
+      if (s_binsum[i]) atomicAdd(&hist[FAV_HIST_HDR + 3 * (size_t)i + 1], s_binsum[i]);
+    const size_t cb = FAV_HIST_HDR + 3 * (size_t)g.n_bins + 6 * (size_t)g.n_buckets;
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x)
+      if (s_cm[i]) atomicAdd(&hist[cb + i], (unsigned long long)s_cm[i]);
   }
-  for (int i = threadIdx.x; i < g.n_bins; i += blockDim.x)
-    if (s_binsum[i]) atomicAdd(&hist[FAV_HIST_HDR + 3 * (size_t)i + 1], s_binsum[i]);
-  const size_t cb = FAV_HIST_HDR + 3 * (size_t)g.n_bins + 6 * (size_t)g.n_buckets;
-  for (int i = threadIdx.x; i < C * C; i += blockDim.x)
-    if (s_cm[i]) atomicAdd(&hist[cb + i], (unsigned long long)s_cm[i]);
 }
 
 }  // namespace fav
